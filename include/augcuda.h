@@ -1,0 +1,265 @@
+/*
+ * augcuda.h — C ABI of libaugcuda.so
+ *
+ * B200-native (sm_100a) implementation of the per-observation augmentation hot
+ * path of AugmentedGPLikelihoods.jl (CAVI update, Gibbs auxiliary draw, ELBO
+ * terms).  The reference has no FFI: its extension mechanism is Julia multiple
+ * dispatch on the verbs exported at src/AugmentedGPLikelihoods.jl:18-30.  Each
+ * entry point below is what a `ccall` from a Julia method of that verb,
+ * specialised on a device-array type, binds to (see INTEGRATION.md and
+ * augmentedgplikelihoods.jl_b200/julia/AugCUDA.jl).  All reference citations are relative to
+ * /root/reference.
+ *
+ * Conventions
+ *  - every function returns int32: 0 = OK, <0 = aug_status, >0 = cudaError_t,
+ *    >=1000 = ncclResult_t + 1000.  No exception crosses the boundary.
+ *  - all data pointers are DEVICE pointers owned by the caller unless the
+ *    name ends in `_host`; the library owns only ctx-internal scratch.
+ *  - all verbs are asynchronous on the ctx stream; scalars are written to
+ *    device memory (read them after aug_ctx_sync or with aug_memcpy_d2h).
+ *  - n is the number of observations held by THIS rank (shard), i0 the global
+ *    index of its first observation (RNG counters use the global index, so
+ *    draws are invariant under re-sharding).
+ *  - dtype of y per likelihood kind: BERNOULLI uint8 (Julia Bool),
+ *    NEGBIN / POISSON int64 (Julia Int), LAPLACE / STUDENTT / HETERO double,
+ *    CAT / CAT_BIJ uint8 one-hot [n][nl] (class index fastest, the flat view of
+ *    the reference's ArrayOfSimilarArrays, src/likelihoods/categorical.jl:63).
+ *  - multi-latent layouts: HETERO latent-major, f at ptr, g at ptr + ld
+ *    (src/likelihoods/heteroscedasticgaussian.jl:38: qfg = (qf, qg));
+ *    CAT observation-major [n][nl] (src/likelihoods/categorical.jl:84).
+ *    Outputs beta/gamma are always latent-major [nlatent][ldo]
+ *    (class-major for CAT: src/likelihoods/categorical.jl:112-136, utils.jl:24).
+ */
+#ifndef AUGCUDA_H
+#define AUGCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUGCUDA_VERSION 100 /* 0.1.0 */
+
+typedef struct aug_ctx aug_ctx;
+
+/* Likelihood kinds = the dispatch tags of src/likelihoods/ (one file per kind) */
+enum aug_kind {
+    AUG_BERNOULLI = 0, /* BernoulliLikelihood{<:LogisticLink}           bernoulli.jl */
+    AUG_NEGBIN    = 1, /* NegativeBinomialLikelihood{<:NBParamFailure}  negativebinomial.jl */
+    AUG_POISSON   = 2, /* PoissonLikelihood{<:ScaledLogistic}           poisson.jl */
+    AUG_LAPLACE   = 3, /* LaplaceLikelihood                             laplace.jl */
+    AUG_STUDENTT  = 4, /* StudentTLikelihood                            studentt.jl */
+    AUG_HETERO    = 5, /* HeteroscedasticGaussianLikelihood{<:InvScaledLogistic} */
+    AUG_CAT_BIJ   = 6, /* CategoricalLikelihood{<:BijectiveSimplexLink{<:LogisticSoftMaxLink}} */
+    AUG_CAT       = 7, /* CategoricalLikelihood{<:LogisticSoftMaxLink} */
+    AUG_NKINDS    = 8
+};
+
+enum aug_status {
+    AUG_OK               = 0,
+    AUG_ERR_BAD_KIND     = -1,
+    AUG_ERR_BAD_ARG      = -2,
+    AUG_ERR_PRECONDITION = -3, /* mirrors the reference's error(...) calls:
+                                  non-bijective KL (categorical.jl:165-170),
+                                  sum(p) >= 1 (negativemultinomial.jl:18-22) */
+    AUG_ERR_NOT_INIT     = -4,
+    AUG_ERR_NO_NCCL      = -5,
+    AUG_ERR_DEVICE_FLAG  = -6  /* a kernel raised the device-side error flag */
+};
+
+/*
+ * Likelihood descriptor (POD, passed by pointer).  Parameters are the struct
+ * fields of the reference likelihood / link types:
+ *   NEGBIN   p[0] = failures r   (negativebinomial.jl:16); r_is_int selects the
+ *            Int methods (negbin_logconst :52, integer-b PG sampler polyagamma.jl:129)
+ *   POISSON  p[0] = lambda       (ScaledLogistic.λ, poisson.jl:1-3)
+ *   LAPLACE  p[0] = beta         (laplace.jl:13-15)
+ *   STUDENTT p[0] = nu, p[1] = sigma (studentt.jl:14-21)
+ *   HETERO   p[0] = lambda       (InvScaledLogistic.λ, heteroscedasticgaussian.jl:1-3)
+ *   CAT*     logtheta = HOST pointer to K doubles (LogisticSoftMaxLink.logθ,
+ *            categorical.jl:6-10); NULL means zeros.  K = nlatent (CAT) or
+ *            nlatent + 1 (CAT_BIJ).
+ */
+typedef struct aug_lik {
+    int32_t kind;
+    int32_t nlatent;
+    int32_t r_is_int;
+    int32_t reserved;
+    double  p[4];
+    const double* logtheta;
+} aug_lik;
+
+/* Slots of the device scalar block written by the reducing verbs */
+enum aug_scalar_slot {
+    AUG_S_EXPECTED_LOGTILT = 0, /* api.jl:219-223 and per-likelihood methods */
+    AUG_S_KL               = 1, /* generic.jl:56-62, laplace.jl:98-104 */
+    AUG_S_EXPECTED_AUGLL   = 2, /* generic.jl:52-54 (the sum, "+"); hetero :129-145 */
+    AUG_S_LOGTILT          = 3, /* generic.jl:40-46 */
+    AUG_S_LOGPRIOR         = 4, /* logdensity_def(aux_prior(lik,y), Ω), generic.jl:49 */
+    AUG_S_AUGLL            = 5, /* generic.jl:48-50; hetero :117-127 */
+    AUG_S_FLAGS            = 6, /* count of rows that tripped a precondition */
+    AUG_S_RESERVED         = 7,
+    AUG_NSCALARS           = 8
+};
+
+/* ---- library / context ------------------------------------------------- */
+int32_t     aug_version(void);
+const char* aug_strerror(int32_t rc);
+
+/* stream: a cudaStream_t to run on, or NULL to let the ctx create its own. */
+int32_t aug_ctx_create(aug_ctx** out, int32_t device, void* stream);
+int32_t aug_ctx_destroy(aug_ctx* ctx);
+/* Counter-based RNG state: replaces the `rng::AbstractRNG` argument of
+ * aux_sample!/init_aux_variables (generic.jl:1-20,32-34).  Every sampling verb
+ * consumes one `offset` tick, so a (seed, offset) pair makes a run resumable. */
+int32_t aug_ctx_seed(aug_ctx* ctx, uint64_t seed, uint64_t offset);
+int32_t aug_ctx_get_offset(aug_ctx* ctx, uint64_t* offset);
+int32_t aug_ctx_sync(aug_ctx* ctx);
+int32_t aug_ctx_stream(aug_ctx* ctx, void** stream);
+int32_t aug_ctx_sm_count(aug_ctx* ctx, int32_t* n);
+/* number of kernels launched by this ctx since creation (bench "gpu_launches") */
+int32_t aug_ctx_launch_count(aug_ctx* ctx, uint64_t* n);
+
+/* memory helpers for callers without their own device allocator */
+int32_t aug_malloc(aug_ctx* ctx, void** dev, size_t bytes);
+int32_t aug_free(aug_ctx* ctx, void* dev);
+int32_t aug_host_alloc(void** host, size_t bytes); /* pinned */
+int32_t aug_host_free(void* host);
+int32_t aug_memcpy_h2d(aug_ctx* ctx, void* dev, const void* host, size_t bytes);
+int32_t aug_memcpy_d2h(aug_ctx* ctx, void* host, const void* dev, size_t bytes);
+
+/* ---- variational (CAVI) side ------------------------------------------- */
+/*
+ * State arrays of qΩ (the struct-of-arrays `only(qΩ.inds)`):
+ *   kind       s0        s1            s2 (optional copy, may be NULL)
+ *   BERNOULLI  c         -             -              bernoulli.jl:7-11
+ *   NEGBIN     c         -             y (int64)      negativebinomial.jl:14-18
+ *   POISSON    c         λ             y (int64)      poisson.jl:20-24
+ *   LAPLACE    μ         -             -              laplace.jl:33-38
+ *   STUDENTT   β         -             -              studentt.jl:39-44
+ *   HETERO     c         λ             ψ (required)   heteroscedasticgaussian.jl:22-26
+ *   CAT*       c [n][nl] p [n][nl]     y (uint8)      categorical.jl:59-70
+ * When s2 is NULL for NEGBIN/POISSON/CAT the y copy of the reference
+ * (`φ.y .= y`) is not materialised and the verbs read the y argument.
+ */
+
+/* init_aux_posterior(T, lik, n): zero-filled state.  (a3) */
+int32_t aug_init_aux_posterior(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                               void* s0, void* s1, void* s2);
+
+/* aux_posterior!(qΩ, lik, y, qf): bernoulli.jl:17-25, negativebinomial.jl:24-33,
+ * poisson.jl:30-39, laplace.jl:44-52, studentt.jl:50-58,
+ * heteroscedasticgaussian.jl:34-46, categorical.jl:80-110.  (a5)
+ * mu/var: means and variances of the marginals of q(f). */
+int32_t aug_aux_posterior(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                          const void* y, const double* mu, const double* var, int64_t ld,
+                          void* s0, void* s1, void* s2);
+
+/* expected_auglik_potential_and_precision(lik, qΩ, y[, qf]) from an existing
+ * state: bernoulli.jl:35-45, negativebinomial.jl:43-49, poisson.jl:49-60,
+ * laplace.jl:62-68, studentt.jl:68-74, heteroscedasticgaussian.jl:68-104,
+ * categorical.jl:121-136.  (a7)  mu is only read for HETERO (means of q(g)).
+ * Either of beta/gamma may be NULL (expected_auglik_potential / _precision). */
+int32_t aug_expected_potential_precision(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                                         const void* y, const double* mu, int64_t ld,
+                                         const void* s0, const void* s1, const void* s2,
+                                         double* beta, double* gamma, int64_t ldo);
+
+/* Fused single-pass CAVI step = aux_posterior! + expected_auglik_potential_and_precision
+ * (+ expected_logtilt, aux_kldivergence, expected_aug_loglik partial sums when
+ * scalars != NULL, written to scalars[AUG_S_EXPECTED_LOGTILT / _KL / _EXPECTED_AUGLL]).
+ * One read of y, mu, var; one write of state, beta, gamma.  This is the call
+ * pattern of examples/bernoulli/script.jl:29-39.  Any of s0..s2, beta, gamma
+ * may be NULL to skip that output. */
+int32_t aug_cavi_step(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                      const void* y, const double* mu, const double* var, int64_t ld,
+                      void* s0, void* s1, void* s2,
+                      double* beta, double* gamma, int64_t ldo,
+                      double* scalars);
+
+/* expected_logtilt / aux_kldivergence / expected_aug_loglik from an existing
+ * state (a9, a11, a13): api.jl:219-223, generic.jl:52-62 and the per-likelihood
+ * methods.  Writes scalars[0..2].  CAT (non-bijective) returns
+ * AUG_ERR_PRECONDITION like categorical.jl:165-170. */
+int32_t aug_expected_elbo_terms(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                                const void* y, const double* mu, const double* var, int64_t ld,
+                                const void* s0, const void* s1, const void* s2,
+                                double* scalars);
+
+/* ---- sampling (Gibbs) side --------------------------------------------- */
+/* Ω is the TupleVector of samples: omega (double) and, for POISSON / HETERO /
+ * CAT*, nvar (int64) — fields ω and n (bernoulli.jl:3-5, poisson.jl:14-18).
+ * CAT*: both are [n][nl]. */
+
+/* init_aux_variables(rng, lik, n): bernoulli.jl:3-5 etc.  (a4) */
+int32_t aug_init_aux_variables(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0,
+                               double* omega, int64_t* nvar);
+
+/* aux_sample!(rng, Ω, lik, y, f): generic.jl:5-12 with the full conditionals of
+ * bernoulli.jl:13-15, negativebinomial.jl:20-22, poisson.jl:26-28,
+ * laplace.jl:40-42, studentt.jl:46-48, heteroscedasticgaussian.jl:28-32,
+ * categorical.jl:72-78.  (a14-a19) */
+int32_t aug_aux_sample(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0,
+                       const void* y, const double* f, int64_t ld,
+                       double* omega, int64_t* nvar);
+
+/* auglik_potential_and_precision(lik, Ω, y[, f]) (a20).  f only read for HETERO. */
+int32_t aug_potential_precision(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                                const void* y, const double* f, int64_t ld,
+                                const double* omega, const int64_t* nvar,
+                                double* beta, double* gamma, int64_t ldo);
+
+/* logtilt (a21) and, when with_prior != 0, also logdensity(aux_prior, Ω) and
+ * aug_loglik (a22-a24: the PG(b,0) log-density series, polyagamma.jl:37-91).
+ * Writes scalars[AUG_S_LOGTILT / _LOGPRIOR / _AUGLL]. */
+int32_t aug_sampled_loglik_terms(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                                 const void* y, const double* f, int64_t ld,
+                                 const double* omega, const int64_t* nvar,
+                                 int32_t with_prior, double* scalars);
+
+/* ---- SpecialDistributions primitives (element-wise, for tests and callers) */
+/* rand(PolyaGamma(b_i, c_i)) (polyagamma.jl:121-164).  b_is_int selects the
+ * Int method (draw_sum :129-134) — b is then rounded to the nearest integer. */
+int32_t aug_pg_rand(aug_ctx* ctx, int64_t n, int64_t i0,
+                    const double* b, const double* c, int32_t b_is_int, double* out);
+/* same with scalar (b, c) broadcast over n draws */
+int32_t aug_pg_rand_bc(aug_ctx* ctx, int64_t n, int64_t i0,
+                       double b, double c, int32_t b_is_int, double* out);
+/* mean(PolyaGamma(b,c)) polyagamma.jl:25-31 */
+int32_t aug_pg_mean(aug_ctx* ctx, int64_t n, const double* b, const double* c, double* out);
+/* kldivergence(PolyaGamma(b,c), PolyaGamma(b,0)) polyagamma.jl:99-110 */
+int32_t aug_pg_kl(aug_ctx* ctx, int64_t n, const double* b, const double* c, double* out);
+/* logpdf(PolyaGamma(b,c), x) polyagamma.jl:37-91 (scalar b, c) */
+int32_t aug_pg_logpdf(aug_ctx* ctx, int64_t n, double b, double c, const double* x, double* out);
+/* approx_expected_logistic(mu, c) utils.jl:11-14 */
+int32_t aug_approx_expected_logistic(aug_ctx* ctx, int64_t n, const double* mu, const double* c,
+                                     double* out);
+
+/* ---- multi-GPU: shard over observations, all-reduce only the scalars ---- */
+int32_t aug_comm_get_unique_id(char uid[128]);
+int32_t aug_comm_init(aug_ctx* ctx, int32_t nranks, int32_t rank, const char uid[128]);
+int32_t aug_comm_destroy(aug_ctx* ctx);
+/* in-place sum over ranks of `count` device doubles, on the ctx stream */
+int32_t aug_allreduce_scalars(aug_ctx* ctx, double* dev, int32_t count);
+
+/* ---- host-buffer plugin call (end-to-end path) --------------------------- */
+/* Same as aug_cavi_step but every data pointer is a HOST buffer (pinned for
+ * full speed); the library stages chunks through device memory, overlapping
+ * H2D, kernel and D2H on internal streams, and returns after the results and
+ * scalars_host[AUG_NSCALARS] are on the host. */
+int32_t aug_cavi_step_host(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                           const void* y, const double* mu, const double* var, int64_t ld,
+                           void* s0, void* s1, void* s2,
+                           double* beta, double* gamma, int64_t ldo,
+                           double* scalars_host);
+/* Same for aux_sample! */
+int32_t aug_aux_sample_host(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0,
+                            const void* y, const double* f, int64_t ld,
+                            double* omega, int64_t* nvar);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUGCUDA_H */
