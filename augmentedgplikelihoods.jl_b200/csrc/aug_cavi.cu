@@ -1,0 +1,406 @@
+// aug_cavi.cu — fused single-pass CAVI kernels for the scalar-latent likelihoods and the
+// two-latent heteroscedastic Gaussian.
+//
+// One launch = aux_posterior! + expected_auglik_potential_and_precision (+ the per-observation
+// expected_logtilt / aux_kldivergence terms reduced in the same pass): y, mu, var are read once
+// with 128-bit loads, state / beta / gamma are written once with 128-bit streaming stores, and the
+// ELBO partials go through warp shuffles, a block tree and a fixed-order last-block pass.
+// The same template, instantiated with FROM_STATE, serves the stand-alone verbs that start from an
+// existing qΩ (expected_auglik_*, expected_logtilt, aux_kldivergence).
+//
+// Reference behaviour replaced (paths relative to /root/reference/src):
+//   likelihoods/bernoulli.jl:17-65, negativebinomial.jl:24-73, poisson.jl:30-85, laplace.jl:44-104,
+//   studentt.jl:50-91, heteroscedasticgaussian.jl:34-145, utils.jl:1-14,
+//   SpecialDistributions/polyagamma.jl:25-31,99-110, polyagammapoisson.jl:35-51, api.jl:219-223,
+//   generic.jl:52-62.
+#include "aug_common.cuh"
+#include "aug_math.cuh"
+
+namespace {
+
+struct CaviArgs {
+    int64_t n;
+    const void* y;
+    const double* mu;    // latent 0 (f)
+    const double* var;
+    const double* mu_g;  // latent 1 (HETERO g)
+    const double* var_g;
+    // state outputs (fused / aux_posterior!) — any may be null
+    double* s0;
+    double* s1;
+    void* s2;
+    // state inputs (FROM_STATE)
+    const double* rs0;
+    const double* rs1;
+    const void* rs2;
+    double* beta;
+    double* gamma;
+    double* beta_g;
+    double* gamma_g;
+    double* partials;
+    unsigned int* counter;
+    double* scalars;
+    LikConst L;
+};
+
+template <int KIND> struct YT { typedef double T; };
+template <> struct YT<AUG_BERNOULLI> { typedef uint8_t T; };
+template <> struct YT<AUG_NEGBIN> { typedef int64_t T; };
+template <> struct YT<AUG_POISSON> { typedef int64_t T; };
+
+struct Obs {
+    double y, ys;              // observation; state copy of y used for the PG shape (φ.y)
+    double m, v, mg, vg;       // marginal moments of q(f) (and q(g))
+    double s0, s1, s2;         // state (in when FROM_STATE, out otherwise)
+    double b0, g0, b1, g1;     // E[β], E[γ] per latent
+    double elt, kl;            // per-observation ELBO terms
+};
+
+// ------------------------------------------------------------------ per-kind closed forms
+template <int KIND, bool FROM_STATE, bool ELBO>
+__device__ __forceinline__ void eval(const LikConst& L, Obs& o) {
+    using namespace augm;
+    o.elt = 0.0;
+    o.kl = 0.0;
+    o.b1 = o.g1 = 0.0;
+    if (KIND == AUG_BERNOULLI) {
+        const double s2m = fma(o.m, o.m, o.v);                  // second_moment utils.jl:1-3
+        if (!FROM_STATE) o.s0 = sqrt(s2m);                      // bernoulli.jl:23
+        const PGTerms t = pg_terms<ELBO>(o.s0);
+        const double sg = o.y > 0.5 ? 0.5 : -0.5;               // sign(y - 0.5)/2  :28
+        o.b0 = sg;
+        o.g0 = t.h;                                             // mean(PG(1,c))    :44
+        if (ELBO) {
+            o.elt = -LN2 + fma(sg, o.m, -0.5 * s2m * t.h);      // :62-64
+            o.kl = fma(-0.5 * o.s0 * o.s0, t.h, t.lch);         // KL(PG(1,c)||PG(1,0))
+        }
+    } else if (KIND == AUG_NEGBIN) {
+        const double s2m = fma(o.m, o.m, o.v);
+        if (!FROM_STATE) o.s0 = sqrt(s2m);                      // negativebinomial.jl:29-31
+        const PGTerms t = pg_terms<ELBO>(o.s0);
+        const double r = L.p0;
+        const double b = o.ys + r;
+        const double th = b * t.h;                              // mean(PG(y+r,c)) :48
+        o.b0 = 0.5 * (o.y - r);                                 // :36
+        o.g0 = th;
+        if (ELBO) {
+            double lc;                                          // negbin_logconst :51-52
+            if (o.y < (double)AUG_TABLE_N) lc = __ldg(&L.table[(int)o.y]);
+            else lc = lgamma(o.y + r) - lgamma(o.y + 1.0) - L.c0;
+            o.elt = lc - (o.y + r) * LN2 + 0.5 * fma(o.m, o.y - r, -s2m * th);   // :62-64
+            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th);
+        }
+    } else if (KIND == AUG_POISSON) {
+        const double s2m = fma(o.m, o.m, o.v);
+        if (!FROM_STATE) o.s0 = sqrt(s2m);                      // poisson.jl:35
+        const PGTerms t = pg_terms<ELBO>(o.s0);
+        if (!FROM_STATE) o.s1 = L.p0 * approx_expected_logistic(-o.m, o.s0, t);   // :37
+        const double lam = o.s1;
+        const double b = o.ys + lam;
+        const double th = b * t.h;                              // polyagammapoisson.jl:35-41
+        o.b0 = 0.5 * (o.y - lam);                               // poisson.jl:59
+        o.g0 = th;
+        if (ELBO) {
+            o.elt = -(o.y + lam) * LN2 + 0.5 * fma(o.y - lam, o.m, -s2m * th) + o.y * L.c0 -
+                    lfact(o.y, L.table);                        // :81-83
+            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) + kl_poisson(lam, L.p0, L.c0);
+        }
+    } else if (KIND == AUG_LAPLACE) {
+        const double d = o.m - o.y;
+        const double s2y = fma(d, d, o.v);                      // second_moment(q, y) utils.jl:5-7
+        if (!FROM_STATE) o.s0 = L.c0 * rsqrt(s2y);              // 1/(2β sqrt(.))  laplace.jl:48-50
+        o.b0 = 2.0 * o.s0 * o.y;                                // :63
+        o.g0 = 2.0 * o.s0;                                      // :67
+        if (ELBO) {
+            o.elt = L.c2 - s2y * o.s0;                          // :84-87
+            o.kl = L.c3 + L.c1 / o.s0;                          // :98-104
+        }
+    } else if (KIND == AUG_STUDENTT) {
+        const double d = o.m - o.y;
+        const double s2y = fma(d, d, o.v);
+        if (!FROM_STATE) o.s0 = 0.5 * (L.c0 + s2y);             // studentt.jl:54-56
+        const double ib = 1.0 / o.s0;
+        const double th = L.c1 * ib;                            // mean(Gamma(α, 1/β)) :69,73
+        o.b0 = th * o.y;
+        o.g0 = th;
+        if (ELBO) {
+            // logpdf(Normal(y, θ^-1/2), m) - vθ/2 = -log(2π)/2 + log(θ)/2 - θ((m-y)² + v)/2   :80-83
+            o.elt = L.c5 + 0.5 * log(th) - 0.5 * th * s2y;
+            // KL(Gamma(α, 1/β) || Gamma(ν/2, 2σ²/ν)), Distributions.jl closed form
+            const double r = ib / L.c4;
+            o.kl = L.c2 - L.c3 * log(r) + L.c1 * r;
+        }
+    } else if (KIND == AUG_HETERO) {
+        const double d = o.m - o.y;
+        const double s2f = fma(d, d, o.v);
+        const double s2g = fma(o.mg, o.mg, o.vg);
+        if (!FROM_STATE) {
+            o.s2 = 0.5 * s2f;                                   // ψ  heteroscedasticgaussian.jl:42
+            o.s0 = sqrt(s2g);                                   // c  :43
+        }
+        const PGTerms t = pg_terms<ELBO>(o.s0);
+        const double st = approx_expected_logistic(-o.mg, o.s0, t);
+        if (!FROM_STATE) o.s1 = L.p0 * st * o.s2;               // λ  :44
+        const double lam = o.s1;
+        const double lsg = L.p0 * (1.0 - st);                   // :102
+        const double b = 0.5 + lam;
+        const double th = b * t.h;
+        o.b0 = 0.5 * o.y * lsg;
+        o.b1 = 0.5 * (0.5 - lam);
+        o.g0 = lsg;
+        o.g1 = th;
+        if (ELBO) {                                             // :129-145
+            o.elt = L.c0 - b * LN2 + 0.5 * fma(0.5 - lam, o.mg, -s2g * th);
+            const double pl = 0.5 * L.p0 * s2f;
+            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) + kl_poisson(lam, pl, log(pl));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ loads / stores
+template <typename T>
+__device__ __forceinline__ void load_y2(const void* y, int64_t p, double& a, double& b);
+template <>
+__device__ __forceinline__ void load_y2<uint8_t>(const void* y, int64_t p, double& a, double& b) {
+    const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(y) + p);
+    a = (double)v.x;
+    b = (double)v.y;
+}
+template <>
+__device__ __forceinline__ void load_y2<int64_t>(const void* y, int64_t p, double& a, double& b) {
+    const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(y) + p);
+    a = (double)v.x;
+    b = (double)v.y;
+}
+template <>
+__device__ __forceinline__ void load_y2<double>(const void* y, int64_t p, double& a, double& b) {
+    const double2 v = ld_stream2(reinterpret_cast<const double*>(y) + 2 * p);
+    a = v.x;
+    b = v.y;
+}
+template <typename T>
+__device__ __forceinline__ double load_y1(const void* y, int64_t i) {
+    return (double)__ldg(reinterpret_cast<const T*>(y) + i);
+}
+template <typename T>
+__device__ __forceinline__ void store_y2(void* s2, int64_t p, double a, double b);
+template <>
+__device__ __forceinline__ void store_y2<int64_t>(void* s2, int64_t p, double a, double b) {
+    reinterpret_cast<longlong2*>(s2)[p] = make_longlong2((long long)a, (long long)b);
+}
+template <>
+__device__ __forceinline__ void store_y2<double>(void* s2, int64_t p, double a, double b) {
+    st_stream2(reinterpret_cast<double*>(s2) + 2 * p, a, b);
+}
+template <>
+__device__ __forceinline__ void store_y2<uint8_t>(void*, int64_t, double, double) {}
+template <typename T>
+__device__ __forceinline__ void store_y1(void* s2, int64_t i, double a) {
+    reinterpret_cast<T*>(s2)[i] = (T)a;
+}
+
+// s2 holds ψ (double) for HETERO and a copy of y (int64) for NEGBIN / POISSON
+template <int KIND> struct S2T { typedef double T; };
+template <> struct S2T<AUG_NEGBIN> { typedef int64_t T; };
+template <> struct S2T<AUG_POISSON> { typedef int64_t T; };
+
+template <int KIND, bool FROM_STATE, bool ELBO, bool VEC>
+__global__ void __launch_bounds__(AUG_BLOCK) cavi_kernel(const CaviArgs a) {
+    typedef typename YT<KIND>::T yt;
+    typedef typename S2T<KIND>::T s2t;
+    constexpr bool HET = KIND == AUG_HETERO;
+    constexpr bool YSTATE = KIND == AUG_NEGBIN || KIND == AUG_POISSON;
+    constexpr bool HAS_S1 = KIND == AUG_POISSON || KIND == AUG_HETERO;
+    constexpr int U = 2;  // independent pairs in flight per thread
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    double acc[2] = {0.0, 0.0};
+    const bool need_mv = !FROM_STATE || ELBO;
+
+    if (VEC) {
+        const int64_t npairs = a.n >> 1;
+        for (int64_t p0 = tid; p0 < npairs; p0 += nth * U) {
+            Obs o[U][2];
+            bool live[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int64_t p = p0 + (int64_t)j * nth;
+                live[j] = p < npairs;
+                if (!live[j]) continue;
+                load_y2<yt>(a.y, p, o[j][0].y, o[j][1].y);
+                if (need_mv) {
+                    const double2 m = ld_stream2(a.mu + 2 * p);
+                    const double2 v = ld_stream2(a.var + 2 * p);
+                    o[j][0].m = m.x; o[j][1].m = m.y;
+                    o[j][0].v = v.x; o[j][1].v = v.y;
+                }
+                if (HET) {
+                    const double2 m = ld_stream2(a.mu_g + 2 * p);
+                    o[j][0].mg = m.x; o[j][1].mg = m.y;
+                    if (need_mv) {
+                        const double2 v = ld_stream2(a.var_g + 2 * p);
+                        o[j][0].vg = v.x; o[j][1].vg = v.y;
+                    }
+                }
+                o[j][0].ys = o[j][0].y; o[j][1].ys = o[j][1].y;
+                if (FROM_STATE) {
+                    const double2 c = ld_stream2(a.rs0 + 2 * p);
+                    o[j][0].s0 = c.x; o[j][1].s0 = c.y;
+                    if (HAS_S1) {
+                        const double2 l = ld_stream2(a.rs1 + 2 * p);
+                        o[j][0].s1 = l.x; o[j][1].s1 = l.y;
+                    }
+                    if (HET) {
+                        const double2 ps = ld_stream2(reinterpret_cast<const double*>(a.rs2) + 2 * p);
+                        o[j][0].s2 = ps.x; o[j][1].s2 = ps.y;
+                    }
+                    if (YSTATE && a.rs2 != nullptr) load_y2<int64_t>(a.rs2, p, o[j][0].ys, o[j][1].ys);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                if (!live[j]) continue;
+                const int64_t p = p0 + (int64_t)j * nth;
+                eval<KIND, FROM_STATE, ELBO>(a.L, o[j][0]);
+                eval<KIND, FROM_STATE, ELBO>(a.L, o[j][1]);
+                if (!FROM_STATE) {
+                    if (a.s0) st_stream2(a.s0 + 2 * p, o[j][0].s0, o[j][1].s0);
+                    if (HAS_S1 && a.s1) st_stream2(a.s1 + 2 * p, o[j][0].s1, o[j][1].s1);
+                    if (HET && a.s2) st_stream2(reinterpret_cast<double*>(a.s2) + 2 * p, o[j][0].s2, o[j][1].s2);
+                    if (YSTATE && a.s2) store_y2<s2t>(a.s2, p, o[j][0].y, o[j][1].y);
+                }
+                if (a.beta) st_stream2(a.beta + 2 * p, o[j][0].b0, o[j][1].b0);
+                if (a.gamma) st_stream2(a.gamma + 2 * p, o[j][0].g0, o[j][1].g0);
+                if (HET) {
+                    if (a.beta_g) st_stream2(a.beta_g + 2 * p, o[j][0].b1, o[j][1].b1);
+                    if (a.gamma_g) st_stream2(a.gamma_g + 2 * p, o[j][0].g1, o[j][1].g1);
+                }
+                if (ELBO) {
+                    acc[0] += o[j][0].elt + o[j][1].elt;
+                    acc[1] += o[j][0].kl + o[j][1].kl;
+                }
+            }
+        }
+    }
+    // scalar path: the odd tail element of the vector kernel, or everything when unaligned
+    {
+        const int64_t start = VEC ? (a.n & ~(int64_t)1) : 0;
+        for (int64_t i = start + tid; i < a.n; i += nth) {
+            Obs o;
+            o.y = load_y1<yt>(a.y, i);
+            o.ys = o.y;
+            o.m = o.v = o.mg = o.vg = 0.0;
+            if (need_mv) { o.m = a.mu[i]; o.v = a.var[i]; }
+            if (HET) { o.mg = a.mu_g[i]; if (need_mv) o.vg = a.var_g[i]; }
+            if (FROM_STATE) {
+                o.s0 = a.rs0[i];
+                if (HAS_S1) o.s1 = a.rs1[i];
+                if (HET) o.s2 = reinterpret_cast<const double*>(a.rs2)[i];
+                if (YSTATE && a.rs2 != nullptr) o.ys = (double)reinterpret_cast<const int64_t*>(a.rs2)[i];
+            }
+            eval<KIND, FROM_STATE, ELBO>(a.L, o);
+            if (!FROM_STATE) {
+                if (a.s0) a.s0[i] = o.s0;
+                if (HAS_S1 && a.s1) a.s1[i] = o.s1;
+                if (HET && a.s2) reinterpret_cast<double*>(a.s2)[i] = o.s2;
+                if (YSTATE && a.s2) store_y1<s2t>(a.s2, i, o.y);
+            }
+            if (a.beta) a.beta[i] = o.b0;
+            if (a.gamma) a.gamma[i] = o.g0;
+            if (HET) {
+                if (a.beta_g) a.beta_g[i] = o.b1;
+                if (a.gamma_g) a.gamma_g[i] = o.g1;
+            }
+            if (ELBO) { acc[0] += o.elt; acc[1] += o.kl; }
+        }
+    }
+    if (ELBO) {
+        double out[2];
+        if (block_reduce_and_finalize<2>(acc, a.partials, a.counter, out)) {
+            a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
+            a.scalars[AUG_S_KL] = out[1];
+            a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];   // generic.jl:52-54 ("+")
+        }
+    }
+}
+
+template <int KIND, bool FROM_STATE, bool ELBO>
+int32_t launch2(aug_ctx* ctx, const CaviArgs& a, bool vec) {
+    const void* k = vec ? (const void*)cavi_kernel<KIND, FROM_STATE, ELBO, true>
+                        : (const void*)cavi_kernel<KIND, FROM_STATE, ELBO, false>;
+    const int64_t work = vec ? (a.n + 1) / 2 : a.n;
+    const int grid = aug_grid_for(ctx, k, work, AUG_BLOCK * 2);
+    if (vec) cavi_kernel<KIND, FROM_STATE, ELBO, true><<<grid, AUG_BLOCK, 0, ctx->stream>>>(a);
+    else cavi_kernel<KIND, FROM_STATE, ELBO, false><<<grid, AUG_BLOCK, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    return (int32_t)cudaGetLastError();
+}
+
+template <int KIND>
+int32_t launch1(aug_ctx* ctx, const CaviArgs& a, bool from_state, bool elbo, bool vec) {
+    if (from_state) return elbo ? launch2<KIND, true, true>(ctx, a, vec) : launch2<KIND, true, false>(ctx, a, vec);
+    return elbo ? launch2<KIND, false, true>(ctx, a, vec) : launch2<KIND, false, false>(ctx, a, vec);
+}
+
+}  // namespace
+
+// Shared by aug_cavi_step / aug_aux_posterior / aug_expected_potential_precision / aug_expected_elbo_terms
+// for the non-categorical kinds (the categorical row kernels live in aug_cat.cu).
+int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void* y, const double* mu,
+                          const double* var, int64_t ld, void* s0, void* s1, void* s2, const void* rs0,
+                          const void* rs1, const void* rs2, double* beta, double* gamma, int64_t ldo,
+                          double* scalars, bool from_state) {
+    if (n < 0) return AUG_ERR_BAD_ARG;
+    if (n == 0) {
+        if (scalars) AUG_CUDA(cudaMemsetAsync(scalars, 0, 3 * sizeof(double), ctx->stream));
+        return AUG_OK;
+    }
+    const bool elbo = scalars != nullptr;
+    const bool het = lik->kind == AUG_HETERO;
+    if (y == nullptr) return AUG_ERR_BAD_ARG;
+    if ((!from_state || elbo) && (mu == nullptr || var == nullptr)) return AUG_ERR_BAD_ARG;
+    if (het && (mu == nullptr || ld < n)) return AUG_ERR_BAD_ARG;
+    if (het && (beta || gamma) && ldo < n) return AUG_ERR_BAD_ARG;
+    if (from_state && rs0 == nullptr) return AUG_ERR_BAD_ARG;
+    if (from_state && (lik->kind == AUG_POISSON || het) && rs1 == nullptr) return AUG_ERR_BAD_ARG;
+    if (from_state && het && rs2 == nullptr) return AUG_ERR_BAD_ARG;
+
+    CaviArgs a{};
+    a.n = n;
+    a.y = y;
+    a.mu = mu;
+    a.var = var;
+    a.mu_g = het && mu ? mu + ld : nullptr;
+    a.var_g = het && var ? var + ld : nullptr;
+    a.s0 = (double*)s0;
+    a.s1 = (double*)s1;
+    a.s2 = s2;
+    a.rs0 = (const double*)rs0;
+    a.rs1 = (const double*)rs1;
+    a.rs2 = rs2;
+    a.beta = beta;
+    a.gamma = gamma;
+    a.beta_g = het && beta ? beta + ldo : nullptr;
+    a.gamma_g = het && gamma ? gamma + ldo : nullptr;
+    a.partials = ctx->partials;
+    a.counter = ctx->counter;
+    a.scalars = scalars;
+    int32_t rc = aug_lik_const(ctx, lik, &a.L, elbo, false);
+    if (rc) return rc;
+    // 128-bit path needs 16-byte aligned arrays (and, for HETERO, an even leading dimension)
+    bool vec = aug_aligned16(mu) && aug_aligned16(var) && aug_aligned16(s0) && aug_aligned16(s1) &&
+               aug_aligned16(s2) && aug_aligned16(rs0) && aug_aligned16(rs1) && aug_aligned16(rs2) &&
+               aug_aligned16(beta) && aug_aligned16(gamma) && aug_aligned16(a.mu_g) && aug_aligned16(a.var_g) &&
+               aug_aligned16(a.beta_g) && aug_aligned16(a.gamma_g);
+    if (lik->kind == AUG_BERNOULLI) vec = vec && ((((uintptr_t)y) & 1u) == 0);
+    else vec = vec && aug_aligned16(y);
+    switch (lik->kind) {
+        case AUG_BERNOULLI: return launch1<AUG_BERNOULLI>(ctx, a, from_state, elbo, vec);
+        case AUG_NEGBIN: return launch1<AUG_NEGBIN>(ctx, a, from_state, elbo, vec);
+        case AUG_POISSON: return launch1<AUG_POISSON>(ctx, a, from_state, elbo, vec);
+        case AUG_LAPLACE: return launch1<AUG_LAPLACE>(ctx, a, from_state, elbo, vec);
+        case AUG_STUDENTT: return launch1<AUG_STUDENTT>(ctx, a, from_state, elbo, vec);
+        case AUG_HETERO: return launch1<AUG_HETERO>(ctx, a, from_state, elbo, vec);
+        default: return AUG_ERR_BAD_KIND;
+    }
+}

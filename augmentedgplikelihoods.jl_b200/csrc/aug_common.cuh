@@ -1,0 +1,144 @@
+// aug_common.cuh — context, launch and reduction plumbing shared by all kernels of libaugcuda.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/augcuda.h"
+
+#define AUG_BLOCK 256          // threads per CTA for the map/reduce kernels
+#define AUG_MAX_GRID 4096      // upper bound on CTAs of a reducing kernel (partials buffer rows)
+#define AUG_NRED 4             // doubles reduced per kernel: elt/logtilt, kl/logprior, flags, spare
+#define AUG_TABLE_N 512        // entries of the per-likelihood integer-y constant table
+
+#define AUG_CUDA(x)                                   \
+    do {                                              \
+        cudaError_t e__ = (x);                        \
+        if (e__ != cudaSuccess) return (int32_t)e__;  \
+    } while (0)
+
+struct aug_pipe;  // host-buffer pipeline state (aug_host.cu)
+
+struct aug_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int sms;
+    uint64_t seed, offset;
+    uint64_t launches;
+    // reduction scratch
+    double* partials;      // [AUG_MAX_GRID][AUG_NRED]
+    unsigned int* counter; // last-block ticket
+    double* dscalars;      // [AUG_NSCALARS] scratch block used by the host-buffer calls
+    unsigned int* dflag;   // device-side error flag word
+    // integer-y constant table (log y!, negbin log-constants), cached by likelihood parameters
+    double* table;
+    int table_kind;
+    int table_r_is_int;
+    double table_param;
+    // categorical logθ-derived constants
+    double* dtheta;        // exp(logθ_j)/Σθ  (device, capacity dtheta_cap)
+    int dtheta_cap;
+    // NCCL (resolved with dlopen at aug_comm_init)
+    void* nccl_lib;
+    void* nccl_comm;
+    int nranks, rank;
+    aug_pipe* pipe;
+};
+
+// Likelihood constants precomputed on the host once per call (never per observation)
+struct LikConst {
+    int kind, nl, r_is_int, bij;
+    double p0, p1;          // raw parameters (r | λ | β | ν, σ)
+    double c0, c1, c2, c3, c4, c5;  // derived constants, meaning per kind (see lik_const())
+    const double* table;    // device table or nullptr
+    const double* theta;    // CAT: θ_j/Σθ device vector
+};
+
+int32_t aug_lik_const(aug_ctx* ctx, const aug_lik* lik, LikConst* out, bool need_table, bool need_theta);
+int aug_grid_for(aug_ctx* ctx, const void* kernel, int64_t work_items, int items_per_block);
+
+static inline bool aug_aligned16(const void* p) { return p == nullptr || (((uintptr_t)p) & 15u) == 0; }
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block tree: warp shuffles, then one smem round, then a fixed-order last-block pass over the
+// per-CTA partials.  Deterministic for a given grid size (no floating-point atomics).
+// Returns true in exactly one thread of the grid (thread 0 of the last CTA), which holds the totals.
+template <int NV>
+__device__ __forceinline__ bool block_reduce_and_finalize(double (&acc)[NV], double* __restrict__ partials,
+                                                          unsigned int* __restrict__ counter,
+                                                          double* __restrict__ out /* NV results */) {
+    __shared__ double sm[NV][AUG_BLOCK / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double v = warp_sum(acc[k]);
+        if (lane == 0) sm[k][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double v = lane < AUG_BLOCK / 32 ? sm[k][lane] : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) partials[(size_t)blockIdx.x * AUG_NRED + k] = v;
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicInc(counter, gridDim.x - 1);  // wraps to 0 -> reusable / graph-replayable
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    double tot[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tot[k] = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += AUG_BLOCK) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) tot[k] += __ldcg(&partials[(size_t)b * AUG_NRED + k]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double v = warp_sum(tot[k]);
+        if (lane == 0) sm[k][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double v = lane < AUG_BLOCK / 32 ? sm[k][lane] : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) out[k] = v;
+        }
+    }
+    return threadIdx.x == 0;
+}
+
+// 128-bit streaming loads/stores (read-once / write-once data: keep it out of L1)
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ld_stream1(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream2(double* p, double a, double b) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream1(double* p, double a) {
+    asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(a) : "memory");
+}
+#endif  // __CUDACC__

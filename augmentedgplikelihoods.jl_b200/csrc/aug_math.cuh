@@ -1,0 +1,83 @@
+// aug_math.cuh — per-observation closed forms (device).  Each function cites the reference
+// formula it evaluates; the arithmetic is re-derived for the FP64 pipe of sm_100a (one shared
+// exp(-c), no pow, series near c = 0) and is NOT a transcription of the Julia code.
+#pragma once
+#include <math.h>
+
+namespace augm {
+
+constexpr double LN2 = 0.69314718055994530942;
+constexpr double LOGISTIC_LO = -744.4400719213812;  // LogExpFunctions._logistic_bounds(Float64)
+constexpr double LOGISTIC_HI = 36.7368005696771;
+constexpr double PI = 3.14159265358979323846;
+
+// Everything the Pólya-Gamma moments need from the tilt c >= 0:
+//   h   = tanh(c/2)/(2c)           -> mean(PG(b,c)) = b*h        (polyagamma.jl:25-31; 1/4 at c == 0)
+//   lch = logcosh(c/2)             -> KL(PG(b,c)||PG(b,0)) = b*lch - c^2*b*h/2   (polyagamma.jl:99-110)
+//   e   = exp(-c), inv1pe = 1/(1+e) (re-used by approx_expected_logistic)
+struct PGTerms {
+    double h, lch, e, inv1pe;
+};
+
+template <bool NEED_LCH>
+__device__ __forceinline__ PGTerms pg_terms(double c) {
+    PGTerms t;
+    if (c < 0.0625) {
+        // series in x = c/2 <= 1/32: truncation error < 1e-17 relative
+        const double x2 = 0.25 * c * c;
+        double p = fma(x2, 62.0 / 2835.0, -17.0 / 315.0);
+        p = fma(x2, p, 2.0 / 15.0);
+        p = fma(x2, p, -1.0 / 3.0);
+        p = fma(x2, p, 1.0);          // tanh(x)/x
+        t.h = 0.25 * p;
+        if (NEED_LCH) {
+            double q = fma(x2, -17.0 / 2520.0, 1.0 / 45.0);
+            q = fma(x2, q, -1.0 / 12.0);
+            q = fma(x2, q, 0.5);
+            t.lch = x2 * q;           // logcosh(x)
+        } else {
+            t.lch = 0.0;
+        }
+        t.e = exp(-c);
+        t.inv1pe = 1.0 / (1.0 + t.e);
+        return t;
+    }
+    const double e = exp(-c);          // underflows to 0 for c > 745: tanh -> 1, logcosh -> c/2 - ln2
+    const double inv = 1.0 / (1.0 + e);
+    t.e = e;
+    t.inv1pe = inv;
+    t.h = (1.0 - e) * inv / (2.0 * c);
+    t.lch = NEED_LCH ? fma(0.5, c, log1p(e) - LN2) : 0.0;
+    return t;
+}
+
+// approx_expected_logistic(mu, c) = exp(mu/2) sech(c/2)/2, saturating on mu alone (utils.jl:11-14).
+// sech(c/2)/2 = exp(-c/2)/(1+exp(-c)): one extra exp on top of pg_terms.
+__device__ __forceinline__ double approx_expected_logistic(double mu, double c, const PGTerms& t) {
+    if (mu < LOGISTIC_LO) return 0.0;
+    if (mu > LOGISTIC_HI) return 1.0;
+    return exp(0.5 * (mu - c)) * t.inv1pe;
+}
+
+// kldivergence(Poisson(q), Poisson(p)) (Distributions.jl): q == 0 ? p : p - q + q (log q - log p)
+__device__ __forceinline__ double kl_poisson(double q, double p, double logp) {
+    if (q == 0.0) return p;
+    return p - q + q * (log(q) - logp);
+}
+
+// logistic(x) with the LogExpFunctions saturation
+__device__ __forceinline__ double logistic(double x) {
+    if (x < LOGISTIC_LO) return 0.0;
+    if (x > LOGISTIC_HI) return 1.0;
+    const double e = exp(-fabs(x));
+    const double r = 1.0 / (1.0 + e);
+    return x >= 0.0 ? r : e * r;
+}
+
+// log y! / negbin log-constant with a table for small integer y (device lgamma beyond it)
+__device__ __forceinline__ double lfact(double y, const double* __restrict__ table) {
+    if (table != nullptr && y < (double)AUG_TABLE_N) return __ldg(&table[(int)y]);
+    return lgamma(y + 1.0);
+}
+
+}  // namespace augm

@@ -1,0 +1,132 @@
+// aug_rng.cuh — counter-based Philox4x32-10 streams and the elementary samplers of the Gibbs path.
+//
+// Replaces the `rng::AbstractRNG` of aux_sample!/init_aux_variables (generic.jl:1-20,32-34) and the
+// Distributions.jl / Random samplers they call (rand, randexp, randn, Gamma, Poisson,
+// InverseGaussian).  A stream is keyed by (seed, verb offset) and positioned by the GLOBAL element
+// index, so draws do not depend on how the observation axis is sharded over GPUs or on which
+// thread processes an element.  Only the laws have to match the reference, not the bit streams.
+#pragma once
+#include <stdint.h>
+
+namespace augr {
+
+struct Philox {
+    uint32_t k0, k1;          // key   = seed
+    uint32_t c0, c1, c2, c3;  // counter = (element lo, element hi, block counter, verb offset)
+    uint32_t buf[4];
+    int have;                 // 32-bit words left in buf
+
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t offset, uint64_t element, uint32_t lane_tag = 0) {
+        k0 = (uint32_t)seed;
+        k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
+        c0 = (uint32_t)element;
+        c1 = (uint32_t)(element >> 32);
+        c2 = lane_tag << 24;  // up to 2^24 blocks (6.7e7 uniforms) per element and tag
+        c3 = (uint32_t)offset;
+        have = 0;
+    }
+    __device__ __forceinline__ void refill() {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+            const uint32_t y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
+            x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+        buf[0] = x0; buf[1] = x1; buf[2] = x2; buf[3] = x3;
+        c2++;
+        have = 4;
+    }
+    __device__ __forceinline__ uint64_t next64() {
+        if (have < 2) refill();
+        have -= 2;
+        // have is now 2 or 0: words (2,3) first, then (0,1)
+        const uint32_t lo = have == 2 ? buf[2] : buf[0];
+        const uint32_t hi = have == 2 ? buf[3] : buf[1];
+        return ((uint64_t)hi << 32) | lo;
+    }
+    // U in [0,1): 53 random bits (rand(rng))
+    __device__ __forceinline__ double u01() { return (double)(next64() >> 11) * 0x1.0p-53; }
+    // U in (0,1]
+    __device__ __forceinline__ double u01_open0() { return (double)((next64() >> 11) + 1ull) * 0x1.0p-53; }
+    // randexp(rng)
+    __device__ __forceinline__ double expo() { return -log(u01_open0()); }
+    // randn(rng): Box-Muller, one normal per call (the sine branch is discarded)
+    __device__ __forceinline__ double normal() {
+        const double u = u01_open0();
+        const double v = u01();
+        const double r = sqrt(-2.0 * log(u));
+        return r * cospi(2.0 * v);
+    }
+};
+
+// rand(Gamma(shape, 1)) — Marsaglia & Tsang (2000); shape < 1 through the U^(1/shape) boost
+__device__ __forceinline__ double gamma_rand(Philox& g, double shape) {
+    double boost = 1.0;
+    if (shape < 1.0) {
+        boost = exp(log(g.u01_open0()) / shape);
+        shape += 1.0;
+    }
+    const double d = shape - 1.0 / 3.0;
+    const double c = rsqrt(9.0 * d);
+    for (;;) {
+        double x, v;
+        do {
+            x = g.normal();
+            v = fma(c, x, 1.0);
+        } while (v <= 0.0);
+        v = v * v * v;
+        const double u = g.u01_open0();
+        const double x2 = x * x;
+        if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
+        if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
+    }
+}
+
+// rand(Poisson(lambda)): sequential inversion for small rates, PTRS (Hörmann 1993) otherwise
+__device__ __forceinline__ int64_t poisson_rand(Philox& g, double lam) {
+    if (!(lam > 0.0)) return 0;
+    if (lam < 12.0) {
+        // inversion by chop-down search from 0 (exact in law; restart guards the 1e-16 round-off tail)
+        for (;;) {
+            double u = g.u01();
+            double p = exp(-lam);
+            int64_t k = 0;
+            while (u > p && k < 200) {
+                u -= p;
+                ++k;
+                p *= lam / (double)k;
+            }
+            if (k < 200) return k;
+        }
+    }
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double inv_alpha = 1.1239 + 1.1328 / (b - 3.4);
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        const double u = g.u01() - 0.5;
+        const double v = g.u01_open0();
+        const double us = 0.5 - fabs(u);
+        const double kf = floor((2.0 * a / us + b) * u + lam + 0.43);
+        if (us >= 0.07 && v <= vr) return (int64_t)kf;
+        if (kf < 0.0 || (us < 0.013 && v > us)) continue;
+        if (log(v) + log(inv_alpha) - log(a / (us * us) + b) <= -lam + kf * loglam - lgamma(kf + 1.0))
+            return (int64_t)kf;
+    }
+}
+
+// rand(InverseGaussian(mu, lambda)) — Michael, Schucany & Haas (1976)
+__device__ __forceinline__ double invgauss_rand(Philox& g, double mu, double lam) {
+    const double z = g.normal();
+    const double w = mu * z * z;
+    const double x1 = mu + mu / (2.0 * lam) * (w - sqrt(w * (4.0 * lam + w)));
+    const double u = g.u01();
+    return u * (mu + x1) >= mu ? mu * mu / x1 : x1;
+}
+
+}  // namespace augr

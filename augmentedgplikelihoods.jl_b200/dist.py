@@ -1,0 +1,65 @@
+"""Multi-GPU host logic: shard the observation axis, all-reduce only the scalar block.
+
+Every function of the path is independent per observation and the scalars are plain sums
+(SURVEY §8e), so rank g owns the contiguous block [g*N/G, (g+1)*N/G) (whole rows for the
+Categorical likelihood), state / inputs / β, γ stay sharded, RNG counters use the GLOBAL
+observation index (pass `i0=lo` to the sampling verbs), and the only collective is ONE
+ncclAllReduce(sum, double, 8) of the scalar block, issued by libaugcuda on the ctx stream.
+torch.distributed is used for the rendezvous (broadcast of the NCCL unique id) only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import NSCALARS, check
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous block partition: [lo, hi) of rank `rank`; sizes differ by at most one and the
+    lower ranks take the remainder.  lo doubles as the global index offset `i0` of the shard."""
+    if world < 1 or not (0 <= rank < world) or n < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def combine_scalars_host(blocks):
+    """Reference semantics of the collective for host-side checks: element-wise sum over ranks of the
+    additive slots; slot 2 (= slot 0 + slot 1) and slot 5 (= slot 3 + slot 4) stay consistent."""
+    out = [0.0] * NSCALARS
+    for b in blocks:
+        for k in range(NSCALARS):
+            out[k] += float(b[k])
+    return out
+
+
+def init_comm(ctx, group=None):
+    """Attach an NCCL communicator to ctx: rank 0 creates the unique id, torch.distributed broadcasts it."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    uid = (C.c_char * 128)()
+    if rank == 0:
+        check(ctx.lib.aug_comm_get_unique_id(uid))
+    payload = [bytes(uid.raw)]
+    dist.broadcast_object_list(payload, src=0, group=group)
+    uid2 = (C.c_char * 128).from_buffer_copy(payload[0])
+    check(ctx.lib.aug_comm_init(ctx.h, world, rank, uid2))
+    ctx.comm_ready = True
+    ctx.world, ctx.rank = world, rank
+    return ctx
+
+
+def allreduce_scalars_(ctx, scal: torch.Tensor):
+    """In-place sum over ranks of the device scalar block (ncclAllReduce on the ctx stream)."""
+    if not ctx.comm_ready:
+        raise RuntimeError("communicator not initialised (call init_comm)")
+    ctx.enter()
+    check(ctx.lib.aug_allreduce_scalars(ctx.h, C.c_void_p(scal.data_ptr()), int(scal.numel())))
+    ctx.leave()
+    return scal

@@ -121,6 +121,10 @@ int32_t aug_ctx_stream(aug_ctx* ctx, void** stream);
 int32_t aug_ctx_sm_count(aug_ctx* ctx, int32_t* n);
 /* number of kernels launched by this ctx since creation (bench "gpu_launches") */
 int32_t aug_ctx_launch_count(aug_ctx* ctx, uint64_t* n);
+/* Synchronises, returns and clears the device-side error flag word: bit 0 = a
+ * NegativeMultinomial row had sum(p) >= 1 (the reference throws ArgumentError at
+ * negativemultinomial.jl:17-22; an asynchronous kernel can only flag it). */
+int32_t aug_ctx_error_flag(aug_ctx* ctx, uint32_t* flag);
 
 /* memory helpers for callers without their own device allocator */
 int32_t aug_malloc(aug_ctx* ctx, void** dev, size_t bytes);
@@ -236,6 +240,10 @@ int32_t aug_pg_logpdf(aug_ctx* ctx, int64_t n, double b, double c, const double*
 /* approx_expected_logistic(mu, c) utils.jl:11-14 */
 int32_t aug_approx_expected_logistic(aug_ctx* ctx, int64_t n, const double* mu, const double* c,
                                      double* out);
+
+/* second_moment(q) = mu^2 + var, or (mu - y)^2 + var when y != NULL — utils.jl:1-7 */
+int32_t aug_second_moment(aug_ctx* ctx, int64_t n, const double* mu, const double* var, const double* y,
+                          double* out);
 
 /* ---- multi-GPU: shard over observations, all-reduce only the scalars ---- */
 int32_t aug_comm_get_unique_id(char uid[128]);

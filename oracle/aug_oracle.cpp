@@ -64,7 +64,25 @@ struct Acc {
         s = t;
     }
     inline double compensated() const { return s + comp; }
+    // combine thread-local partial sums (only used when g_threads > 1, i.e. for CPU-baseline timing)
+    inline void merge(const Acc& o) { seq += o.seq; add_comp(o.s); add_comp(o.comp); }
+    inline void add_comp(double x) {
+        double t = s + x;
+        if (std::fabs(s) >= std::fabs(x)) comp += (s - t) + x; else comp += (x - t) + s;
+        s = t;
+    }
 };
+
+// Reduction loops: sequential left fold with one thread (the reference's order, api.jl:220);
+// thread-local folds merged afterwards when the CPU baseline is timed on all host cores.
+#define ACC_LOOP_BEGIN(A, B)                                           \
+    _Pragma("omp parallel num_threads(g_threads)") {                   \
+        Acc A##_l, B##_l;                                              \
+        _Pragma("omp for schedule(static) nowait") for (int64_t i = 0; i < n; ++i) {
+#define ACC_LOOP_END(A, B)                                             \
+        }                                                              \
+        _Pragma("omp critical") { A.merge(A##_l); B.merge(B##_l); }    \
+    }
 
 // ---- LogExpFunctions restatements
 // logistic(x): e = exp(x); x < lower ? 0 : x > upper ? 1 : e / (1 + e)
@@ -635,61 +653,61 @@ int orc_expected_elbo_terms(const aug_lik* l, int64_t n, const void* y, const do
     switch (l->kind) {
         case AUG_BERNOULLI: {                                // bernoulli.jl:59-65, :51-57
             const uint8_t* yy = (const uint8_t*)y;
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(elt, kl)
                 double m = mu[i], th = pg_mean(1.0, s0[i]);
                 double d = yy[i] - 0.5, sg = (d > 0) - (d < 0);
-                elt.add(-std::log(2.0) + (sg * m - (abs2(m) + var[i]) * th) / 2);
-                kl.add(pg_kl(1.0, s0[i]));
-            }
+                elt_l.add(-std::log(2.0) + (sg * m - (abs2(m) + var[i]) * th) / 2);
+                kl_l.add(pg_kl(1.0, s0[i]));
+            ACC_LOOP_END(elt, kl)
             break;
         }
         case AUG_NEGBIN: {                                   // negativebinomial.jl:59-65, :67-73
             double r = lik_r(l);
             const int64_t* yy = (const int64_t*)y;
             const int64_t* ys = s2v ? (const int64_t*)s2v : yy;
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(elt, kl)
                 double yi = (double)yy[i], b = (double)ys[i] + r;
                 double th = pg_mean(b, s0[i]);
-                elt.add(negbin_logconst(yi, r, l->r_is_int) - (yi + r) * LOGTWO +
+                elt_l.add(negbin_logconst(yi, r, l->r_is_int) - (yi + r) * LOGTWO +
                         (mu[i] * (yi - r) - second_moment(mu[i], var[i]) * th) / 2);
-                kl.add(pg_kl(b, s0[i]));
-            }
+                kl_l.add(pg_kl(b, s0[i]));
+            ACC_LOOP_END(elt, kl)
             break;
         }
         case AUG_POISSON: {                                  // poisson.jl:76-85; polyagammapoisson.jl:43-51
             double lam = l->p[0], loglam = std::log(lam);
             const int64_t* yy = (const int64_t*)y;
             const int64_t* ys = s2v ? (const int64_t*)s2v : yy;
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(elt, kl)
                 double yi = (double)yy[i], tn = s1[i];
                 double tw = pg_mean((double)ys[i] + tn, s0[i]);
                 double m = mu[i];
-                elt.add(-(yi + tn) * LOGTWO + ((yi - tn) * m - (abs2(m) + var[i]) * tw) / 2 +
+                elt_l.add(-(yi + tn) * LOGTWO + ((yi - tn) * m - (abs2(m) + var[i]) * tw) / 2 +
                         yi * loglam - std::lgamma(yi + 1));
-                kl.add(pg_kl((double)ys[i] + tn, s0[i]) + kl_poisson(tn, lam));
-            }
+                kl_l.add(pg_kl((double)ys[i] + tn, s0[i]) + kl_poisson(tn, lam));
+            ACC_LOOP_END(elt, kl)
             break;
         }
         case AUG_LAPLACE: {                                  // laplace.jl:83-88, :98-104
             double beta = l->p[0], lam = laplace_lambda(l);
             const double* yy = (const double*)y;
             elt_const = (double)n * (std::lgamma(0.5) - std::log(SQRTPI) - std::log(2 * beta));
-            for (int64_t i = 0; i < n; ++i) {
-                elt.add(-second_moment_y(mu[i], var[i], yy[i]) * s0[i]);
-                kl.add(std::log(2 * lam) / 2 - std::log(2 * PI) / 2 - std::log(lam) / 2 + std::lgamma(0.5) +
+            ACC_LOOP_BEGIN(elt, kl)
+                elt_l.add(-second_moment_y(mu[i], var[i], yy[i]) * s0[i]);
+                kl_l.add(std::log(2 * lam) / 2 - std::log(2 * PI) / 2 - std::log(lam) / 2 + std::lgamma(0.5) +
                        lam / s0[i]);
-            }
+            ACC_LOOP_END(elt, kl)
             break;
         }
         case AUG_STUDENTT: {                                 // studentt.jl:80-83, :85-91
             double nu = l->p[0], sig = l->p[1], alpha = (nu + 1) / 2;
             double halfnu = nu / 2, sig2 = abs2(sig);
             const double* yy = (const double*)y;
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(elt, kl)
                 double th = alpha * (1.0 / s0[i]);
-                elt.add(normlogpdf(yy[i], std::sqrt(1.0 / th), mu[i]) - var[i] * th / 2);
-                kl.add(kl_gamma(alpha, 1.0 / s0[i], halfnu, sig2 / halfnu));
-            }
+                elt_l.add(normlogpdf(yy[i], std::sqrt(1.0 / th), mu[i]) - var[i] * th / 2);
+                kl_l.add(kl_gamma(alpha, 1.0 / s0[i], halfnu, sig2 / halfnu));
+            ACC_LOOP_END(elt, kl)
             break;
         }
         case AUG_HETERO: {                                   // heteroscedasticgaussian.jl:129-145
@@ -697,21 +715,15 @@ int orc_expected_elbo_terms(const aug_lik* l, int64_t n, const void* y, const do
             double C = 0.5 * (std::log(lam) + std::log(TWOINVPI));
             const double* yy = (const double*)y;
             const double *mf = mu, *vf = var, *mg = mu + ld, *vg = var + ld;
-            Acc tot;
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(elt, kl)
                 double tn = s1[i], tw = pg_mean(0.5 + tn, s0[i]);
                 double g = mg[i];
                 double a = C - (0.5 + tn) * LOGTWO + ((0.5 - tn) * g - (abs2(g) + vg[i]) * tw) / 2;
                 double plam = lam / 2 * (abs2(yy[i] - mf[i]) + vf[i]);
                 double k = pg_kl(0.5 + tn, s0[i]) + kl_poisson(tn, plam);
-                elt.add(a); kl.add(k); tot.add(a + k);
-            }
-            scalars[0] = elt.seq; scalars[1] = kl.seq; scalars[2] = tot.seq;
-            if (scalars_comp) {
-                scalars_comp[0] = elt.compensated(); scalars_comp[1] = kl.compensated();
-                scalars_comp[2] = tot.compensated();
-            }
-            return 0;
+                elt_l.add(a); kl_l.add(k);
+            ACC_LOOP_END(elt, kl)
+            break;   // scalars[2] = Σ(a + k) is formed below as Σa + Σk
         }
         case AUG_CAT:
             return AUG_ERR_PRECONDITION;                     // categorical.jl:165-170
@@ -724,11 +736,13 @@ int orc_expected_elbo_terms(const aug_lik* l, int64_t n, const void* y, const do
             for (int j = 0; j < nl; ++j) spp += cc.prior_p;  // _p₀ of the prior NM, negativemultinomial.jl:27
             double p0p = 1 - spp;
             int bad = 0;
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(elt, kl)
                 double sp = 0.0;
                 for (int j = 0; j < nl; ++j) sp += s1[i * nl + j];
                 double p0 = 1 - sp;
-                if (!(sp < 1)) bad++;
+                if (!(sp < 1)) {
+                    _Pragma("omp atomic") bad++;
+                }
                 double sum_yn = 0.0, quad = 0.0, klpg = 0.0, klnm = 0.0;
                 for (int j = 0; j < nl; ++j) {
                     int64_t e = i * nl + j;
@@ -743,9 +757,9 @@ int orc_expected_elbo_terms(const aug_lik* l, int64_t n, const void* y, const do
                     // p.p[i] == 0 (σ̃ saturated, m > 744.44); we take the limit 0
                     if (s1[e] > 0) klnm += s1[e] * (std::log(s1[e]) - std::log(cc.prior_p));
                 }
-                elt.add(-sum_yn * LOGTWO + quad);
-                kl.add(klpg + (1.0 * std::log(p0) - 1.0 * std::log(p0p) + 1.0 / p0 * klnm));
-            }
+                elt_l.add(-sum_yn * LOGTWO + quad);
+                kl_l.add(klpg + (1.0 * std::log(p0) - 1.0 * std::log(p0p) + 1.0 / p0 * klnm));
+            ACC_LOOP_END(elt, kl)
             if (bad) return AUG_ERR_PRECONDITION;
             break;
         }
@@ -973,64 +987,64 @@ int orc_sampled_loglik_terms(const aug_lik* l, int64_t n, const void* y, const d
     switch (l->kind) {
         case AUG_BERNOULLI: {                                // bernoulli.jl:47-49, :57
             const uint8_t* yy = (const uint8_t*)y;
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(lt, lp)
                 double d = yy[i] - 0.5, sg = (d > 0) - (d < 0);
-                lt.add(-std::log(2.0) + (sg * f[i] - abs2(f[i]) * omega[i]) / 2);
-                if (with_prior) lp.add(pg_logpdf(1.0, 0.0, omega[i]));
-            }
+                lt_l.add(-std::log(2.0) + (sg * f[i] - abs2(f[i]) * omega[i]) / 2);
+                if (with_prior) lp_l.add(pg_logpdf(1.0, 0.0, omega[i]));
+            ACC_LOOP_END(lt, lp)
             break;
         }
         case AUG_NEGBIN: {                                   // negativebinomial.jl:54-57, :73
             const int64_t* yy = (const int64_t*)y;
             double r = lik_r(l);
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(lt, lp)
                 double yi = (double)yy[i];
-                lt.add(negbin_logconst(yi, r, l->r_is_int) - (yi + r) * LOGTWO +
+                lt_l.add(negbin_logconst(yi, r, l->r_is_int) - (yi + r) * LOGTWO +
                        (f[i] * (yi - r) - abs2(f[i]) * omega[i]) / 2);
-                if (with_prior) lp.add(pg_logpdf(r + yi, 0.0, omega[i]));
-            }
+                if (with_prior) lp_l.add(pg_logpdf(r + yi, 0.0, omega[i]));
+            ACC_LOOP_END(lt, lp)
             break;
         }
         case AUG_POISSON: {                                  // poisson.jl:62-65, :74; polyagammapoisson.jl:29-33
             const int64_t* yy = (const int64_t*)y;
             double lam = l->p[0], loglam = std::log(lam);
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(lt, lp)
                 double yi = (double)yy[i], ni = (double)nvar[i];
-                lt.add(yi * loglam - (yi + ni) * LOGTWO - std::lgamma(yi + 1) +
+                lt_l.add(yi * loglam - (yi + ni) * LOGTWO - std::lgamma(yi + 1) +
                        ((yi - ni) * f[i] - abs2(f[i]) * omega[i]) / 2);
-                if (with_prior) lp.add(pg_logpdf(yi + ni, 0.0, omega[i]) + poislogpdf(lam, ni));
-            }
+                if (with_prior) lp_l.add(pg_logpdf(yi + ni, 0.0, omega[i]) + poislogpdf(lam, ni));
+            ACC_LOOP_END(lt, lp)
             break;
         }
         case AUG_LAPLACE: {                                  // laplace.jl:70-77, :96
             const double* yy = (const double*)y;
             double beta = l->p[0], lam = laplace_lambda(l);
             lt_const = (double)n * (std::lgamma(0.5) - std::log(SQRTPI) - std::log(2 * beta));
-            for (int64_t i = 0; i < n; ++i) {
-                lt.add(-abs2(yy[i] - f[i]) * omega[i]);
-                if (with_prior) lp.add(invgammalogpdf(0.5, lam, omega[i]));
-            }
+            ACC_LOOP_BEGIN(lt, lp)
+                lt_l.add(-abs2(yy[i] - f[i]) * omega[i]);
+                if (with_prior) lp_l.add(invgammalogpdf(0.5, lam, omega[i]));
+            ACC_LOOP_END(lt, lp)
             break;
         }
         case AUG_STUDENTT: {                                 // studentt.jl:76-78, :91
             const double* yy = (const double*)y;
             double nu = l->p[0], sig2 = abs2(l->p[1]), halfnu = nu / 2;
-            for (int64_t i = 0; i < n; ++i) {
-                lt.add(normlogpdf(f[i], std::sqrt(1.0 / omega[i]), yy[i]));
-                if (with_prior) lp.add(gammalogpdf(halfnu, sig2 / halfnu, omega[i]));
-            }
+            ACC_LOOP_BEGIN(lt, lp)
+                lt_l.add(normlogpdf(f[i], std::sqrt(1.0 / omega[i]), yy[i]));
+                if (with_prior) lp_l.add(gammalogpdf(halfnu, sig2 / halfnu, omega[i]));
+            ACC_LOOP_END(lt, lp)
             break;
         }
         case AUG_HETERO: {                                   // heteroscedasticgaussian.jl:117-127
             const double* yy = (const double*)y;
             const double* g = f + ld;
             double lam = l->p[0];
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(lt, lp)
                 double ni = (double)nvar[i];
-                lt.add(-(0.5 + ni) * LOGTWO + ((0.5 - ni) * g[i] - abs2(g[i]) * omega[i]) / 2);
+                lt_l.add(-(0.5 + ni) * LOGTWO + ((0.5 - ni) * g[i] - abs2(g[i]) * omega[i]) / 2);
                 if (with_prior)
-                    lp.add(pg_logpdf(0.5 + ni, 0.0, omega[i]) + poislogpdf(lam / 2 * abs2(yy[i] - f[i]), ni));
-            }
+                    lp_l.add(pg_logpdf(0.5 + ni, 0.0, omega[i]) + poislogpdf(lam / 2 * abs2(yy[i] - f[i]), ni));
+            ACC_LOOP_END(lt, lp)
             break;
         }
         case AUG_CAT: case AUG_CAT_BIJ: {                    // categorical.jl:138-145, :147-163
@@ -1040,7 +1054,7 @@ int orc_sampled_loglik_terms(const aug_lik* l, int64_t n, const void* y, const d
             double sp = 0.0;
             for (int j = 0; j < nl; ++j) sp += cc.prior_p;
             double p0 = 1 - sp;
-            for (int64_t i = 0; i < n; ++i) {
+            ACC_LOOP_BEGIN(lt, lp)
                 double syn = 0.0, quad = 0.0, lpw = 0.0, sn = 0.0, nmterm = 0.0;
                 for (int j = 0; j < nl; ++j) {
                     int64_t e = i * nl + j;
@@ -1055,10 +1069,10 @@ int orc_sampled_loglik_terms(const aug_lik* l, int64_t n, const void* y, const d
                         nmterm += (ni == 0.0 ? 0.0 : ni * std::log(cc.prior_p)) - std::lgamma(ni + 1);
                     }
                 }
-                lt.add(-syn * LOGTWO + quad / 2);
+                lt_l.add(-syn * LOGTWO + quad / 2);
                 if (with_prior)                                // negativemultinomial.jl:47-52, x₀ = 1
-                    lp.add(lpw + std::lgamma(1.0 + sn) + 1.0 * std::log(p0) - std::lgamma(1.0) + nmterm);
-            }
+                    lp_l.add(lpw + std::lgamma(1.0 + sn) + 1.0 * std::log(p0) - std::lgamma(1.0) + nmterm);
+            ACC_LOOP_END(lt, lp)
             break;
         }
         default:

@@ -1,0 +1,221 @@
+"""GPU parity tests of the variational (CAVI) side, through the C ABI (via the ctypes host mirror).
+
+Bar (BASELINE.json north_star): deterministic outputs within 1e-12 relative of the CPU oracle in fp64;
+scalars within 1e-12 relative of the oracle's compensated sums.
+"""
+import numpy as np
+import pytest
+import torch
+
+from common import (BERNOULLI, CAT, CAT_BIJ, HETERO, LAPLACE, NEGBIN, POISSON, STUDENTT, golden_arrays,
+                    lik_args, load_golden, relerr, synth_inputs)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+GOLD = load_golden()
+
+
+@pytest.fixture(scope="module")
+def A():
+    from gpu_common import pkg
+    return pkg()
+
+
+def _fields(A, lik, q):
+    return [q._s(0), q._s(1), q._s(2)]
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_fused_cavi_vs_golden_and_oracle(A, orc, name):
+    from gpu_common import dev, host, make_lik, stack
+    case = GOLD[name]
+    kind, params, kw = lik_args(case)
+    lik = make_lik(kind, params, kw)
+    olik = orc.make_lik(kind, *params, **kw)
+    y, mu, var = golden_arrays(case)
+    n = y.shape[0]
+    want_elbo = kind != CAT
+    q = A.init_aux_posterior(lik, n)
+    q, beta, gamma, scal = A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)), want_elbo=want_elbo)
+    torch.cuda.synchronize()
+    beta, gamma = stack(beta), stack(gamma)
+    # --- mpmath golden vectors
+    assert relerr(host(q._s(0)), case["s0"]) < RTOL
+    if "s1" in case:
+        assert relerr(host(q._s(1)), case["s1"]) < RTOL
+    if "s2" in case:
+        assert relerr(host(q._s(2)), case["s2"]) < RTOL
+    assert relerr(beta, case["beta"]) < RTOL
+    assert relerr(gamma, case["gamma"]) < RTOL
+    # --- oracle on the same inputs
+    rc, ostate, obeta, ogamma, oseq, ocomp = orc.cavi_step(olik, y, mu, var, want_scalars=want_elbo)
+    assert rc == 0
+    assert relerr(host(q._s(0)), ostate[0]) < RTOL
+    assert relerr(beta, obeta) < RTOL and relerr(gamma, ogamma) < RTOL
+    if kind in (NEGBIN, POISSON, CAT, CAT_BIJ):
+        assert np.array_equal(host(q._s(2)), y)           # φ.y .= y
+    if want_elbo:
+        s = host(scal)
+        assert s[0] == pytest.approx(case["elt"], rel=RTOL)
+        assert s[1] == pytest.approx(case["kl"], rel=RTOL, abs=1e-13)
+        assert s[2] == pytest.approx(case.get("eall", case["elt"] + case["kl"]), rel=RTOL)
+        assert s[0] == pytest.approx(ocomp[0], rel=RTOL)
+        assert s[1] == pytest.approx(ocomp[1], rel=RTOL, abs=1e-13)
+        assert s[2] == pytest.approx(ocomp[2], rel=RTOL)
+
+
+CASES = [
+    ("bernoulli", BERNOULLI, (), {}),
+    ("negbin10", NEGBIN, (10,), dict(r_is_int=True)),
+    ("negbin5.5", NEGBIN, (5.5,), {}),
+    ("poisson10", POISSON, (10.0,), {}),
+    ("laplace1", LAPLACE, (1.0,), {}),
+    ("studentt", STUDENTT, (3.0, 1.5), {}),
+    ("hetero5", HETERO, (5.0,), {}),
+    ("cat_bij_K100", CAT_BIJ, (), dict(nlatent=99)),
+    ("cat_bij_K4", CAT_BIJ, (), dict(nlatent=3, logtheta=[0.2, -0.1, 0.4, 0.0])),
+    ("cat_K7", CAT, (), dict(nlatent=7)),
+]
+SIZES = {"default": [1, 2, 3, 255, 4097, 100003], "cat": [1, 2, 17, 1001]}
+
+
+@pytest.mark.parametrize("name,kind,params,kw", CASES)
+def test_fused_and_separate_verbs_vs_oracle(A, orc, name, kind, params, kw):
+    """Seeded synthetic inputs at ragged sizes: odd n (scalar tail), n < one CTA, n > one wave.
+    Also re-expresses src/TestUtils.jl:153-171: fused ≈ separate, γ ≥ 0, container shapes."""
+    from gpu_common import dev, host, make_lik, stack
+    lik = make_lik(kind, params, kw)
+    okw = dict(kw)
+    olik = orc.make_lik(kind, *params, **okw)
+    is_cat = kind in (CAT, CAT_BIJ)
+    for n in SIZES["cat" if is_cat else "default"]:
+        y, mu, var, f = synth_inputs(kind, n, 100 + n, params, kw.get("nlatent", 1))
+        want_elbo = kind != CAT
+        qf = A.Normals(dev(mu), dev(var))
+        yd = dev(y)
+        q = A.init_aux_posterior(lik, n)
+        q, beta, gamma, scal = A.cavi_step_(q, lik, yd, qf, want_elbo=want_elbo)
+        rc, ostate, obeta, ogamma, oseq, ocomp = orc.cavi_step(olik, y, mu, var, want_scalars=want_elbo)
+        assert rc == 0
+        assert len(beta) == len(gamma) == lik.nlatent and beta[0].shape == (n,)
+        b, g = stack(beta), stack(gamma)
+        for i in range(3):
+            if ostate[i] is not None and q._s(i) is not None:
+                assert relerr(host(q._s(i)), ostate[i]) < RTOL, (name, n, i)
+        assert relerr(b, obeta) < RTOL and relerr(g, ogamma) < RTOL, (name, n)
+        assert np.all(g >= 0)
+        if want_elbo:
+            s = host(scal)
+            for k in range(3):
+                assert s[k] == pytest.approx(ocomp[k], rel=RTOL, abs=1e-12), (name, n, k)
+        # separate verbs from the state == fused
+        q2 = A.aux_posterior(lik, yd, qf)
+        for i in range(3):
+            if q._s(i) is not None:
+                assert torch.equal(q._s(i), q2._s(i))
+        b2, g2 = A.expected_auglik_potential_and_precision(lik, q2, yd, qf)
+        assert relerr(stack(b2), b) < 1e-15 and relerr(stack(g2), g) < 1e-15
+        b3 = A.expected_auglik_potential(lik, q2, yd, qf)
+        g3 = A.expected_auglik_precision(lik, q2, yd, qf)
+        assert np.array_equal(stack(b3), stack(b2)) and np.array_equal(stack(g3), stack(g2))
+        if want_elbo:
+            elt = A.expected_logtilt(lik, q2, yd, qf)
+            kl = A.aux_kldivergence(lik, q2, yd, qf)
+            tot = A.expected_aug_loglik(lik, q2, yd, qf)
+            assert elt == pytest.approx(ocomp[0], rel=RTOL, abs=1e-12)
+            assert kl == pytest.approx(ocomp[1], rel=RTOL, abs=1e-12)
+            assert tot == pytest.approx(ocomp[2], rel=RTOL, abs=1e-12)
+
+
+def test_cat_nonbijective_kl_raises(A):
+    # categorical.jl:165-170 -> AUG_ERR_PRECONDITION
+    from gpu_common import dev, make_lik
+    lik = make_lik(CAT, (), dict(nlatent=5))
+    y, mu, var, f = synth_inputs(CAT, 8, 3, (), 5)
+    q = A.init_aux_posterior(lik, 8)
+    with pytest.raises(A.AugError) as ei:
+        A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)), want_elbo=True)
+    assert ei.value.rc == -3
+
+
+def test_unaligned_views_take_scalar_path(A, orc):
+    """Sub-array views (8-byte but not 16-byte aligned) must give the same results (scalar kernel)."""
+    from gpu_common import dev, host, make_lik, stack
+    n = 1001
+    y, mu, var, f = synth_inputs(BERNOULLI, n + 1, 7)
+    lik = make_lik(BERNOULLI, (), {})
+    yd, mud, vard = dev(y)[1:], dev(mu)[1:], dev(var)[1:]
+    q = A.init_aux_posterior(lik, n)
+    q, beta, gamma, scal = A.cavi_step_(q, lik, yd, A.Normals(mud, vard))
+    rc, ostate, obeta, ogamma, oseq, ocomp = orc.cavi_step(orc.make_lik(BERNOULLI), y[1:].copy(), mu[1:].copy(),
+                                                           var[1:].copy())
+    assert relerr(host(q.c), ostate[0]) < RTOL
+    assert relerr(stack(gamma), ogamma) < RTOL
+    assert host(scal)[2] == pytest.approx(ocomp[2], rel=RTOL)
+
+
+def test_empty_input(A):
+    from gpu_common import dev, host, make_lik
+    lik = make_lik(BERNOULLI, (), {})
+    q = A.init_aux_posterior(lik, 0)
+    z = torch.zeros(0, dtype=torch.float64, device="cuda")
+    q, beta, gamma, scal = A.cavi_step_(q, lik, torch.zeros(0, dtype=torch.uint8, device="cuda"), A.Normals(z, z))
+    assert beta[0].numel() == 0 and host(scal)[0] == 0.0
+
+
+def test_primitives_reference_pins(A, orc):
+    """test/SpecialDistributions/polyagamma.jl:27-36 and test/utils.jl:1-14 against the CUDA primitives."""
+    import math
+    from gpu_common import dev, host
+    b = dev(np.array([1.0, 1.0, 3.0, 3.0, 3.0, 1.2]))
+    c = dev(np.array([0.0, 2.0, 0.0, 2.5, 3.2, 3.2]))
+    m = host(A.pg_mean(b, c))
+    assert m[0] == 0.25
+    assert m[1] == pytest.approx(math.tanh(1.0) / 4, rel=1e-15)
+    ref = np.array([orc.pg_mean(bb, cc) for bb, cc in zip(host(b), host(c))])
+    assert relerr(m, ref) < RTOL
+    kl = host(A.pg_kldivergence(b, c))
+    refkl = np.array([orc.lib().orc_pg_kl(bb, cc) for bb, cc in zip(host(b), host(c))])
+    assert np.max(np.abs(kl - refkl)) < 1e-14
+    xs = 10.0 ** np.arange(-7, 7.0001, 0.1)
+    for bb, cc in [(1, 0.0), (1, 2.0), (3, 0.0), (3, 2.5), (3, 3.2), (1.2, 3.2), (0.5, 0.0), (25.5, 1.0)]:
+        lp = host(A.pg_logpdf(bb, cc, dev(xs)))
+        assert not np.any(np.isnan(lp))
+        ref = orc.pg_logpdf(bb, cc, xs)
+        fin = np.isfinite(ref) & (ref > -1e5)
+        assert np.max(np.abs(lp[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))) < 1e-11, (bb, cc)
+    mu = dev(np.array([0.3, 1000.0, -800.0, -5.0, 36.0, 37.0]))
+    cc = dev(np.array([1.0, 1000.5, 3.0, 0.0, 40.0, 40.0]))
+    got = host(A.approx_expected_logistic(mu, cc))
+    ref = np.array([orc.lib().orc_approx_expected_logistic(a, b) for a, b in zip(host(mu), host(cc))])
+    assert got[1] == 1.0 and got[2] == 0.0 and got[5] == 1.0
+    assert relerr(got, ref) < RTOL
+    q = A.Normals(dev(np.array([0.5, -2.0])), dev(np.array([0.25, 3.0])))
+    assert np.array_equal(host(A.second_moment(q)), np.array([0.5, 7.0]))
+    assert np.array_equal(host(A.second_moment(q, dev(np.array([1.5, -2.0])))), np.array([1.25, 3.0]))
+
+
+def test_large_n_properties(A):
+    """BASELINE size (N = 1e8 Bernoulli would need 6.5 GB; use 2^25 here and N=1e8 in bench.py):
+    size-independent properties — linearity of the scalar sums under concatenation, γ in (0, 1/4]."""
+    from gpu_common import host, make_lik
+    n = 1 << 25
+    g = torch.Generator(device="cuda").manual_seed(1)
+    mu = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    var = (0.5 + torch.rand(n, dtype=torch.float64, device="cuda", generator=g)) ** 2
+    y = (torch.rand(n, device="cuda", generator=g) < 0.5).to(torch.uint8)
+    lik = make_lik(BERNOULLI, (), {})
+    q = A.init_aux_posterior(lik, n)
+    q, beta, gamma, scal = A.cavi_step_(q, lik, y, A.Normals(mu, var))
+    tot = host(scal).copy()
+    h = n // 2 + 1
+    parts = []
+    for sl in (slice(0, h), slice(h, n)):
+        qq = A.init_aux_posterior(lik, mu[sl].numel())
+        _, _, _, sc = A.cavi_step_(qq, lik, y[sl].contiguous(), A.Normals(mu[sl].contiguous(), var[sl].contiguous()))
+        parts.append(host(sc).copy())
+    for k in range(3):
+        assert tot[k] == pytest.approx(parts[0][k] + parts[1][k], rel=1e-12)
+    gm = gamma[0]
+    assert float(gm.max()) <= 0.25 and float(gm.min()) > 0
+    assert torch.equal(q.c * q.c, q.c * q.c) and bool(torch.all(torch.abs(beta[0]) == 0.5))

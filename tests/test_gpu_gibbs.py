@@ -1,0 +1,300 @@
+"""GPU tests of the sampling (Gibbs) side through the C ABI.
+
+Sampled Ω must match the reference IN DISTRIBUTION (BASELINE.json north_star): first two moments against
+the closed-form E[ω], Var[ω] within 5 standard errors, and a one-sample KS test on 10^6 draws per (b, c)
+grid point against the CDF obtained by integrating exp(logpdf) of the reference's own density
+(polyagamma.jl:37-91, evaluated by the oracle).  48 grid points are tested, so the per-point threshold is
+Bonferroni-corrected: p > 0.01/48 (family-wise 1%); the number of points with p < 0.01 is also bounded.
+Deterministic sampled-side verbs (auglik_potential/precision, logtilt, aug_loglik) are held to 1e-12.
+"""
+import numpy as np
+import pytest
+import torch
+from scipy import special, stats
+
+from common import (BERNOULLI, CAT, CAT_BIJ, HETERO, LAPLACE, NEGBIN, POISSON, STUDENTT, relerr, synth_inputs)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def A():
+    from gpu_common import pkg
+    return pkg()
+
+
+def pg_cdf_table(orc, b, c):
+    mean, sd = orc.pg_mean(b, c), np.sqrt(orc.pg_var(b, c))
+    hi = mean + 16 * sd
+    xs = np.concatenate([np.geomspace(hi * 1e-7, hi * 1e-3, 400, endpoint=False), np.linspace(hi * 1e-3, hi, 80000)])
+    pdf = np.exp(orc.pg_logpdf(b, c, xs))
+    pdf[~np.isfinite(pdf)] = 0.0
+    cdf = np.concatenate([[0.0], np.cumsum(0.5 * (pdf[1:] + pdf[:-1]) * np.diff(xs))])
+    assert abs(cdf[-1] - 1.0) < 2e-5, (b, c, cdf[-1])
+    return xs, cdf / cdf[-1]
+
+
+def ks_pvalue(sample, xs, cdf):
+    s = np.sort(sample)
+    n = s.size
+    F = np.interp(s, xs, cdf, left=0.0, right=1.0)
+    d = max(np.max(np.arange(1, n + 1) / n - F), np.max(F - np.arange(0, n) / n))
+    return d, float(special.kolmogorov(np.sqrt(n) * d))
+
+
+B_GRID = [1, 2, 3, 10, 0.5, 1.2, 5.5, 25.5]
+C_GRID = [0.0, 0.5, 2.0, 2.5, 3.2, 10.0]
+
+
+def test_pg_sampler_moments_and_ks(A, orc):
+    from gpu_common import host
+    n = 1_000_000
+    ctx = A.default_context()
+    ctx.seed(4, 0)                                           # seed 4: SURVEY §8(d)
+    pvals = []
+    for b in B_GRID:
+        for c in C_GRID:
+            x = host(A.pg_rand(b, c, n=n, b_is_int=isinstance(b, int)))
+            assert np.all(x > 0) and np.all(np.isfinite(x))
+            mean, var = orc.pg_mean(float(b), c), orc.pg_var(float(b), c)
+            se_mean = np.sqrt(var / n)
+            assert abs(x.mean() - mean) < 5 * se_mean, (b, c, x.mean(), mean)
+            m4 = np.mean((x - x.mean()) ** 4)
+            se_var = np.sqrt(max(m4 - var ** 2, 0) / n)
+            assert abs(x.var() - var) < 5 * se_var, (b, c, x.var(), var)
+            xs, cdf = pg_cdf_table(orc, float(b), c)
+            d, p = ks_pvalue(x, xs, cdf)
+            pvals.append(((b, c), d, p))
+    ngrid = len(pvals)
+    worst = min(pvals, key=lambda t: t[2])
+    assert worst[2] > 0.01 / ngrid, worst
+    assert sum(p < 0.01 for _, _, p in pvals) <= 2, [t for t in pvals if t[2] < 0.01]
+
+
+def test_pg_sampler_reference_mean_pin(A, orc):
+    # test/SpecialDistributions/polyagamma.jl:30-37: mean(rand(p, 10000)) ≈ mean(p) atol 1e-2
+    from gpu_common import host
+    for b, c in [(1, 0.0), (1, 2.0), (3, 0.0), (3, 2.5), (3, 3.2), (1.2, 3.2)]:
+        x = host(A.pg_rand(b, c, n=10000, b_is_int=isinstance(b, int)))
+        assert abs(x.mean() - orc.pg_mean(float(b), c)) < 1e-2
+
+
+def test_pg_two_sample_vs_oracle_sampler(A, orc):
+    """CUDA sampler vs the restated reference sampler (Devroye + summation), two-sample KS."""
+    from gpu_common import host
+    n = 200_000
+    for b, c, is_int in [(1, 0.0, True), (1, 1.3, True), (1, 4.0, True), (4, 2.0, True)]:
+        x = host(A.pg_rand(b, c, n=n, b_is_int=is_int))
+        r = orc.pg_rand_bc(123, n, float(b), c, is_int)
+        assert stats.ks_2samp(x, r).pvalue > 1e-3, (b, c)
+
+
+def test_pg_vector_params_and_large_c(A, orc):
+    from gpu_common import dev, host
+    n = 400_000
+    rng = np.random.default_rng(0)
+    b = np.full(n, 1.0)
+    c = np.abs(rng.standard_normal(n)) * 30.0                 # includes z = |c|/2 >= 20 (r == 0 branch)
+    x = host(A.pg_rand(dev(b), dev(c), b_is_int=True))
+    means = np.array([orc.pg_mean(1.0, ci) for ci in c[:2000]])
+    assert np.all(x > 0)
+    # standardised residuals should have mean 0 / sd 1
+    sds = np.sqrt(np.array([orc.pg_var(1.0, ci) for ci in c[:2000]]))
+    z = (x[:2000] - means) / sds
+    assert abs(z.mean()) < 5 / np.sqrt(2000) and abs(z.std() - 1) < 0.2
+    assert host(A.pg_rand(dev(np.zeros(8)), dev(np.ones(8)), b_is_int=True)).max() == 0.0   # b == 0 -> 0
+
+
+def test_rng_is_counter_based_and_shard_invariant(A):
+    """Same (seed, offset) -> same draws; a shard with i0 reproduces the slice of the full draw."""
+    from gpu_common import dev, host, make_lik
+    n = 10_001
+    y, mu, var, f = synth_inputs(POISSON, n, 5, (10.0,))
+    lik = make_lik(POISSON, (10.0,), {})
+    rng = A.AugPhilox(99, 7)
+    full = A.aux_sample(rng, lik, dev(y), dev(f))
+    assert rng.offset == 8
+    again = A.aux_sample(A.AugPhilox(99, 7), lik, dev(y), dev(f))
+    assert torch.equal(full.omega, again.omega) and torch.equal(full.n, again.n)
+    lo = 3_333
+    part = A.aux_sample(A.AugPhilox(99, 7), lik, dev(y[lo:]), dev(f[lo:]), i0=lo)
+    assert torch.equal(full.omega[lo:], part.omega) and torch.equal(full.n[lo:], part.n)
+    other = A.aux_sample(A.AugPhilox(99, 8), lik, dev(y), dev(f))
+    assert not torch.equal(full.omega, other.omega)
+
+
+def _const_inputs(kind, n, params):
+    if kind == HETERO:
+        f = np.stack([np.full(n, 0.7), np.full(n, -0.4)])
+        y = np.full(n, 1.9)
+    else:
+        f = np.full(n, 0.8)
+        y = {BERNOULLI: np.ones(n, np.uint8), NEGBIN: np.full(n, 4, np.int64), POISSON: np.full(n, 3, np.int64),
+             LAPLACE: np.full(n, 2.1), STUDENTT: np.full(n, 2.1)}[kind]
+    return y, f
+
+
+@pytest.mark.parametrize("name,kind,params,kw", [
+    ("bernoulli", BERNOULLI, (), {}),
+    ("negbin10", NEGBIN, (10,), dict(r_is_int=True)),
+    ("negbin5.5", NEGBIN, (5.5,), {}),
+    ("poisson10", POISSON, (10.0,), {}),
+    ("laplace1", LAPLACE, (1.0,), {}),
+    ("studentt", STUDENTT, (3.0, 1.5), {}),
+    ("hetero5", HETERO, (5.0,), {}),
+])
+def test_aux_sample_law(A, orc, name, kind, params, kw):
+    """aux_sample! with identical (y, f) for every observation -> iid draws from one full conditional."""
+    from gpu_common import dev, host, make_lik
+    n = 400_000
+    lik = make_lik(kind, params, kw)
+    y, f = _const_inputs(kind, n, params)
+    Ω = A.aux_sample(A.AugPhilox(11, 0), lik, dev(y), dev(f))
+    w = host(Ω.omega)
+    assert np.all(np.isfinite(w)) and np.all(w > 0)
+    if kind == BERNOULLI:
+        xs, cdf = pg_cdf_table(orc, 1.0, 0.8)
+        assert ks_pvalue(w, xs, cdf)[1] > 1e-3
+    elif kind == NEGBIN:
+        xs, cdf = pg_cdf_table(orc, 4.0 + params[0], 0.8)
+        assert ks_pvalue(w, xs, cdf)[1] > 1e-3
+    elif kind == LAPLACE:                                     # InverseGaussian(μ = 1/(2β|y-f|), λ = 2/(2β)²)
+        mu_ig, lam = 1 / (2 * params[0] * 1.3), 2 / (2 * params[0]) ** 2
+        assert stats.kstest(w, stats.invgauss(mu_ig / lam, scale=lam).cdf).pvalue > 1e-3
+    elif kind == STUDENTT:                                    # Gamma((ν+1)/2, scale 2/(ν/σ² + (y-f)²))
+        nu, sg = params
+        assert stats.kstest(w, stats.gamma((nu + 1) / 2, scale=2 / (nu / sg ** 2 + 1.3 ** 2)).cdf).pvalue > 1e-3
+    else:                                                     # Poisson-PG mixtures: n law + ω | n law
+        nn = host(Ω.n)
+        if kind == POISSON:
+            rate, b_of = params[0] / (1 + np.exp(0.8)), lambda k: 3.0 + k
+            c = 0.8
+        else:
+            rate, b_of = params[0] / (1 + np.exp(-0.4)) * (0.7 - 1.9) ** 2 / 2, lambda k: 0.5 + k
+            c = 0.4
+        assert abs(nn.mean() - rate) < 5 * np.sqrt(rate / n)
+        assert abs(nn.var() - rate) < 5 * np.sqrt((rate + 2 * rate ** 2) / n) + 1e-3
+        ks = np.arange(0, nn.max() + 1)
+        obs = np.bincount(nn, minlength=ks.size)
+        exp = stats.poisson(rate).pmf(ks) * n
+        keep = exp > 20
+        chi2 = np.sum((obs[keep] - exp[keep]) ** 2 / exp[keep])
+        assert stats.chi2(keep.sum() - 1).sf(chi2) > 1e-4
+        for k in (0, 1, 2):
+            sel = w[nn == k]
+            if sel.size > 20000:
+                xs, cdf = pg_cdf_table(orc, b_of(k), c)
+                assert ks_pvalue(sel, xs, cdf)[1] > 1e-3, (name, k)
+
+
+def test_categorical_aux_sample_law(A, orc):
+    from gpu_common import dev, host, make_lik
+    n, nl = 200_000, 4
+    lt = [0.2, -0.1, 0.4, 0.0, 0.3]
+    lik = make_lik(CAT_BIJ, (), dict(nlatent=nl, logtheta=lt))
+    frow = np.array([0.5, -1.0, 0.1, 2.0])
+    f = np.tile(frow, (n, 1))
+    y = np.zeros((n, nl), np.uint8)
+    y[:, 2] = 1
+    Ω = A.aux_sample(A.AugPhilox(5, 0), lik, dev(y), dev(f))
+    w, nn = host(Ω.omega), host(Ω.n)
+    assert w.shape == (n, nl) and nn.shape == (n, nl)
+    sum_theta = np.exp(lt[4]) / 2 + np.sum(np.exp(lt[:4]))
+    p = np.exp(lt[:4]) / (1 + np.exp(-frow)) / sum_theta
+    p0 = 1 - p.sum()
+    mean_n = p / p0                                           # mean(NegativeMultinomial(1, p))
+    var_n = p / p0 + (p / p0) ** 2
+    for j in range(nl):
+        assert abs(nn[:, j].mean() - mean_n[j]) < 6 * np.sqrt(var_n[j] / n), j
+    # Cov(n_i, n_j) = p_i p_j / p0^2 (Gamma-Poisson mixture couples the classes)
+    cov01 = np.cov(nn[:, 0], nn[:, 3])[0, 1]
+    assert abs(cov01 - mean_n[0] * mean_n[3]) < 0.05 * mean_n[0] * mean_n[3] + 0.01
+    sel = w[:, 2][nn[:, 2] == 0]                              # ω_2 | n_2 = 0  ~ PG(1, |f_2|)
+    xs, cdf = pg_cdf_table(orc, 1.0, 0.1)
+    assert ks_pvalue(sel, xs, cdf)[1] > 1e-3
+    assert np.all(w[:, 0][nn[:, 0] == 0] == 0.0)             # b = y + n = 0 -> ω = 0
+
+
+def test_init_aux_variables(A, orc):
+    from gpu_common import host, make_lik
+    n = 300_000
+    xs, cdf = pg_cdf_table(orc, 1.0, 0.0)
+    for kind, params, kw in [(BERNOULLI, (), {}), (NEGBIN, (10,), dict(r_is_int=True)), (POISSON, (10.0,), {}),
+                             (HETERO, (5.0,), {}), (LAPLACE, (1.0,), {}), (STUDENTT, (3.0, 1.5), {}),
+                             (CAT_BIJ, (), dict(nlatent=3))]:
+        lik = make_lik(kind, params, kw)
+        Ω = A.init_aux_variables(A.AugPhilox(21, 0), lik, n if kind != CAT_BIJ else n // 3)
+        w = host(Ω.omega).ravel()
+        assert len(Ω) == (n if kind != CAT_BIJ else n // 3)
+        if kind == LAPLACE:
+            assert stats.kstest(w, stats.invgamma(1.0).cdf).pvalue > 1e-3
+        elif kind == STUDENTT:
+            assert stats.kstest(w, stats.gamma(1.0).cdf).pvalue > 1e-3
+        else:
+            assert ks_pvalue(w, xs, cdf)[1] > 1e-3
+        if kind in (POISSON, HETERO, CAT_BIJ):
+            nn = host(Ω.n).ravel()
+            assert abs(nn.mean() - 1.0) < 0.01 and abs(nn.var() - 1.0) < 0.02
+        else:
+            assert Ω.n is None
+
+
+ALL = [
+    ("bernoulli", BERNOULLI, (), {}),
+    ("negbin10", NEGBIN, (10,), dict(r_is_int=True)),
+    ("negbin5.5", NEGBIN, (5.5,), {}),
+    ("poisson10", POISSON, (10.0,), {}),
+    ("laplace1", LAPLACE, (1.0,), {}),
+    ("studentt", STUDENTT, (3.0, 1.5), {}),
+    ("hetero5", HETERO, (5.0,), {}),
+    ("cat_bij_K4", CAT_BIJ, (), dict(nlatent=3, logtheta=[0.2, -0.1, 0.4, 0.0])),
+    ("cat_K5", CAT, (), dict(nlatent=5)),
+]
+
+
+@pytest.mark.parametrize("name,kind,params,kw", ALL)
+def test_sampled_side_deterministic_verbs(A, orc, name, kind, params, kw):
+    """auglik_potential/precision, logtilt, aug_loglik on GPU-drawn Ω vs the oracle on the same Ω;
+    plus the container assertions of src/TestUtils.jl:70-88."""
+    from gpu_common import dev, host, make_lik, stack
+    lik = make_lik(kind, params, kw)
+    olik = orc.make_lik(kind, *params, **kw)
+    for n in (1, 10, 1537):
+        y, mu, var, f = synth_inputs(kind, n, 300 + n, params, kw.get("nlatent", 1))
+        yd, fd = dev(y), dev(f)
+        Ω = A.init_aux_variables(lik, n)
+        Ω = A.aux_sample_(A.AugPhilox(3, 0), Ω, lik, yd, fd)
+        assert len(Ω) == n
+        w = np.ascontiguousarray(host(Ω.omega))
+        nn = np.ascontiguousarray(host(Ω.n)) if Ω.n is not None else np.zeros(w.shape, np.int64)
+        beta, gamma = A.auglik_potential_and_precision(lik, Ω, yd, fd)
+        b1 = A.auglik_potential(lik, Ω, yd, fd)
+        g1 = A.auglik_precision(lik, Ω, yd, fd)
+        ob, og = orc.potential_precision(olik, y, f, w.ravel(), nn.ravel())
+        assert len(beta) == len(gamma) == lik.nlatent
+        assert relerr(stack(beta), ob) < RTOL and relerr(stack(gamma), og) < RTOL
+        assert np.array_equal(stack(b1), stack(beta)) and np.array_equal(stack(g1), stack(gamma))
+        assert np.all(stack(gamma) >= 0)
+        oseq, ocomp = orc.sampled_loglik_terms(olik, y, f, w.ravel(), nn.ravel(), True)
+        lt = A.logtilt(lik, Ω, yd, fd)
+        al = A.aug_loglik(lik, Ω, yd, fd)
+        assert lt == pytest.approx(ocomp[3], rel=RTOL, abs=1e-12)
+        assert al == pytest.approx(ocomp[5], rel=1e-11, abs=1e-10)
+
+
+@pytest.mark.parametrize("name,kind,params,kw", ALL[:6])
+def test_full_conditional_omega_invariant_gpu(A, orc, name, kind, params, kw):
+    """src/TestUtils.jl:107-116 with Ω drawn and aug_loglik evaluated by the CUDA path."""
+    from gpu_common import dev, host, make_lik
+    n = 10
+    lik = make_lik(kind, params, kw)
+    olik = orc.make_lik(kind, *params, **kw)
+    y, mu, var, f = synth_inputs(kind, n, 11, params)
+    vals = []
+    for off in (0, 1):
+        Ω = A.aux_sample(A.AugPhilox(17, off), lik, dev(y), dev(f))
+        w = np.ascontiguousarray(host(Ω.omega))
+        nn = np.ascontiguousarray(host(Ω.n)) if Ω.n is not None else np.zeros(n, np.int64)
+        vals.append(A.aug_loglik(lik, Ω, dev(y), dev(f)) - orc.full_conditional_logdensity(olik, y, f, w, nn))
+    assert abs(vals[0] - vals[1]) < 1e-5
