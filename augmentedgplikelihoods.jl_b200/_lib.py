@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaugcuda.so")
+# AUGCUDA_LIB lets a tuning run load an alternative BUILD of the same library (never a different backend)
+LIB_PATH = os.environ.get("AUGCUDA_LIB") or os.path.join(_HERE, "libaugcuda.so")
 
 BERNOULLI, NEGBIN, POISSON, LAPLACE, STUDENTT, HETERO, CAT_BIJ, CAT = range(8)
 NSCALARS = 8
@@ -65,6 +66,7 @@ SIGNATURES = {
     "aug_pg_logpdf": [_vp, _i64, _d, _d, _vp, _vp],
     "aug_approx_expected_logistic": [_vp, _i64, _vp, _vp, _vp],
     "aug_second_moment": [_vp, _i64, _vp, _vp, _vp, _vp],
+    "aug_fastmath_eval": [_vp, _i32, _i64, _vp, _vp],
     "aug_comm_get_unique_id": [C.c_char * 128],
     "aug_comm_init": [_vp, _i32, _i32, C.c_char * 128],
     "aug_comm_destroy": [_vp],

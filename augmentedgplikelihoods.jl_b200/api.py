@@ -630,3 +630,13 @@ def second_moment(q: Normals, y=None, ctx=None):
     check(ctx.lib.aug_second_moment(ctx.h, q.mu.numel(), _ptr(q.mu), _ptr(q.var), _ptr(y), _ptr(out)))
     ctx.leave()
     return out
+
+
+def fastmath_eval(fn: int, x, ctx=None):
+    """diagnostics: csrc/aug_fastmath.cuh functions (0 rcp, 1 rsqrt, 2 exp, 3 log, 4 log on [1,2], 5 sqrt)"""
+    ctx = ctx or default_context()
+    ctx.enter()
+    out = ctx.empty(x.shape)
+    check(ctx.lib.aug_fastmath_eval(ctx.h, int(fn), x.numel(), _ptr(x), _ptr(out)))
+    ctx.leave()
+    return out

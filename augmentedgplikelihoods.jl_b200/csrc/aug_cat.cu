@@ -76,11 +76,23 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_cavi_kernel(const CatArgs a) {
                 v = ld_stream1(a.var + base + e);
             }
             const double s2m = fma(m, m, v);
-            if (FROM_STATE) c = ld_stream1(a.rs0 + base + e);
-            else c = sqrt(s2m);                                       // categorical.jl:88,105
-            const PGTerms t = pg_terms<ELBO>(c);
-            if (FROM_STATE) p = ld_stream1(a.rs1 + base + e);
-            else p = approx_expected_logistic(-m, c, t) * inv_denom;  // :90-92, :107
+            // straight-line fast math when the element is in range, IEEE / libdevice otherwise
+            PGTerms t;
+            if (FROM_STATE) {
+                c = ld_stream1(a.rs0 + base + e);
+                p = ld_stream1(a.rs1 + base + e);
+                if (c >= 0.0 && c <= 700.0) t = pg_terms<ELBO, false>(c);
+                else t = pg_terms<ELBO, true>(c);
+            } else if (augf::in_range(s2m) && fabs(m) <= 700.0 && v <= 4e5) {
+                double ic;
+                augf::sqrt_inv(s2m, c, ic);                           // categorical.jl:88,105
+                t = pg_terms_ic<ELBO, false>(c, ic);
+                p = approx_expected_logistic<false>(-m, c, t) * inv_denom;   // :90-92, :107
+            } else {
+                c = sqrt(s2m);
+                t = pg_terms_ic<ELBO, true>(c, 0.0);
+                p = approx_expected_logistic<true>(-m, c, t) * inv_denom;
+            }
             double ys = yv;
             if (FROM_STATE && a.rs2) ys = (double)__ldg(a.rs2 + base + e);
             if (!FROM_STATE) {
@@ -114,7 +126,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_cavi_kernel(const CatArgs a) {
                 if (ELBO) {
                     sx1 += X1[i * nlp + j];
                     sx2 += X2[i * nlp + j];
-                    if (p > 0.0) sx3 += p * (log(p) - a.L.c2);       // negativemultinomial.jl:79-81
+                    if (p > 0.0) sx3 += p * ((p >= 1e-290 ? augf::log_(p) : log(p)) - a.L.c2);       // negativemultinomial.jl:79-81
                 }
             }
             sp = warp_sum(sp);

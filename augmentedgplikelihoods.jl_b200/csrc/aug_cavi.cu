@@ -16,6 +16,16 @@
 #include "aug_common.cuh"
 #include "aug_math.cuh"
 
+#ifndef CAVI_MIN_BLOCKS
+#define CAVI_MIN_BLOCKS 4
+#endif
+#ifndef CAVI_U
+#define CAVI_U 1
+#endif
+#ifndef CAVI_PREFETCH
+#define CAVI_PREFETCH 0
+#endif
+
 namespace {
 
 struct CaviArgs {
@@ -56,8 +66,43 @@ struct Obs {
     double elt, kl;            // per-observation ELBO terms
 };
 
-// ------------------------------------------------------------------ per-kind closed forms
+// c = sqrt(second moment) (fused) or the stored c (FROM_STATE), and the PG terms of that tilt
+template <bool FROM_STATE, bool ELBO, bool SAFE>
+__device__ __forceinline__ augm::PGTerms terms(double s2, double& c) {
+    if (FROM_STATE) return augm::pg_terms<ELBO, SAFE>(c);
+    double ic = 0.0;
+    if (SAFE) c = sqrt(s2);
+    else augf::sqrt_inv(s2, c, ic);
+    return augm::pg_terms_ic<ELBO, SAFE>(c, ic);
+}
+
+// Can the straight-line (SAFE = false) instantiation be used for this observation?  False for zero /
+// denormal / huge / non-finite second moments, |m| beyond the exp range, integer y beyond the
+// constant table — inputs the IEEE + libdevice instantiation handles instead.
 template <int KIND, bool FROM_STATE, bool ELBO>
+__device__ __forceinline__ bool fast_ok(const Obs& o) {
+    bool ok = true;
+    if (KIND == AUG_BERNOULLI || KIND == AUG_NEGBIN || KIND == AUG_POISSON) {
+        if (FROM_STATE) ok = o.s0 >= 0.0 && o.s0 <= 700.0;
+        if (!FROM_STATE || ELBO) ok = ok && augf::in_range(fma(o.m, o.m, o.v)) && fabs(o.m) <= 700.0 && o.v <= 4e5;
+        if (ELBO && KIND != AUG_BERNOULLI) ok = ok && o.y < (double)AUG_TABLE_N;
+        if (KIND == AUG_POISSON && FROM_STATE) ok = ok && o.s1 >= 0.0 && o.s1 <= 1e290;
+    } else if (KIND == AUG_LAPLACE || KIND == AUG_STUDENTT) {
+        const double d = o.m - o.y;
+        if (!FROM_STATE || ELBO) ok = augf::in_range(fma(d, d, o.v));
+        if (FROM_STATE) ok = ok && o.s0 >= 1e-290 && o.s0 <= 1e290;
+    } else if (KIND == AUG_HETERO) {
+        const double d = o.m - o.y;
+        if (FROM_STATE) ok = o.s0 >= 0.0 && o.s0 <= 700.0 && o.s1 >= 0.0 && o.s1 <= 1e290;
+        if (!FROM_STATE || ELBO) ok = ok && augf::in_range(fma(o.mg, o.mg, o.vg)) && o.vg <= 4e5 &&
+                                      augf::in_range(fma(d, d, o.v));
+        ok = ok && fabs(o.mg) <= 700.0;
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------ per-kind closed forms
+template <int KIND, bool FROM_STATE, bool ELBO, bool SAFE>
 __device__ __forceinline__ void eval(const LikConst& L, Obs& o) {
     using namespace augm;
     o.elt = 0.0;
@@ -65,8 +110,7 @@ __device__ __forceinline__ void eval(const LikConst& L, Obs& o) {
     o.b1 = o.g1 = 0.0;
     if (KIND == AUG_BERNOULLI) {
         const double s2m = fma(o.m, o.m, o.v);                  // second_moment utils.jl:1-3
-        if (!FROM_STATE) o.s0 = sqrt(s2m);                      // bernoulli.jl:23
-        const PGTerms t = pg_terms<ELBO>(o.s0);
+        const PGTerms t = terms<FROM_STATE, ELBO, SAFE>(s2m, o.s0);   // c = sqrt(.)  bernoulli.jl:23
         const double sg = o.y > 0.5 ? 0.5 : -0.5;               // sign(y - 0.5)/2  :28
         o.b0 = sg;
         o.g0 = t.h;                                             // mean(PG(1,c))    :44
@@ -76,8 +120,7 @@ __device__ __forceinline__ void eval(const LikConst& L, Obs& o) {
         }
     } else if (KIND == AUG_NEGBIN) {
         const double s2m = fma(o.m, o.m, o.v);
-        if (!FROM_STATE) o.s0 = sqrt(s2m);                      // negativebinomial.jl:29-31
-        const PGTerms t = pg_terms<ELBO>(o.s0);
+        const PGTerms t = terms<FROM_STATE, ELBO, SAFE>(s2m, o.s0);   // negativebinomial.jl:29-31
         const double r = L.p0;
         const double b = o.ys + r;
         const double th = b * t.h;                              // mean(PG(y+r,c)) :48
@@ -85,61 +128,70 @@ __device__ __forceinline__ void eval(const LikConst& L, Obs& o) {
         o.g0 = th;
         if (ELBO) {
             double lc;                                          // negbin_logconst :51-52
-            if (o.y < (double)AUG_TABLE_N) lc = __ldg(&L.table[(int)o.y]);
+            if (!SAFE) lc = __ldg(&L.table[(int)fmin(fmax(o.y, 0.0), (double)(AUG_TABLE_N - 1))]);
+            else if (o.y < (double)AUG_TABLE_N) lc = __ldg(&L.table[(int)o.y]);
             else lc = lgamma(o.y + r) - lgamma(o.y + 1.0) - L.c0;
             o.elt = lc - (o.y + r) * LN2 + 0.5 * fma(o.m, o.y - r, -s2m * th);   // :62-64
             o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th);
         }
     } else if (KIND == AUG_POISSON) {
         const double s2m = fma(o.m, o.m, o.v);
-        if (!FROM_STATE) o.s0 = sqrt(s2m);                      // poisson.jl:35
-        const PGTerms t = pg_terms<ELBO>(o.s0);
-        if (!FROM_STATE) o.s1 = L.p0 * approx_expected_logistic(-o.m, o.s0, t);   // :37
+        const PGTerms t = terms<FROM_STATE, ELBO, SAFE>(s2m, o.s0);   // poisson.jl:35
+        if (!FROM_STATE) o.s1 = L.p0 * approx_expected_logistic<SAFE>(-o.m, o.s0, t);   // :37
         const double lam = o.s1;
         const double b = o.ys + lam;
         const double th = b * t.h;                              // polyagammapoisson.jl:35-41
         o.b0 = 0.5 * (o.y - lam);                               // poisson.jl:59
         o.g0 = th;
         if (ELBO) {
-            o.elt = -(o.y + lam) * LN2 + 0.5 * fma(o.y - lam, o.m, -s2m * th) + o.y * L.c0 -
-                    lfact(o.y, L.table);                        // :81-83
-            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) + kl_poisson(lam, L.p0, L.c0);
+            double lf;                                          // logfactorial(y)
+            if (!SAFE) lf = __ldg(&L.table[(int)fmin(fmax(o.y, 0.0), (double)(AUG_TABLE_N - 1))]);
+            else lf = lfact(o.y, L.table);
+            o.elt = -(o.y + lam) * LN2 + 0.5 * fma(o.y - lam, o.m, -s2m * th) + o.y * L.c0 - lf;   // :81-83
+            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) + kl_poisson<SAFE>(lam, L.p0, L.c0);
         }
     } else if (KIND == AUG_LAPLACE) {
         const double d = o.m - o.y;
         const double s2y = fma(d, d, o.v);                      // second_moment(q, y) utils.jl:5-7
-        if (!FROM_STATE) o.s0 = L.c0 * rsqrt(s2y);              // 1/(2β sqrt(.))  laplace.jl:48-50
+        if (!FROM_STATE) {                                      // 1/(2β sqrt(.))  laplace.jl:48-50
+            if (SAFE) {
+                o.s0 = 1.0 / (2.0 * L.p0 * sqrt(s2y));
+            } else {
+                double c_, ic_;
+                augf::sqrt_inv(s2y, c_, ic_);
+                o.s0 = L.c0 * ic_;
+            }
+        }
         o.b0 = 2.0 * o.s0 * o.y;                                // :63
         o.g0 = 2.0 * o.s0;                                      // :67
         if (ELBO) {
             o.elt = L.c2 - s2y * o.s0;                          // :84-87
-            o.kl = L.c3 + L.c1 / o.s0;                          // :98-104
+            o.kl = L.c3 + (SAFE ? L.c1 / o.s0 : L.c1 * augf::rcp(o.s0));   // :98-104
         }
     } else if (KIND == AUG_STUDENTT) {
         const double d = o.m - o.y;
         const double s2y = fma(d, d, o.v);
         if (!FROM_STATE) o.s0 = 0.5 * (L.c0 + s2y);             // studentt.jl:54-56
-        const double ib = 1.0 / o.s0;
+        const double ib = SAFE ? 1.0 / o.s0 : augf::rcp(o.s0);
         const double th = L.c1 * ib;                            // mean(Gamma(α, 1/β)) :69,73
         o.b0 = th * o.y;
         o.g0 = th;
         if (ELBO) {
             // logpdf(Normal(y, θ^-1/2), m) - vθ/2 = -log(2π)/2 + log(θ)/2 - θ((m-y)² + v)/2   :80-83
-            o.elt = L.c5 + 0.5 * log(th) - 0.5 * th * s2y;
             // KL(Gamma(α, 1/β) || Gamma(ν/2, 2σ²/ν)), Distributions.jl closed form
             const double r = ib / L.c4;
-            o.kl = L.c2 - L.c3 * log(r) + L.c1 * r;
+            const double lth = SAFE ? log(th) : augf::log_(th);
+            const double lr = SAFE ? log(r) : lth - L.p1;       // log r = log θ − log(α θq)  (L.p1 holds it)
+            o.elt = L.c5 + 0.5 * lth - 0.5 * th * s2y;
+            o.kl = L.c2 - L.c3 * lr + L.c1 * r;
         }
     } else if (KIND == AUG_HETERO) {
         const double d = o.m - o.y;
         const double s2f = fma(d, d, o.v);
         const double s2g = fma(o.mg, o.mg, o.vg);
-        if (!FROM_STATE) {
-            o.s2 = 0.5 * s2f;                                   // ψ  heteroscedasticgaussian.jl:42
-            o.s0 = sqrt(s2g);                                   // c  :43
-        }
-        const PGTerms t = pg_terms<ELBO>(o.s0);
-        const double st = approx_expected_logistic(-o.mg, o.s0, t);
+        if (!FROM_STATE) o.s2 = 0.5 * s2f;                      // ψ  heteroscedasticgaussian.jl:42
+        const PGTerms t = terms<FROM_STATE, ELBO, SAFE>(s2g, o.s0);   // c  :43
+        const double st = approx_expected_logistic<SAFE>(-o.mg, o.s0, t);
         if (!FROM_STATE) o.s1 = L.p0 * st * o.s2;               // λ  :44
         const double lam = o.s1;
         const double lsg = L.p0 * (1.0 - st);                   // :102
@@ -152,7 +204,8 @@ __device__ __forceinline__ void eval(const LikConst& L, Obs& o) {
         if (ELBO) {                                             // :129-145
             o.elt = L.c0 - b * LN2 + 0.5 * fma(0.5 - lam, o.mg, -s2g * th);
             const double pl = 0.5 * L.p0 * s2f;
-            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) + kl_poisson(lam, pl, log(pl));
+            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) +
+                   kl_poisson<SAFE>(lam, pl, SAFE ? log(pl) : augf::log_(pl));
         }
     }
 }
@@ -205,20 +258,125 @@ template <> struct S2T<AUG_NEGBIN> { typedef int64_t T; };
 template <> struct S2T<AUG_POISSON> { typedef int64_t T; };
 
 template <int KIND, bool FROM_STATE, bool ELBO, bool VEC>
-__global__ void __launch_bounds__(AUG_BLOCK) cavi_kernel(const CaviArgs a) {
+__global__ void __launch_bounds__(AUG_BLOCK, CAVI_MIN_BLOCKS) cavi_kernel(const CaviArgs a) {
     typedef typename YT<KIND>::T yt;
     typedef typename S2T<KIND>::T s2t;
     constexpr bool HET = KIND == AUG_HETERO;
     constexpr bool YSTATE = KIND == AUG_NEGBIN || KIND == AUG_POISSON;
     constexpr bool HAS_S1 = KIND == AUG_POISSON || KIND == AUG_HETERO;
-    constexpr int U = 2;  // independent pairs in flight per thread
+    constexpr int U = HET ? 1 : CAVI_U;  // independent pairs in flight per thread
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     double acc[2] = {0.0, 0.0};
     const bool need_mv = !FROM_STATE || ELBO;
+    const int64_t npairs = VEC ? (a.n >> 1) : 0;
+
+    // One observation through the IEEE / libdevice instantiation (any input).  Used for the odd tail
+    // element, for unaligned arrays, and to redo the pairs of a thread that met an out-of-range value.
+    auto scalar_obs = [&](int64_t i) {
+        Obs o;
+        o.y = load_y1<yt>(a.y, i);
+        o.ys = o.y;
+        o.m = o.v = o.mg = o.vg = 0.0;
+        o.s0 = o.s1 = o.s2 = 0.0;
+        if (need_mv) { o.m = a.mu[i]; o.v = a.var[i]; }
+        if (HET) { o.mg = a.mu_g[i]; if (need_mv) o.vg = a.var_g[i]; }
+        if (FROM_STATE) {
+            o.s0 = a.rs0[i];
+            if (HAS_S1) o.s1 = a.rs1[i];
+            if (HET) o.s2 = reinterpret_cast<const double*>(a.rs2)[i];
+            if (YSTATE && a.rs2 != nullptr) o.ys = (double)reinterpret_cast<const int64_t*>(a.rs2)[i];
+        }
+        eval<KIND, FROM_STATE, ELBO, true>(a.L, o);
+        if (!FROM_STATE) {
+            if (a.s0) a.s0[i] = o.s0;
+            if (HAS_S1 && a.s1) a.s1[i] = o.s1;
+            if (HET && a.s2) reinterpret_cast<double*>(a.s2)[i] = o.s2;
+            if (YSTATE && a.s2) store_y1<s2t>(a.s2, i, o.y);
+        }
+        if (a.beta) a.beta[i] = o.b0;
+        if (a.gamma) a.gamma[i] = o.g0;
+        if (HET) {
+            if (a.beta_g) a.beta_g[i] = o.b1;
+            if (a.gamma_g) a.gamma_g[i] = o.g1;
+        }
+        if (ELBO) { acc[0] += o.elt; acc[1] += o.kl; }
+    };
+
+    // loads of one pair (two consecutive observations) — all 128-bit except the 16-bit Bool pair
+    auto load_pair = [&](int64_t p, Obs& o0, Obs& o1) {
+        load_y2<yt>(a.y, p, o0.y, o1.y);
+        if (need_mv) {
+            const double2 m = ld_stream2(a.mu + 2 * p);
+            const double2 v = ld_stream2(a.var + 2 * p);
+            o0.m = m.x; o1.m = m.y;
+            o0.v = v.x; o1.v = v.y;
+        }
+        if (HET) {
+            const double2 m = ld_stream2(a.mu_g + 2 * p);
+            o0.mg = m.x; o1.mg = m.y;
+            if (need_mv) {
+                const double2 v = ld_stream2(a.var_g + 2 * p);
+                o0.vg = v.x; o1.vg = v.y;
+            }
+        }
+        o0.ys = o0.y; o1.ys = o1.y;
+        if (FROM_STATE) {
+            const double2 c = ld_stream2(a.rs0 + 2 * p);
+            o0.s0 = c.x; o1.s0 = c.y;
+            if (HAS_S1) {
+                const double2 l = ld_stream2(a.rs1 + 2 * p);
+                o0.s1 = l.x; o1.s1 = l.y;
+            }
+            if (HET) {
+                const double2 ps = ld_stream2(reinterpret_cast<const double*>(a.rs2) + 2 * p);
+                o0.s2 = ps.x; o1.s2 = ps.y;
+            }
+            if (YSTATE && a.rs2 != nullptr) load_y2<int64_t>(a.rs2, p, o0.ys, o1.ys);
+        }
+    };
+    auto dead_pair = [&](Obs& o0, Obs& o1) {   // harmless inputs for the straight-line math of a dead slot
+        o0.y = o1.y = o0.ys = o1.ys = 0.0;
+        o0.m = o1.m = o0.mg = o1.mg = 0.0;
+        o0.v = o1.v = o0.vg = o1.vg = 1.0;
+        o0.s0 = o1.s0 = o0.s1 = o1.s1 = o0.s2 = o1.s2 = 1.0;
+    };
+    auto store_pair = [&](int64_t p, const Obs& o0, const Obs& o1) {
+        if (!FROM_STATE) {
+            if (a.s0) st_stream2(a.s0 + 2 * p, o0.s0, o1.s0);
+            if (HAS_S1 && a.s1) st_stream2(a.s1 + 2 * p, o0.s1, o1.s1);
+            if (HET && a.s2) st_stream2(reinterpret_cast<double*>(a.s2) + 2 * p, o0.s2, o1.s2);
+            if (YSTATE && a.s2) store_y2<s2t>(a.s2, p, o0.y, o1.y);
+        }
+        if (a.beta) st_stream2(a.beta + 2 * p, o0.b0, o1.b0);
+        if (a.gamma) st_stream2(a.gamma + 2 * p, o0.g0, o1.g0);
+        if (HET) {
+            if (a.beta_g) st_stream2(a.beta_g + 2 * p, o0.b1, o1.b1);
+            if (a.gamma_g) st_stream2(a.gamma_g + 2 * p, o0.g1, o1.g1);
+        }
+        if (ELBO) {
+            acc[0] += o0.elt + o1.elt;
+            acc[1] += o0.kl + o1.kl;
+        }
+    };
 
     if (VEC) {
-        const int64_t npairs = a.n >> 1;
+        bool bad = false;   // some observation of this thread was outside the fast-math range
+#if CAVI_PREFETCH
+        // software pipeline: the loads of the next pair are in flight while this one is evaluated
+        Obs c0, c1, n0, n1;
+        if (tid < npairs) load_pair(tid, c0, c1);
+        for (int64_t p = tid; p < npairs; p += nth) {
+            const int64_t pn = p + nth;
+            if (pn < npairs) load_pair(pn, n0, n1);
+            bad = bad || !fast_ok<KIND, FROM_STATE, ELBO>(c0) || !fast_ok<KIND, FROM_STATE, ELBO>(c1);
+            eval<KIND, FROM_STATE, ELBO, false>(a.L, c0);
+            eval<KIND, FROM_STATE, ELBO, false>(a.L, c1);
+            store_pair(p, c0, c1);
+            c0 = n0;
+            c1 = n1;
+        }
+#else
         for (int64_t p0 = tid; p0 < npairs; p0 += nth * U) {
             Obs o[U][2];
             bool live[U];
@@ -226,94 +384,34 @@ __global__ void __launch_bounds__(AUG_BLOCK) cavi_kernel(const CaviArgs a) {
             for (int j = 0; j < U; ++j) {
                 const int64_t p = p0 + (int64_t)j * nth;
                 live[j] = p < npairs;
-                if (!live[j]) continue;
-                load_y2<yt>(a.y, p, o[j][0].y, o[j][1].y);
-                if (need_mv) {
-                    const double2 m = ld_stream2(a.mu + 2 * p);
-                    const double2 v = ld_stream2(a.var + 2 * p);
-                    o[j][0].m = m.x; o[j][1].m = m.y;
-                    o[j][0].v = v.x; o[j][1].v = v.y;
-                }
-                if (HET) {
-                    const double2 m = ld_stream2(a.mu_g + 2 * p);
-                    o[j][0].mg = m.x; o[j][1].mg = m.y;
-                    if (need_mv) {
-                        const double2 v = ld_stream2(a.var_g + 2 * p);
-                        o[j][0].vg = v.x; o[j][1].vg = v.y;
-                    }
-                }
-                o[j][0].ys = o[j][0].y; o[j][1].ys = o[j][1].y;
-                if (FROM_STATE) {
-                    const double2 c = ld_stream2(a.rs0 + 2 * p);
-                    o[j][0].s0 = c.x; o[j][1].s0 = c.y;
-                    if (HAS_S1) {
-                        const double2 l = ld_stream2(a.rs1 + 2 * p);
-                        o[j][0].s1 = l.x; o[j][1].s1 = l.y;
-                    }
-                    if (HET) {
-                        const double2 ps = ld_stream2(reinterpret_cast<const double*>(a.rs2) + 2 * p);
-                        o[j][0].s2 = ps.x; o[j][1].s2 = ps.y;
-                    }
-                    if (YSTATE && a.rs2 != nullptr) load_y2<int64_t>(a.rs2, p, o[j][0].ys, o[j][1].ys);
-                }
+                if (live[j]) load_pair(p, o[j][0], o[j][1]);
+                else dead_pair(o[j][0], o[j][1]);
             }
+            // straight-line evaluation of all 2U observations (no branch: the compiler interleaves them)
 #pragma unroll
             for (int j = 0; j < U; ++j) {
-                if (!live[j]) continue;
-                const int64_t p = p0 + (int64_t)j * nth;
-                eval<KIND, FROM_STATE, ELBO>(a.L, o[j][0]);
-                eval<KIND, FROM_STATE, ELBO>(a.L, o[j][1]);
-                if (!FROM_STATE) {
-                    if (a.s0) st_stream2(a.s0 + 2 * p, o[j][0].s0, o[j][1].s0);
-                    if (HAS_S1 && a.s1) st_stream2(a.s1 + 2 * p, o[j][0].s1, o[j][1].s1);
-                    if (HET && a.s2) st_stream2(reinterpret_cast<double*>(a.s2) + 2 * p, o[j][0].s2, o[j][1].s2);
-                    if (YSTATE && a.s2) store_y2<s2t>(a.s2, p, o[j][0].y, o[j][1].y);
-                }
-                if (a.beta) st_stream2(a.beta + 2 * p, o[j][0].b0, o[j][1].b0);
-                if (a.gamma) st_stream2(a.gamma + 2 * p, o[j][0].g0, o[j][1].g0);
-                if (HET) {
-                    if (a.beta_g) st_stream2(a.beta_g + 2 * p, o[j][0].b1, o[j][1].b1);
-                    if (a.gamma_g) st_stream2(a.gamma_g + 2 * p, o[j][0].g1, o[j][1].g1);
-                }
-                if (ELBO) {
-                    acc[0] += o[j][0].elt + o[j][1].elt;
-                    acc[1] += o[j][0].kl + o[j][1].kl;
-                }
+                bad = bad || !fast_ok<KIND, FROM_STATE, ELBO>(o[j][0]) || !fast_ok<KIND, FROM_STATE, ELBO>(o[j][1]);
+                eval<KIND, FROM_STATE, ELBO, false>(a.L, o[j][0]);
+                eval<KIND, FROM_STATE, ELBO, false>(a.L, o[j][1]);
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (live[j]) store_pair(p0 + (int64_t)j * nth, o[j][0], o[j][1]);
+        }
+#endif
+        if (bad) {
+            // rare: redo every pair of this thread with the any-input instantiation (outputs are
+            // simply overwritten, the thread's partial sums restart from zero)
+            acc[0] = acc[1] = 0.0;
+            for (int64_t p = tid; p < npairs; p += nth) {
+                scalar_obs(2 * p);
+                scalar_obs(2 * p + 1);
             }
         }
     }
-    // scalar path: the odd tail element of the vector kernel, or everything when unaligned
-    {
-        const int64_t start = VEC ? (a.n & ~(int64_t)1) : 0;
-        for (int64_t i = start + tid; i < a.n; i += nth) {
-            Obs o;
-            o.y = load_y1<yt>(a.y, i);
-            o.ys = o.y;
-            o.m = o.v = o.mg = o.vg = 0.0;
-            if (need_mv) { o.m = a.mu[i]; o.v = a.var[i]; }
-            if (HET) { o.mg = a.mu_g[i]; if (need_mv) o.vg = a.var_g[i]; }
-            if (FROM_STATE) {
-                o.s0 = a.rs0[i];
-                if (HAS_S1) o.s1 = a.rs1[i];
-                if (HET) o.s2 = reinterpret_cast<const double*>(a.rs2)[i];
-                if (YSTATE && a.rs2 != nullptr) o.ys = (double)reinterpret_cast<const int64_t*>(a.rs2)[i];
-            }
-            eval<KIND, FROM_STATE, ELBO>(a.L, o);
-            if (!FROM_STATE) {
-                if (a.s0) a.s0[i] = o.s0;
-                if (HAS_S1 && a.s1) a.s1[i] = o.s1;
-                if (HET && a.s2) reinterpret_cast<double*>(a.s2)[i] = o.s2;
-                if (YSTATE && a.s2) store_y1<s2t>(a.s2, i, o.y);
-            }
-            if (a.beta) a.beta[i] = o.b0;
-            if (a.gamma) a.gamma[i] = o.g0;
-            if (HET) {
-                if (a.beta_g) a.beta_g[i] = o.b1;
-                if (a.gamma_g) a.gamma_g[i] = o.g1;
-            }
-            if (ELBO) { acc[0] += o.elt; acc[1] += o.kl; }
-        }
-    }
+    // the odd tail element of the vector kernel, or everything when the arrays are not 16-byte aligned
+    for (int64_t i = 2 * npairs + tid; i < a.n; i += nth) scalar_obs(i);
+
     if (ELBO) {
         double out[2];
         if (block_reduce_and_finalize<2>(acc, a.partials, a.counter, out)) {
@@ -329,7 +427,7 @@ int32_t launch2(aug_ctx* ctx, const CaviArgs& a, bool vec) {
     const void* k = vec ? (const void*)cavi_kernel<KIND, FROM_STATE, ELBO, true>
                         : (const void*)cavi_kernel<KIND, FROM_STATE, ELBO, false>;
     const int64_t work = vec ? (a.n + 1) / 2 : a.n;
-    const int grid = aug_grid_for(ctx, k, work, AUG_BLOCK * 2);
+    const int grid = aug_grid_for(ctx, k, work, AUG_BLOCK * (KIND == AUG_HETERO ? 1 : CAVI_U));
     if (vec) cavi_kernel<KIND, FROM_STATE, ELBO, true><<<grid, AUG_BLOCK, 0, ctx->stream>>>(a);
     else cavi_kernel<KIND, FROM_STATE, ELBO, false><<<grid, AUG_BLOCK, 0, ctx->stream>>>(a);
     ctx->launches++;

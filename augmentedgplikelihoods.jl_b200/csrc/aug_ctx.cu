@@ -118,6 +118,7 @@ int32_t aug_lik_const(aug_ctx* ctx, const aug_lik* lik, LikConst* L, bool need_t
             L->c3 = aq;
             L->c4 = tq;
             L->c5 = -0.5 * log(2 * PI_);
+            L->p1 = log(alpha * tq);   // log(θ/r): lets the kernel reuse log θ for the KL's log r
             break;
         }
         case AUG_HETERO:

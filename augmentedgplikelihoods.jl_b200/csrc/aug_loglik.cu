@@ -189,10 +189,21 @@ __global__ void __launch_bounds__(AUG_BLOCK) ew_kernel(int op, int64_t n, const 
             out[i] = pg_logpdf_dev(s0, s1, p[i]);
         } else if (op == 3) {         // approx_expected_logistic(mu, c) utils.jl:11-14
             const double c = fabs(q[i]);
-            out[i] = augm::approx_expected_logistic(p[i], c, augm::pg_terms<false>(c));
-        } else {                      // second_moment(q[, y]) utils.jl:1-7; s0 != 0: y given in out's twin r
+            out[i] = augm::approx_expected_logistic<true>(p[i], c, augm::pg_terms<false>(c));
+        } else if (op == 4) {         // second_moment(q[, y]) utils.jl:1-7
             const double d = r ? p[i] - r[i] : p[i];
             out[i] = fma(d, d, q[i]);
+        } else {                      // op >= 10: the straight-line functions of aug_fastmath.cuh (accuracy tests)
+            const double x = p[i];
+            double c_, ic_;
+            switch (op) {
+                case 10: out[i] = augf::rcp(x); break;
+                case 11: out[i] = augf::rsqrt_(x); break;
+                case 12: out[i] = augf::exp_(x); break;
+                case 13: out[i] = augf::log_(x); break;
+                case 14: out[i] = augf::log_1to2(x); break;
+                default: augf::sqrt_inv(x, c_, ic_); out[i] = c_; break;
+            }
         }
     }
 }
@@ -233,6 +244,9 @@ int32_t aug_sampled_loglik_terms(aug_ctx* c, const aug_lik* lik, int64_t n, cons
     }
     if (lik->kind == AUG_CAT || lik->kind == AUG_CAT_BIJ) {
         if (!nvar) return AUG_ERR_BAD_ARG;
+        // aux_prior of the non-bijective link is NegativeMultinomial(1, fill(1/nl, nl)) (categorical.jl:158-163,
+        // "we just pretend this will work"): sum(p) = 1 fails the constructor check (negativemultinomial.jl:18)
+        if (with_prior && lik->kind == AUG_CAT) return AUG_ERR_PRECONDITION;
         LikConst L;
         int32_t rc = aug_lik_const(c, lik, &L, false, false);
         if (rc) return rc;
@@ -296,6 +310,13 @@ int32_t aug_pg_logpdf(aug_ctx* c, int64_t n, double b, double cc, const double* 
 int32_t aug_approx_expected_logistic(aug_ctx* c, int64_t n, const double* mu, const double* cc, double* out) {
     if (!cc) return AUG_ERR_BAD_ARG;
     return ew_launch(c, 3, n, mu, cc, 0, 0, out);
+}
+
+/* diagnostics: evaluate one of the aug_fastmath.cuh functions element-wise (0 rcp, 1 rsqrt, 2 exp, 3 log,
+ * 4 log on [1,2], 5 sqrt) on arguments inside its stated range */
+int32_t aug_fastmath_eval(aug_ctx* c, int32_t fn, int64_t n, const double* x, double* out) {
+    if (fn < 0 || fn > 5) return AUG_ERR_BAD_ARG;
+    return ew_launch(c, 10 + fn, n, x, nullptr, 0, 0, out);
 }
 
 int32_t aug_second_moment(aug_ctx* c, int64_t n, const double* mu, const double* var, const double* y,

@@ -4,6 +4,8 @@
 #pragma once
 #include <math.h>
 
+#include "aug_fastmath.cuh"
+
 namespace augm {
 
 constexpr double LN2 = 0.69314718055994530942;
@@ -19,11 +21,30 @@ struct PGTerms {
     double h, lch, e, inv1pe;
 };
 
-template <bool NEED_LCH>
-__device__ __forceinline__ PGTerms pg_terms(double c) {
+// SAFE = false: straight-line code on top of aug_fastmath.cuh, valid for 0 <= c <= 1e290 (exp(-c) is
+// evaluated at min(c, 708): beyond that e < 1e-307 changes nothing in double precision); inv_c = 1/c is
+// only read when c >= 1/16 and the c < 1/16 series is a select.
+// SAFE = true: the same formulas with IEEE sqrt / div and the libdevice exp / log1p for any input.
+template <bool NEED_LCH, bool SAFE>
+__device__ __forceinline__ PGTerms pg_terms_ic(double c, double inv_c) {
     PGTerms t;
+    double e, inv;
+    if (SAFE) {
+        e = exp(-c);
+        inv = 1.0 / (1.0 + e);
+        t.h = (1.0 - e) * inv / (2.0 * c);
+        t.lch = NEED_LCH ? fma(0.5, c, log1p(e) - LN2) : 0.0;
+    } else {
+        e = augf::exp_(-fmin(c, 708.0));
+        const double d = 1.0 + e;
+        inv = augf::rcp(d);
+        t.h = (1.0 - e) * inv * (0.5 * inv_c);
+        t.lch = NEED_LCH ? fma(0.5, c, augf::log_1to2(d) - LN2) : 0.0;
+    }
+    t.e = e;
+    t.inv1pe = inv;
     if (c < 0.0625) {
-        // series in x = c/2 <= 1/32: truncation error < 1e-17 relative
+        // series in x = c/2 <= 1/32: truncation error < 1e-17 relative (also covers c == 0 -> 1/4)
         const double x2 = 0.25 * c * c;
         double p = fma(x2, 62.0 / 2835.0, -17.0 / 315.0);
         p = fma(x2, p, 2.0 / 15.0);
@@ -35,34 +56,36 @@ __device__ __forceinline__ PGTerms pg_terms(double c) {
             q = fma(x2, q, -1.0 / 12.0);
             q = fma(x2, q, 0.5);
             t.lch = x2 * q;           // logcosh(x)
-        } else {
-            t.lch = 0.0;
         }
-        t.e = exp(-c);
-        t.inv1pe = 1.0 / (1.0 + t.e);
-        return t;
     }
-    const double e = exp(-c);          // underflows to 0 for c > 745: tanh -> 1, logcosh -> c/2 - ln2
-    const double inv = 1.0 / (1.0 + e);
-    t.e = e;
-    t.inv1pe = inv;
-    t.h = (1.0 - e) * inv / (2.0 * c);
-    t.lch = NEED_LCH ? fma(0.5, c, log1p(e) - LN2) : 0.0;
     return t;
+}
+
+template <bool NEED_LCH, bool SAFE = true>
+__device__ __forceinline__ PGTerms pg_terms(double c) {
+    const double ic = SAFE ? 0.0 : augf::rcp(fmin(fmax(c, 0.0625), 1e290));
+    return pg_terms_ic<NEED_LCH, SAFE>(c, ic);
 }
 
 // approx_expected_logistic(mu, c) = exp(mu/2) sech(c/2)/2, saturating on mu alone (utils.jl:11-14).
 // sech(c/2)/2 = exp(-c/2)/(1+exp(-c)): one extra exp on top of pg_terms.
+// SAFE = false needs |mu - c| <= 1416.
+template <bool SAFE>
 __device__ __forceinline__ double approx_expected_logistic(double mu, double c, const PGTerms& t) {
-    if (mu < LOGISTIC_LO) return 0.0;
-    if (mu > LOGISTIC_HI) return 1.0;
-    return exp(0.5 * (mu - c)) * t.inv1pe;
+    const double v = (SAFE ? exp(0.5 * (mu - c)) : augf::exp_(0.5 * (mu - c))) * t.inv1pe;
+    return mu < LOGISTIC_LO ? 0.0 : (mu > LOGISTIC_HI ? 1.0 : v);
 }
 
-// kldivergence(Poisson(q), Poisson(p)) (Distributions.jl): q == 0 ? p : p - q + q (log q - log p)
+// kldivergence(Poisson(q), Poisson(p)) (Distributions.jl): q == 0 ? p : p - q + q (log q - log p).
+// SAFE = false: q log q is dropped below 1e-290 (it is < 1e-287 there).
+template <bool SAFE>
 __device__ __forceinline__ double kl_poisson(double q, double p, double logp) {
-    if (q == 0.0) return p;
-    return p - q + q * (log(q) - logp);
+    if (SAFE) {
+        if (q == 0.0) return p;
+        return p - q + q * (log(q) - logp);
+    }
+    const double lq = augf::log_(fmax(q, 1e-290));
+    return q < 1e-290 ? p - q : p - q + q * (lq - logp);
 }
 
 // logistic(x) with the LogExpFunctions saturation

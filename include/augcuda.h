@@ -245,6 +245,11 @@ int32_t aug_approx_expected_logistic(aug_ctx* ctx, int64_t n, const double* mu, 
 int32_t aug_second_moment(aug_ctx* ctx, int64_t n, const double* mu, const double* var, const double* y,
                           double* out);
 
+/* diagnostics: evaluates one of the straight-line fp64 functions the kernels use (csrc/aug_fastmath.cuh)
+ * element-wise, for accuracy tests.  fn: 0 rcp, 1 rsqrt, 2 exp (|x| <= 708), 3 log (normal x > 0),
+ * 4 log on [1,2], 5 sqrt (1e-290 <= x <= 1e290). */
+int32_t aug_fastmath_eval(aug_ctx* ctx, int32_t fn, int64_t n, const double* x, double* out);
+
 /* ---- multi-GPU: shard over observations, all-reduce only the scalars ---- */
 int32_t aug_comm_get_unique_id(char uid[128]);
 int32_t aug_comm_init(aug_ctx* ctx, int32_t nranks, int32_t rank, const char uid[128]);

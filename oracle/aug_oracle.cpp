@@ -1048,6 +1048,8 @@ int orc_sampled_loglik_terms(const aug_lik* l, int64_t n, const void* y, const d
             break;
         }
         case AUG_CAT: case AUG_CAT_BIJ: {                    // categorical.jl:138-145, :147-163
+            // non-bijective prior NM(1, fill(1/nl, nl)) has sum(p) = 1: ctor check fails (negativemultinomial.jl:18)
+            if (with_prior && l->kind == AUG_CAT) return AUG_ERR_PRECONDITION;
             CatConst cc = cat_const(l);
             int nl = cc.nl;
             const uint8_t* yy = (const uint8_t*)y;

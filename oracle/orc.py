@@ -202,6 +202,8 @@ def sampled_loglik_terms(lik, y, f, omega, nvar, with_prior=True):
     comp = np.zeros(8)
     rc = lib().orc_sampled_loglik_terms(C.byref(lik), C.c_int64(n), _p(y), _p(f), C.c_int64(_ld(lik, f)),
                                         _p(omega), _p(nvar), C.c_int(int(with_prior)), _p(seq), _p(comp))
+    if rc == -3:
+        raise ArithmeticError("precondition (oracle rc=-3)")
     if rc:
         raise RuntimeError(f"oracle rc={rc}")
     return seq, comp

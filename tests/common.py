@@ -32,10 +32,13 @@ def lik_args(case):
     return case["kind"], case["params"], kw
 
 
-def relerr(a, b):
+def relerr(a, b, floor=1e-300):
+    """max |a-b| / max(|b|, floor).  floor > 0 turns the bound into an absolute one for small |b|: used for
+    beta = (y - E[n])/2 of the Poisson-type likelihoods, which cancels when E[n] ~ y (a conditioning effect:
+    the 1e-12 bar then applies relative to the operands y, E[n] = O(1), not to their difference)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
-    den = np.maximum(np.abs(b), 1e-300)
+    den = np.maximum(np.abs(b), floor)
     err = np.abs(a - b) / den
     err = np.where((a == b), 0.0, err)
     return float(np.max(err)) if err.size else 0.0
