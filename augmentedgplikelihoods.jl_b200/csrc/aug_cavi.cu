@@ -13,6 +13,8 @@
 //   studentt.jl:50-91, heteroscedasticgaussian.jl:34-145, utils.jl:1-14,
 //   SpecialDistributions/polyagamma.jl:25-31,99-110, polyagammapoisson.jl:35-51, api.jl:219-223,
 //   generic.jl:52-62.
+#include <stdlib.h>
+
 #include "aug_common.cuh"
 #include "aug_math.cuh"
 
@@ -50,6 +52,7 @@ struct CaviArgs {
     double* partials;
     unsigned int* counter;
     double* scalars;
+    int accumulate;       // add to the scalars already in memory (second launch of one verb)
     LikConst L;
 };
 
@@ -257,6 +260,17 @@ template <int KIND> struct S2T { typedef double T; };
 template <> struct S2T<AUG_NEGBIN> { typedef int64_t T; };
 template <> struct S2T<AUG_POISSON> { typedef int64_t T; };
 
+__device__ __forceinline__ void write_scalars(const CaviArgs& a, const double (&out)[2]) {
+    double e = out[0], k = out[1];
+    if (a.accumulate) {
+        e += a.scalars[AUG_S_EXPECTED_LOGTILT];
+        k += a.scalars[AUG_S_KL];
+    }
+    a.scalars[AUG_S_EXPECTED_LOGTILT] = e;
+    a.scalars[AUG_S_KL] = k;
+    a.scalars[AUG_S_EXPECTED_AUGLL] = e + k;   // generic.jl:52-54 ("+")
+}
+
 template <int KIND, bool FROM_STATE, bool ELBO, bool VEC>
 __global__ void __launch_bounds__(AUG_BLOCK, CAVI_MIN_BLOCKS) cavi_kernel(const CaviArgs a) {
     typedef typename YT<KIND>::T yt;
@@ -414,12 +428,243 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_MIN_BLOCKS) cavi_kernel(const 
 
     if (ELBO) {
         double out[2];
-        if (block_reduce_and_finalize<2>(acc, a.partials, a.counter, out)) {
-            a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
-            a.scalars[AUG_S_KL] = out[1];
-            a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];   // generic.jl:52-54 ("+")
+        if (block_reduce_and_finalize<2>(acc, a.partials, a.counter, out)) write_scalars(a, out);
+    }
+}
+
+
+// ------------------------------------------------------------------ bulk-async (TMA) staged variant
+// ncu on the direct-load kernel (profiles/r1b): 60% of the stall cycles are long-scoreboard waits on the
+// global loads — with 64 registers/thread there are only ~35 KB of loads in flight per SM, below what
+// Little's law asks for at 6.4 TB/s.  Here one elected thread streams whole input tiles into a shared-memory
+// ring with cp.async.bulk (SASS: UBLKCP) completing on mbarriers, so the bytes in flight are set by the
+// ring (STAGES x tile bytes per CTA), not by registers or occupancy; the 256 threads consume a stage with
+// conflict-free 128-bit LDS, evaluate the straight-line math, and write state / beta / gamma straight to
+// global with 128-bit streaming stores.
+#ifndef CAVI_TILE
+#define CAVI_TILE 2048      // observations per stage
+#endif
+#ifndef CAVI_STAGES
+#define CAVI_STAGES 3
+#endif
+#ifndef CAVI_TMA_BLOCKS
+#define CAVI_TMA_BLOCKS 2   // CTAs per SM the ring is sized for
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+template <int KIND>
+struct TileLayout {
+    typedef typename YT<KIND>::T yt;
+    static constexpr bool HET = KIND == AUG_HETERO;
+    static constexpr int T = CAVI_TILE;
+    static constexpr int Y_BYTES = T * (int)sizeof(yt);
+    static constexpr int D_BYTES = T * 8;
+    static constexpr int OFF_MU = (Y_BYTES + 127) / 128 * 128;
+    static constexpr int OFF_VAR = OFF_MU + D_BYTES;
+    static constexpr int OFF_MUG = OFF_VAR + D_BYTES;
+    static constexpr int OFF_VARG = OFF_MUG + D_BYTES;
+    static constexpr int STAGE_BYTES = HET ? OFF_VARG + D_BYTES : OFF_MUG;
+    static constexpr int TX_BYTES = Y_BYTES + D_BYTES * (HET ? 4 : 2);
+    static constexpr int SMEM_BYTES = STAGE_BYTES * CAVI_STAGES + 64;
+};
+
+template <typename T>
+__device__ __forceinline__ void lds_y2(const unsigned char* ys, int q, double& a, double& b);
+template <>
+__device__ __forceinline__ void lds_y2<uint8_t>(const unsigned char* ys, int q, double& a, double& b) {
+    const uchar2 v = reinterpret_cast<const uchar2*>(ys)[q];
+    a = (double)v.x;
+    b = (double)v.y;
+}
+template <>
+__device__ __forceinline__ void lds_y2<int64_t>(const unsigned char* ys, int q, double& a, double& b) {
+    const longlong2 v = reinterpret_cast<const longlong2*>(ys)[q];
+    a = (double)v.x;
+    b = (double)v.y;
+}
+template <>
+__device__ __forceinline__ void lds_y2<double>(const unsigned char* ys, int q, double& a, double& b) {
+    const double2 v = reinterpret_cast<const double2*>(ys)[q];
+    a = v.x;
+    b = v.y;
+}
+
+// Fused (not FROM_STATE) CAVI step over the full tiles [0, ntiles * CAVI_TILE) of the shard.
+template <int KIND, bool ELBO>
+__global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(const CaviArgs a, const int64_t ntiles) {
+    typedef TileLayout<KIND> TL;
+    typedef typename YT<KIND>::T yt;
+    typedef typename S2T<KIND>::T s2t;
+    constexpr bool HET = KIND == AUG_HETERO;
+    constexpr bool YSTATE = KIND == AUG_NEGBIN || KIND == AUG_POISSON;
+    constexpr bool HAS_S1 = KIND == AUG_POISSON || KIND == AUG_HETERO;
+    constexpr int T = CAVI_TILE, S = CAVI_STAGES;
+    extern __shared__ __align__(128) unsigned char ring[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)TL::STAGE_BYTES * S);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t tile, int s) {   // one thread: arm the barrier, then the bulk copies of one tile
+        unsigned char* st = ring + (size_t)s * TL::STAGE_BYTES;
+        const int64_t o = tile * T;
+        mbar_expect_tx(&full[s], TL::TX_BYTES);
+        bulk_g2s(st, reinterpret_cast<const unsigned char*>(a.y) + o * sizeof(yt), TL::Y_BYTES, &full[s]);
+        bulk_g2s(st + TL::OFF_MU, a.mu + o, TL::D_BYTES, &full[s]);
+        bulk_g2s(st + TL::OFF_VAR, a.var + o, TL::D_BYTES, &full[s]);
+        if (HET) {
+            bulk_g2s(st + TL::OFF_MUG, a.mu_g + o, TL::D_BYTES, &full[s]);
+            bulk_g2s(st + TL::OFF_VARG, a.var_g + o, TL::D_BYTES, &full[s]);
+        }
+    };
+
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int64_t t = first + (int64_t)s * stride;
+            if (t < ntiles) issue(t, s);
         }
     }
+    double acc[2] = {0.0, 0.0};
+    bool bad = false;
+    int64_t k = 0;
+    for (int64_t tile = first; tile < ntiles; tile += stride, ++k) {
+        const int s = (int)(k % S);
+        mbar_wait(&full[s], (uint32_t)((k / S) & 1));
+        const unsigned char* st = ring + (size_t)s * TL::STAGE_BYTES;
+        const double2* smu = reinterpret_cast<const double2*>(st + TL::OFF_MU);
+        const double2* svar = reinterpret_cast<const double2*>(st + TL::OFF_VAR);
+        const double2* smug = reinterpret_cast<const double2*>(st + TL::OFF_MUG);
+        const double2* svarg = reinterpret_cast<const double2*>(st + TL::OFF_VARG);
+        const int64_t base = tile * T;
+#pragma unroll 1
+        for (int q = tid; q < T / 2; q += AUG_BLOCK) {
+            Obs o0, o1;
+            lds_y2<yt>(st, q, o0.y, o1.y);
+            const double2 m = smu[q], v = svar[q];
+            o0.m = m.x; o1.m = m.y;
+            o0.v = v.x; o1.v = v.y;
+            o0.mg = o1.mg = o0.vg = o1.vg = 0.0;
+            if (HET) {
+                const double2 mg = smug[q], vg = svarg[q];
+                o0.mg = mg.x; o1.mg = mg.y;
+                o0.vg = vg.x; o1.vg = vg.y;
+            }
+            o0.ys = o0.y; o1.ys = o1.y;
+            bad = bad || !fast_ok<KIND, false, ELBO>(o0) || !fast_ok<KIND, false, ELBO>(o1);
+            eval<KIND, false, ELBO, false>(a.L, o0);
+            eval<KIND, false, ELBO, false>(a.L, o1);
+            const int64_t i = base + 2 * q;
+            if (a.s0) st_stream2(a.s0 + i, o0.s0, o1.s0);
+            if (HAS_S1 && a.s1) st_stream2(a.s1 + i, o0.s1, o1.s1);
+            if (HET && a.s2) st_stream2(reinterpret_cast<double*>(a.s2) + i, o0.s2, o1.s2);
+            if (YSTATE && a.s2) store_y2<s2t>(a.s2, i >> 1, o0.y, o1.y);
+            if (a.beta) st_stream2(a.beta + i, o0.b0, o1.b0);
+            if (a.gamma) st_stream2(a.gamma + i, o0.g0, o1.g0);
+            if (HET) {
+                if (a.beta_g) st_stream2(a.beta_g + i, o0.b1, o1.b1);
+                if (a.gamma_g) st_stream2(a.gamma_g + i, o0.g1, o1.g1);
+            }
+            if (ELBO) {
+                acc[0] += o0.elt + o1.elt;
+                acc[1] += o0.kl + o1.kl;
+            }
+        }
+        __syncthreads();   // every thread is done reading stage s: it can be refilled
+        if (tid == 0) {
+            const int64_t nt = tile + (int64_t)S * stride;
+            if (nt < ntiles) issue(nt, s);
+        }
+    }
+    if (bad) {
+        // rare: this thread met a value outside the fast-math range -> redo its observations of every tile
+        // of this CTA from global memory with the any-input instantiation (outputs are overwritten)
+        acc[0] = acc[1] = 0.0;
+        for (int64_t tile = first; tile < ntiles; tile += stride) {
+            for (int q = tid; q < T / 2; q += AUG_BLOCK) {
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t i = tile * T + 2 * q + e;
+                    Obs o;
+                    o.y = load_y1<yt>(a.y, i);
+                    o.ys = o.y;
+                    o.m = a.mu[i]; o.v = a.var[i];
+                    o.mg = o.vg = 0.0;
+                    o.s0 = o.s1 = o.s2 = 0.0;
+                    if (HET) { o.mg = a.mu_g[i]; o.vg = a.var_g[i]; }
+                    eval<KIND, false, ELBO, true>(a.L, o);
+                    if (a.s0) a.s0[i] = o.s0;
+                    if (HAS_S1 && a.s1) a.s1[i] = o.s1;
+                    if (HET && a.s2) reinterpret_cast<double*>(a.s2)[i] = o.s2;
+                    if (YSTATE && a.s2) store_y1<s2t>(a.s2, i, o.y);
+                    if (a.beta) a.beta[i] = o.b0;
+                    if (a.gamma) a.gamma[i] = o.g0;
+                    if (HET) {
+                        if (a.beta_g) a.beta_g[i] = o.b1;
+                        if (a.gamma_g) a.gamma_g[i] = o.g1;
+                    }
+                    if (ELBO) { acc[0] += o.elt; acc[1] += o.kl; }
+                }
+            }
+        }
+    }
+    if (ELBO) {
+        double out[2];
+        if (block_reduce_and_finalize<2>(acc, a.partials, a.counter, out)) write_scalars(a, out);
+    }
+}
+
+template <int KIND, bool ELBO>
+int32_t launch_tma(aug_ctx* ctx, const CaviArgs& a, int64_t ntiles) {
+    typedef TileLayout<KIND> TL;
+    const void* k = (const void*)cavi_tma_kernel<KIND, ELBO>;
+    static bool configured = false;
+    static int occ = 1;
+    if (!configured) {
+        AUG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM_BYTES));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, AUG_BLOCK, TL::SMEM_BYTES) != cudaSuccess || occ < 1)
+            occ = 1;
+        configured = true;
+    }
+    int64_t grid = (int64_t)ctx->sms * occ;
+    if (grid > AUG_MAX_GRID) grid = AUG_MAX_GRID;
+    if (grid > ntiles) grid = ntiles;
+    cavi_tma_kernel<KIND, ELBO><<<(unsigned)grid, AUG_BLOCK, TL::SMEM_BYTES, ctx->stream>>>(a, ntiles);
+    ctx->launches++;
+    return (int32_t)cudaGetLastError();
+}
+
+template <int KIND>
+int32_t launch_tma1(aug_ctx* ctx, const CaviArgs& a, int64_t ntiles, bool elbo) {
+    return elbo ? launch_tma<KIND, true>(ctx, a, ntiles) : launch_tma<KIND, false>(ctx, a, ntiles);
 }
 
 template <int KIND, bool FROM_STATE, bool ELBO>
@@ -438,6 +683,15 @@ template <int KIND>
 int32_t launch1(aug_ctx* ctx, const CaviArgs& a, bool from_state, bool elbo, bool vec) {
     if (from_state) return elbo ? launch2<KIND, true, true>(ctx, a, vec) : launch2<KIND, true, false>(ctx, a, vec);
     return elbo ? launch2<KIND, false, true>(ctx, a, vec) : launch2<KIND, false, false>(ctx, a, vec);
+}
+
+bool getenv_no_tma() {   // AUGCUDA_NO_TMA=1 keeps every call on the direct-load kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AUGCUDA_NO_TMA");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 }  // namespace
@@ -492,13 +746,52 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
                aug_aligned16(a.beta_g) && aug_aligned16(a.gamma_g);
     if (lik->kind == AUG_BERNOULLI) vec = vec && ((((uintptr_t)y) & 1u) == 0);
     else vec = vec && aug_aligned16(y);
-    switch (lik->kind) {
-        case AUG_BERNOULLI: return launch1<AUG_BERNOULLI>(ctx, a, from_state, elbo, vec);
-        case AUG_NEGBIN: return launch1<AUG_NEGBIN>(ctx, a, from_state, elbo, vec);
-        case AUG_POISSON: return launch1<AUG_POISSON>(ctx, a, from_state, elbo, vec);
-        case AUG_LAPLACE: return launch1<AUG_LAPLACE>(ctx, a, from_state, elbo, vec);
-        case AUG_STUDENTT: return launch1<AUG_STUDENTT>(ctx, a, from_state, elbo, vec);
-        case AUG_HETERO: return launch1<AUG_HETERO>(ctx, a, from_state, elbo, vec);
-        default: return AUG_ERR_BAD_KIND;
+    // Fused calls on 16-byte aligned arrays: the full CAVI_TILE-observation tiles go through the bulk-async
+    // staged kernel, the ragged remainder (< one tile) through the direct-load kernel, whose scalars the
+    // staged kernel then accumulates onto.
+    const bool use_tma = !from_state && vec && !getenv_no_tma() && aug_aligned16(y) && n >= 4 * (int64_t)CAVI_TILE;
+    const int64_t ntiles = use_tma ? n / CAVI_TILE : 0;
+    const int64_t n0 = ntiles * CAVI_TILE;   // observations handled by the staged kernel
+    CaviArgs t = a;                          // remainder [n0, n)
+    if (n0 > 0) {
+        const size_t ysz = lik->kind == AUG_BERNOULLI ? 1 : 8;
+        t.n = n - n0;
+        t.y = (const unsigned char*)y + n0 * ysz;
+        t.mu = mu + n0;
+        t.var = var + n0;
+        if (a.mu_g) t.mu_g = a.mu_g + n0;
+        if (a.var_g) t.var_g = a.var_g + n0;
+        if (a.s0) t.s0 = a.s0 + n0;
+        if (a.s1) t.s1 = a.s1 + n0;
+        if (a.s2) t.s2 = (unsigned char*)a.s2 + n0 * 8;
+        if (a.beta) t.beta = a.beta + n0;
+        if (a.gamma) t.gamma = a.gamma + n0;
+        if (a.beta_g) t.beta_g = a.beta_g + n0;
+        if (a.gamma_g) t.gamma_g = a.gamma_g + n0;
     }
+    if (t.n > 0) {
+        switch (lik->kind) {
+            case AUG_BERNOULLI: rc = launch1<AUG_BERNOULLI>(ctx, t, from_state, elbo, vec); break;
+            case AUG_NEGBIN: rc = launch1<AUG_NEGBIN>(ctx, t, from_state, elbo, vec); break;
+            case AUG_POISSON: rc = launch1<AUG_POISSON>(ctx, t, from_state, elbo, vec); break;
+            case AUG_LAPLACE: rc = launch1<AUG_LAPLACE>(ctx, t, from_state, elbo, vec); break;
+            case AUG_STUDENTT: rc = launch1<AUG_STUDENTT>(ctx, t, from_state, elbo, vec); break;
+            case AUG_HETERO: rc = launch1<AUG_HETERO>(ctx, t, from_state, elbo, vec); break;
+            default: return AUG_ERR_BAD_KIND;
+        }
+        if (rc) return rc;
+    }
+    if (ntiles > 0) {
+        a.accumulate = (t.n > 0 && elbo) ? 1 : 0;
+        switch (lik->kind) {
+            case AUG_BERNOULLI: return launch_tma1<AUG_BERNOULLI>(ctx, a, ntiles, elbo);
+            case AUG_NEGBIN: return launch_tma1<AUG_NEGBIN>(ctx, a, ntiles, elbo);
+            case AUG_POISSON: return launch_tma1<AUG_POISSON>(ctx, a, ntiles, elbo);
+            case AUG_LAPLACE: return launch_tma1<AUG_LAPLACE>(ctx, a, ntiles, elbo);
+            case AUG_STUDENTT: return launch_tma1<AUG_STUDENTT>(ctx, a, ntiles, elbo);
+            case AUG_HETERO: return launch_tma1<AUG_HETERO>(ctx, a, ntiles, elbo);
+            default: return AUG_ERR_BAD_KIND;
+        }
+    }
+    return AUG_OK;
 }
