@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_sample_kernel(const CatSampleAr
             const int64_t nn = augr::poisson_rand(g, P[e] * rscale[i]);
             const int64_t yv = (int64_t)__ldg(a.y + base + e);
             a.nvar[base + e] = nn;
-            st_stream1(a.omega + base + e, augp::pg_draw(g, (double)(nn + yv), true, a.f[base + e]));
+            st_stream1(a.omega + base + e, augp::pg_draw(g, (double)(nn + yv), true, a.f[base + e], a.L.pgtab));
         }
         __syncthreads();
     }

@@ -9,6 +9,9 @@
 #define AUG_MAX_GRID 4096      // upper bound on CTAs of a reducing kernel (partials buffer rows)
 #define AUG_NRED 4             // doubles reduced per kernel: elt/logtilt, kl/logprior, flags, spare
 #define AUG_TABLE_N 512        // entries of the per-likelihood integer-y constant table
+#define AUG_PGTAB_H 0.125       // interval width of the r(z) table
+#define AUG_PGTAB_N 160        // intervals: z in [0, 20)
+#define AUG_PGTAB_DEG 8        // coefficients per interval (degree 7)
 
 #define AUG_CUDA(x)                                   \
     do {                                              \
@@ -35,6 +38,7 @@ struct aug_ctx {
     int table_kind;
     int table_r_is_int;
     double table_param;
+    double* pgtab;         // piecewise polynomial table of the PG(1,z) proposal mass r(z) (aug_pg.cuh)
     // categorical logθ-derived constants
     double* dtheta;        // exp(logθ_j)/Σθ  (device, capacity dtheta_cap)
     int dtheta_cap;
@@ -51,6 +55,7 @@ struct LikConst {
     double p0, p1;          // raw parameters (r | λ | β | ν, σ)
     double c0, c1, c2, c3, c4, c5;  // derived constants, meaning per kind (see lik_const())
     const double* table;    // device table or nullptr
+    const double* pgtab;    // r(z) table (always set)
     const double* theta;    // CAT: θ_j/Σθ device vector
 };
 

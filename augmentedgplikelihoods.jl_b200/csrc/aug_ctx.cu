@@ -37,6 +37,55 @@ double digamma_host(double x) {
 
 bool is_cat(int kind) { return kind == AUG_CAT || kind == AUG_CAT_BIJ; }
 
+// r(z) = mass of the truncated-exponential part of Devroye's PG(1,z) proposal (mass_texpon,
+// SpecialDistributions/polyagamma.jl:179-192), evaluated on the host in the log domain.
+double pg_tail_mass_host(double z) {
+    const double t = 0.64, K = PI_ * PI_ / 8 + z * z / 2;
+    const double b = sqrt(1 / t) * (t * z - 1), a = -sqrt(1 / t) * (t * z + 1);
+    auto logcdf = [](double x) {   // log Phi(x)
+        const double y = -x * 0.70710678118654752440;
+        if (y > 5.0) {             // log(erfc(y)/2) through the scaled complementary error function
+            const double w = 1.0 / (y * y);
+            const double asym = 1 + w * (-0.5 + w * (0.75 + w * (-1.875 + w * (6.5625 + w * (-29.53125 + w * 162.421875)))));
+            return y < 25.0 ? log(erfc(y) / 2) : -y * y + log(asym / (y * sqrt(PI_)) / 2);
+        }
+        return log(erfc(y) / 2);
+    };
+    const double x0 = log(K) + K * t;
+    const double xb = x0 - z + logcdf(b), xa = x0 + z + logcdf(a);
+    const double qdivp = 4 / PI_ * (exp(xb) + exp(xa));
+    return 1 / (1 + qdivp);
+}
+
+// Degree-7 interpolant of r on each [k h, (k+1) h) at the Chebyshev nodes, stored as monomial coefficients in
+// s = 2 (z - k h)/h - 1; interpolation error < 1e-15.
+void build_pg_table(double* tab) {
+    const int D = AUG_PGTAB_DEG;
+    for (int k = 0; k < AUG_PGTAB_N; ++k) {
+        const double a = k * AUG_PGTAB_H;
+        double fx[AUG_PGTAB_DEG], cheb[AUG_PGTAB_DEG];
+        for (int j = 0; j < D; ++j) {
+            const double xj = cos(PI_ * (j + 0.5) / D);
+            fx[j] = pg_tail_mass_host(a + 0.5 * AUG_PGTAB_H * (xj + 1));
+        }
+        for (int m = 0; m < D; ++m) {
+            double acc = 0;
+            for (int j = 0; j < D; ++j) acc += fx[j] * cos(PI_ * m * (j + 0.5) / D);
+            cheb[m] = acc * (m == 0 ? 1.0 : 2.0) / D;
+        }
+        // Chebyshev -> monomial: T_0 = 1, T_1 = s, T_{m+1} = 2 s T_m - T_{m-1}
+        double mono[AUG_PGTAB_DEG] = {0}, Tm1[AUG_PGTAB_DEG] = {0}, Tm[AUG_PGTAB_DEG] = {0}, Tn[AUG_PGTAB_DEG];
+        Tm1[0] = 1;
+        Tm[1] = 1;
+        for (int i = 0; i < D; ++i) mono[i] += cheb[0] * Tm1[i] + cheb[1] * Tm[i];
+        for (int m = 2; m < D; ++m) {
+            for (int i = 0; i < D; ++i) Tn[i] = (i > 0 ? 2 * Tm[i - 1] : 0) - Tm1[i];
+            for (int i = 0; i < D; ++i) { mono[i] += cheb[m] * Tn[i]; Tm1[i] = Tm[i]; Tm[i] = Tn[i]; }
+        }
+        for (int i = 0; i < D; ++i) tab[k * D + i] = mono[D - 1 - i];   // highest degree first (Horner order)
+    }
+}
+
 int32_t check_lik(const aug_lik* lik) {
     if (lik == nullptr) return AUG_ERR_BAD_ARG;
     if (lik->kind < 0 || lik->kind >= AUG_NKINDS) return AUG_ERR_BAD_KIND;
@@ -83,6 +132,7 @@ int32_t aug_lik_const(aug_ctx* ctx, const aug_lik* lik, LikConst* L, bool need_t
     L->r_is_int = lik->r_is_int;
     L->p0 = lik->p[0];
     L->p1 = lik->p[1];
+    L->pgtab = ctx->pgtab;
     double tab_param = 0.0;
     bool want_table = false;
     switch (lik->kind) {
@@ -292,6 +342,13 @@ int32_t aug_ctx_create(aug_ctx** out, int32_t device, void* stream) {
     if (e == cudaSuccess) e = cudaMalloc(&c->dflag, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->dflag, 0, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->table, sizeof(double) * AUG_TABLE_N);
+    if (e == cudaSuccess) e = cudaMalloc(&c->pgtab, sizeof(double) * AUG_PGTAB_N * AUG_PGTAB_DEG);
+    if (e == cudaSuccess) {
+        static double htab[AUG_PGTAB_N * AUG_PGTAB_DEG];
+        static bool built = false;
+        if (!built) { build_pg_table(htab); built = true; }
+        e = cudaMemcpy(c->pgtab, htab, sizeof(htab), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) { aug_ctx_destroy(c); return (int32_t)e; }
     c->seed = 0x243F6A8885A308D3ull;
     c->offset = 0;
@@ -309,6 +366,7 @@ int32_t aug_ctx_destroy(aug_ctx* c) {
     if (c->dscalars) cudaFree(c->dscalars);
     if (c->dflag) cudaFree(c->dflag);
     if (c->table) cudaFree(c->table);
+    if (c->pgtab) cudaFree(c->pgtab);
     if (c->dtheta) cudaFree(c->dtheta);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;

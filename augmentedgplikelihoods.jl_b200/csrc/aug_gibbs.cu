@@ -32,15 +32,15 @@ __global__ void __launch_bounds__(AUG_BLOCK) aux_sample_kernel(const GibbsArgs a
         g.init(a.seed, a.offset, (uint64_t)(a.i0 + i));
         const double f = ld_stream1(a.f + i);
         if (KIND == AUG_BERNOULLI) {                              // PG(1, |f|)  bernoulli.jl:13-15
-            st_stream1(a.omega + i, augp::pg_draw(g, 1.0, true, f));
+            st_stream1(a.omega + i, augp::pg_draw(g, 1.0, true, f, a.L.pgtab));
         } else if (KIND == AUG_NEGBIN) {                          // PG(y + r, |f|)  negativebinomial.jl:20-22
             const double y = (double)__ldg(reinterpret_cast<const int64_t*>(a.y) + i);
-            st_stream1(a.omega + i, augp::pg_draw(g, y + a.L.p0, a.L.r_is_int != 0, f));
+            st_stream1(a.omega + i, augp::pg_draw(g, y + a.L.p0, a.L.r_is_int != 0, f, a.L.pgtab));
         } else if (KIND == AUG_POISSON) {                         // poisson.jl:26-28, polyagammapoisson.jl:23-27
             const int64_t y = __ldg(reinterpret_cast<const int64_t*>(a.y) + i);
             const int64_t nn = augr::poisson_rand(g, a.L.p0 * augm::logistic(-f));
             a.nvar[i] = nn;
-            st_stream1(a.omega + i, augp::pg_draw(g, (double)(nn + y), true, f));
+            st_stream1(a.omega + i, augp::pg_draw(g, (double)(nn + y), true, f, a.L.pgtab));
         } else if (KIND == AUG_LAPLACE) {                         // IG(1/(2β|y-f|), 2λ)  laplace.jl:40-42
             const double y = ld_stream1(reinterpret_cast<const double*>(a.y) + i);
             const double mu = a.L.c0 / fabs(y - f);
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) aux_sample_kernel(const GibbsArgs a
             const double rate = a.L.p0 * augm::logistic(-gg) * d * d * 0.5;
             const int64_t nn = augr::poisson_rand(g, rate);
             a.nvar[i] = nn;
-            st_stream1(a.omega + i, augp::pg_draw(g, (double)nn + 0.5, false, gg));
+            st_stream1(a.omega + i, augp::pg_draw(g, (double)nn + 0.5, false, gg, a.L.pgtab));
         }
     }
 }
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) aux_sample_kernel(const GibbsArgs a
 // bernoulli.jl:3-5, negativebinomial.jl:10-12, poisson.jl:14-18, laplace.jl:29-31, studentt.jl:35-37,
 // heteroscedasticgaussian.jl:16-20, categorical.jl:52-57 (m = nl * n elements)
 __global__ void __launch_bounds__(AUG_BLOCK) init_aux_kernel(int kind, int64_t m, int64_t e0, uint64_t seed,
-                                                              uint64_t offset, double* omega, int64_t* nvar) {
+                                                              uint64_t offset, double* omega, int64_t* nvar, const double* pgtab) {
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += nth) {
         augr::Philox g;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) init_aux_kernel(int kind, int64_t m
         } else if (kind == AUG_STUDENTT) {
             omega[i] = augr::gamma_rand(g, 1.0);
         } else {
-            omega[i] = augp::pg_draw(g, 1.0, true, 0.0);
+            omega[i] = augp::pg_draw(g, 1.0, true, 0.0, pgtab);
             if (nvar) nvar[i] = augr::poisson_rand(g, 1.0);
         }
     }
@@ -83,14 +83,14 @@ __global__ void __launch_bounds__(AUG_BLOCK) init_aux_kernel(int kind, int64_t m
 
 __global__ void __launch_bounds__(AUG_BLOCK) pg_rand_kernel(int64_t n, int64_t i0, uint64_t seed, uint64_t offset,
                                                              const double* b, const double* c, double bs, double cs,
-                                                             int b_is_int, double* out) {
+                                                             int b_is_int, double* out, const double* pgtab) {
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) {
         augr::Philox g;
         g.init(seed, offset, (uint64_t)(i0 + i));
         const double bi = b ? b[i] : bs;
         const double ci = c ? c[i] : cs;
-        out[i] = augp::pg_draw(g, bi, b_is_int != 0, ci);
+        out[i] = augp::pg_draw(g, bi, b_is_int != 0, ci, pgtab);
     }
 }
 
@@ -216,7 +216,7 @@ int32_t aug_init_aux_variables(aug_ctx* c, const aug_lik* lik, int64_t n, int64_
     const int64_t m = n * per;
     const int grid = aug_grid_for(c, (const void*)init_aux_kernel, m, AUG_BLOCK);
     init_aux_kernel<<<grid, AUG_BLOCK, 0, c->stream>>>(lik->kind, m, i0 * per, c->seed, off, omega,
-                                                        needs_n ? nvar : nullptr);
+                                                        needs_n ? nvar : nullptr, c->pgtab);
     c->launches++;
     return (int32_t)cudaGetLastError();
 }
@@ -229,7 +229,7 @@ static int32_t pg_rand_common(aug_ctx* c, int64_t n, int64_t i0, const double* b
     const uint64_t off = c->offset++;
     if (n == 0) return AUG_OK;
     const int grid = aug_grid_for(c, (const void*)pg_rand_kernel, n, AUG_BLOCK);
-    pg_rand_kernel<<<grid, AUG_BLOCK, 0, c->stream>>>(n, i0, c->seed, off, b, cc, bs, cs, b_is_int, out);
+    pg_rand_kernel<<<grid, AUG_BLOCK, 0, c->stream>>>(n, i0, c->seed, off, b, cc, bs, cs, b_is_int, out, c->pgtab);
     c->launches++;
     return (int32_t)cudaGetLastError();
 }

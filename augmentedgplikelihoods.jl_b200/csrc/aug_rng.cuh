@@ -8,6 +8,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "aug_fastmath.cuh"
+
 namespace augr {
 
 struct Philox {
@@ -40,25 +42,31 @@ struct Philox {
         c2++;
         have = 4;
     }
+    // words are consumed from buf[3] down to buf[0] (selects, not a dynamically indexed array)
+    __device__ __forceinline__ uint32_t next32() {
+        if (have < 1) refill();
+        const uint32_t w = have == 4 ? buf[3] : (have == 3 ? buf[2] : (have == 2 ? buf[1] : buf[0]));
+        have -= 1;
+        return w;
+    }
     __device__ __forceinline__ uint64_t next64() {
-        if (have < 2) refill();
-        have -= 2;
-        // have is now 2 or 0: words (2,3) first, then (0,1)
-        const uint32_t lo = have == 2 ? buf[2] : buf[0];
-        const uint32_t hi = have == 2 ? buf[3] : buf[1];
+        const uint32_t lo = next32();
+        const uint32_t hi = next32();
         return ((uint64_t)hi << 32) | lo;
     }
     // U in [0,1): 53 random bits (rand(rng))
     __device__ __forceinline__ double u01() { return (double)(next64() >> 11) * 0x1.0p-53; }
     // U in (0,1]
     __device__ __forceinline__ double u01_open0() { return (double)((next64() >> 11) + 1ull) * 0x1.0p-53; }
-    // randexp(rng)
-    __device__ __forceinline__ double expo() { return -log(u01_open0()); }
+    // U in (0,1) on a 2^-32 grid: for accept/reject DECISIONS only (never for a returned value)
+    __device__ __forceinline__ double u01_32() { return ((double)next32() + 0.5) * 0x1.0p-32; }
+    // randexp(rng): u in (0,1] is a normal double, so the straight-line log is valid
+    __device__ __forceinline__ double expo() { return -augf::log_(u01_open0()); }
     // randn(rng): Box-Muller, one normal per call (the sine branch is discarded)
     __device__ __forceinline__ double normal() {
         const double u = u01_open0();
         const double v = u01();
-        const double r = sqrt(-2.0 * log(u));
+        const double r = sqrt(-2.0 * augf::log_(u));
         return r * cospi(2.0 * v);
     }
 };
