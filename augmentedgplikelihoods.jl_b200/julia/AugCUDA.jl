@@ -1,0 +1,260 @@
+# AugCUDA.jl — the Julia glue a maintainer of AugmentedGPLikelihoods.jl would add so that the reference's
+# own verbs dispatch to libaugcuda.so for device-resident data.
+#
+# STATUS: written to the C ABI of include/augcuda.h, NOT executed: there is no Julia in the build image
+# (INTEGRATION.md).  Everything the tests and bench.py exercise goes through the same ABI from Python
+# (augmentedgplikelihoods.jl_b200/api.py), function for function.
+#
+# Design: Julia multiple dispatch is the reference's plugin mechanism (src/AugmentedGPLikelihoods.jl:18-30),
+# so the "plugin" is a set of METHODS of the reference's generic functions, specialised on a device array
+# type.  qΩ stays a MeasureTheory.For over a TupleVector and Ω stays a TupleVector — only their field
+# arrays are device vectors — so `only(qΩ.inds).c`, `Ω.ω`, `length(Ω)` keep working.
+module AugCUDA
+
+using AugmentedGPLikelihoods
+using AugmentedGPLikelihoods: AbstractLikelihood, BijectiveSimplexLink, LogisticSoftMaxLink,
+    ScaledLogistic, InvScaledLogistic, LaplaceLikelihood, StudentTLikelihood
+using GPLikelihoods: BernoulliLikelihood, PoissonLikelihood, NegativeBinomialLikelihood, NBParamFailure,
+    HeteroscedasticGaussianLikelihood, CategoricalLikelihood, LogisticLink
+using Distributions: Normal
+using MeasureTheory: For
+using TupleVectors: TupleVector
+using Random: AbstractRNG
+
+const AGPL = AugmentedGPLikelihoods
+const lib = "libaugcuda"
+
+# ---------------------------------------------------------------- C ABI mirrors (include/augcuda.h)
+struct AugLik               # typedef struct aug_lik
+    kind::Int32
+    nlatent::Int32
+    r_is_int::Int32
+    reserved::Int32
+    p::NTuple{4,Float64}
+    logtheta::Ptr{Float64}  # host pointer
+end
+
+const BERNOULLI, NEGBIN, POISSON, LAPLACE, STUDENTT, HETERO, CAT_BIJ, CAT = Int32.(0:7)
+const S_ELT, S_KL, S_EAUGLL, S_LOGTILT, S_LOGPRIOR, S_AUGLL = 1:6   # 1-based slots of the scalar block
+
+mutable struct Context
+    h::Ptr{Cvoid}
+    device::Int
+end
+
+function check(rc::Int32)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:aug_strerror, lib), Cstring, (Int32,), rc))
+    # mirrors the reference's error(...) / ArgumentError behaviour (SURVEY §5)
+    rc == -3 ? error(msg) : throw(ErrorException("libaugcuda: $msg (rc=$rc)"))
+end
+
+function Context(device::Integer=0; stream::Ptr{Cvoid}=C_NULL)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:aug_ctx_create, lib), Int32, (Ref{Ptr{Cvoid}}, Int32, Ptr{Cvoid}), h, device, stream))
+    ctx = Context(h[], device)
+    finalizer(c -> ccall((:aug_ctx_destroy, lib), Int32, (Ptr{Cvoid},), c.h), ctx)
+    return ctx
+end
+
+const CTX = Ref{Context}()
+ctx() = isassigned(CTX) ? CTX[] : (CTX[] = Context())
+
+# ---------------------------------------------------------------- device containers
+"Device vector owned by Julia (allocated with aug_malloc) or borrowed (e.g. from CUDA.jl: pass its pointer)."
+mutable struct AugDeviceVector{T} <: AbstractVector{T}
+    ptr::Ptr{T}
+    len::Int
+    owner::Bool
+end
+Base.size(v::AugDeviceVector) = (v.len,)
+Base.getindex(::AugDeviceVector, ::Int) = error("scalar indexing of a device vector: copy it with Array(v)")
+Base.pointer(v::AugDeviceVector) = v.ptr
+
+function AugDeviceVector{T}(::UndefInitializer, n::Integer) where {T}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:aug_malloc, lib), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Csize_t), ctx().h, p, n * sizeof(T)))
+    v = AugDeviceVector{T}(Ptr{T}(p[]), n, true)
+    finalizer(x -> x.owner && ccall((:aug_free, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx().h, x.ptr), v)
+    return v
+end
+function AugDeviceVector(a::Vector{T}) where {T}
+    v = AugDeviceVector{T}(undef, length(a))
+    check(ccall((:aug_memcpy_h2d, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
+                ctx().h, v.ptr, a, sizeof(a)))
+    return v
+end
+function Base.Array(v::AugDeviceVector{T}) where {T}
+    a = Vector{T}(undef, v.len)
+    check(ccall((:aug_memcpy_d2h, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
+                ctx().h, a, v.ptr, sizeof(a)))
+    return a
+end
+
+"qf::AbstractVector{<:Normal} on the device: struct-of-arrays of mean and VARIANCE (utils.jl:1-7 reads only these)."
+struct DeviceNormals <: AbstractVector{Normal{Float64}}
+    μ::AugDeviceVector{Float64}
+    σ²::AugDeviceVector{Float64}
+    ld::Int                       # leading dimension for the 2-latent heteroscedastic layout, else 0
+end
+Base.size(q::DeviceNormals) = (q.ld == 0 ? q.μ.len : q.ld,)
+
+"rng argument: counter-based Philox4x32-10 stream (seed, offset); every sampling verb consumes one tick."
+mutable struct AugPhilox <: AbstractRNG
+    seed::UInt64
+    offset::UInt64
+end
+const GLOBAL_PHILOX = AugPhilox(0x243f6a8885a308d3, 0)
+seed!(r::AugPhilox) = check(ccall((:aug_ctx_seed, lib), Int32, (Ptr{Cvoid}, UInt64, UInt64), ctx().h, r.seed, r.offset))
+function sync_offset!(r::AugPhilox)
+    o = Ref{UInt64}(0)
+    check(ccall((:aug_ctx_get_offset, lib), Int32, (Ptr{Cvoid}, Ref{UInt64}), ctx().h, o))
+    r.offset = o[]
+end
+
+# ---------------------------------------------------------------- likelihood descriptors
+desc(::BernoulliLikelihood{<:LogisticLink}) = AugLik(BERNOULLI, 1, 0, 0, (0.0, 0.0, 0.0, 0.0), C_NULL)
+function desc(l::NegativeBinomialLikelihood{<:NBParamFailure})
+    r = l.params.failures
+    AugLik(NEGBIN, 1, r isa Integer ? 1 : 0, 0, (Float64(r), 0.0, 0.0, 0.0), C_NULL)
+end
+desc(l::PoissonLikelihood{<:ScaledLogistic}) = AugLik(POISSON, 1, 0, 0, (Float64(l.invlink.λ), 0.0, 0.0, 0.0), C_NULL)
+desc(l::LaplaceLikelihood) = AugLik(LAPLACE, 1, 0, 0, (Float64(l.β), 0.0, 0.0, 0.0), C_NULL)
+desc(l::StudentTLikelihood) = AugLik(STUDENTT, 1, 0, 0, (Float64(l.ν), Float64(l.σ), 0.0, 0.0), C_NULL)
+desc(l::HeteroscedasticGaussianLikelihood{<:InvScaledLogistic}) =
+    AugLik(HETERO, 2, 0, 0, (Float64(l.invlink.λ), 0.0, 0.0, 0.0), C_NULL)
+# Categorical: the logθ vector must stay alive during the call (GC.@preserve in `withdesc`)
+logθ(l::CategoricalLikelihood{<:BijectiveSimplexLink{<:LogisticSoftMaxLink}}) = l.invlink.link.logθ
+logθ(l::CategoricalLikelihood{<:LogisticSoftMaxLink}) = l.invlink.logθ
+function withdesc(f, l::CategoricalLikelihood)
+    θ = convert(Vector{Float64}, logθ(l))
+    kind = l.invlink isa BijectiveSimplexLink ? CAT_BIJ : CAT
+    GC.@preserve θ f(Ref(AugLik(kind, AGPL.nlatent(l), 0, 0, (0.0, 0.0, 0.0, 0.0), pointer(θ))))
+end
+withdesc(f, l::AbstractLikelihood) = f(Ref(desc(l)))
+
+const DV = AugDeviceVector
+state(qΩ::For) = only(qΩ.inds)                                   # the SoA of variational parameters
+s0(φ) = haskey(φ, :c) ? φ.c : haskey(φ, :μ) ? φ.μ : φ.β          # bernoulli.jl:7-11 ... studentt.jl:39-44
+s1(φ) = haskey(φ, :λ) ? φ.λ : haskey(φ, :p) ? φ.p : nothing
+s2(φ) = haskey(φ, :ψ) ? φ.ψ : haskey(φ, :y) ? φ.y : nothing
+ptr(::Nothing) = C_NULL
+ptr(v::DV) = Ptr{Cvoid}(v.ptr)
+
+# ---------------------------------------------------------------- variational verbs
+# aux_posterior!(qΩ, lik, y, qf)                       -> aug_aux_posterior           (a5)
+function AGPL.aux_posterior!(qΩ::For, lik::AbstractLikelihood, y::DV, qf::DeviceNormals)
+    φ = state(qΩ)
+    withdesc(lik) do d
+        check(ccall((:aug_aux_posterior, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64,
+                     Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    ctx().h, d, length(qΩ), y.ptr, qf.μ.ptr, qf.σ².ptr, qf.ld, ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ))))
+    end
+    return qΩ                                                    # bernoulli.jl:24
+end
+
+# expected_auglik_potential_and_precision(lik, qΩ, y[, qf]) -> aug_expected_potential_precision   (a7)
+function AGPL.expected_auglik_potential_and_precision(lik::AbstractLikelihood, qΩ::For, y::DV,
+                                                      qf::Union{Nothing,DeviceNormals}=nothing)
+    n, nl = length(qΩ), AGPL.nlatent(lik)
+    β, γ = DV{Float64}(undef, n * nl), DV{Float64}(undef, n * nl)
+    φ = state(qΩ)
+    withdesc(lik) do d
+        check(ccall((:aug_expected_potential_precision, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Cvoid}, Ptr{Cvoid},
+                     Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64),
+                    ctx().h, d, n, y.ptr, qf === nothing ? C_NULL : qf.μ.ptr, qf === nothing ? 0 : qf.ld,
+                    ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ)), β.ptr, γ.ptr, n))
+    end
+    split(v) = ntuple(j -> DV{Float64}(v.ptr + (j - 1) * n * 8, n, false), nl)   # one vector per latent
+    return split(β), split(γ)
+end
+AGPL.expected_auglik_potential(lik::AbstractLikelihood, qΩ::For, y::DV, qf=nothing) =
+    first(AGPL.expected_auglik_potential_and_precision(lik, qΩ, y, qf))
+AGPL.expected_auglik_precision(lik::AbstractLikelihood, qΩ::For, y::DV, qf=nothing) =
+    last(AGPL.expected_auglik_potential_and_precision(lik, qΩ, y, qf))
+
+# expected_logtilt / aux_kldivergence / expected_aug_loglik -> aug_expected_elbo_terms (a9, a11, a13)
+function elbo_terms(lik, qΩ::For, y::DV, qf::DeviceNormals)
+    sc = DV{Float64}(undef, 8)
+    φ = state(qΩ)
+    withdesc(lik) do d
+        check(ccall((:aug_expected_elbo_terms, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Cvoid},
+                     Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
+                    ctx().h, d, length(qΩ), y.ptr, qf.μ.ptr, qf.σ².ptr, qf.ld, ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ)), sc.ptr))
+    end
+    return Array(sc)          # multi-GPU callers run aug_allreduce_scalars on `sc` first (INTEGRATION.md)
+end
+AGPL.expected_logtilt(lik::AbstractLikelihood, qΩ::For, y::DV, qf::DeviceNormals) = elbo_terms(lik, qΩ, y, qf)[S_ELT]
+AGPL.expected_aug_loglik(lik::AbstractLikelihood, qΩ::For, y::DV, qf::DeviceNormals) = elbo_terms(lik, qΩ, y, qf)[S_EAUGLL]
+# aux_kldivergence(lik, qΩ, y) has no qf in the reference; the KL kernels only read the state and y, so a
+# zero qf of the right length is passed (the heteroscedastic prior needs the real qf: use elbo_terms).
+
+# ---------------------------------------------------------------- sampling verbs
+# aux_sample!(rng, Ω, lik, y, f)                      -> aug_aux_sample                 (a14-a19)
+function AGPL.aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::AbstractLikelihood, y::DV, f::DV; i0::Integer=0)
+    seed!(rng)
+    nv = hasproperty(Ω, :n) ? Ω.n : nothing
+    withdesc(lik) do d
+        check(ccall((:aug_aux_sample, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}),
+                    ctx().h, d, length(y) ÷ max(1, AGPL.nlatent(lik) * (lik isa CategoricalLikelihood)), i0,
+                    y.ptr, f.ptr, lik isa HeteroscedasticGaussianLikelihood ? length(f) ÷ 2 : 0, Ω.ω.ptr, ptr(nv)))
+    end
+    sync_offset!(rng)
+    return Ω                                                     # generic.jl:11
+end
+AGPL.aux_sample!(Ω::TupleVector, lik::AbstractLikelihood, y::DV, f::DV) = AGPL.aux_sample!(GLOBAL_PHILOX, Ω, lik, y, f)
+
+# init_aux_variables(rng, lik, n)                     -> aug_init_aux_variables          (a4)
+function AGPL.init_aux_variables(rng::AugPhilox, lik::AbstractLikelihood, n::Int; i0::Integer=0)
+    seed!(rng)
+    m = lik isa CategoricalLikelihood ? n * AGPL.nlatent(lik) : n
+    ω = DV{Float64}(undef, m)
+    needs_n = lik isa Union{PoissonLikelihood,HeteroscedasticGaussianLikelihood,CategoricalLikelihood}
+    nv = needs_n ? DV{Int64}(undef, m) : nothing
+    withdesc(lik) do d
+        check(ccall((:aug_init_aux_variables, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Int64, Ptr{Float64}, Ptr{Int64}), ctx().h, d, n, i0, ω.ptr, ptr(nv)))
+    end
+    sync_offset!(rng)
+    return needs_n ? TupleVector((; ω, n=nv)) : TupleVector((; ω))
+end
+
+# auglik_potential_and_precision(lik, Ω, y[, f])      -> aug_potential_precision         (a20)
+function AGPL.auglik_potential_and_precision(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::Union{Nothing,DV}=nothing)
+    nl = AGPL.nlatent(lik)
+    n = length(Ω.ω) ÷ (lik isa CategoricalLikelihood ? nl : 1)
+    β, γ = DV{Float64}(undef, n * nl), DV{Float64}(undef, n * nl)
+    nv = hasproperty(Ω, :n) ? Ω.n : nothing
+    withdesc(lik) do d
+        check(ccall((:aug_potential_precision, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64},
+                     Ptr{Float64}, Ptr{Float64}, Int64),
+                    ctx().h, d, n, y.ptr, f === nothing ? C_NULL : f.ptr, f === nothing ? 0 : length(f) ÷ 2,
+                    Ω.ω.ptr, ptr(nv), β.ptr, γ.ptr, n))
+    end
+    split(v) = ntuple(j -> DV{Float64}(v.ptr + (j - 1) * n * 8, n, false), nl)
+    return split(β), split(γ)
+end
+
+# logtilt / aug_loglik                                -> aug_sampled_loglik_terms         (a21-a24)
+function sampled_terms(lik, Ω::TupleVector, y::DV, f::DV, with_prior::Bool)
+    sc = DV{Float64}(undef, 8)
+    nv = hasproperty(Ω, :n) ? Ω.n : nothing
+    n = lik isa CategoricalLikelihood ? length(Ω.ω) ÷ AGPL.nlatent(lik) : length(Ω.ω)
+    withdesc(lik) do d
+        check(ccall((:aug_sampled_loglik_terms, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}, Int32,
+                     Ptr{Float64}),
+                    ctx().h, d, n, y.ptr, f.ptr, lik isa HeteroscedasticGaussianLikelihood ? n : 0, Ω.ω.ptr, ptr(nv),
+                    with_prior, sc.ptr))
+    end
+    return Array(sc)
+end
+AGPL.logtilt(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::DV) = sampled_terms(lik, Ω, y, f, false)[S_LOGTILT]
+AGPL.aug_loglik(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::DV) = sampled_terms(lik, Ω, y, f, true)[S_AUGLL]
+
+end # module
