@@ -151,7 +151,15 @@ __device__ __forceinline__ void eval(const LikConst& L, Obs& o) {
             if (!SAFE) lf = __ldg(&L.table[(int)fmin(fmax(o.y, 0.0), (double)(AUG_TABLE_N - 1))]);
             else lf = lfact(o.y, L.table);
             o.elt = -(o.y + lam) * LN2 + 0.5 * fma(o.y - lam, o.m, -s2m * th) + o.y * L.c0 - lf;   // :81-83
-            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) + kl_poisson<SAFE>(lam, L.p0, L.c0);
+            // KL(Po(λ̂) || Po(λ)): fused, log(λ̂/λ) = log σ̃ = (−m − c)/2 − log(1+e) needs no extra log
+            double klp;
+            if (FROM_STATE) klp = kl_poisson<SAFE>(lam, L.p0, L.c0);
+            else {
+                const double mneg = -o.m;
+                const double lst = mneg > LOGISTIC_HI ? 0.0 : fma(0.5, mneg - o.s0, -t.l1pe);
+                klp = kl_poisson_lr(lam, L.p0, lst);
+            }
+            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) + klp;
         }
     } else if (KIND == AUG_LAPLACE) {
         const double d = o.m - o.y;
@@ -207,8 +215,14 @@ __device__ __forceinline__ void eval(const LikConst& L, Obs& o) {
         if (ELBO) {                                             // :129-145
             o.elt = L.c0 - b * LN2 + 0.5 * fma(0.5 - lam, o.mg, -s2g * th);
             const double pl = 0.5 * L.p0 * s2f;
-            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) +
-                   kl_poisson<SAFE>(lam, pl, SAFE ? log(pl) : augf::log_(pl));
+            double klp;   // KL(Po(λ̂) || Po(λψ)) with λ̂ = λψσ̃: log(λ̂/(λψ)) = log σ̃, no log needed when fused
+            if (FROM_STATE) klp = kl_poisson<SAFE>(lam, pl, SAFE ? log(pl) : augf::log_(pl));
+            else {
+                const double mneg = -o.mg;
+                const double lst = mneg > LOGISTIC_HI ? 0.0 : fma(0.5, mneg - o.s0, -t.l1pe);
+                klp = kl_poisson_lr(lam, pl, lst);
+            }
+            o.kl = fma(b, t.lch, -0.5 * o.s0 * o.s0 * th) + klp;
         }
     }
 }
@@ -441,15 +455,12 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_MIN_BLOCKS) cavi_kernel(const 
 // ring (STAGES x tile bytes per CTA), not by registers or occupancy; the 256 threads consume a stage with
 // conflict-free 128-bit LDS, evaluate the straight-line math, and write state / beta / gamma straight to
 // global with 128-bit streaming stores.
-#ifndef CAVI_TILE
-#define CAVI_TILE 2048      // observations per stage
-#endif
-#ifndef CAVI_STAGES
-#define CAVI_STAGES 3
-#endif
 #ifndef CAVI_TMA_BLOCKS
-#define CAVI_TMA_BLOCKS 2   // CTAs per SM the ring is sized for
+#define CAVI_TMA_BLOCKS 2   // CTAs per SM the ring is sized for (~100 KB of ring per CTA)
 #endif
+// tile (observations per stage) and ring depth per likelihood: ~25-35 KB per stage, ~100 KB per CTA
+__host__ __device__ constexpr int cavi_tile(int kind) { return kind == AUG_BERNOULLI ? 2048 : (kind == AUG_HETERO ? 512 : 1024); }
+__host__ __device__ constexpr int cavi_stages(int kind) { return kind == AUG_BERNOULLI ? 3 : (kind == AUG_HETERO ? 5 : 4); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -479,7 +490,8 @@ template <int KIND>
 struct TileLayout {
     typedef typename YT<KIND>::T yt;
     static constexpr bool HET = KIND == AUG_HETERO;
-    static constexpr int T = CAVI_TILE;
+    static constexpr int T = cavi_tile(KIND);
+    static constexpr int S = cavi_stages(KIND);
     static constexpr int Y_BYTES = T * (int)sizeof(yt);
     static constexpr int D_BYTES = T * 8;
     static constexpr int OFF_MU = (Y_BYTES + 127) / 128 * 128;
@@ -488,7 +500,7 @@ struct TileLayout {
     static constexpr int OFF_VARG = OFF_MUG + D_BYTES;
     static constexpr int STAGE_BYTES = HET ? OFF_VARG + D_BYTES : OFF_MUG;
     static constexpr int TX_BYTES = Y_BYTES + D_BYTES * (HET ? 4 : 2);
-    static constexpr int SMEM_BYTES = STAGE_BYTES * CAVI_STAGES + 64;
+    static constexpr int SMEM_BYTES = STAGE_BYTES * S + 64;
 };
 
 template <typename T>
@@ -512,7 +524,7 @@ __device__ __forceinline__ void lds_y2<double>(const unsigned char* ys, int q, d
     b = v.y;
 }
 
-// Fused (not FROM_STATE) CAVI step over the full tiles [0, ntiles * CAVI_TILE) of the shard.
+// Fused (not FROM_STATE) CAVI step over the full tiles [0, ntiles * tile) of the shard.
 template <int KIND, bool ELBO>
 __global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(const CaviArgs a, const int64_t ntiles) {
     typedef TileLayout<KIND> TL;
@@ -521,7 +533,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(co
     constexpr bool HET = KIND == AUG_HETERO;
     constexpr bool YSTATE = KIND == AUG_NEGBIN || KIND == AUG_POISSON;
     constexpr bool HAS_S1 = KIND == AUG_POISSON || KIND == AUG_HETERO;
-    constexpr int T = CAVI_TILE, S = CAVI_STAGES;
+    constexpr int T = TL::T, S = TL::S;
     extern __shared__ __align__(128) unsigned char ring[];
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)TL::STAGE_BYTES * S);
 
@@ -746,12 +758,13 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
                aug_aligned16(a.beta_g) && aug_aligned16(a.gamma_g);
     if (lik->kind == AUG_BERNOULLI) vec = vec && ((((uintptr_t)y) & 1u) == 0);
     else vec = vec && aug_aligned16(y);
-    // Fused calls on 16-byte aligned arrays: the full CAVI_TILE-observation tiles go through the bulk-async
+    // Fused calls on 16-byte aligned arrays: the full tiles (cavi_tile(kind) observations) go through the bulk-async
     // staged kernel, the ragged remainder (< one tile) through the direct-load kernel, whose scalars the
     // staged kernel then accumulates onto.
-    const bool use_tma = !from_state && vec && !getenv_no_tma() && aug_aligned16(y) && n >= 4 * (int64_t)CAVI_TILE;
-    const int64_t ntiles = use_tma ? n / CAVI_TILE : 0;
-    const int64_t n0 = ntiles * CAVI_TILE;   // observations handled by the staged kernel
+    const int64_t tile = cavi_tile(lik->kind);
+    const bool use_tma = !from_state && vec && !getenv_no_tma() && aug_aligned16(y) && n >= 4 * tile;
+    const int64_t ntiles = use_tma ? n / tile : 0;
+    const int64_t n0 = ntiles * tile;   // observations handled by the staged kernel
     CaviArgs t = a;                          // remainder [n0, n)
     if (n0 > 0) {
         const size_t ysz = lik->kind == AUG_BERNOULLI ? 1 : 8;

@@ -19,6 +19,7 @@ constexpr double PI = 3.14159265358979323846;
 //   e   = exp(-c), inv1pe = 1/(1+e) (re-used by approx_expected_logistic)
 struct PGTerms {
     double h, lch, e, inv1pe;
+    double l1pe;   // log(1 + e) (only when NEED_LCH)
 };
 
 // SAFE = false: straight-line code on top of aug_fastmath.cuh, valid for 0 <= c <= 1e290 (exp(-c) is
@@ -33,13 +34,15 @@ __device__ __forceinline__ PGTerms pg_terms_ic(double c, double inv_c) {
         e = exp(-c);
         inv = 1.0 / (1.0 + e);
         t.h = (1.0 - e) * inv / (2.0 * c);
-        t.lch = NEED_LCH ? fma(0.5, c, log1p(e) - LN2) : 0.0;
+        t.l1pe = NEED_LCH ? log1p(e) : 0.0;
+        t.lch = NEED_LCH ? fma(0.5, c, t.l1pe - LN2) : 0.0;
     } else {
         e = augf::exp_(-fmin(c, 708.0));
         const double d = 1.0 + e;
         inv = augf::rcp(d);
         t.h = (1.0 - e) * inv * (0.5 * inv_c);
-        t.lch = NEED_LCH ? fma(0.5, c, augf::log_1to2(d) - LN2) : 0.0;
+        t.l1pe = NEED_LCH ? augf::log_1to2(d) : 0.0;
+        t.lch = NEED_LCH ? fma(0.5, c, t.l1pe - LN2) : 0.0;
     }
     t.e = e;
     t.inv1pe = inv;
@@ -78,6 +81,12 @@ __device__ __forceinline__ double approx_expected_logistic(double mu, double c, 
 
 // kldivergence(Poisson(q), Poisson(p)) (Distributions.jl): q == 0 ? p : p - q + q (log q - log p).
 // SAFE = false: q log q is dropped below 1e-290 (it is < 1e-287 there).
+// KL(Poisson(q) || Poisson(p)) when log(q/p) is already known (fused CAVI: q = p * sigma~, so
+// log(q/p) = log sigma~ = (mu - c)/2 - log(1+e) comes for free); q == 0 -> p.
+__device__ __forceinline__ double kl_poisson_lr(double q, double p, double log_q_over_p) {
+    return q == 0.0 ? p : p - q + q * log_q_over_p;
+}
+
 template <bool SAFE>
 __device__ __forceinline__ double kl_poisson(double q, double p, double logp) {
     if (SAFE) {

@@ -17,6 +17,8 @@ struct Philox {
     uint32_t c0, c1, c2, c3;  // counter = (element lo, element hi, block counter, verb offset)
     uint32_t buf[4];
     int have;                 // 32-bit words left in buf
+    double spare;             // second Box-Muller normal
+    bool has_spare;
 
     __device__ __forceinline__ void init(uint64_t seed, uint64_t offset, uint64_t element, uint32_t lane_tag = 0) {
         k0 = (uint32_t)seed;
@@ -26,6 +28,7 @@ struct Philox {
         c2 = lane_tag << 24;  // up to 2^24 blocks (6.7e7 uniforms) per element and tag
         c3 = (uint32_t)offset;
         have = 0;
+        has_spare = false;
     }
     __device__ __forceinline__ void refill() {
         uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
@@ -62,12 +65,20 @@ struct Philox {
     __device__ __forceinline__ double u01_32() { return ((double)next32() + 0.5) * 0x1.0p-32; }
     // randexp(rng): u in (0,1] is a normal double, so the straight-line log is valid
     __device__ __forceinline__ double expo() { return -augf::log_(u01_open0()); }
-    // randn(rng): Box-Muller, one normal per call (the sine branch is discarded)
+    // randn(rng): Box-Muller; the sine branch is kept for the next call
     __device__ __forceinline__ double normal() {
+        if (has_spare) {
+            has_spare = false;
+            return spare;
+        }
         const double u = u01_open0();
         const double v = u01();
         const double r = sqrt(-2.0 * augf::log_(u));
-        return r * cospi(2.0 * v);
+        double sn, cs;
+        sincospi(2.0 * v, &sn, &cs);
+        spare = r * sn;
+        has_spare = true;
+        return r * cs;
     }
 };
 
@@ -75,11 +86,12 @@ struct Philox {
 __device__ __forceinline__ double gamma_rand(Philox& g, double shape) {
     double boost = 1.0;
     if (shape < 1.0) {
-        boost = exp(log(g.u01_open0()) / shape);
+        const double la = augf::log_(g.u01_open0()) / shape;   // U^(1/shape)
+        boost = la > -700.0 ? augf::exp_(la) : 0.0;
         shape += 1.0;
     }
     const double d = shape - 1.0 / 3.0;
-    const double c = rsqrt(9.0 * d);
+    const double c = augf::rsqrt_(9.0 * d);
     for (;;) {
         double x, v;
         do {
@@ -87,10 +99,10 @@ __device__ __forceinline__ double gamma_rand(Philox& g, double shape) {
             v = fma(c, x, 1.0);
         } while (v <= 0.0);
         v = v * v * v;
-        const double u = g.u01_open0();
+        const double u = g.u01_32();
         const double x2 = x * x;
         if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
-        if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
+        if (augf::log_(u) < 0.5 * x2 + d * (1.0 - v + augf::log_(v))) return boost * d * v;
     }
 }
 
