@@ -41,6 +41,12 @@ struct CatArgs {
     LikConst L;
 };
 
+// inputs for which the straight-line instantiation is valid (exp_ needs |(-m-c)/2| <= 708)
+__device__ __forceinline__ bool cat_fast_ok(double m, double v) {
+    const double s2 = fma(m, m, v);   // s2 <= 2.4e5 bounds |m| and c by 490: |(-m-c)/2| <= 490
+    return s2 >= 1e-290 && s2 <= 2.4e5;
+}
+
 // dynamic shared memory carve-up: P, H [, X1, X2, X3] (R*nlp doubles each), rinv[R], rows[R][3], Y bytes
 template <bool FROM_STATE, bool ELBO>
 __global__ void __launch_bounds__(AUG_BLOCK) cat_cavi_kernel(const CatArgs a) {
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_cavi_kernel(const CatArgs a) {
                 p = ld_stream1(a.rs1 + base + e);
                 if (c >= 0.0 && c <= 700.0) t = pg_terms<ELBO, false>(c);
                 else t = pg_terms<ELBO, true>(c);
-            } else if (augf::in_range(s2m) && fabs(m) <= 700.0 && v <= 4e5) {
+            } else if (cat_fast_ok(m, v)) {
                 double ic;
                 augf::sqrt_inv(s2m, c, ic);                           // categorical.jl:88,105
                 t = pg_terms_ic<ELBO, false>(c, ic);
@@ -163,6 +169,279 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_cavi_kernel(const CatArgs a) {
     if (ELBO) {
         double out[3];
         if (block_reduce_and_finalize<3>(acc, a.partials, a.counter, out)) {
+            a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
+            a.scalars[AUG_S_KL] = out[1];
+            a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
+            a.scalars[AUG_S_FLAGS] = out[2];
+            if (out[2] > 0.0) atomicOr(a.dflag, 1u);
+        }
+    } else if (acc[2] > 0.0) {
+        atomicOr(a.dflag, 1u);
+    }
+}
+
+// ------------------------------------------------------------------ bulk-async (TMA) staged variant
+// ncu on cat_cavi_kernel (profiles/r1d): 490 issued instructions per (obs, class) element — an integer
+// division per element in phases 1 and 3, a log per element in phase 2, scalar 8-byte loads whose latency
+// (long-scoreboard = 30% of the stall cycles) only occupancy could hide — so the kernel was issue-bound at
+// 2.3-3.5 TB/s.  This variant, for the full tiles of a fused call on 16-byte aligned arrays:
+//   * an elected thread streams each tile (R rows = ONE contiguous span of y, mu, var) into a shared-memory ring
+//     with cp.async.bulk completing on mbarriers (SASS: UBLKCP / SYNCS), 2 CTAs per SM;
+//   * phase 1 handles two consecutive elements per thread per iteration (128-bit LDS / st.global.v2, the two
+//     straight-line evaluations interleave), with the (row, class) index advanced incrementally;
+//   * log p_ij comes from quantities already at hand (log σ̃ = (−m−c)/2 − log(1+e^{-c})), so phase 2 is pure
+//     additions: Σp, Σ p(−ln2 − m/2 − s2 h/2), Σ p(lch − c²h/2 + log p − log p_prior) per row;
+//   * phase 3 walks 16-row groups (one 128-byte segment per class and group) with shifts instead of divisions.
+struct CatTmaArgs {
+    CatArgs a;               // a.n = rows covered by full tiles
+    int64_t ntiles;
+    int E;                   // elements per tile = R * nl (even; a multiple of 16 bytes of y)
+    int S;                   // ring depth
+    int off_mu, off_var, stage_bytes;
+    int di, dj;              // (2*AUG_BLOCK) / nl and % nl: row/class step of a thread between phase-1 iterations
+    int rs;                  // row stride of the staged tiles in doubles: nl (odd nl) or nl + 2 (even nl)
+    int accumulate;          // add onto the scalars the ragged-tail launch left in memory
+    double log_inv_denom;    // log(1/(D + nl)) resp. log(1/nl)
+};
+
+// One (obs, class) element.  SAFE = false is straight-line code valid for 2^-8 <= m² + v <= 2.4e5 (so that
+// c >= 1/16: no series branch, |(-m-c)/2| <= 490: exp_ in range); SAFE = true takes any input.
+template <bool ELBO, bool SAFE>
+__device__ __forceinline__ void cat_elem(const double m, const double v, const bool yb, const double inv_denom,
+                                         const double log_inv_denom, const double c2, double& c, double& p,
+                                         double& h, double& x1, double& x23, double& a0, double& a1) {
+    using namespace augm;
+    const double s2m = fma(m, m, v);
+    PGTerms t;
+    double sig, logp;
+    if (SAFE) {
+        c = sqrt(s2m);                                                    // categorical.jl:88,105
+        t = pg_terms_ic<ELBO, true>(c, 0.0);
+        sig = approx_expected_logistic<true>(-m, c, t);                   // :90-92, :107
+        p = sig * inv_denom;
+        logp = p > 0.0 ? log(p) : 0.0;
+    } else {
+        double ic;
+        augf::sqrt_inv(s2m, c, ic);
+        t = pg_terms_ic<ELBO, false, false>(c, ic);
+        const double ah = 0.5 * (-m - c);
+        const double w = augf::exp_(ah) * t.inv1pe;                       // exp(-m/2) sech(c/2)/2
+        const bool hi = -m > LOGISTIC_HI;                                 // utils.jl:12-13 (|m| <= 490: never below LO)
+        sig = hi ? 1.0 : w;
+        p = sig * inv_denom;
+        logp = (hi ? 0.0 : ah - t.l1pe) + log_inv_denom;                  // log p without a log
+    }
+    h = t.h;
+    if (ELBO) {
+        const double hb = 0.5 * s2m * t.h;
+        const double d = fma(-0.5 * c * c, t.h, t.lch);
+        x1 = p * (-LN2 - 0.5 * m - hb);
+        x23 = p * (d + (logp - c2));                                      // + q_j (log q_j − log p_j), negativemultinomial.jl:79-81
+        // row-independent parts: y_j (−ln2 + m/2 − s2 h/2) and y_j (lch − c² h/2); y is 0/1 (selects, no I2F)
+        a0 += yb ? (-LN2 + 0.5 * m - hb) : 0.0;
+        a1 += yb ? d : 0.0;
+    }
+}
+
+// out-of-range test of the straight-line instantiation on the high word of m² + v (integer pipe; NaN, negative
+// and infinite values land outside too): not in [2^-8, 2.4e5)
+__device__ __forceinline__ bool cat_slow(double m, double v) {
+    const unsigned hi = (unsigned)__double2hiint(fma(m, m, v));
+    return hi - 0x3f700000u >= 0x410d4c00u - 0x3f700000u;
+}
+
+// EVEN: nl is even -> element pairs never straddle rows and the staged rows are padded by two doubles
+// (conflict-free-enough transposed reads); odd nl -> the staged tiles are the plain linear span.
+template <bool ELBO, bool EVEN>
+__global__ void __launch_bounds__(AUG_BLOCK, 2) cat_tma_kernel(const CatTmaArgs ta) {
+    const CatArgs& a = ta.a;
+    extern __shared__ __align__(128) unsigned char cat_ring[];
+    const int nl = a.nl, R = a.R, E = ta.E, S = ta.S, rs = ta.rs;
+    const int tile_sz = R * rs;
+    unsigned char* ring = cat_ring;
+    double* P = reinterpret_cast<double*>(ring + (size_t)S * ta.stage_bytes);
+    double* H = P + tile_sz;
+    double* X1 = ELBO ? H + tile_sz : nullptr;
+    double* X23 = ELBO ? X1 + tile_sz : nullptr;
+    double* rinv = ELBO ? X23 + tile_sz : H + tile_sz;
+    uint64_t* full = reinterpret_cast<uint64_t*>(rinv + R);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t tile, int s) {
+        unsigned char* st = ring + (size_t)s * ta.stage_bytes;
+        const int64_t o = tile * E;
+        mbar_expect_tx(&full[s], (uint32_t)E * 17u);
+        bulk_g2s(st, a.y + o, (uint32_t)E, &full[s]);
+        bulk_g2s(st + ta.off_mu, a.mu + o, (uint32_t)E * 8u, &full[s]);
+        bulk_g2s(st + ta.off_var, a.var + o, (uint32_t)E * 8u, &full[s]);
+    };
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            const int64_t t = first + (int64_t)s * stride;
+            if (t < ta.ntiles) issue(t, s);
+        }
+    }
+    const int i_first = (2 * tid) / nl, j_first = 2 * tid - i_first * nl;   // row, class of element 2*tid
+    const int l8 = lane & 7, l16 = lane & 15;
+    const int jj_first = 4 * warp + (lane >> 3);                            // phase 3: class of this thread
+    const double inv_denom = 1.0 / a.L.c0;
+    const bool vec_out = ((a.ldo & 1) == 0) && ((((uintptr_t)a.beta) | ((uintptr_t)a.gamma)) & 15u) == 0;
+    const bool both_out = a.beta != nullptr && a.gamma != nullptr && vec_out;
+    double acc[3] = {0.0, 0.0, 0.0};
+    int s = 0;
+    uint32_t parity = 0;
+    for (int64_t tile = first; tile < ta.ntiles; tile += stride) {
+        mbar_wait(&full[s], parity);
+        const unsigned char* st = ring + (size_t)s * ta.stage_bytes;
+        const uchar2* sy = reinterpret_cast<const uchar2*>(st);
+        const double2* smu = reinterpret_cast<const double2*>(st + ta.off_mu);
+        const double2* svar = reinterpret_cast<const double2*>(st + ta.off_var);
+        // ---- phase 1: element pairs, straight-line
+        {
+            double* ps0 = a.s0 ? a.s0 + tile * E + 2 * tid : nullptr;
+            double* ps1 = a.s1 ? a.s1 + tile * E + 2 * tid : nullptr;
+            uint8_t* ps2 = a.s2 ? a.s2 + tile * E + 2 * tid : nullptr;
+            int i = i_first, j = j_first;
+            bool bad = false;
+            double t0 = 0.0, t1 = 0.0;   // this tile's ELBO terms of the thread (discarded if the tile is redone)
+#pragma unroll 1
+            for (int q = tid; q < (E >> 1); q += AUG_BLOCK) {
+                const uchar2 yy = sy[q];
+                const double2 m = smu[q], v = svar[q];
+                const bool y0 = yy.x != 0, y1 = yy.y != 0;
+                bad = bad || cat_slow(m.x, v.x) || cat_slow(m.y, v.y);
+                double c0, p0, h0, c1, p1, h1, xa0 = 0.0, xb0 = 0.0, xa1 = 0.0, xb1 = 0.0;
+                cat_elem<ELBO, false>(m.x, v.x, y0, inv_denom, ta.log_inv_denom, a.L.c2, c0, p0, h0, xa0, xb0, t0, t1);
+                cat_elem<ELBO, false>(m.y, v.y, y1, inv_denom, ta.log_inv_denom, a.L.c2, c1, p1, h1, xa1, xb1, t0, t1);
+                if (ps0) { st_stream2(ps0, c0, c1); ps0 += 2 * AUG_BLOCK; }
+                if (ps1) { st_stream2(ps1, p0, p1); ps1 += 2 * AUG_BLOCK; }
+                if (ps2) { *reinterpret_cast<uchar2*>(ps2) = yy; ps2 += 2 * AUG_BLOCK; }   // φᵢ.y .= y[i]  categorical.jl:89,106
+                const int se = 2 * q + (EVEN ? 2 * i : 0);
+                *reinterpret_cast<double2*>(P + se) = make_double2(p0, p1);
+                // h = tanh(c/2)/(2c) > 0 always: its sign bit carries y_ij to phase 3 (no separate y tile, no I2F)
+                *reinterpret_cast<double2*>(H + se) = make_double2(y0 ? -h0 : h0, y1 ? -h1 : h1);
+                if (ELBO) {
+                    *reinterpret_cast<double2*>(X1 + se) = make_double2(xa0, xa1);
+                    *reinterpret_cast<double2*>(X23 + se) = make_double2(xb0, xb1);
+                }
+                if (EVEN) {
+                    i += ta.di;
+                    j += ta.dj;
+                    if (j >= nl) { j -= nl; ++i; }
+                }
+            }
+            if (!bad) {
+                acc[0] += t0;
+                acc[1] += t1;
+            } else {
+                // rare: some element of this thread is outside the straight-line range -> redo the thread's pairs of
+                // this tile with the any-input instantiation (the stage is still resident; outputs are overwritten)
+                i = i_first;
+                j = j_first;
+                for (int q = tid; q < (E >> 1); q += AUG_BLOCK) {
+                    const uchar2 yy = sy[q];
+                    const double2 m = smu[q], v = svar[q];
+                    const bool y0 = yy.x != 0, y1 = yy.y != 0;
+                    double c0, p0, h0, c1, p1, h1, xa0 = 0.0, xb0 = 0.0, xa1 = 0.0, xb1 = 0.0;
+                    cat_elem<ELBO, true>(m.x, v.x, y0, inv_denom, ta.log_inv_denom, a.L.c2, c0, p0, h0, xa0, xb0, acc[0], acc[1]);
+                    cat_elem<ELBO, true>(m.y, v.y, y1, inv_denom, ta.log_inv_denom, a.L.c2, c1, p1, h1, xa1, xb1, acc[0], acc[1]);
+                    const int64_t o = tile * E + 2 * q;
+                    if (a.s0) st_stream2(a.s0 + o, c0, c1);
+                    if (a.s1) st_stream2(a.s1 + o, p0, p1);
+                    const int se = 2 * q + (EVEN ? 2 * i : 0);
+                    *reinterpret_cast<double2*>(P + se) = make_double2(p0, p1);
+                    *reinterpret_cast<double2*>(H + se) = make_double2(y0 ? -h0 : h0, y1 ? -h1 : h1);
+                    if (ELBO) {
+                        *reinterpret_cast<double2*>(X1 + se) = make_double2(xa0, xa1);
+                        *reinterpret_cast<double2*>(X23 + se) = make_double2(xb0, xb1);
+                    }
+                    if (EVEN) {
+                        i += ta.di;
+                        j += ta.dj;
+                        if (j >= nl) { j -= nl; ++i; }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // P/H/X complete; every thread is done reading stage s
+        if (tid == 0) {
+            const int64_t nt = tile + (int64_t)S * stride;
+            if (nt < ta.ntiles) issue(nt, s);
+        }
+        if (++s == S) { s = 0; parity ^= 1u; }
+        // ---- phase 2: 16 lanes per row (two rows per warp step): Σ_j p_ij -> 1/p0, log p0
+        for (int r = 2 * warp + (lane >> 4); r < R; r += 2 * (AUG_BLOCK / 32)) {
+            const double* Pr = P + r * rs;
+            double sp = 0.0;
+            for (int jj = l16; jj < nl; jj += 16) sp += Pr[jj];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+            if (l16 == 0) {
+                const double p0 = 1.0 - sp;                               // _p₀ negativemultinomial.jl:27
+                const bool ok = p0 >= 1e-290;
+                rinv[r] = ok ? augf::rcp(p0) : 1.0 / p0;
+                if (!(sp < 1.0)) acc[2] += 1.0;                           // ctor precondition :18-22
+                // KL(NM(1,q)||NM(1,p)) = log p0q − log p0p + (1/p0q) Σ q_j (log q_j − log p_j)  :72-82
+                if (ELBO) acc[1] += (ok ? augf::log_(p0) : log(p0)) - a.L.c3;
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: class-major; 8 lanes x 2 rows = 16 consecutive rows = one 128-byte segment per array;
+        //      a warp covers 4 classes, the CTA 32 classes per step
+        if (ELBO || a.beta || a.gamma) {
+            for (int g = 0; g < (R >> 4); ++g) {
+                const int r = (g << 4) + 2 * l8;
+                const double2 ri = *reinterpret_cast<const double2*>(rinv + r);
+                const double* Pp = P + r * rs + jj_first;
+                const double* Hp = H + r * rs + jj_first;
+                int64_t o = (int64_t)jj_first * a.ldo + (tile * R + r);
+                const int64_t ostep = 4 * (AUG_BLOCK / 32) * a.ldo;
+#pragma unroll 2
+                for (int jj = jj_first; jj < nl; jj += 4 * (AUG_BLOCK / 32)) {
+                    const double hs0 = Hp[0], hs1 = Hp[rs];
+                    const double y0 = __double2hiint(hs0) < 0 ? 1.0 : 0.0, y1 = __double2hiint(hs1) < 0 ? 1.0 : 0.0;
+                    const double n0 = Pp[0] * ri.x, n1 = Pp[rs] * ri.y;                  // mean(NM(1,p)) :54
+                    const double b0 = 0.5 * (y0 - n0), b1 = 0.5 * (y1 - n1);             // categorical.jl:124,135
+                    const double g0 = (y0 + n0) * fabs(hs0), g1 = (y1 + n1) * fabs(hs1); // :128; pgnm.jl:41-54
+                    if (both_out) {
+                        st_stream2(a.beta + o, b0, b1);
+                        st_stream2(a.gamma + o, g0, g1);
+                    } else if (vec_out) {
+                        if (a.beta) st_stream2(a.beta + o, b0, b1);
+                        if (a.gamma) st_stream2(a.gamma + o, g0, g1);
+                    } else {
+                        if (a.beta) { st_stream1(a.beta + o, b0); st_stream1(a.beta + o + 1, b1); }
+                        if (a.gamma) { st_stream1(a.gamma + o, g0); st_stream1(a.gamma + o + 1, g1); }
+                    }
+                    if (ELBO) {   // the n̄-proportional parts of expected_logtilt and KL
+                        const double* X1p = X1 + (Pp - P);
+                        const double* X23p = X23 + (Pp - P);
+                        acc[0] = fma(ri.x, X1p[0], fma(ri.y, X1p[rs], acc[0]));
+                        acc[1] = fma(ri.x, X23p[0], fma(ri.y, X23p[rs], acc[1]));
+                    }
+                    Pp += 4 * (AUG_BLOCK / 32);
+                    Hp += 4 * (AUG_BLOCK / 32);
+                    o += ostep;
+                }
+            }
+        }
+        __syncthreads();   // P/H/rinv are rewritten by the next tile
+    }
+    if (ELBO) {
+        double out[3];
+        if (block_reduce_and_finalize<3>(acc, a.partials, a.counter, out)) {
+            if (ta.accumulate) {
+                out[0] += a.scalars[AUG_S_EXPECTED_LOGTILT];
+                out[1] += a.scalars[AUG_S_KL];
+                out[2] += a.scalars[AUG_S_FLAGS];
+            }
             a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
             a.scalars[AUG_S_KL] = out[1];
             a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
@@ -286,6 +565,38 @@ int pick_rows(int nl, size_t bytes_per_elem, size_t fixed_per_row, size_t budget
     return R;
 }
 
+bool cat_no_tma() {   // AUGCUDA_NO_TMA=1 keeps every call on the direct-load kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AUGCUDA_NO_TMA");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+// the direct-load row kernel: any alignment, FROM_STATE verbs, ragged tails, rows too wide for the staged ring
+int32_t launch_cat_direct(aug_ctx* ctx, CatArgs a, bool elbo, bool from_state) {
+    const size_t per_elem = (elbo ? 4 : 2) * sizeof(double);
+    const size_t budget = 96 * 1024;
+    a.R = pick_rows(a.nl, per_elem, sizeof(double) + a.nl, budget);
+    const size_t smem = (size_t)a.R * a.nlp * per_elem + (size_t)a.R * sizeof(double) + (size_t)a.R * a.nl + 16;
+    if (smem > 200 * 1024) return AUG_ERR_BAD_ARG;   // nl too large for a 2-row tile
+    const void* k;
+    if (from_state) k = elbo ? (const void*)cat_cavi_kernel<true, true> : (const void*)cat_cavi_kernel<true, false>;
+    else k = elbo ? (const void*)cat_cavi_kernel<false, true> : (const void*)cat_cavi_kernel<false, false>;
+    AUG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, AUG_BLOCK, smem) != cudaSuccess || occ < 1) occ = 1;
+    const int64_t ntiles = (a.n + a.R - 1) / a.R;
+    int64_t grid = (int64_t)ctx->sms * occ;
+    if (grid > AUG_MAX_GRID) grid = AUG_MAX_GRID;
+    if (grid > ntiles) grid = ntiles;
+    void* args[] = {(void*)&a};
+    AUG_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(AUG_BLOCK), args, smem, ctx->stream));
+    ctx->launches++;
+    return AUG_OK;
+}
+
 }  // namespace
 
 int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void* y, const double* mu,
@@ -324,25 +635,71 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
     a.dflag = ctx->dflag;
     int32_t rc = aug_lik_const(ctx, lik, &a.L, false, false);
     if (rc) return rc;
-    const size_t per_elem = (elbo ? 4 : 2) * sizeof(double);
-    const size_t budget = 96 * 1024;
-    a.R = pick_rows(a.nl, per_elem, sizeof(double) + a.nl, budget);
-    const size_t smem = (size_t)a.R * a.nlp * per_elem + (size_t)a.R * sizeof(double) + (size_t)a.R * a.nl + 16;
-    if (smem > 200 * 1024) return AUG_ERR_BAD_ARG;   // nl too large for a 2-row tile
-    const void* k;
-    if (from_state) k = elbo ? (const void*)cat_cavi_kernel<true, true> : (const void*)cat_cavi_kernel<true, false>;
-    else k = elbo ? (const void*)cat_cavi_kernel<false, true> : (const void*)cat_cavi_kernel<false, false>;
-    AUG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, AUG_BLOCK, smem) != cudaSuccess || occ < 1) occ = 1;
-    const int64_t ntiles = (n + a.R - 1) / a.R;
-    int64_t grid = (int64_t)ctx->sms * occ;
-    if (grid > AUG_MAX_GRID) grid = AUG_MAX_GRID;
-    if (grid > ntiles) grid = ntiles;
-    void* args[] = {(void*)&a};
-    AUG_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(AUG_BLOCK), args, smem, ctx->stream));
-    ctx->launches++;
-    return AUG_OK;
+    // ---- full tiles of a fused call on 16-byte aligned arrays: the bulk-async staged kernel
+    int64_t n0 = 0;   // rows it covers; the ragged tail [n0, n) goes through the direct-load kernel below
+    if (!from_state && !cat_no_tma() && aug_aligned16(y) && aug_aligned16(mu) && aug_aligned16(var) &&
+        aug_aligned16(s0) && aug_aligned16(s1) && aug_aligned16(s2)) {
+        CatTmaArgs ta{};
+        ta.a = a;
+        const int nl = a.nl;
+        int R = (1792 / nl) & ~15;
+        if (R < 16) R = 16;
+        if (R > 1024) R = 1024;
+        ta.a.R = R;
+        ta.E = R * nl;
+        ta.off_mu = (ta.E + 127) & ~127;
+        ta.off_var = ta.off_mu + ta.E * 8;
+        ta.stage_bytes = (ta.off_var + ta.E * 8 + 127) & ~127;
+        ta.di = (2 * AUG_BLOCK) / nl;
+        ta.dj = (2 * AUG_BLOCK) % nl;
+        ta.log_inv_denom = -log(a.L.c0);
+        const bool even = (nl & 1) == 0;
+        ta.rs = even ? nl + 2 : nl;
+        const size_t fixed = (size_t)R * ta.rs * sizeof(double) * (elbo ? 4 : 2) + (size_t)R * sizeof(double) +
+                             8 * sizeof(uint64_t) + 128;
+        const size_t per_cta2 = (size_t)(ctx->smem_per_sm - 2 * 1024) / 2, per_cta1 = (size_t)ctx->smem_optin;
+        int S = 0;
+        if (fixed + 2 * (size_t)ta.stage_bytes <= per_cta2) S = (int)((per_cta2 - fixed) / ta.stage_bytes);
+        else if (fixed + 2 * (size_t)ta.stage_bytes <= per_cta1) S = (int)((per_cta1 - fixed) / ta.stage_bytes);
+        if (S > 4) S = 4;
+        ta.ntiles = n / R;
+        if (S >= 2 && ta.ntiles >= 1) {
+            ta.S = S;
+            n0 = ta.ntiles * R;
+            ta.a.n = n0;
+            const size_t smem = fixed + (size_t)S * ta.stage_bytes;
+            const void* k = elbo ? (even ? (const void*)cat_tma_kernel<true, true> : (const void*)cat_tma_kernel<true, false>)
+                                 : (even ? (const void*)cat_tma_kernel<false, true> : (const void*)cat_tma_kernel<false, false>);
+            AUG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, AUG_BLOCK, smem) != cudaSuccess || occ < 1) occ = 1;
+            int64_t grid = (int64_t)ctx->sms * occ;
+            if (grid > AUG_MAX_GRID) grid = AUG_MAX_GRID;
+            if (grid > ta.ntiles) grid = ta.ntiles;
+            // the tail launch (if any) goes first and this one accumulates onto its scalars
+            ta.accumulate = (elbo && n0 < n) ? 1 : 0;
+            if (n0 < n) {
+                const int64_t eo = n0 * nl;
+                CatArgs t = a;
+                t.n = n - n0;
+                t.y = a.y + eo;
+                t.mu = a.mu + eo;
+                t.var = a.var + eo;
+                if (a.s0) t.s0 = a.s0 + eo;
+                if (a.s1) t.s1 = a.s1 + eo;
+                if (a.s2) t.s2 = a.s2 + eo;
+                if (a.beta) t.beta = a.beta + n0;
+                if (a.gamma) t.gamma = a.gamma + n0;
+                rc = launch_cat_direct(ctx, t, elbo, false);
+                if (rc) return rc;
+            }
+            void* args[] = {(void*)&ta};
+            AUG_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(AUG_BLOCK), args, smem, ctx->stream));
+            ctx->launches++;
+            return AUG_OK;
+        }
+    }
+    return launch_cat_direct(ctx, a, elbo, from_state);
 }
 
 int32_t aug_cat_sample(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0, const void* y, const double* f,

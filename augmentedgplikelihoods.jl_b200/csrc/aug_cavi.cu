@@ -87,7 +87,12 @@ __device__ __forceinline__ bool fast_ok(const Obs& o) {
     bool ok = true;
     if (KIND == AUG_BERNOULLI || KIND == AUG_NEGBIN || KIND == AUG_POISSON) {
         if (FROM_STATE) ok = o.s0 >= 0.0 && o.s0 <= 700.0;
-        if (!FROM_STATE || ELBO) ok = ok && augf::in_range(fma(o.m, o.m, o.v)) && fabs(o.m) <= 700.0 && o.v <= 4e5;
+        if (!FROM_STATE || ELBO) {
+            const double s2 = fma(o.m, o.m, o.v);
+            ok = ok && augf::in_range(s2) && fabs(o.m) <= 700.0 && o.v <= 4e5;
+            // approx_expected_logistic evaluates exp_((-m-c)/2): s2 <= 2.4e5 keeps |m|, c <= 490
+            if (KIND == AUG_POISSON) ok = ok && s2 <= 2.4e5;
+        }
         if (ELBO && KIND != AUG_BERNOULLI) ok = ok && o.y < (double)AUG_TABLE_N;
         if (KIND == AUG_POISSON && FROM_STATE) ok = ok && o.s1 >= 0.0 && o.s1 <= 1e290;
     } else if (KIND == AUG_LAPLACE || KIND == AUG_STUDENTT) {
@@ -97,9 +102,9 @@ __device__ __forceinline__ bool fast_ok(const Obs& o) {
     } else if (KIND == AUG_HETERO) {
         const double d = o.m - o.y;
         if (FROM_STATE) ok = o.s0 >= 0.0 && o.s0 <= 700.0 && o.s1 >= 0.0 && o.s1 <= 1e290;
-        if (!FROM_STATE || ELBO) ok = ok && augf::in_range(fma(o.mg, o.mg, o.vg)) && o.vg <= 4e5 &&
+        if (!FROM_STATE || ELBO) ok = ok && augf::in_range(fma(o.mg, o.mg, o.vg)) && fma(o.mg, o.mg, o.vg) <= 2.4e5 &&
                                       augf::in_range(fma(d, d, o.v));
-        ok = ok && fabs(o.mg) <= 700.0;
+        ok = ok && fabs(o.mg) <= 490.0;
     }
     return ok;
 }
@@ -461,30 +466,6 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_MIN_BLOCKS) cavi_kernel(const 
 // tile (observations per stage) and ring depth per likelihood: ~25-35 KB per stage, ~100 KB per CTA
 __host__ __device__ constexpr int cavi_tile(int kind) { return kind == AUG_BERNOULLI ? 2048 : (kind == AUG_HETERO ? 512 : 1024); }
 __host__ __device__ constexpr int cavi_stages(int kind) { return kind == AUG_BERNOULLI ? 3 : (kind == AUG_HETERO ? 5 : 4); }
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
 
 template <int KIND>
 struct TileLayout {

@@ -26,6 +26,7 @@ struct aug_ctx {
     cudaStream_t stream;
     bool own_stream;
     int sms;
+    int smem_per_sm, smem_optin;   // shared memory per SM / per CTA (opt-in) in bytes
     uint64_t seed, offset;
     uint64_t launches;
     // reduction scratch
@@ -145,5 +146,29 @@ __device__ __forceinline__ void st_stream2(double* p, double a, double b) {
 }
 __device__ __forceinline__ void st_stream1(double* p, double a) {
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(a) : "memory");
+}
+// ---------------------------------------------------------------- bulk-async (TMA 1-D) + mbarrier helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
 }
 #endif  // __CUDACC__

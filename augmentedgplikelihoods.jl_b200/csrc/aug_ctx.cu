@@ -334,6 +334,8 @@ int32_t aug_ctx_create(aug_ctx** out, int32_t device, void* stream) {
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess) {
         c->sms = prop.multiProcessorCount;
+        c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;     // 233472 on sm_100
+        c->smem_optin = (int)prop.sharedMemPerBlockOptin;          // 232448
         e = cudaMalloc(&c->partials, sizeof(double) * AUG_MAX_GRID * AUG_NRED);
     }
     if (e == cudaSuccess) e = cudaMalloc(&c->counter, sizeof(unsigned int) * 4);

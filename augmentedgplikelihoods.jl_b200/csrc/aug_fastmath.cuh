@@ -59,10 +59,23 @@ __device__ __forceinline__ double exp_(double a) {
     const double fn = t - MAGIC;
     double r = fma(fn, -LN2_HI, a);
     r = fma(fn, -LN2_LO, r);
-    double p = EXP_C[0];
-#pragma unroll
-    for (int k = 1; k < 12; ++k) p = fma(p, r, EXP_C[k]);
-    p = fma(p, r, 1.0);
+    // e^r = 1 + r + r^2 q(r), q = sum_{k=2..12} r^(k-2)/k! split into its even and odd halves: two Horner chains
+    // in r^2 that issue side by side (dependent depth 9 instead of 13; ncu showed the kernels stalled on
+    // fixed-latency dependencies, not on the FP64 pipe)
+    const double r2 = r * r;
+    double qe = EXP_C[0];            // 1/12!
+    double qo = EXP_C[1];            // 1/11!
+    qe = fma(qe, r2, EXP_C[2]);      // 1/10!
+    qo = fma(qo, r2, EXP_C[3]);      // 1/9!
+    qe = fma(qe, r2, EXP_C[4]);      // 1/8!
+    qo = fma(qo, r2, EXP_C[5]);      // 1/7!
+    qe = fma(qe, r2, EXP_C[6]);      // 1/6!
+    qo = fma(qo, r2, EXP_C[7]);      // 1/5!
+    qe = fma(qe, r2, EXP_C[8]);      // 1/4!
+    qo = fma(qo, r2, EXP_C[9]);      // 1/3!
+    qe = fma(qe, r2, EXP_C[10]);     // 1/2!
+    const double q = fma(r, qo, qe);
+    double p = fma(r2, q, r) + 1.0;
     // p in [0.70, 1.42]; scale by 2^n through the exponent field (result stays normal for |a| <= 708)
     return __hiloint2double(__double2hiint(p) + n * 1048576, __double2loint(p));
 }

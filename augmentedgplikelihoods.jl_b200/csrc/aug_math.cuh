@@ -26,7 +26,8 @@ struct PGTerms {
 // evaluated at min(c, 708): beyond that e < 1e-307 changes nothing in double precision); inv_c = 1/c is
 // only read when c >= 1/16 and the c < 1/16 series is a select.
 // SAFE = true: the same formulas with IEEE sqrt / div and the libdevice exp / log1p for any input.
-template <bool NEED_LCH, bool SAFE>
+// SERIES = false drops the c < 1/16 branch: for callers that route such c to the SAFE instantiation themselves.
+template <bool NEED_LCH, bool SAFE, bool SERIES = true>
 __device__ __forceinline__ PGTerms pg_terms_ic(double c, double inv_c) {
     PGTerms t;
     double e, inv;
@@ -46,7 +47,7 @@ __device__ __forceinline__ PGTerms pg_terms_ic(double c, double inv_c) {
     }
     t.e = e;
     t.inv1pe = inv;
-    if (c < 0.0625) {
+    if (SERIES && c < 0.0625) {
         // series in x = c/2 <= 1/32: truncation error < 1e-17 relative (also covers c == 0 -> 1/4)
         const double x2 = 0.25 * c * c;
         double p = fma(x2, 62.0 / 2835.0, -17.0 / 315.0);

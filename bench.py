@@ -31,6 +31,15 @@ BYTES_CAVI = 41   # R y 1 + mu 8 + var 8, W c 8 + beta 8 + gamma 
 BYTES_GIBBS = 16  # R f 8, W omega 8
 
 
+_OUT = None
+
+
+def emit(line):
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -145,10 +154,16 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner under
+    # NCCL_DEBUG, torchrun notices) is sent to stderr; the result line is written to the saved descriptor.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -228,7 +243,10 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+    time.sleep(0.25)                                 # every rank waits for the sampler's first rows ...
+    if world > 1:
+        dist.barrier()                               # ... and all ranks enter the timed region together
+    torch.cuda.synchronize()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     l0 = ctx.launches()
     t_start = torch.cuda.Event(enable_timing=True)
@@ -354,7 +372,7 @@ def main():
         line["speedup_vs_cpu"] = {"value_vs_all_threads": line["value"] / cpu["value"],
                                   "pg_draws_vs_single_thread": line["parts"]["pg_draws_per_s"] /
                                   cpu["single_thread"]["pg_draws_per_s"]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

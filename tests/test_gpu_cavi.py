@@ -223,3 +223,133 @@ def test_large_n_properties(A):
     gm = gamma[0]
     assert float(gm.max()) <= 0.25 and float(gm.min()) > 0
     assert torch.equal(q.c * q.c, q.c * q.c) and bool(torch.all(torch.abs(beta[0]) == 0.5))
+
+
+@pytest.mark.parametrize("nl,bij,n", [(1, True, 5000), (2, False, 3001), (16, True, 700), (31, True, 333),
+                                      (99, True, 2000), (100, False, 2000), (130, True, 515), (100, True, 16),
+                                      (257, True, 100)])
+def test_categorical_staged_kernel_vs_oracle(A, orc, nl, bij, n):
+    """The bulk-async staged kernel (full 16k-row tiles) + the direct-load kernel on the ragged tail, at class
+    counts that put rows on every alignment; extreme inputs (|m| beyond the straight-line range, saturation of
+    approx_expected_logistic on mu alone, c == 0) are planted inside full tiles."""
+    from gpu_common import dev, host, make_lik, stack
+    kind = CAT_BIJ if bij else CAT
+    K = nl + 1 if bij else nl
+    rng = np.random.default_rng(nl * 1000 + n)
+    kw = dict(nlatent=nl, logtheta=list(rng.normal(0, 0.3, K)))
+    lik = make_lik(kind, (), kw)
+    olik = orc.make_lik(kind, **kw)
+    y, mu, var, f = synth_inputs(kind, n, 11 + nl, (), nl)
+    flat_mu, flat_var = mu.reshape(-1), var.reshape(-1)
+    plant = [(3, 40.0, 2.0), (7, -40.0, 2.0), (11, 400.0, 1.0), (12, -400.0, 1.0), (13, 0.0, 0.0),
+             (20, 1e-200, 1e-300), (21, -760.0, 4.0), (22, 30.0, 3e5)]
+    for pos, m, v in plant:
+        if pos < flat_mu.size:
+            flat_mu[pos], flat_var[pos] = m, v
+    for want_elbo in ([True, False] if bij else [False]):
+        q = A.init_aux_posterior(lik, n)
+        q, beta, gamma, scal = A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)), want_elbo=want_elbo)
+        rc, ostate, obeta, ogamma, oseq, ocomp = orc.cavi_step(olik, y, mu, var, want_scalars=want_elbo)
+        assert rc == 0
+        assert relerr(host(q._s(0)), ostate[0]) < RTOL
+        assert relerr(host(q._s(1)), ostate[1]) < RTOL
+        assert np.array_equal(host(q._s(2)), y)
+        b, g = stack(beta), stack(gamma)
+        assert b.shape == (nl, n)
+        assert relerr(b, obeta, floor=1.0) < RTOL and relerr(g, ogamma) < RTOL
+        if want_elbo:
+            s = host(scal)
+            for k in range(3):
+                assert s[k] == pytest.approx(ocomp[k], rel=RTOL, abs=1e-12), (nl, n, k)
+            # state-only verbs (direct-load kernel) agree with the fused staged kernel
+            assert A.expected_logtilt(lik, q, dev(y), A.Normals(dev(mu), dev(var))) == pytest.approx(s[0], rel=RTOL)
+            assert A.aux_kldivergence(lik, q, dev(y), A.Normals(dev(mu), dev(var))) == pytest.approx(s[1], rel=RTOL)
+
+
+def test_categorical_sum_p_precondition_flag(A):
+    """Σ_j p_ij >= 1 is the reference's ArgumentError (negativemultinomial.jl:17-22): device flag, both kernels."""
+    from gpu_common import dev, make_lik
+    nl, n = 4, 1000
+    lik = make_lik(CAT, (), dict(nlatent=nl))
+    mu = np.full((n, nl), -50.0)          # sigma~(-m) saturates to 1 -> p = 1/nl each -> sum = 1
+    var = np.ones((n, nl))
+    y = np.zeros((n, nl), dtype=np.uint8)
+    q = A.init_aux_posterior(lik, n)
+    ctx = A.default_context()
+    ctx.error_flag()                       # reads and clears
+    A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)), want_elbo=False)
+    assert ctx.error_flag() & 1
+    assert ctx.error_flag() == 0
+    mu[:] = 0.0                            # a healthy call leaves the flag clear
+    A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)), want_elbo=False)
+    assert ctx.error_flag() == 0
+
+
+def test_categorical_large_n_properties(A):
+    """K = 100 at N = 2^18 rows (2.6e7 elements): scalar sums are additive under row concatenation and the
+    class-major outputs of a split call equal the slices of the full call (to the last ulps: rows that fall in
+    the ragged tail of a split go through the direct-load kernel, which divides where the staged one uses rcp)."""
+    from gpu_common import host, make_lik
+    nl, n = 99, (1 << 18) + 5
+    lik = make_lik(CAT_BIJ, (), dict(nlatent=nl))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    mu = torch.randn(n, nl, dtype=torch.float64, device="cuda", generator=g)
+    var = (0.5 + torch.rand(n, nl, dtype=torch.float64, device="cuda", generator=g)) ** 2
+    cls = torch.randint(0, nl + 1, (n,), device="cuda", generator=g)
+    y = torch.zeros(n, nl, dtype=torch.uint8, device="cuda")
+    ok = (cls < nl).nonzero().squeeze(1)
+    y[ok, cls[ok]] = 1
+    q = A.init_aux_posterior(lik, n)
+    q, beta, gamma, scal = A.cavi_step_(q, lik, y, A.Normals(mu, var))
+    tot = host(scal).copy()
+    h = 16 * 5000 + 3
+    acc = np.zeros(3)
+    for sl in (slice(0, h), slice(h, n)):
+        m = sl.stop - sl.start
+        qq = A.init_aux_posterior(lik, m)
+        qq, b2, g2, sc = A.cavi_step_(qq, lik, y[sl].contiguous(), A.Normals(mu[sl].contiguous(), var[sl].contiguous()))
+        acc += host(sc)[:3]
+        assert relerr(host(torch.stack(list(b2))), host(torch.stack(list(beta))[:, sl]), floor=1.0) < 1e-14
+        assert relerr(host(torch.stack(list(g2))), host(torch.stack(list(gamma))[:, sl])) < 1e-14
+    for k in range(3):
+        assert tot[k] == pytest.approx(acc[k], rel=1e-12)
+    G = torch.stack(list(gamma))
+    assert float(G.min()) >= 0 and float(G.max()) <= 0.5 * 1.01
+
+
+@pytest.mark.parametrize("name,kind,params,kw", CASES[:7])
+def test_extreme_inputs_take_the_any_input_instantiation(A, orc, name, kind, params, kw):
+    """Inputs outside the straight-line fast-math range (huge / tiny moments, saturation of
+    approx_expected_logistic, exp underflow of (−m−c)/2) planted in a large batch: same results as the oracle."""
+    from gpu_common import dev, host, make_lik, stack
+    n = 20000
+    lik = make_lik(kind, params, kw)
+    olik = orc.make_lik(kind, *params, **kw)
+    y, mu, var, f = synth_inputs(kind, n, 77, params, kw.get("nlatent", 1))
+    ext = [(700.0, 4e5), (-700.0, 4e5), (650.0, 1.0), (-650.0, 1.0), (0.0, 0.0), (1e-170, 1e-320), (40.0, 1.0),
+           (-40.0, 1.0), (-760.0, 4.0), (760.0, 4.0), (30.0, 3e5), (1e150, 1.0), (3.0, 1e300)]
+    mm, vv = (mu[1], var[1]) if kind == HETERO else (mu, var)
+    for k, (m, v) in enumerate(ext):
+        mm[37 + 211 * k], vv[37 + 211 * k] = m, v
+    if kind in (LAPLACE, STUDENTT):          # keep the residual (m − y) extreme too
+        for k, (m, v) in enumerate(ext):
+            y[37 + 211 * k] = 0.0
+    q = A.init_aux_posterior(lik, n)
+    q, beta, gamma, scal = A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)))
+    rc, ostate, obeta, ogamma, oseq, ocomp = orc.cavi_step(olik, y, mu, var)
+    assert rc == 0
+    with np.errstate(all="ignore"):
+        for i in range(3):
+            if ostate[i] is not None and q._s(i) is not None:
+                assert relerr(host(q._s(i)), ostate[i]) < RTOL, (name, i)
+        b, g = stack(beta), stack(gamma)
+        fin = np.isfinite(obeta)
+        assert np.array_equal(np.isfinite(b), fin)
+        assert relerr(b[fin], obeta[fin], floor=1.0) < RTOL
+        fin = np.isfinite(ogamma)
+        assert np.array_equal(np.isfinite(g), fin)
+        assert relerr(g[fin], ogamma[fin]) < RTOL
+        s = host(scal)
+        for k in range(3):
+            if np.isfinite(ocomp[k]):
+                assert s[k] == pytest.approx(ocomp[k], rel=1e-11), (name, k)

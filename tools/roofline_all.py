@@ -35,9 +35,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100_000_000)
     ap.add_argument("--ncat", type=int, default=10_000_000)
+    ap.add_argument("--only", type=str, default="", help="comma-separated case names (for ncu captures)")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--clocks", action="store_true", help="sample nvidia-smi SM clocks / throttle reasons during the run")
     args = ap.parse_args()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    sampler = None
+    if args.clocks:
+        from bench import ClockSampler
+        sampler = ClockSampler(0)
+        sampler.start()
     ctx = A.Context(0)
     A.set_default_context(ctx)
     st = ctx.stream
@@ -58,7 +66,10 @@ def main():
         ("hetero", A.HeteroscedasticGaussianLikelihood(5.0)),
         ("cat_bij_K100", A.CategoricalLikelihood(100)), ("cat_K100", A.CategoricalLikelihood(100, bijective=False)),
     ]
+    only = [s for s in args.only.split(",") if s]
     for name, lik in cases:
+        if only and name not in only:
+            continue
         cat = name.startswith("cat")
         n = args.ncat if cat else args.n
         nl = lik.nlatent
@@ -88,8 +99,9 @@ def main():
         gamma = torch.empty((nl, n), dtype=torch.float64, device=dev)
         scal = torch.zeros(8, dtype=torch.float64, device=dev)
         want = name != "cat_K100"
-        t_elbo = timeit(lambda: A.cavi_step_(q, lik, y, qf, want_elbo=want, out=(beta, gamma, scal if want else None)), st)
-        t_plain = timeit(lambda: A.cavi_step_(q, lik, y, qf, want_elbo=False, out=(beta, gamma, None)), st)
+        t_elbo = timeit(lambda: A.cavi_step_(q, lik, y, qf, want_elbo=want, out=(beta, gamma, scal if want else None)), st,
+                        reps=args.reps)
+        t_plain = timeit(lambda: A.cavi_step_(q, lik, y, qf, want_elbo=False, out=(beta, gamma, None)), st, reps=args.reps)
         del beta, gamma
         Ω = A.init_aux_variables(lik, n)
         t_gibbs = timeit(lambda: A.aux_sample_(Ω, lik, y, f), st, reps=3, warm=1)
@@ -103,6 +115,8 @@ def main():
         print(json.dumps(rows[-1]), flush=True)
         del q, Ω, mu, var, f, y, qf
         torch.cuda.empty_cache()
+    if sampler:
+        print("clocks:", json.dumps(sampler.finish()))
     print("\n| likelihood | N | B/unit | CAVI+ELBO ms | GB/s | of measured | CAVI ms | of measured | Gibbs ms | draws/s |")
     print("|---|---|---|---|---|---|---|---|---|---|")
     for r in rows:
