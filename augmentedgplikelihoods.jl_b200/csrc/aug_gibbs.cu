@@ -7,6 +7,8 @@
 //   SpecialDistributions/polyagamma.jl:112-257, polyagammapoisson.jl:23-27.
 // One thread owns one observation and one Philox stream positioned by the GLOBAL observation
 // index, so the draws are identical for any sharding of the observation axis.
+#include <stdlib.h>
+
 #include "aug_common.cuh"
 #include "aug_math.cuh"
 #include "aug_pg.cuh"
@@ -58,6 +60,158 @@ __global__ void __launch_bounds__(AUG_BLOCK) aux_sample_kernel(const GibbsArgs a
             a.nvar[i] = nn;
             st_stream1(a.omega + i, augp::pg_draw(g, (double)nn + 0.5, false, gg, a.L.pgtab));
         }
+    }
+}
+
+// ------------------------------------------------------------------ PG(1, c): warp-compacted sampler
+// (design notes in aug_pg.cuh).  A warp walks chunks of 32 consecutive elements; a FRESH step starts one round for
+// each lane's element — the exponential-branch lanes (~58%) finish in it — and everything that needs more work
+// (first truncated-IG attempt, rejected attempts, the rare rejected round) is pushed onto the warp's queue; whenever
+// the queue holds >= 32 items a full warp pops them and performs one attempt each.  Queue item: element offset in
+// the shard (32 bits), round | attempt << 8, the round's accept uniform, z.
+struct Pg1Args {
+    int64_t n, i0;
+    uint64_t seed, offset;
+    const double* c;     // tilt per element (aux_sample!: f), or nullptr -> cs
+    double cs;
+    double* out;
+    const double* tab;
+};
+
+// counters exhausted (probability < 1e-14 per draw): finish one draw on a private sequential stream
+__device__ __noinline__ double pg1_finish_sequential(uint64_t seed, uint64_t offset, uint64_t gi, double z, const double* tab) {
+    augr::Philox g;
+    g.init(seed, offset, gi, 3u);
+    const augp::PG1 s = augp::pg1_setup(2.0 * z, tab);
+    return augp::pg1_draw(g, s);
+}
+
+#define PG1_QCAP 64
+#define PG1_MAXCTR 255u
+
+__global__ void __launch_bounds__(AUG_BLOCK, 3) pg1_compact_kernel(const Pg1Args a) {
+    __shared__ __align__(16) double tab_s[AUG_PGTAB_N * AUG_PGTAB_DEG];   // r(z) table: 10 KB, read by every fresh step
+    __shared__ uint32_t qel_s[AUG_BLOCK / 32][PG1_QCAP];
+    __shared__ uint32_t qra_s[AUG_BLOCK / 32][PG1_QCAP];
+    __shared__ uint32_t quacc_s[AUG_BLOCK / 32][PG1_QCAP];
+    __shared__ double qz_s[AUG_BLOCK / 32][PG1_QCAP];
+    for (int t = threadIdx.x; t < AUG_PGTAB_N * AUG_PGTAB_DEG; t += AUG_BLOCK) tab_s[t] = __ldg(a.tab + t);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* qel = qel_s[warp];
+    uint32_t* qra = qra_s[warp];
+    uint32_t* quacc = quacc_s[warp];
+    double* qz = qz_s[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t nchunks = (uint32_t)((a.n + 31) >> 5);                 // n < 2^32 (host-checked)
+    const uint32_t W = gridDim.x * (AUG_BLOCK / 32);
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32);
+    const uint32_t c3 = (uint32_t)a.offset;
+    int qn = 0;
+
+    // push (warp-uniform call): lanes with `want` append their item
+    auto push = [&](bool want, uint32_t el, uint32_t ra, uint32_t uacc, double z) {
+        const uint32_t m = __ballot_sync(0xffffffffu, want);
+        if (want) {
+            const int pos = qn + __popc(m & lt_mask);
+            qel[pos] = el;
+            qra[pos] = ra;
+            quacc[pos] = uacc;
+            qz[pos] = z;
+        }
+        qn += __popc(m);
+        __syncwarp();
+    };
+
+    uint32_t ch = blockIdx.x * (AUG_BLOCK / 32) + warp;
+    // the tilt of the NEXT fresh chunk is loaded one step ahead (its latency hides behind the work steps)
+    auto load_c = [&](uint32_t chunk) {
+        const uint32_t e = (chunk << 5) + lane;
+        return (chunk < nchunks && e < a.n) ? (a.c ? ld_stream1(a.c + e) : a.cs) : 0.0;
+    };
+    double c_next = load_c(ch);
+    for (;;) {
+        if (qn < 32 && ch < nchunks) {
+            // ---- fresh step: round 0 of 32 consecutive elements
+            const uint32_t el = (ch << 5) + lane;
+            const bool valid = el < a.n;
+            const double c = c_next;
+            c_next = load_c(ch + W);
+            const augp::PG1 s = augp::pg1_setup<true>(c, tab_s);
+            const uint64_t gi = (uint64_t)a.i0 + el;
+            const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
+            uint32_t w[4];
+            augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(0u, 0u, 0u), c3, w);
+            const bool exp_branch = augr::u32_mid(w[0]) < s.r;                     // mass_texpon, polyagamma.jl:179-192
+            const double x = fma(-augf::log_(augr::u53_open0(w[1], w[2])), s.invK, augp::T);   // truncated exponential on (t, inf)
+            bool again = valid && !exp_branch;
+            uint32_t ra = 1u << 8;                                                 // round 0, first IG attempt
+            if (valid && exp_branch) {
+                if (augp::pg1_accept(x, w[3], k0, k1, e_lo, e_hi, c3, 0u)) {
+                    st_stream1(a.out + el, 0.25 * x);
+                } else {
+                    again = true;
+                    ra = 1u;                                                       // round 1, attempt 0
+                }
+            }
+            push(again, el, ra, w[3], s.z);
+            ch += W;
+            continue;
+        }
+        if (qn == 0) break;
+        // ---- work step: one attempt for each of the last min(qn, 32) queued items
+        const int cnt = qn < 32 ? qn : 32;
+        const bool active = lane < cnt;
+        uint32_t el = 0, ra = 0, uacc = 0;
+        double z = 0.0;
+        if (active) {
+            const int idx = qn - cnt + lane;
+            el = qel[idx];
+            ra = qra[idx];
+            uacc = quacc[idx];
+            z = qz[idx];
+        }
+        __syncwarp();
+        qn -= cnt;
+        const uint32_t round = ra & 0xffu, attempt = ra >> 8;
+        const uint64_t gi = (uint64_t)a.i0 + el;
+        const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
+        bool again = false;
+        if (active) {
+            double x = -1.0;
+            if (attempt != 0 && attempt < PG1_MAXCTR && round < PG1_MAXCTR) {
+                uint32_t w[4];
+                augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(1u, round, attempt), c3, w);
+                x = augp::trunc_ig_attempt_w(w, z);
+                if (x < 0.0) {
+                    again = true;
+                    ra += 1u << 8;                                                 // next attempt of this round
+                }
+            } else if (attempt == 0 && round < PG1_MAXCTR) {
+                // rare: a new round after a rejected proposal
+                const augp::PG1 s = augp::pg1_setup<true>(2.0 * z, tab_s);
+                uint32_t w[4];
+                augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(0u, round, 0u), c3, w);
+                uacc = w[3];
+                if (augr::u32_mid(w[0]) < s.r) {
+                    x = fma(-augf::log_(augr::u53_open0(w[1], w[2])), s.invK, augp::T);
+                } else {
+                    again = true;
+                    ra |= 1u << 8;                                                 // first IG attempt
+                }
+            } else {
+                st_stream1(a.out + el, pg1_finish_sequential(a.seed, a.offset, gi, z, a.tab));
+            }
+            if (x > 0.0) {
+                if (augp::pg1_accept(x, uacc, k0, k1, e_lo, e_hi, c3, round)) {
+                    st_stream1(a.out + el, 0.25 * x);
+                } else {
+                    again = true;
+                    ra = round + 1u;                                               // new round, attempt 0
+                }
+            }
+        }
+        push(again, el, ra, uacc, z);
     }
 }
 
@@ -146,7 +300,45 @@ int32_t launch_map(aug_ctx* ctx, K kernel, const A& a, int64_t n) {
     return (int32_t)cudaGetLastError();
 }
 
+// PG(1, c) for n elements through the warp-compacted kernel; false if the shape does not fit its item encoding
+bool launch_pg1_compact(aug_ctx* ctx, int64_t n, int64_t i0, uint64_t off, const double* c, double cs, double* out,
+                        int32_t* rc) {
+    static int occ = 0;
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pg1_compact_kernel, AUG_BLOCK, 0) != cudaSuccess || occ < 1)
+            occ = 1;
+    }
+    int64_t grid = (int64_t)ctx->sms * occ;
+    const int64_t nchunks = (n + 31) / 32;
+    const int64_t need = (nchunks + (AUG_BLOCK / 32) - 1) / (AUG_BLOCK / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (n >= ((int64_t)1 << 32) - 64) return false;   // element offsets are queued as 32-bit words
+    Pg1Args a{};
+    a.n = n;
+    a.i0 = i0;
+    a.seed = ctx->seed;
+    a.offset = off;
+    a.c = c;
+    a.cs = cs;
+    a.out = out;
+    a.tab = ctx->pgtab;
+    pg1_compact_kernel<<<(unsigned)grid, AUG_BLOCK, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    *rc = (int32_t)cudaGetLastError();
+    return true;
+}
+
 bool is_cat(int k) { return k == AUG_CAT || k == AUG_CAT_BIJ; }
+
+bool pg1_no_compact() {   // AUGCUDA_NO_COMPACT=1 keeps PG(1) draws on the one-thread-one-draw kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AUGCUDA_NO_COMPACT");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 }  // namespace
 
@@ -178,6 +370,10 @@ int32_t aug_aux_sample_dev(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i0
     if (lik->kind == AUG_HETERO) {
         if (ld < n) return AUG_ERR_BAD_ARG;
         a.g = f + ld;
+    }
+    if (lik->kind == AUG_BERNOULLI && !pg1_no_compact()) {      // PG(1, |f|)  bernoulli.jl:13-15
+        int32_t r2 = 0;
+        if (launch_pg1_compact(c, n, i0, off, f, 0.0, omega, &r2)) return r2;
     }
     switch (lik->kind) {
         case AUG_BERNOULLI: return launch_map(c, aux_sample_kernel<AUG_BERNOULLI>, a, n);
@@ -228,6 +424,10 @@ static int32_t pg_rand_common(aug_ctx* c, int64_t n, int64_t i0, const double* b
     AUG_CUDA(cudaSetDevice(c->device));
     const uint64_t off = c->offset++;
     if (n == 0) return AUG_OK;
+    if (!b && b_is_int && bs == 1.0 && !pg1_no_compact()) {     // all draws are PG(1, c)
+        int32_t r2 = 0;
+        if (launch_pg1_compact(c, n, i0, off, cc, cs, out, &r2)) return r2;
+    }
     const int grid = aug_grid_for(c, (const void*)pg_rand_kernel, n, AUG_BLOCK);
     pg_rand_kernel<<<grid, AUG_BLOCK, 0, c->stream>>>(n, i0, c->seed, off, b, cc, bs, cs, b_is_int, out, c->pgtab);
     c->launches++;

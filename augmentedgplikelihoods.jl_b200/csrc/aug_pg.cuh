@@ -34,6 +34,7 @@ struct PG1 {
 // r(z) = p/(p+q), the mass of the exponential part of the proposal (mass_texpon, polyagamma.jl:179-192).
 // It only depends on z, so it is read from the degree-7 piecewise polynomial table the host builds once per
 // context from the log-domain formula (aug_ctx.cu: build_pg_table; |error| < 1e-15); r < 1e-40 beyond z = 20.
+template <bool TAB_SHARED = false>
 __device__ __forceinline__ PG1 pg1_setup(double c, const double* __restrict__ tab) {
     PG1 s;
     s.z = 0.5 * fabs(c);
@@ -46,7 +47,9 @@ __device__ __forceinline__ PG1 pg1_setup(double c, const double* __restrict__ ta
         const int k = (int)u;
         const double x = fma(2.0, u - (double)k, -1.0);
         const double2* row = reinterpret_cast<const double2*>(tab + k * AUG_PGTAB_DEG);
-        const double2 a = __ldg(row), b = __ldg(row + 1), cc = __ldg(row + 2), d = __ldg(row + 3);
+        double2 a, b, cc, d;
+        if (TAB_SHARED) { a = row[0]; b = row[1]; cc = row[2]; d = row[3]; }
+        else { a = __ldg(row); b = __ldg(row + 1); cc = __ldg(row + 2); d = __ldg(row + 3); }
         double p = fma(a.x, x, a.y);
         p = fma(p, x, b.x);
         p = fma(p, x, b.y);
@@ -173,6 +176,77 @@ __device__ __forceinline__ double pg_draw(augr::Philox& g, double b, bool b_is_i
         return acc;
     }
     return pg_gamma_conv(g, b, c);
+}
+
+// ------------------------------------------------------------------ PG(1, c), warp-compacted (aug_gibbs.cu: pg1_compact_kernel)
+// The per-thread loop above diverges: ncu on aux_sample_kernel<BERNOULLI> counted 9.6 active lanes per issued
+// instruction (the cheap exponential proposal, 58% of draws, waits for the truncated-inverse-Gaussian rejection loop
+// of its neighbours).  The compacted kernel instead runs every draw as a sequence of uniform STEPS and keeps the
+// unfinished ones in a per-warp shared-memory queue, so that each step is executed by (up to) 32 lanes that all need
+// it.  A step owns one Philox block keyed by (element, round, attempt): the law of the output and its dependence on
+// (seed, offset, global element index) only are unchanged, the order in which a warp works is irrelevant.
+//   block A (tag 0; round):          w0 branch selector, (w1,w2) the Exp(1) of the exponential proposal, w3 the
+//                                    uniform of the final alternating-series test;
+//   block B (tag 1; round, attempt): one truncated-IG proposal attempt: (w0,w1) Exp(1) / radius, w2, w3 decisions;
+//   block C (tag 2; round):          32 more bits for the series uniform in the 0.6% of rounds the squeeze leaves open.
+__device__ __forceinline__ uint32_t pg1_ctr(uint32_t tag, uint32_t round, uint32_t attempt) {
+    return (tag << 28) | (round << 14) | attempt;
+}
+
+// final accept/reject of a proposal x: alternating series of rho_n = a_n/a_0 = (2n+1) exp(q n(n+1)) with
+// q = -pi^2 x/2 for x > t, -2/x for x <= t   (polyagamma.jl:243-255, 167-177)
+__device__ __forceinline__ bool pg1_accept(double x, uint32_t uacc, uint32_t k0, uint32_t k1, uint32_t e_lo,
+                                           uint32_t e_hi, uint32_t c3, uint32_t round) {
+    // squeeze on rho_1(x) = 3 exp(-pi^2 x) (x > t) resp. 3 exp(-4/x) (x <= t), which peaks at x = t (0.0058):
+    //   x in [0.5, 0.8]: rho_1 <= 0.0058 -> accept if u <= 0.994;   x in [0.4, 1.0]: rho_1 <= 0.00111 -> u <= 0.9988;
+    //   elsewhere: rho_1 <= 1.6e-4 -> u <= 0.9998.   (u = (uacc + 0.5) 2^-32; compares are on the high word of x > 0)
+    const int xh = __double2hiint(x);
+    const bool mid = xh >= 0x3fe00000 && xh < 0x3fe99999;      // [0.5, 0.8)
+    const bool wide = xh >= 0x3fd99999 && xh < 0x3ff00000;     // [0.39999, 1.0)
+    const uint32_t thr = mid ? 4269197491u : (wide ? 4289813334u : 4294108302u);
+    if (uacc <= thr) return true;
+    double u = augr::u32_mid(uacc);
+    const double q = x > T ? -0.5 * PI * PI * x : -2.0 / x;
+    uint32_t w[4];
+    augr::philox4x32_10(k0, k1, e_lo, e_hi, pg1_ctr(2u, round, 0u), c3, w);
+    u += ((double)w[0] - 2147483648.0) * 0x1.0p-64;   // refine the uniform to 64 bits
+    double sum = 1.0;
+    for (int n = 1;; ++n) {
+        const double rho = (double)(2 * n + 1) * exp(q * (double)(n * (n + 1)));
+        if (n & 1) {
+            sum -= rho;
+            if (u <= sum) return true;
+        } else {
+            sum += rho;
+            if (u > sum) return false;
+        }
+    }
+}
+
+// one proposal attempt from the truncated inverse Gaussian on (0, t] out of one Philox block; < 0: rejected
+__device__ __forceinline__ double trunc_ig_attempt_w(const uint32_t (&w)[4], double z) {
+    if (z < 1.0 / T) {
+        const double E = -augf::log_(augr::u53_open0(w[0], w[1]));
+        const double a1 = 0.5 * T * E * E;
+        // accept E with probability exp(-a1): evaluated without a branch (the squeezes 1-a <= e^-a <= 1-a+a^2/2
+        // leave ~5% of the lanes undecided, i.e. nearly every warp would run the exp anyway, at low occupancy)
+        if (augr::u32_mid(w[2]) > augf::exp_(-fmin(a1, 700.0))) return -1.0;
+        const double d = fma(T, E, 1.0);
+        const double x = T * augf::rcp(d * d);
+        const double a2 = 0.5 * z * z * x;
+        const double u2 = augr::u32_mid(w[3]);
+        if (u2 > 1.0 - a2) {
+            if (u2 > fma(0.5 * a2, a2, 1.0 - a2) || u2 > augf::exp_(-a2)) return -1.0;
+        }
+        return x;
+    }
+    const double mu = 1.0 / z;
+    const double rad2 = -2.0 * augf::log_(augr::u53_open0(w[0], w[1]));
+    const double cs = cospi(2.0 * augr::u32_mid(w[2]));
+    const double muy = mu * rad2 * cs * cs;                      // mu * N(0,1)^2
+    double x = mu + 0.5 * mu * muy - 0.5 * mu * sqrt(fma(muy, muy, 4.0 * muy));
+    if (augr::u32_mid(w[3]) * (mu + x) > mu) x = mu * mu / x;
+    return x > T ? -1.0 : x;
 }
 
 }  // namespace augp

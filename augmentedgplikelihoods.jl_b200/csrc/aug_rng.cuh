@@ -12,6 +12,28 @@
 
 namespace augr {
 
+// One Philox4x32-10 block: 128 random bits as a pure function of (key, counter).
+__device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                                              uint32_t c3, uint32_t (&w)[4]) {
+    uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+        const uint32_t y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
+        x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    w[0] = x0; w[1] = x1; w[2] = x2; w[3] = x3;
+}
+
+// uniforms from raw words: 53-bit (0,1] for values that are returned, 32-bit mid-point (0,1) for decisions
+__device__ __forceinline__ double u53_open0(uint32_t lo, uint32_t hi) {
+    return (double)(((((uint64_t)hi << 32) | lo) >> 11) + 1ull) * 0x1.0p-53;
+}
+__device__ __forceinline__ double u32_mid(uint32_t w) { return fma((double)w, 0x1.0p-32, 0x1.0p-33); }
+
 struct Philox {
     uint32_t k0, k1;          // key   = seed
     uint32_t c0, c1, c2, c3;  // counter = (element lo, element hi, block counter, verb offset)
@@ -31,17 +53,7 @@ struct Philox {
         has_spare = false;
     }
     __device__ __forceinline__ void refill() {
-        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, a = k0, b = k1;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
-            const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-            const uint32_t y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
-            x0 = y0; x1 = y1; x2 = y2; x3 = y3;
-            a += 0x9E3779B9u;
-            b += 0xBB67AE85u;
-        }
-        buf[0] = x0; buf[1] = x1; buf[2] = x2; buf[3] = x3;
+        philox4x32_10(k0, k1, c0, c1, c2, c3, buf);
         c2++;
         have = 4;
     }

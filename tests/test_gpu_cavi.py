@@ -334,22 +334,31 @@ def test_extreme_inputs_take_the_any_input_instantiation(A, orc, name, kind, par
     if kind in (LAPLACE, STUDENTT):          # keep the residual (m − y) extreme too
         for k, (m, v) in enumerate(ext):
             y[37 + 211 * k] = 0.0
-    q = A.init_aux_posterior(lik, n)
-    q, beta, gamma, scal = A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)))
-    rc, ostate, obeta, ogamma, oseq, ocomp = orc.cavi_step(olik, y, mu, var)
-    assert rc == 0
-    with np.errstate(all="ignore"):
-        for i in range(3):
-            if ostate[i] is not None and q._s(i) is not None:
-                assert relerr(host(q._s(i)), ostate[i]) < RTOL, (name, i)
-        b, g = stack(beta), stack(gamma)
-        fin = np.isfinite(obeta)
-        assert np.array_equal(np.isfinite(b), fin)
-        assert relerr(b[fin], obeta[fin], floor=1.0) < RTOL
-        fin = np.isfinite(ogamma)
-        assert np.array_equal(np.isfinite(g), fin)
-        assert relerr(g[fin], ogamma[fin]) < RTOL
-        s = host(scal)
-        for k in range(3):
-            if np.isfinite(ocomp[k]):
-                assert s[k] == pytest.approx(ocomp[k], rel=1e-11), (name, k)
+    for with_huge in (True, False):
+        if not with_huge:
+            # the two 1e150-scale plants make the ELBO sums cancel at the 1e149 level (any summation order loses
+            # everything else): the scalar comparison is made without them
+            for k in (11, 12):
+                mm[37 + 211 * k], vv[37 + 211 * k] = 0.5, 1.0
+        q = A.init_aux_posterior(lik, n)
+        q, beta, gamma, scal = A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)))
+        rc, ostate, obeta, ogamma, oseq, ocomp = orc.cavi_step(olik, y, mu, var)
+        assert rc == 0
+        with np.errstate(all="ignore"):
+            for i in range(3):
+                if ostate[i] is not None and q._s(i) is not None:
+                    assert relerr(host(q._s(i)), ostate[i]) < RTOL, (name, i)
+            b, g = stack(beta), stack(gamma)
+            fin = np.isfinite(obeta)
+            assert np.array_equal(np.isfinite(b), fin)
+            assert relerr(b[fin], obeta[fin], floor=1.0) < RTOL
+            fin = np.isfinite(ogamma)
+            assert np.array_equal(np.isfinite(g), fin)
+            assert relerr(g[fin], ogamma[fin]) < RTOL
+            if not with_huge:
+                s = host(scal)
+                for k in range(3):
+                    if np.isfinite(ocomp[k]):
+                        assert s[k] == pytest.approx(ocomp[k], rel=1e-11), (name, k)
+                    else:       # e.g. Laplace/StudentT with a zero residual and zero variance: 1/0 in the reference too
+                        assert not np.isfinite(s[k]), (name, k)
