@@ -512,6 +512,350 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_sample_kernel(const CatSampleAr
     }
 }
 
+// ------------------------------------------------------------------ Gibbs for CAT, warp-compacted
+// ncu on cat_sample_kernel (profiles/r1d): 640 issue slots per (obs, class) element at 20.8 active lanes of 32 —
+// ~97% of the elements have b = y + n = 0 (omega = 0) but their warps wait for the few lanes that run Devroye's
+// PG(1) sampler; libdevice exp / IEEE division in logistic and in the Poisson inversion; an integer division per
+// element.  Here the element pass is straight-line (fast exp / rcp, Poisson by an unrolled chop-down on a single
+// 53-bit uniform) and every element that needs a Polya-Gamma draw is QUEUED per warp:
+//   F: fresh PG(1) rounds (b == 1, or a new round after a rejected proposal)   -> pg1 round start
+//   G: truncated-inverse-Gaussian proposal attempts                            -> one attempt per step
+//   B: b >= 2 (about 1e-3 of the elements)                                     -> Gamma convolution
+// and a queue is worked on by a full warp as soon as it holds 32 items (see aug_pg.cuh for the PG(1) step machine,
+// which is the one of pg1_compact_kernel).  Streams are keyed by the GLOBAL row / element index.
+struct CatGibbsArgs {
+    int64_t n, i0, ntiles;
+    int nl, R, E, di, dj;        // di, dj = AUG_BLOCK / nl, AUG_BLOCK % nl
+    uint64_t seed, offset;
+    const uint8_t* y;
+    const double* f;
+    double* omega;
+    int64_t* nvar;
+    unsigned int* dflag;
+    int bulk_ok;                 // f and y are 16-byte aligned and R * nl is a multiple of 16
+    LikConst L;
+};
+
+#define CG_STAGES 3
+#define CG_QCAP 96
+#define CG_BCAP 64
+
+// logistic(x) with the LogExpFunctions saturation (categorical.jl:23), straight-line
+__device__ __forceinline__ double logistic_fast(double x) {
+    const double ax = fmin(fabs(x), 708.0);
+    const double e = augf::exp_(-ax);
+    const double r = augf::rcp(1.0 + e);
+    const double v = x >= 0.0 ? r : e * r;
+    return x < augm::LOGISTIC_LO ? 0.0 : (x > augm::LOGISTIC_HI ? 1.0 : v);
+}
+
+__device__ __noinline__ int64_t poisson_slow(uint64_t seed, uint64_t offset, uint64_t gi, double lam) {
+    augr::Philox g;
+    g.init(seed, offset, gi, 4u);
+    return augr::poisson_rand(g, lam);
+}
+__device__ __noinline__ double pg_slow(uint64_t seed, uint64_t offset, uint64_t gi, double b, double c, const double* tab) {
+    augr::Philox g;
+    g.init(seed, offset, gi, 6u);
+    return augp::pg_draw(g, b, true, c, tab);
+}
+__device__ __noinline__ double pg1_finish_sequential_cat(uint64_t seed, uint64_t offset, uint64_t gi, double z, const double* tab) {
+    augr::Philox g;
+    g.init(seed, offset, gi, 3u);
+    const augp::PG1 s = augp::pg1_setup(2.0 * z, tab);
+    return augp::pg1_draw(g, s);
+}
+
+__global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsArgs a) {
+    extern __shared__ __align__(128) unsigned char cg_smem[];
+    const int nl = a.nl, R = a.R, E = a.E;
+    // ring of CG_STAGES input tiles (f: E doubles, y: E bytes), filled by cp.async.bulk two tiles ahead
+    unsigned char* ring = cg_smem;
+    const int off_y = E * 8, stage_bytes = (E * 9 + 127) & ~127;
+    double* tab_s = reinterpret_cast<double*>(ring + CG_STAGES * stage_bytes);   // r(z) table
+    double* Pb = tab_s + AUG_PGTAB_N * AUG_PGTAB_DEG;                        // [2][E]   p_ij of two tiles in flight
+    double* rsc = Pb + 2 * E;                                                // [2][R]   Exp(1)/p0 per row
+    double* qz_all = rsc + 2 * R;                                            // per warp: F and G items
+    uint32_t* qw_all = reinterpret_cast<uint32_t*>(qz_all + (AUG_BLOCK / 32) * 2 * CG_QCAP);
+    uint64_t* full = reinterpret_cast<uint64_t*>(qw_all + (AUG_BLOCK / 32) * (5 * CG_QCAP + 2 * CG_BCAP));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* fz = qz_all + warp * 2 * CG_QCAP;
+    double* gz = fz + CG_QCAP;
+    uint32_t* fel = qw_all + warp * (5 * CG_QCAP + 2 * CG_BCAP);
+    uint32_t* fra = fel + CG_QCAP;
+    uint32_t* gel = fra + CG_QCAP;
+    uint32_t* gra = gel + CG_QCAP;
+    uint32_t* gua = gra + CG_QCAP;
+    uint32_t* bel = gua + CG_QCAP;
+    uint32_t* bbv = bel + CG_BCAP;
+    if (tid == 0) {
+        for (int s = 0; s < CG_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // a tile is bulk-copied when it is a full one (its y span is then a multiple of 16 bytes at a 16-byte aligned
+    // offset); the ragged last tile is loaded by the threads themselves
+    auto issue = [&](int64_t t, int s) {
+        if (t >= a.ntiles || (t + 1) * R > a.n || !a.bulk_ok) return;
+        unsigned char* st = ring + (size_t)s * stage_bytes;
+        const int64_t o = t * E;
+        mbar_expect_tx(&full[s], (uint32_t)E * 9u);
+        bulk_g2s(st, a.f + o, (uint32_t)E * 8u, &full[s]);
+        bulk_g2s(st + off_y, a.y + o, (uint32_t)E, &full[s]);
+    };
+    for (int t = tid; t < AUG_PGTAB_N * AUG_PGTAB_DEG; t += AUG_BLOCK) tab_s[t] = __ldg(a.L.pgtab + t);
+    __syncthreads();
+    if (tid == 0) {
+        issue((int64_t)blockIdx.x, 0);
+        issue((int64_t)blockIdx.x + gridDim.x, 1);
+    }
+
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32);
+    const uint32_t c3 = (uint32_t)a.offset;
+    const uint64_t e_base = (uint64_t)a.i0 * (uint64_t)nl;                   // global index of the shard's first element
+    int nf = 0, ng = 0, nb = 0;
+
+    auto push_f = [&](bool want, uint32_t el, uint32_t ra, double z) {
+        const uint32_t m = __ballot_sync(0xffffffffu, want);
+        if (want) {
+            const int pos = nf + __popc(m & lt_mask);
+            fel[pos] = el; fra[pos] = ra; fz[pos] = z;
+        }
+        nf += __popc(m);
+    };
+    auto push_g = [&](bool want, uint32_t el, uint32_t ra, uint32_t ua, double z) {
+        const uint32_t m = __ballot_sync(0xffffffffu, want);
+        if (want) {
+            const int pos = ng + __popc(m & lt_mask);
+            gel[pos] = el; gra[pos] = ra; gua[pos] = ua; gz[pos] = z;
+        }
+        ng += __popc(m);
+    };
+    // accept/reject of a proposal x of (el, round); on rejection the element starts a new round
+    auto finish = [&](bool have_x, double x, uint32_t el, uint32_t round, uint32_t ua, double z, uint32_t e_lo, uint32_t e_hi) {
+        bool newround = false;
+        if (have_x) {
+            if (augp::pg1_accept(x, ua, k0, k1, e_lo, e_hi, c3, round)) st_stream1(a.omega + el, 0.25 * x);
+            else newround = true;
+        }
+        push_f(newround, el, round + 1u, z);
+    };
+
+    const int i_first = tid / nl, j_first = tid - i_first * nl;
+    const int l16 = lane & 15;
+    // state of the element pass (phase C) of the current tile; e0 >= Et: the next tile has to be set up first
+    int64_t tile = (int64_t)blockIdx.x - gridDim.x;
+    int buf = 1, Et = 0, e0 = 0, ci = 0, cj = 0;
+    int stg = CG_STAGES - 1;          // stage of the current tile
+    uint32_t par = 1;                 // its mbarrier phase parity (flips when stg wraps to 0)
+    uint32_t base = 0;
+    const double* P = Pb;
+    const double* rs = rsc;
+    const double* Fs = nullptr;       // staged f and y of the current tile
+    const unsigned char* Ys = nullptr;
+    bool drain = false;
+    for (;;) {
+        if (nf >= 32 || (drain && nf > 0)) {
+            // ---- F: round start for the last min(nf, 32) items
+            const int cnt = nf < 32 ? nf : 32;
+            const bool active = lane < cnt;
+            uint32_t el = 0, round = 0;
+            double z = 0.0;
+            if (active) { const int idx = nf - cnt + lane; el = fel[idx]; round = fra[idx]; z = fz[idx]; }
+            __syncwarp();
+            nf -= cnt;
+            const uint64_t gi = e_base + el;
+            const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
+            bool have_x = false, to_g = false;
+            double x = 0.0;
+            uint32_t ua = 0;
+            if (active) {
+                if (round < 255u) {
+                    const augp::PG1 s = augp::pg1_setup<true>(2.0 * z, tab_s);
+                    uint32_t w[4];
+                    augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(0u, round, 0u), c3, w);
+                    ua = w[3];
+                    x = fma(-augf::log_(augr::u53_open0(w[1], w[2])), s.invK, augp::T);
+                    have_x = augr::u32_mid(w[0]) < s.r;
+                    to_g = !have_x;
+                } else {
+                    st_stream1(a.omega + el, pg1_finish_sequential_cat(a.seed, a.offset, gi, z, a.L.pgtab));
+                }
+            }
+            push_g(to_g, el, round | (1u << 8), ua, z);
+            finish(have_x, x, el, round, ua, z, e_lo, e_hi);
+            __syncwarp();
+            continue;
+        }
+        if (ng >= 32 || (drain && ng > 0)) {
+            // ---- G: one truncated-IG attempt for the last min(ng, 32) items
+            const int cnt = ng < 32 ? ng : 32;
+            const bool active = lane < cnt;
+            uint32_t el = 0, ra = 0, ua = 0;
+            double z = 0.0;
+            if (active) { const int idx = ng - cnt + lane; el = gel[idx]; ra = gra[idx]; ua = gua[idx]; z = gz[idx]; }
+            __syncwarp();
+            ng -= cnt;
+            const uint32_t round = ra & 0xffu, attempt = ra >> 8;
+            const uint64_t gi = e_base + el;
+            const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
+            bool have_x = false, again = false;
+            double x = 0.0;
+            if (active) {
+                if (attempt < 255u) {
+                    uint32_t w[4];
+                    augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(1u, round, attempt), c3, w);
+                    x = augp::trunc_ig_attempt_w(w, z);
+                    have_x = x > 0.0;
+                    again = !have_x;
+                } else {
+                    st_stream1(a.omega + el, pg1_finish_sequential_cat(a.seed, a.offset, gi, z, a.L.pgtab));
+                }
+            }
+            push_g(again, el, ra + (1u << 8), ua, z);
+            finish(have_x, x, el, round, ua, z, e_lo, e_hi);
+            __syncwarp();
+            continue;
+        }
+        if (nb >= 32 || (drain && nb > 0)) {
+            // ---- B: PG(b >= 2, c) by the Gamma convolution (rare)
+            const int cnt = nb < 32 ? nb : 32;
+            if (lane < cnt) {
+                const int idx = nb - cnt + lane;
+                const uint32_t el = bel[idx];
+                st_stream1(a.omega + el, pg_slow(a.seed, a.offset, e_base + el, (double)bbv[idx], a.f[el], a.L.pgtab));
+            }
+            __syncwarp();
+            nb -= cnt;
+            continue;
+        }
+        if (drain) break;
+        if (e0 >= Et) {
+            // ---- next tile of this CTA (every warp takes this branch once per tile, in the same order)
+            tile += gridDim.x;
+            if (tile >= a.ntiles) { drain = true; continue; }
+            buf ^= 1;
+            if (++stg == CG_STAGES) { stg = 0; par ^= 1u; }
+            const int64_t row0 = tile * R;
+            const int rows = (int)min((int64_t)R, a.n - row0);
+            Et = rows * nl;
+            base = (uint32_t)(row0 * nl);                                        // n * nl < 2^32 (host-checked)
+            double* Pw = Pb + buf * E;
+            double* rw = rsc + buf * R;
+            double* Fw = reinterpret_cast<double*>(ring + (size_t)stg * stage_bytes);
+            unsigned char* Yw = ring + (size_t)stg * stage_bytes + off_y;
+            const bool bulk = rows == R && a.bulk_ok;
+            if (bulk) {
+                mbar_wait(&full[stg], par);
+            } else {
+                for (int e = tid; e < Et; e += AUG_BLOCK) {
+                    Fw[e] = ld_stream1(a.f + base + e);
+                    Yw[e] = __ldg(a.y + base + e);
+                }
+            }
+            // phase A: p_ij = theta_j logistic(f_ij) / sum(theta)   categorical.jl:72-78
+            {
+                int j = j_first;
+                for (int e = tid; e < Et; e += AUG_BLOCK) {
+                    Pw[e] = __ldg(a.L.theta + j) * logistic_fast(Fw[e]);
+                    j += a.dj;
+                    if (j >= nl) j -= nl;
+                }
+            }
+            __syncthreads();
+            // every warp is past the element pass of the previous tile: its stage can take the tile after next
+            if (tid == 0) issue(tile + 2 * (int64_t)gridDim.x, stg == 0 ? CG_STAGES - 1 : stg - 1);
+            // phase B: 16 lanes per row: p0 = 1 - sum_j p_ij, tau/(1-p0) = Exp(1)/p0   negativemultinomial.jl:35-45
+            for (int r0 = 2 * warp; r0 < rows; r0 += 2 * (AUG_BLOCK / 32)) {       // warp-uniform bound (shuffles)
+                const int r = r0 + (lane >> 4);
+                const bool rv = r < rows;
+                const double* Pr = Pw + r * nl;
+                double sp = 0.0;
+                if (rv) for (int jj = l16; jj < nl; jj += 16) sp += Pr[jj];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+                if (rv && l16 == 0) {
+                    const double p0 = 1.0 - sp;
+                    if (!(sp < 1.0)) atomicOr(a.dflag, 1u);                      // ctor precondition :17-22
+                    const uint64_t gr = (uint64_t)(a.i0 + row0 + r);
+                    uint32_t w[4];
+                    augr::philox4x32_10(k0, k1, (uint32_t)gr, (uint32_t)(gr >> 32), 7u << 28, c3, w);
+                    rw[r] = -augf::log_(augr::u53_open0(w[0], w[1])) / p0;
+                }
+            }
+            __syncthreads();
+            // (no third barrier: the tile after this one writes the OTHER buffer, and nobody reaches it before
+            //  every warp has passed the barrier after its phase A, i.e. has finished the element pass of this one)
+            P = Pw;
+            rs = rw;
+            Fs = Fw;
+            Ys = Yw;
+            e0 = 0;
+            ci = i_first;
+            cj = j_first;
+            continue;
+        }
+        // ---- element pass step (phase C): n_ij ~ Poisson(p_ij tau/(1-p0)), b = y + n; queue what needs a PG draw
+        {
+            const int e = e0 + tid;
+            const bool valid = e < Et;
+            const uint32_t el = base + (uint32_t)e;
+            double lam = 0.0;
+            int yv = 0;
+            if (valid) {
+                lam = P[e] * rs[ci];
+                yv = (int)Ys[e];
+            }
+            const uint64_t gi = e_base + el;
+            uint32_t w[4];
+            augr::philox4x32_10(k0, k1, (uint32_t)gi, (uint32_t)(gi >> 32), 5u << 28, c3, w);
+            // inversion by chop-down from 0 on one 53-bit uniform: 4 terms straight-line, the rest in a loop
+            int64_t nn = 0;
+            if (valid && lam > 0.0) {
+                if (lam < 12.0) {
+                    double u = (double)(((((uint64_t)w[1] << 32) | w[0]) >> 11)) * 0x1.0p-53;
+                    double p = augf::exp_(-lam);
+                    int k = 0;
+                    if (u > p) {                                                 // P = 1 - exp(-lam): a few percent of the lanes
+                        while (u > p && k < 200) {
+                            u -= p;
+                            ++k;
+                            p *= lam / (double)k;
+                        }
+                        if (k >= 200) k = (int)poisson_slow(a.seed, a.offset, gi, lam);   // round-off tail
+                    }
+                    nn = k;
+                } else {
+                    nn = poisson_slow(a.seed, a.offset, gi, lam);
+                }
+            }
+            const int b = yv + (int)min(nn, (int64_t)1 << 30);
+            if (valid) {
+                a.nvar[el] = nn;
+                if (b == 0) st_stream1(a.omega + el, 0.0);
+            }
+            const bool needs = valid && b >= 1;
+            const double z = needs ? 0.5 * fabs(Fs[e]) : 0.0;
+            push_f(needs && b == 1, el, 0u, z);
+            {
+                const bool wb = needs && b >= 2;
+                const uint32_t m = __ballot_sync(0xffffffffu, wb);
+                if (wb) {
+                    const int pos = nb + __popc(m & lt_mask);
+                    bel[pos] = el;
+                    bbv[pos] = (uint32_t)b;
+                }
+                nb += __popc(m);
+            }
+            __syncwarp();
+            e0 += AUG_BLOCK;
+            ci += a.di;
+            cj += a.dj;
+            if (cj >= nl) { cj -= nl; ++ci; }
+        }
+    }
+}
+
 // auglik_potential / auglik_precision (sampled), transposed: categorical.jl:112-119
 struct CatPotArgs {
     int64_t n;
@@ -705,6 +1049,48 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
 int32_t aug_cat_sample(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0, const void* y, const double* f,
                        double* omega, int64_t* nvar, uint64_t offset) {
     if (!y || !f || !omega || !nvar) return AUG_ERR_BAD_ARG;
+    const int nl = lik->nlatent;
+    // the warp-compacted kernel queues 32-bit element offsets and keeps two tiles of p in shared memory
+    if (!cat_no_tma() && n * (int64_t)nl < ((int64_t)1 << 32) - 4096 && nl <= 4096) {
+        CatGibbsArgs g{};
+        g.n = n;
+        g.i0 = i0;
+        g.nl = nl;
+        int R = 1792 / nl;
+        if (R < 1) R = 1;
+        if (R >= 16) R &= ~15;
+        if (R > 1024) R = 1024;
+        g.R = R;
+        g.bulk_ok = (((int64_t)R * nl) % 16 == 0) && aug_aligned16(y) && aug_aligned16(f);
+        g.E = R * nl;
+        g.ntiles = (n + R - 1) / R;
+        g.di = AUG_BLOCK / nl;
+        g.dj = AUG_BLOCK % nl;
+        g.seed = ctx->seed;
+        g.offset = offset;
+        g.y = (const uint8_t*)y;
+        g.f = f;
+        g.omega = omega;
+        g.nvar = nvar;
+        g.dflag = ctx->dflag;
+        int32_t rc = aug_lik_const(ctx, lik, &g.L, false, true);
+        if (rc) return rc;
+        const size_t smem = (size_t)CG_STAGES * (((size_t)g.E * 9 + 127) & ~(size_t)127) +
+                            sizeof(double) * (AUG_PGTAB_N * AUG_PGTAB_DEG + 2 * (size_t)g.E + 2 * (size_t)R) +
+                            (AUG_BLOCK / 32) * (2 * CG_QCAP * sizeof(double) + (5 * CG_QCAP + 2 * CG_BCAP) * sizeof(uint32_t)) +
+                            CG_STAGES * sizeof(uint64_t) + 128;
+        if (smem <= (size_t)ctx->smem_optin) {
+            AUG_CUDA(cudaFuncSetAttribute(cat_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cat_gibbs_kernel, AUG_BLOCK, smem) != cudaSuccess || occ < 1)
+                occ = 1;
+            int64_t grid = (int64_t)ctx->sms * occ;
+            if (grid > g.ntiles) grid = g.ntiles;
+            cat_gibbs_kernel<<<(unsigned)grid, AUG_BLOCK, smem, ctx->stream>>>(g);
+            ctx->launches++;
+            return (int32_t)cudaGetLastError();
+        }
+    }
     CatSampleArgs a{};
     a.n = n;
     a.i0 = i0;
