@@ -71,6 +71,13 @@ SIGNATURES = {
     "aug_comm_init": [_vp, _i32, _i32, C.c_char * 128],
     "aug_comm_destroy": [_vp],
     "aug_allreduce_scalars": [_vp, _vp, _i32],
+    "aug_comm_p2p_export": [_vp, _vp, C.POINTER(_vp)],
+    "aug_comm_p2p_attach": [_vp, _i32, _i32, C.c_char_p],
+    "aug_comm_p2p_attach_ptrs": [_vp, _i32, _i32, C.POINTER(_vp), C.POINTER(_i32)],
+    "aug_comm_p2p_detach": [_vp],
+    "aug_comm_set_fused": [_vp, _i32],
+    "aug_comm_get_fused": [_vp, C.POINTER(_i32)],
+    "aug_allreduce_scalars_p2p": [_vp, _vp, _i32],
     "aug_cavi_step_host": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "aug_aux_sample_host": [_vp, C.POINTER(AugLik), _i64, _i64, _vp, _vp, _i64, _vp, _vp],
 }

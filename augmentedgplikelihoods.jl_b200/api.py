@@ -213,7 +213,9 @@ class Context:
         h = C.c_void_p()
         check(self.lib.aug_ctx_create(C.byref(h), self.device, C.c_void_p(self.stream.cuda_stream)))
         self.h = h
-        self.comm_ready = False
+        self.comm_ready = False     # NCCL communicator attached (dist.init_comm)
+        self.p2p_ready = False      # peer-memory mailbox attached (dist.init_p2p)
+        self.fused = False          # scalar-producing verbs already return sums over all ranks
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
@@ -432,6 +434,8 @@ def _elbo_terms(lik, qΩ, y, qf, ctx):
 def _reduce(ctx, scal):
     """sum the scalar block over ranks when a communicator is attached"""
     ctx = ctx or default_context()
+    if ctx.fused:                   # exchanged inside the reducing kernel over peer memory
+        return scal
     if ctx.comm_ready:
         ctx.enter()
         check(ctx.lib.aug_allreduce_scalars(ctx.h, _ptr(scal), NSCALARS))

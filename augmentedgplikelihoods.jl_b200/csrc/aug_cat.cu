@@ -37,6 +37,7 @@ struct CatArgs {
     double* partials;
     unsigned int* counter;
     double* scalars;
+    AugXchDev* xch;          // final launch of a verb in fused multi-GPU mode (aug_common.cuh)
     unsigned int* dflag;
     LikConst L;
 };
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_cavi_kernel(const CatArgs a) {
     if (ELBO) {
         double out[3];
         if (block_reduce_and_finalize<3>(acc, a.partials, a.counter, out)) {
+            if (a.xch) xch_allreduce<3>(a.xch, out);
             a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
             a.scalars[AUG_S_KL] = out[1];
             a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_tma_kernel(const CatTmaArgs 
                 out[1] += a.scalars[AUG_S_KL];
                 out[2] += a.scalars[AUG_S_FLAGS];
             }
+            if (a.xch) xch_allreduce<3>(a.xch, out);
             a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
             a.scalars[AUG_S_KL] = out[1];
             a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
@@ -947,11 +950,14 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
                          const double* var, void* s0, void* s1, void* s2, const void* rs0, const void* rs1,
                          const void* rs2, double* beta, double* gamma, int64_t ldo, double* scalars,
                          bool from_state) {
-    if (n < 0 || !y) return AUG_ERR_BAD_ARG;
+    if (n < 0 || (!y && n > 0)) return AUG_ERR_BAD_ARG;
     const bool elbo = scalars != nullptr;
     if (elbo && lik->kind == AUG_CAT) return AUG_ERR_PRECONDITION;   // categorical.jl:165-170
     if (n == 0) {
-        if (scalars) AUG_CUDA(cudaMemsetAsync(scalars, 0, AUG_NSCALARS * sizeof(double), ctx->stream));
+        if (scalars) {
+            AUG_CUDA(cudaMemsetAsync(scalars, 0, AUG_NSCALARS * sizeof(double), ctx->stream));
+            if (aug_xch_for(ctx)) return aug_xch_zero_contribution(ctx, scalars, AUG_S_EXPECTED_LOGTILT, 3);
+        }
         return AUG_OK;
     }
     if ((!from_state || elbo) && (!mu || !var)) return AUG_ERR_BAD_ARG;
@@ -977,6 +983,7 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
     a.counter = ctx->counter;
     a.scalars = scalars;
     a.dflag = ctx->dflag;
+    a.xch = elbo ? aug_xch_for(ctx) : nullptr;
     int32_t rc = aug_lik_const(ctx, lik, &a.L, false, false);
     if (rc) return rc;
     // ---- full tiles of a fused call on 16-byte aligned arrays: the bulk-async staged kernel
@@ -1025,6 +1032,7 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
             if (n0 < n) {
                 const int64_t eo = n0 * nl;
                 CatArgs t = a;
+                t.xch = nullptr;                 // the staged launch below is the verb's last one
                 t.n = n - n0;
                 t.y = a.y + eo;
                 t.mu = a.mu + eo;

@@ -53,6 +53,7 @@ struct CaviArgs {
     unsigned int* counter;
     double* scalars;
     int accumulate;       // add to the scalars already in memory (second launch of one verb)
+    AugXchDev* xch;       // non-null on the final launch of a verb in fused multi-GPU mode: all-reduce over peer memory
     LikConst L;
 };
 
@@ -284,6 +285,12 @@ __device__ __forceinline__ void write_scalars(const CaviArgs& a, const double (&
     if (a.accumulate) {
         e += a.scalars[AUG_S_EXPECTED_LOGTILT];
         k += a.scalars[AUG_S_KL];
+    }
+    if (a.xch) {
+        double v[2] = {e, k};
+        xch_allreduce<2>(a.xch, v);
+        e = v[0];
+        k = v[1];
     }
     a.scalars[AUG_S_EXPECTED_LOGTILT] = e;
     a.scalars[AUG_S_KL] = k;
@@ -697,7 +704,10 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
                           double* scalars, bool from_state) {
     if (n < 0) return AUG_ERR_BAD_ARG;
     if (n == 0) {
-        if (scalars) AUG_CUDA(cudaMemsetAsync(scalars, 0, 3 * sizeof(double), ctx->stream));
+        if (scalars) {
+            AUG_CUDA(cudaMemsetAsync(scalars, 0, 3 * sizeof(double), ctx->stream));
+            if (aug_xch_for(ctx)) return aug_xch_zero_contribution(ctx, scalars, AUG_S_EXPECTED_LOGTILT, 2);
+        }
         return AUG_OK;
     }
     const bool elbo = scalars != nullptr;
@@ -747,6 +757,7 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
     const int64_t ntiles = use_tma ? n / tile : 0;
     const int64_t n0 = ntiles * tile;   // observations handled by the staged kernel
     CaviArgs t = a;                          // remainder [n0, n)
+    if (elbo) (ntiles > 0 ? a.xch : t.xch) = aug_xch_for(ctx);   // the verb's last launch carries the exchange
     if (n0 > 0) {
         const size_t ysz = lik->kind == AUG_BERNOULLI ? 1 : 8;
         t.n = n - n0;

@@ -12,6 +12,9 @@
 #define AUG_PGTAB_H 0.125       // interval width of the r(z) table
 #define AUG_PGTAB_N 160        // intervals: z in [0, 20)
 #define AUG_PGTAB_DEG 8        // coefficients per interval (degree 7)
+#define AUG_MAX_RANKS 8        // GPUs of one NVSwitch box that can share a peer-memory mailbox
+#define AUG_XCH_SLOT 8         // 64-bit words per mailbox slot: 7 values + 1 epoch flag
+#define AUG_XCH_WORDS (2 * AUG_MAX_RANKS * AUG_XCH_SLOT)   // [parity][source rank][slot]
 
 #define AUG_CUDA(x)                                   \
     do {                                              \
@@ -20,6 +23,20 @@
     } while (0)
 
 struct aug_pipe;  // host-buffer pipeline state (aug_host.cu)
+
+// Peer-memory exchange of the scalar block (aug_ctx.cu: aug_comm_p2p_*).  Lives in device memory of the owning rank;
+// box[r] is rank r's mailbox mapped into this process (cudaIpc, or a plain peer pointer inside one process).
+// The finalising thread of a reducing kernel pushes its partial sums into slot [epoch & 1][rank] of EVERY rank's
+// mailbox over NVLink, publishes the epoch, waits for the nranks slots of its own mailbox and adds them in rank
+// order: an all-reduce fused into the kernel that produced the sums, bit-identical on all ranks.  `epoch` is a
+// device-side counter (one tick per exchanging launch), so the launch is graph-replayable.
+struct AugXchDev {
+    unsigned long long* box[AUG_MAX_RANKS];
+    int nranks, rank;
+    unsigned long long epoch;
+    unsigned int* err;                 // ctx error flag word: bit 1 = a peer did not arrive within timeout_ns
+    unsigned long long timeout_ns;
+};
 
 struct aug_ctx {
     int device;
@@ -47,6 +64,13 @@ struct aug_ctx {
     void* nccl_lib;
     void* nccl_comm;
     int nranks, rank;
+    // peer-memory mailbox (aug_comm_p2p_*): the all-reduce of the scalar block fused into the reducing kernels
+    unsigned long long* mailbox;                   // this rank's mailbox [AUG_XCH_WORDS] (cudaMalloc, IPC-exported)
+    unsigned long long* peer_box[AUG_MAX_RANKS];   // mapped mailboxes of all ranks (peer_box[rank] == mailbox)
+    bool peer_ipc[AUG_MAX_RANKS];                  // opened with cudaIpcOpenMemHandle (to be closed)
+    AugXchDev* xch;                                // device copy of the exchange descriptor (nullptr: not attached)
+    int xch_ranks, xch_rank;
+    int fused;                                     // reducing verbs return globally reduced scalars
     aug_pipe* pipe;
 };
 
@@ -62,6 +86,10 @@ struct LikConst {
 
 int32_t aug_lik_const(aug_ctx* ctx, const aug_lik* lik, LikConst* out, bool need_table, bool need_theta);
 int aug_grid_for(aug_ctx* ctx, const void* kernel, int64_t work_items, int items_per_block);
+// exchange descriptor for the FINAL launch of a scalar-producing verb, or nullptr when the ctx is not in fused mode
+static inline AugXchDev* aug_xch_for(aug_ctx* ctx) { return (ctx->fused && ctx->xch) ? ctx->xch : nullptr; }
+// fused mode with an empty shard: the rank still has to take part in the exchange (aug_ctx.cu)
+int32_t aug_xch_zero_contribution(aug_ctx* ctx, double* scalars, int first_slot, int nslots);
 
 static inline bool aug_aligned16(const void* p) { return p == nullptr || (((uintptr_t)p) & 15u) == 0; }
 
@@ -128,6 +156,61 @@ __device__ __forceinline__ bool block_reduce_and_finalize(double (&acc)[NV], dou
         }
     }
     return threadIdx.x == 0;
+}
+
+// ---------------------------------------------------------------- all-reduce over peer memory, fused into the finaliser
+__device__ __forceinline__ unsigned long long xch_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Called by ONE thread of the grid (the finaliser).  v[0..NV) in: this rank's sums; out: the sums over all ranks.
+template <int NV>
+__device__ __forceinline__ void xch_allreduce(AugXchDev* __restrict__ x, double (&v)[NV]) {
+    static_assert(NV < AUG_XCH_SLOT, "slot holds 7 values + flag");
+    const int nr = x->nranks, me = x->rank;
+    const unsigned long long ep = x->epoch + 1ull;
+    x->epoch = ep;
+    const size_t half = (size_t)(ep & 1ull) * AUG_MAX_RANKS * AUG_XCH_SLOT;
+    const size_t mine = half + (size_t)me * AUG_XCH_SLOT;
+    for (int r = 0; r < nr; ++r) {                         // push (posted stores over NVLink; local for r == me)
+        unsigned long long* p = x->box[r] + mine;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p + k), "l"(__double_as_longlong(v[k])) : "memory");
+    }
+    __threadfence_system();
+    for (int r = 0; r < nr; ++r)                           // publish
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(x->box[r] + mine + (AUG_XCH_SLOT - 1)), "l"(ep) : "memory");
+    double tot[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) tot[k] = 0.0;
+    const unsigned long long t0 = xch_globaltimer();
+    bool ok = true;
+    for (int r = 0; r < nr && ok; ++r) {                   // gather in rank order: identical bits on every rank
+        const unsigned long long* p = x->box[me] + half + (size_t)r * AUG_XCH_SLOT;
+        for (;;) {
+            unsigned long long f;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(p + (AUG_XCH_SLOT - 1)) : "memory");
+            if (f == ep) break;
+            if (xch_globaltimer() - t0 > x->timeout_ns) { ok = false; break; }
+            __nanosleep(64);
+        }
+        if (!ok) break;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            unsigned long long w;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p + k) : "memory");
+            tot[k] += __longlong_as_double((long long)w);
+        }
+    }
+    if (!ok) {
+        atomicOr(x->err, 2u);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) tot[k] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = tot[k];
 }
 
 // 128-bit streaming loads/stores (read-once / write-once data: keep it out of L1)

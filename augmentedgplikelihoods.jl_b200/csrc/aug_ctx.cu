@@ -290,7 +290,27 @@ const int NCCL_SUM = 0;      // ncclSum
 
 void aug_pipe_destroy(aug_ctx* ctx);  // aug_host.cu
 
+namespace {
+__global__ void xch_only_kernel(AugXchDev* x, double* vals, int count, int first, int mode) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double v[AUG_XCH_SLOT - 1];
+#pragma unroll
+    for (int k = 0; k < AUG_XCH_SLOT - 1; ++k) v[k] = (mode == 0 && k < count) ? vals[k] : 0.0;
+    xch_allreduce<AUG_XCH_SLOT - 1>(x, v);
+    if (mode == 0) {                       // plain all-reduce of vals[0..count)
+        for (int k = 0; k < count; ++k) vals[k] = v[k];
+    } else {                               // zero contribution of an empty shard to a verb's slots
+        vals[first] = v[0];
+        vals[first + 1] = v[1];
+        vals[first + 2] = v[0] + v[1];
+        if (count == 3) vals[AUG_S_FLAGS] = v[2];
+    }
+}
+}  // namespace
+
 extern "C" {
+static void p2p_close(aug_ctx* c);
+
 
 int32_t aug_version(void) { return AUGCUDA_VERSION; }
 
@@ -363,6 +383,8 @@ int32_t aug_ctx_destroy(aug_ctx* c) {
     cudaSetDevice(c->device);
     aug_pipe_destroy(c);
     if (c->nccl_comm && g_nccl.destroy) g_nccl.destroy(c->nccl_comm);
+    p2p_close(c);
+    if (c->mailbox) cudaFree(c->mailbox);
     if (c->partials) cudaFree(c->partials);
     if (c->counter) cudaFree(c->counter);
     if (c->dscalars) cudaFree(c->dscalars);
@@ -545,6 +567,134 @@ int32_t aug_comm_destroy(aug_ctx* c) {
     c->nranks = 0;
     return AUG_OK;
 }
+// ---------------------------------------------------------------------------- peer-memory mailbox (NVLink / NVSwitch)
+// The scalar block is 64 bytes: an NCCL all-reduce of it is pure launch + protocol latency.  With the mailbox attached
+// (one cudaMalloc'ed kilobyte per rank, exported by cudaIpc or shared as a raw pointer inside one process), the
+// finalising thread of the reducing kernel itself pushes the sums to all peers and gathers theirs (xch_allreduce,
+// aug_common.cuh): kernel + collective in ONE launch, no host round trip, deterministic rank-order sum.
+int32_t aug_comm_p2p_export(aug_ctx* c, char handle[64], void** local_ptr) {
+    if (!c) return AUG_ERR_NOT_INIT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    AUG_CUDA(cudaSetDevice(c->device));
+    if (!c->mailbox) {
+        AUG_CUDA(cudaMalloc(&c->mailbox, sizeof(unsigned long long) * AUG_XCH_WORDS));
+        AUG_CUDA(cudaMemset(c->mailbox, 0, sizeof(unsigned long long) * AUG_XCH_WORDS));
+    }
+    if (handle) {
+        cudaIpcMemHandle_t h;
+        AUG_CUDA(cudaIpcGetMemHandle(&h, c->mailbox));
+        memcpy(handle, &h, 64);
+    }
+    if (local_ptr) *local_ptr = c->mailbox;
+    return AUG_OK;
+}
+
+static void p2p_close(aug_ctx* c) {
+    for (int r = 0; r < AUG_MAX_RANKS; ++r) {
+        if (c->peer_ipc[r] && c->peer_box[r]) cudaIpcCloseMemHandle(c->peer_box[r]);
+        c->peer_box[r] = nullptr;
+        c->peer_ipc[r] = false;
+    }
+    if (c->xch) cudaFree(c->xch);
+    c->xch = nullptr;
+    c->xch_ranks = 0;
+    c->fused = 0;
+}
+
+static int32_t p2p_finish_attach(aug_ctx* c, int32_t nranks, int32_t rank) {
+    AugXchDev h;
+    memset(&h, 0, sizeof(h));
+    for (int r = 0; r < nranks; ++r) h.box[r] = c->peer_box[r];
+    h.nranks = nranks;
+    h.rank = rank;
+    h.epoch = 0;
+    h.err = c->dflag;
+    h.timeout_ns = 5000000000ull;      // 5 s: a rank that never launches the matching verb raises flag bit 1
+    const char* e = getenv("AUGCUDA_XCH_TIMEOUT_MS");
+    if (e && atof(e) > 0) h.timeout_ns = (unsigned long long)(atof(e) * 1e6);
+    cudaError_t ce = cudaMalloc(&c->xch, sizeof(AugXchDev));
+    if (ce == cudaSuccess) ce = cudaMemcpy(c->xch, &h, sizeof(h), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { p2p_close(c); return (int32_t)ce; }
+    c->xch_ranks = nranks;
+    c->xch_rank = rank;
+    return AUG_OK;
+}
+
+// one process per GPU: handles = nranks x 64 bytes (cudaIpcMemHandle_t of every rank's mailbox, own slot ignored).
+// Every rank must have exported before any rank attaches, and all ranks must attach before the first fused verb
+// (the caller's rendezvous — torch.distributed all_gather + barrier — provides both).
+int32_t aug_comm_p2p_attach(aug_ctx* c, int32_t nranks, int32_t rank, const char* handles) {
+    if (!c || !c->mailbox) return AUG_ERR_NOT_INIT;
+    if (nranks < 1 || nranks > AUG_MAX_RANKS || rank < 0 || rank >= nranks || !handles) return AUG_ERR_BAD_ARG;
+    AUG_CUDA(cudaSetDevice(c->device));
+    p2p_close(c);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { c->peer_box[r] = c->mailbox; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) { p2p_close(c); return (int32_t)ce; }
+        c->peer_box[r] = (unsigned long long*)p;
+        c->peer_ipc[r] = true;
+    }
+    return p2p_finish_attach(c, nranks, rank);
+}
+
+// several ctxs inside ONE process: ptrs[r] = the local_ptr aug_comm_p2p_export returned for rank r, devices[r] its device
+int32_t aug_comm_p2p_attach_ptrs(aug_ctx* c, int32_t nranks, int32_t rank, void* const* ptrs, const int32_t* devices) {
+    if (!c || !c->mailbox) return AUG_ERR_NOT_INIT;
+    if (nranks < 1 || nranks > AUG_MAX_RANKS || rank < 0 || rank >= nranks || !ptrs || !devices) return AUG_ERR_BAD_ARG;
+    AUG_CUDA(cudaSetDevice(c->device));
+    p2p_close(c);
+    for (int r = 0; r < nranks; ++r) {
+        if (r != rank && devices[r] != c->device) {
+            int can = 0;
+            AUG_CUDA(cudaDeviceCanAccessPeer(&can, c->device, devices[r]));
+            if (!can) return AUG_ERR_PRECONDITION;
+            cudaError_t ce = cudaDeviceEnablePeerAccess(devices[r], 0);
+            if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) return (int32_t)ce;
+            (void)cudaGetLastError();
+        }
+        c->peer_box[r] = (unsigned long long*)ptrs[r];
+    }
+    return p2p_finish_attach(c, nranks, rank);
+}
+
+int32_t aug_comm_p2p_detach(aug_ctx* c) {
+    if (!c) return AUG_ERR_NOT_INIT;
+    AUG_CUDA(cudaSetDevice(c->device));
+    AUG_CUDA(cudaStreamSynchronize(c->stream));
+    p2p_close(c);
+    return AUG_OK;
+}
+
+// on != 0: every scalar-producing verb (aug_cavi_step, aug_expected_elbo_terms, aug_sampled_loglik_terms) returns
+// the sums over ALL ranks, exchanged inside its own reducing kernel.  Collective semantics: every rank must call
+// the same sequence of such verbs (an empty shard, n = 0, still takes part).
+int32_t aug_comm_set_fused(aug_ctx* c, int32_t on) {
+    if (!c) return AUG_ERR_NOT_INIT;
+    if (on && !c->xch) return AUG_ERR_NOT_INIT;
+    c->fused = on ? 1 : 0;
+    return AUG_OK;
+}
+int32_t aug_comm_get_fused(aug_ctx* c, int32_t* on) {
+    if (!c || !on) return AUG_ERR_NOT_INIT;
+    *on = c->fused;
+    return AUG_OK;
+}
+
+
+// in-place sum over ranks of count <= 7 device doubles through the mailbox, on the ctx stream (no NCCL involved)
+int32_t aug_allreduce_scalars_p2p(aug_ctx* c, double* dev, int32_t count) {
+    if (!c || !c->xch) return AUG_ERR_NOT_INIT;
+    if (!dev || count < 1 || count > AUG_XCH_SLOT - 1) return AUG_ERR_BAD_ARG;
+    AUG_CUDA(cudaSetDevice(c->device));
+    xch_only_kernel<<<1, 32, 0, c->stream>>>(c->xch, dev, count, 0, 0);
+    c->launches++;
+    return (int32_t)cudaGetLastError();
+}
+
 int32_t aug_allreduce_scalars(aug_ctx* c, double* dev, int32_t count) {
     if (!c || !c->nccl_comm) return AUG_ERR_NOT_INIT;
     if (!dev || count < 1) return AUG_ERR_BAD_ARG;
@@ -555,3 +705,9 @@ int32_t aug_allreduce_scalars(aug_ctx* c, double* dev, int32_t count) {
 }
 
 }  // extern "C"
+
+int32_t aug_xch_zero_contribution(aug_ctx* c, double* scalars, int first_slot, int nslots) {
+    xch_only_kernel<<<1, 32, 0, c->stream>>>(c->xch, scalars, nslots, first_slot, 1);
+    c->launches++;
+    return (int32_t)cudaGetLastError();
+}

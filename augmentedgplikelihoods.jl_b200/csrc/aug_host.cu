@@ -115,6 +115,13 @@ int32_t aug_cavi_step_host(aug_ctx* c, const aug_lik* lik, int64_t n, const void
     if (cat && (beta || gamma) && ldo < n) return AUG_ERR_BAD_ARG;
     if (scalars_host) memset(scalars_host, 0, sizeof(double) * AUG_NSCALARS);
     if (n == 0) return AUG_OK;
+    // per-chunk scalars are summed on the host: the in-kernel peer exchange (fused multi-GPU mode) stays off here
+    struct FusedOff {
+        aug_ctx* c;
+        int was;
+        explicit FusedOff(aug_ctx* cc) : c(cc), was(cc->fused) { cc->fused = 0; }
+        ~FusedOff() { c->fused = was; }
+    } fused_off(c);
 
     int64_t chunk = ((int64_t)1 << 22) / per;
     if (chunk < 2) chunk = 2;

@@ -69,6 +69,7 @@ struct LLArgs {
     double* partials;
     unsigned int* counter;
     double* scalars;
+    AugXchDev* xch;          // fused multi-GPU mode: all-reduce over peer memory in the finaliser
     LikConst L;
 };
 
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) loglik_kernel(const LLArgs a) {
     }
     double out[2];
     if (block_reduce_and_finalize<2>(acc, a.partials, a.counter, out)) {
+        if (a.xch) xch_allreduce<2>(a.xch, out);
         a.scalars[AUG_S_LOGTILT] = out[0];
         a.scalars[AUG_S_LOGPRIOR] = out[1];
         a.scalars[AUG_S_AUGLL] = out[0] + out[1];             // generic.jl:48-50
@@ -140,6 +142,7 @@ struct CatLLArgs {
     double* partials;
     unsigned int* counter;
     double* scalars;
+    AugXchDev* xch;          // fused multi-GPU mode: all-reduce over peer memory in the finaliser
 };
 
 __global__ void __launch_bounds__(AUG_BLOCK) cat_loglik_kernel(const CatLLArgs a) {
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_loglik_kernel(const CatLLArgs a
     }
     double out[2];
     if (block_reduce_and_finalize<2>(acc, a.partials, a.counter, out)) {
+        if (a.xch) xch_allreduce<2>(a.xch, out);
         a.scalars[AUG_S_LOGTILT] = out[0];
         a.scalars[AUG_S_LOGPRIOR] = out[1];
         a.scalars[AUG_S_AUGLL] = out[0] + out[1];
@@ -240,6 +244,7 @@ int32_t aug_sampled_loglik_terms(aug_ctx* c, const aug_lik* lik, int64_t n, cons
     AUG_CUDA(cudaSetDevice(c->device));
     if (n == 0) {
         AUG_CUDA(cudaMemsetAsync(scalars + AUG_S_LOGTILT, 0, 3 * sizeof(double), c->stream));
+        if (aug_xch_for(c)) return aug_xch_zero_contribution(c, scalars, AUG_S_LOGTILT, 2);
         return AUG_OK;
     }
     if (lik->kind == AUG_CAT || lik->kind == AUG_CAT_BIJ) {
@@ -263,6 +268,7 @@ int32_t aug_sampled_loglik_terms(aug_ctx* c, const aug_lik* lik, int64_t n, cons
         a.partials = c->partials;
         a.counter = c->counter;
         a.scalars = scalars;
+    a.xch = aug_xch_for(c);
         return launch_red(c, cat_loglik_kernel, a, n * 32);
     }
     LLArgs a{};
@@ -275,6 +281,7 @@ int32_t aug_sampled_loglik_terms(aug_ctx* c, const aug_lik* lik, int64_t n, cons
     a.partials = c->partials;
     a.counter = c->counter;
     a.scalars = scalars;
+    a.xch = aug_xch_for(c);
     int32_t rc = aug_lik_const(c, lik, &a.L, true, false);
     if (rc) return rc;
     if ((lik->kind == AUG_POISSON || lik->kind == AUG_HETERO) && !nvar) return AUG_ERR_BAD_ARG;

@@ -63,3 +63,41 @@ def allreduce_scalars_(ctx, scal: torch.Tensor):
     check(ctx.lib.aug_allreduce_scalars(ctx.h, C.c_void_p(scal.data_ptr()), int(scal.numel())))
     ctx.leave()
     return scal
+
+
+def init_p2p(ctx, group=None, fused=True):
+    """Attach the peer-memory mailbox (NVLink / NVSwitch): every rank exports a cudaIpc handle of its 1 KiB mailbox,
+    torch.distributed all-gathers the handles, every rank maps its peers.  With fused=True the scalar-producing
+    verbs (cavi_step_ with want_elbo, expected_elbo_terms, sampled_loglik_terms) return the sums over ALL ranks,
+    exchanged inside their own reducing kernel — no separate all-reduce launch (include/augcuda.h)."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    h = (C.c_char * 64)()
+    check(ctx.lib.aug_comm_p2p_export(ctx.h, h, None))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bytes(h.raw), group=group)
+    check(ctx.lib.aug_comm_p2p_attach(ctx.h, world, rank, b"".join(gathered)))
+    dist.barrier(group=group)                      # nobody starts exchanging before everybody has mapped everybody
+    ctx.p2p_ready = True
+    ctx.world, ctx.rank = world, rank
+    if fused:
+        set_fused(ctx, True)
+    return ctx
+
+
+def set_fused(ctx, on=True):
+    check(ctx.lib.aug_comm_set_fused(ctx.h, 1 if on else 0))
+    ctx.fused = bool(on)
+    return ctx
+
+
+def allreduce_scalars_p2p_(ctx, scal: torch.Tensor, count: int = 7):
+    """In-place sum over ranks of the first `count` (<= 7) doubles of the scalar block through the mailbox."""
+    if not getattr(ctx, "p2p_ready", False):
+        raise RuntimeError("mailbox not attached (call init_p2p)")
+    ctx.enter()
+    check(ctx.lib.aug_allreduce_scalars_p2p(ctx.h, C.c_void_p(scal.data_ptr()), int(count)))
+    ctx.leave()
+    return scal

@@ -6,7 +6,9 @@ A step = one pass of the hot path over one batch of N synthetic Bernoulli-logist
   (1) the fused CAVI update  — aux_posterior! + expected_auglik_potential_and_precision + the
       expected_logtilt / aux_kldivergence partial sums (one kernel), and
   (2) the Gibbs draw         — aux_sample!: one PG(1, |f_i|) draw per observation (one kernel),
-  (3) for N > 1 GPUs, the single ncclAllReduce of the 8-double scalar block.
+  (3) for N > 1 GPUs, the all-reduce of the 64-byte scalar block: by default FUSED into kernel (1) over the
+      peer-memory mailbox (NVLink stores + epoch flags, include/augcuda.h); `--collective nccl` issues the
+      library's ncclAllReduce after the step instead.
 `value` = observations through BOTH halves per second, whole job, inputs resident in HBM;
 `parts` gives each half on its own (CAVI obs/s, PG draws/s) from CUDA events inside the timed region.
 `e2e` = the same step through the host-buffer C-ABI calls (aug_cavi_step_host + aug_aux_sample_host)
@@ -97,18 +99,23 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_reference(n, threads, seed=1, repeats=1):
-    """The reference's CPU path (C++ oracle restatement — Julia is not installable here), structured like
-    the reference: separate passes + temporaries, sequential ELBO sums, per-element Devroye sampler."""
+def cpu_inputs(n, seed=1):
     import numpy as np
-    from oracle import orc
-    orc.lib()
-    orc.set_threads(threads)
     rng = np.random.default_rng(seed)
     mu = rng.standard_normal(n)
     var = (0.5 + rng.random(n)) ** 2
     f = rng.standard_normal(n)
     y = (rng.random(n) < 1 / (1 + np.exp(-f))).astype(np.uint8)
+    return y, mu, var, f
+
+
+def cpu_reference(n, threads, seed=1, repeats=1, inputs=None):
+    """The reference's CPU path (C++ oracle restatement — Julia is not installable here), structured like
+    the reference: separate passes + temporaries, sequential ELBO sums, per-element Devroye sampler."""
+    from oracle import orc
+    orc.lib()
+    orc.set_threads(threads)
+    y, mu, var, f = inputs if inputs is not None else cpu_inputs(n, seed)
     lik = orc.make_lik(orc.BERNOULLI)
     best = None
     for _ in range(repeats):
@@ -124,19 +131,23 @@ def cpu_reference(n, threads, seed=1, repeats=1):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores (all threads)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (all threads).
+    Each step is a bounded sample of the workload, sized from a probe so that K steps take about a minute."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import orc
     orc.lib()
     threads = orc.max_threads()
-    n = args.ref_n
-    for _ in range(args.warmup):
-        cpu_reference(min(n, 1_000_000), threads)
+    probe = cpu_inputs(1_000_000)
+    for _ in range(max(1, args.warmup)):
+        tp = cpu_reference(1_000_000, threads, inputs=probe)[0]
+    rate = 1_000_000 / tp
+    n = int(min(args.ref_n, max(1_000_000, 60.0 * rate / max(1, args.steps))))
+    inputs = cpu_inputs(n)
     tot = cavi = gib = 0.0
     for k in range(args.steps):
-        t, tc, tg = cpu_reference(n, threads, seed=k + 1)
+        t, tc, tg = cpu_reference(n, threads, seed=k + 1, inputs=inputs)
         tot += t
         cavi += tc
         gib += tg
@@ -166,12 +177,15 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n", type=int, default=100_000_000, help="observations per GPU (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-n", type=int, default=20_000_000, help="CPU sample size per step of the reference arm")
     ap.add_argument("--cpu-n", type=int, default=20_000_000, help="CPU sample of the cpu_baseline leg")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: all-reduce of the scalar block fused into the CAVI kernel over peer memory (p2p) or "
+                         "a separate ncclAllReduce (nccl)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -196,7 +210,10 @@ def main():
     ctx = A.Context(local_rank)
     A.set_default_context(ctx)
     if world > 1:
-        A.dist.init_comm(ctx)
+        if args.collective == "nccl":
+            A.dist.init_comm(ctx)
+        else:
+            A.dist.init_p2p(ctx, fused=True)
     n = args.n
     i0 = rank * n                                    # global index of this rank's first observation
     lik = A.BernoulliLikelihood()
@@ -229,8 +246,8 @@ def main():
         A.aux_sample_(Ω, lik, y, f, i0=i0)
         if ev:
             ev[2].record(st)
-        if world > 1:
-            A.dist.allreduce_scalars_(ctx, scal)
+        if world > 1 and args.collective == "nccl":
+            A.dist.allreduce_scalars_(ctx, scal)          # p2p: already summed over ranks inside the CAVI kernel
         if ev:
             ev[3].record(st)
 
@@ -355,13 +372,16 @@ def main():
                    "obs_per_gpu": n, "global_obs": n * world, "likelihood": "BernoulliLikelihood(LogisticLink)",
                    "l2": "inputs+outputs 5.7 GB per step >> 126 MB L2 (no flush needed)",
                    "sharding": f"contiguous observation blocks, {world} rank(s); only the 8-double scalar block "
-                               "is all-reduced (NCCL)"},
+                               "is all-reduced",
+                   "collective": ("none (1 rank)" if world == 1 else
+                                  "fused into cavi_tma_kernel's finaliser over the peer-memory mailbox (NVLink)"
+                                  if args.collective == "p2p" else "ncclAllReduce(sum, double, 8) after the step")},
         "parts": {"cavi_obs_per_s": n * world / (ms_cavi * 1e-3), "pg_draws_per_s": n * world / (ms_gibbs * 1e-3),
                   "ms_cavi": ms_cavi, "ms_gibbs": ms_gibbs, "ms_allreduce": ms_coll},
-        "roofline": {"kernel": "cavi_kernel<BERNOULLI, fused, ELBO, vec>", "bound": "hbm", "achieved": ach,
+        "roofline": {"kernel": "cavi_tma_kernel<BERNOULLI, ELBO> (aux_posterior! + expected potential/precision + ELBO sums)", "bound": "hbm", "achieved": ach,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
                      "frac_of_8TBs_nominal": ach / 8000.0, "bytes_per_obs": BYTES_CAVI, "traffic": traffic},
-        "roofline_gibbs": {"kernel": "aux_sample_kernel<BERNOULLI>", "bound": "fp64 pipe / issue (not HBM)",
+        "roofline_gibbs": {"kernel": "pg1_compact_kernel (warp-compacted Devroye PG(1,c))", "bound": "fp64 pipe / issue (not HBM)",
                            "achieved": BYTES_GIBBS * n / (ms_gibbs * 1e-3) / 1e9, "unit": "GB/s",
                            "frac_hbm": BYTES_GIBBS * n / (ms_gibbs * 1e-3) / 1e9 / peak,
                            "pg_draws_per_s_per_gpu": n / (ms_gibbs * 1e-3)},

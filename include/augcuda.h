@@ -257,6 +257,29 @@ int32_t aug_comm_destroy(aug_ctx* ctx);
 /* in-place sum over ranks of `count` device doubles, on the ctx stream */
 int32_t aug_allreduce_scalars(aug_ctx* ctx, double* dev, int32_t count);
 
+/* Peer-memory mailbox over NVLink / NVSwitch: the all-reduce of the scalar block FUSED into the reducing kernel.
+ * The block is 64 bytes, so an NCCL call is pure launch + protocol latency; with the mailbox attached the
+ * finalising thread of aug_cavi_step / aug_expected_elbo_terms / aug_sampled_loglik_terms pushes its sums into
+ * every rank's mailbox with peer stores, publishes an epoch flag, gathers the other ranks' sums from its own
+ * mailbox and adds them in rank order (bit-identical on all ranks) before it writes `scalars` — kernel and
+ * collective are ONE launch.  Set-up: every rank calls aug_comm_p2p_export, the caller all-gathers the 64-byte
+ * cudaIpc handles (torch.distributed / MPI / Julia Distributed), every rank calls aug_comm_p2p_attach, and after a
+ * barrier aug_comm_set_fused(ctx, 1).  From then on the scalar-producing verbs are COLLECTIVE: every rank must call
+ * the same sequence of them (an empty shard, n = 0, still takes part).  A peer that does not arrive within 5 s
+ * (AUGCUDA_XCH_TIMEOUT_MS) makes the kernel write NaN and raise bit 1 of aug_ctx_error_flag instead of hanging.
+ * The reference has no counterpart (it is single-process); the sums are those of api.jl:219-223,
+ * generic.jl:40-62 over the union of the shards. */
+int32_t aug_comm_p2p_export(aug_ctx* ctx, char handle[64], void** local_ptr);
+int32_t aug_comm_p2p_attach(aug_ctx* ctx, int32_t nranks, int32_t rank, const char* handles /* nranks x 64 B */);
+/* several ctxs inside one process: raw mailbox pointers (local_ptr of each rank's export) and their devices */
+int32_t aug_comm_p2p_attach_ptrs(aug_ctx* ctx, int32_t nranks, int32_t rank, void* const* ptrs,
+                                 const int32_t* devices);
+int32_t aug_comm_p2p_detach(aug_ctx* ctx);
+int32_t aug_comm_set_fused(aug_ctx* ctx, int32_t on);
+int32_t aug_comm_get_fused(aug_ctx* ctx, int32_t* on);
+/* in-place sum over ranks of count <= 7 device doubles through the mailbox (one 32-thread kernel, no NCCL) */
+int32_t aug_allreduce_scalars_p2p(aug_ctx* ctx, double* dev, int32_t count);
+
 /* ---- host-buffer plugin call (end-to-end path) --------------------------- */
 /* Same as aug_cavi_step but every data pointer is a HOST buffer (pinned for
  * full speed); the library stages chunks through device memory, overlapping
