@@ -67,6 +67,10 @@ SIGNATURES = {
     "aug_approx_expected_logistic": [_vp, _i64, _vp, _vp, _vp],
     "aug_second_moment": [_vp, _i64, _vp, _vp, _vp, _vp],
     "aug_fastmath_eval": [_vp, _i32, _i64, _vp, _vp],
+    "aug_hetero_lambda_stats": [_vp, _i64, _vp, _vp, _vp, _i64, _vp],
+    "aug_hetero_lambda_stats_sampled": [_vp, _i64, _vp, _vp, _i64, _vp],
+    "aug_logisticsoftmax": [_vp, C.POINTER(AugLik), _i64, _vp, _vp],
+    "aug_approx_expected_logisticsoftmax": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _vp],
     "aug_comm_get_unique_id": [C.c_char * 128],
     "aug_comm_init": [_vp, _i32, _i32, C.c_char * 128],
     "aug_comm_destroy": [_vp],

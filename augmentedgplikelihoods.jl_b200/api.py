@@ -644,3 +644,71 @@ def fastmath_eval(fn: int, x, ctx=None):
     check(ctx.lib.aug_fastmath_eval(ctx.h, int(fn), x.numel(), _ptr(x), _ptr(out)))
     ctx.leave()
     return out
+
+
+# ----------------------------------------------------------------------------- SURVEY §8(f) rows 3 and 4
+def hetero_lambda_stats(y, qfg: Normals, ctx=None) -> float:
+    """dot(ψ, 1 .- σ̃g) of opt_lik — examples/heteroscedasticgaussian/script.jl:41-51 (summed over all ranks in
+    fused multi-GPU mode).  qfg: Normals with mu/var of shape [2][n] (f then g)."""
+    ctx = ctx or default_context()
+    n = y.numel()
+    ctx.enter()
+    out = ctx.empty((1,))
+    check(ctx.lib.aug_hetero_lambda_stats(ctx.h, n, _ptr(_f64(y, "y")), _ptr(_f64(qfg.mu, "mu")),
+                                          _ptr(_f64(qfg.var, "var")), qfg.mu.shape[-1], _ptr(out)))
+    ctx.leave()
+    return float(out.item())
+
+
+def opt_lik(lik: HeteroscedasticGaussianLikelihood, qfg: Normals, y, ctx=None, n_total=None):
+    """opt_lik(lik, (qf, qg), y): λ = max(N / (2 dot(ψ, 1 .- σ̃g)), λ_old) — script.jl:41-51.
+    n_total: the global number of observations when y is a shard (fused multi-GPU mode)."""
+    s = hetero_lambda_stats(y, qfg, ctx)
+    n = y.numel() if n_total is None else int(n_total)
+    return HeteroscedasticGaussianLikelihood(max(n / (2.0 * s), lik.lam))
+
+
+def hetero_lambda_stats_sampled(y, fg, ctx=None) -> float:
+    """Σ σ(gᵢ)/2 (yᵢ − fᵢ)²: rate increment of the Gamma full conditional of λ —
+    docs/src/likelihoods/heteroscedasticgaussian.md:80-84.  fg: [2][n]."""
+    ctx = ctx or default_context()
+    n = y.numel()
+    ctx.enter()
+    out = ctx.empty((1,))
+    check(ctx.lib.aug_hetero_lambda_stats_sampled(ctx.h, n, _ptr(_f64(y, "y")), _ptr(_f64(fg, "f")),
+                                                  fg.shape[-1], _ptr(out)))
+    ctx.leave()
+    return float(out.item())
+
+
+def logisticsoftmax(f, lik: Optional[CategoricalLikelihood] = None, ctx=None):
+    """logisticsoftmax(x) (categorical.jl:1-4) when lik is None, else lik's inverse link applied row-wise:
+    LogisticSoftMaxLink(logθ)(f) (categorical.jl:32-35), with the bijective link's appended zero latent.
+    f: [n][nl] -> [n][K]."""
+    ctx = ctx or default_context()
+    f2 = f if f.dim() == 2 else f.reshape(1, -1)
+    if lik is None:
+        lik = CategoricalLikelihood(f2.shape[1], bijective=False)
+    if f2.shape[1] != lik.nlatent:
+        raise ValueError("f must have nlatent(lik) columns")
+    K = lik.nlatent + 1 if lik.bijective else lik.nlatent
+    d = lik._desc()
+    ctx.enter()
+    out = ctx.empty((f2.shape[0], K))
+    check(ctx.lib.aug_logisticsoftmax(ctx.h, C.byref(d), f2.shape[0], _ptr(_f64(f2, "f")), _ptr(out)))
+    ctx.leave()
+    return out if f.dim() == 2 else out.reshape(-1)
+
+
+def approx_expected_logisticsoftmax(mu, c, lik: CategoricalLikelihood, ctx=None):
+    """approx_expected_logisticsoftmax(μ, c, θ) — utils.jl:17-22, θ = exp.(logθ) of a bijective link.  [n][nl]."""
+    ctx = ctx or default_context()
+    if not lik.bijective:
+        raise TypeError("approx_expected_logisticsoftmax needs the bijective link (θ has one more entry than μ)")
+    d = lik._desc()
+    ctx.enter()
+    out = ctx.empty(mu.shape)
+    check(ctx.lib.aug_approx_expected_logisticsoftmax(ctx.h, C.byref(d), mu.shape[0], _ptr(_f64(mu, "mu")),
+                                                      _ptr(_f64(c, "c")), _ptr(out)))
+    ctx.leave()
+    return out

@@ -250,6 +250,26 @@ int32_t aug_second_moment(aug_ctx* ctx, int64_t n, const double* mu, const doubl
  * 4 log on [1,2], 5 sqrt (1e-290 <= x <= 1e290). */
 int32_t aug_fastmath_eval(aug_ctx* ctx, int32_t fn, int64_t n, const double* x, double* out);
 
+/* ---- callers on either side of the path -------- */
+/* opt_lik of examples/heteroscedasticgaussian/script.jl:41-51: out[0] = dot(ψ, 1 .- σ̃g) with
+ * ψ = second_moment.(qf .- y)/2, c = sqrt.(second_moment.(qg)), σ̃g = approx_expected_logistic.(-mean.(qg), c);
+ * the caller forms λ = max(N / (2 out[0]), λ_old).  mu/var latent-major [2][ld] like aug_cavi_step (HETERO).
+ * One 40 B/obs map-reduce pass; in fused multi-GPU mode the sum is over all ranks. */
+int32_t aug_hetero_lambda_stats(aug_ctx* ctx, int64_t n, const double* y, const double* mu, const double* var,
+                                int64_t ld, double* out /* device, 1 double */);
+/* Gibbs counterpart, docs/src/likelihoods/heteroscedasticgaussian.md:80-84: out[0] = Σᵢ σ(gᵢ)/2 (yᵢ − fᵢ)², the
+ * rate increment of the Gamma full conditional of λ.  f latent-major [2][ld] (f then g). */
+int32_t aug_hetero_lambda_stats_sampled(aug_ctx* ctx, int64_t n, const double* y, const double* f, int64_t ld,
+                                        double* out /* device, 1 double */);
+/* (l::LogisticSoftMaxLink)(f) / logisticsoftmax(x): likelihoods/categorical.jl:1-4, 32-35; for AUG_CAT_BIJ the
+ * BijectiveSimplexLink appends a zero latent (categorical.jl:12-14).  f [n][nl] class fastest;
+ * out [n][K], K = nl (AUG_CAT) or nl + 1 (AUG_CAT_BIJ). */
+int32_t aug_logisticsoftmax(aug_ctx* ctx, const aug_lik* lik, int64_t n, const double* f, double* out);
+/* approx_expected_logisticsoftmax(μ, c, θ) utils.jl:17-22 (AUG_CAT_BIJ only: θ has nl + 1 entries).
+ * mu, c, out: [n][nl]. */
+int32_t aug_approx_expected_logisticsoftmax(aug_ctx* ctx, const aug_lik* lik, int64_t n, const double* mu,
+                                            const double* c, double* out);
+
 /* ---- multi-GPU: shard over observations, all-reduce only the scalars ---- */
 int32_t aug_comm_get_unique_id(char uid[128]);
 int32_t aug_comm_init(aug_ctx* ctx, int32_t nranks, int32_t rank, const char uid[128]);

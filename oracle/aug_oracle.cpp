@@ -1146,4 +1146,73 @@ int orc_full_conditional_logdensity(const aug_lik* l, int64_t n, const void* y, 
     return 0;
 }
 
+// ------------------------------------------------------------------ SURVEY §8(f) rows 3 and 4
+// opt_lik of examples/heteroscedasticgaussian/script.jl:41-51:
+//   ψ = second_moment.(qf .- y) / 2; c = sqrt.(second_moment.(qg)); σ̃g = approx_expected_logistic.(-mean.(qg), c)
+//   λ = max(length(y) / (2 * dot(ψ, 1 .- σ̃g)), lik.invlink.λ)
+// out[0] = dot(ψ, 1 .- σ̃g) (compensated), out[1] = the same as a sequential left fold (dot's order).
+int orc_hetero_lambda_stats(int64_t n, const double* y, const double* mu, const double* var, int64_t ld, double* out) {
+    Acc a;
+    for (int64_t i = 0; i < n; ++i) {
+        double psi = second_moment_y(mu[i], var[i], y[i]) / 2;      // Normal − y shifts the mean (heteroscedasticgaussian.jl:42)
+        double c = std::sqrt(second_moment(mu[ld + i], var[ld + i]));
+        double sg = approx_expected_logistic(-mu[ld + i], c);
+        a.add(psi * (1 - sg));
+    }
+    out[0] = a.compensated();
+    out[1] = a.seq;
+    return 0;
+}
+// Rate increment of the collapsed Gamma full conditional of λ, docs/src/likelihoods/heteroscedasticgaussian.md:80-84:
+//   Σᵢ σ(gᵢ)/2 · (yᵢ − fᵢ)²     (f = latent 0, g = latent 1)
+int orc_hetero_lambda_stats_sampled(int64_t n, const double* y, const double* f, int64_t ld, double* out) {
+    Acc a;
+    for (int64_t i = 0; i < n; ++i) a.add(logistic(f[ld + i]) / 2 * abs2(y[i] - f[i]));
+    out[0] = a.compensated();
+    out[1] = a.seq;
+    return 0;
+}
+// (l::LogisticSoftMaxLink)(f): σs = exp.(logθ) .* logistic.(f); σs ./ sum(σs)   categorical.jl:32-35
+// (logisticsoftmax(x), categorical.jl:1-4, is the logθ = 0 case); BijectiveSimplexLink appends a zero latent
+// (GPLikelihoods: l.link(vcat(f, 0))), consistent with _get_const, categorical.jl:12-14.
+// f: [n][nl] class fastest; out: [n][K], K = nl (CAT) or nl + 1 (CAT_BIJ).
+int orc_logisticsoftmax(const aug_lik* l, int64_t n, const double* f, double* out) {
+    const int nl = l->nlatent;
+    const bool bij = l->kind == AUG_CAT_BIJ;
+    if (!bij && l->kind != AUG_CAT) return AUG_ERR_BAD_KIND;
+    const int K = bij ? nl + 1 : nl;
+    std::vector<double> sig(K);
+    for (int64_t i = 0; i < n; ++i) {
+        double tot = 0;
+        for (int j = 0; j < K; ++j) {
+            double lt = l->logtheta ? l->logtheta[j] : 0.0;
+            double fj = j < nl ? f[i * nl + j] : 0.0;
+            sig[j] = std::exp(lt) * logistic(fj);
+            tot += sig[j];
+        }
+        for (int j = 0; j < K; ++j) out[i * K + j] = sig[j] / tot;
+    }
+    return 0;
+}
+// approx_expected_logisticsoftmax(μ, c, θ)  utils.jl:17-22:
+//   σs = θ[1:end-1] .* approx_expected_logistic.(μ, c); σs / (θ[end] * logistic(0) + sum(σs))
+// mu, c: [n][nl]; θ = exp.(logθ) has nl + 1 entries; out [n][nl].
+int orc_approx_expected_logisticsoftmax(const aug_lik* l, int64_t n, const double* mu, const double* c, double* out) {
+    if (l->kind != AUG_CAT_BIJ) return AUG_ERR_BAD_KIND;
+    const int nl = l->nlatent;
+    std::vector<double> sig(nl);
+    for (int64_t i = 0; i < n; ++i) {
+        double tot = 0;
+        for (int j = 0; j < nl; ++j) {
+            double th = l->logtheta ? std::exp(l->logtheta[j]) : 1.0;
+            sig[j] = th * approx_expected_logistic(mu[i * nl + j], c[i * nl + j]);
+            tot += sig[j];
+        }
+        double thK = l->logtheta ? std::exp(l->logtheta[nl]) : 1.0;
+        double den = thK * logistic(0.0) + tot;
+        for (int j = 0; j < nl; ++j) out[i * nl + j] = sig[j] / den;
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -247,3 +247,41 @@ def pg_mean(b, c):
 
 def pg_var(b, c):
     return lib().orc_pg_var(b, c)
+
+
+# ---- SURVEY §8(f) rows 3 and 4 ------------------------------------------------------------------
+def hetero_lambda_stats(y, mu, var):
+    """(compensated, sequential) value of dot(ψ, 1 .- σ̃g) — opt_lik, examples/heteroscedasticgaussian/script.jl:41-51.
+    mu, var: [2][n] latent-major."""
+    n = y.shape[0]
+    out = np.zeros(2)
+    rc = lib().orc_hetero_lambda_stats(C.c_int64(n), _p(np.ascontiguousarray(y, dtype=np.float64)),
+                                       _p(np.ascontiguousarray(mu)), _p(np.ascontiguousarray(var)),
+                                       C.c_int64(n), _p(out))
+    assert rc == 0
+    return out[0], out[1]
+
+
+def hetero_lambda_stats_sampled(y, f):
+    n = y.shape[0]
+    out = np.zeros(2)
+    rc = lib().orc_hetero_lambda_stats_sampled(C.c_int64(n), _p(np.ascontiguousarray(y, dtype=np.float64)),
+                                               _p(np.ascontiguousarray(f)), C.c_int64(n), _p(out))
+    assert rc == 0
+    return out[0], out[1]
+
+
+def logisticsoftmax(lik, f):
+    n, nl = f.shape
+    K = nl + 1 if lik.kind == CAT_BIJ else nl
+    out = np.zeros((n, K))
+    rc = lib().orc_logisticsoftmax(C.byref(lik), C.c_int64(n), _p(np.ascontiguousarray(f)), _p(out))
+    return rc, out
+
+
+def approx_expected_logisticsoftmax(lik, mu, c):
+    n, nl = mu.shape
+    out = np.zeros((n, nl))
+    rc = lib().orc_approx_expected_logisticsoftmax(C.byref(lik), C.c_int64(n), _p(np.ascontiguousarray(mu)),
+                                                   _p(np.ascontiguousarray(c)), _p(out))
+    return rc, out

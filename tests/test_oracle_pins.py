@@ -214,3 +214,45 @@ def test_fused_equals_separate(orc):
         assert rc == 0 and rc2 == 0
         assert np.array_equal(b1, b2) and np.array_equal(g1, g2)
         assert np.all(g1 >= 0)          # :88,171
+
+
+# ---- the oracle restatements against independent numpy / mpmath evaluations
+def test_next_rows_oracle_vs_independent(orc):
+    import mpmath as mp
+    rng = np.random.default_rng(12)
+    n = 40
+    y = rng.standard_normal(n)
+    mu = rng.standard_normal((2, n))
+    var = (0.5 + rng.random((2, n))) ** 2
+    f = rng.standard_normal((2, n))
+    mp.mp.dps = 40
+    tot = mp.mpf(0)
+    tots = mp.mpf(0)
+    for i in range(n):
+        psi = ((mp.mpf(mu[0, i]) - mp.mpf(y[i])) ** 2 + mp.mpf(var[0, i])) / 2
+        c = mp.sqrt(mp.mpf(mu[1, i]) ** 2 + mp.mpf(var[1, i]))
+        sg = mp.exp(-mp.mpf(mu[1, i]) / 2) * mp.sech(c / 2) / 2
+        tot += psi * (1 - sg)
+        tots += 1 / (1 + mp.exp(-mp.mpf(f[1, i]))) / 2 * (mp.mpf(y[i]) - mp.mpf(f[0, i])) ** 2
+    comp, seq = orc.hetero_lambda_stats(y, mu, var)
+    assert comp == pytest.approx(float(tot), rel=1e-14) and seq == pytest.approx(float(tot), rel=1e-13)
+    comps, _ = orc.hetero_lambda_stats_sampled(y, f)
+    assert comps == pytest.approx(float(tots), rel=1e-14)
+    # links
+    nl = 4
+    lt = rng.normal(0, 0.3, nl + 1)
+    ff = rng.standard_normal((6, nl))
+    sig = 1 / (1 + np.exp(-np.c_[ff, np.zeros(6)]))
+    ref = np.exp(lt) * sig
+    ref /= ref.sum(1, keepdims=True)
+    rc, got = orc.logisticsoftmax(orc.make_lik(orc.CAT_BIJ, nlatent=nl, logtheta=lt), ff)
+    assert rc == 0 and np.allclose(got, ref, rtol=1e-14, atol=0)
+    rc, got = orc.logisticsoftmax(orc.make_lik(orc.CAT, nlatent=nl), ff)            # logisticsoftmax(x)
+    s4 = sig[:, :nl]
+    assert rc == 0 and np.allclose(got, s4 / s4.sum(1, keepdims=True), rtol=1e-14, atol=0)
+    m = rng.standard_normal((6, nl))
+    c = np.sqrt(m * m + 1.0)
+    sg = np.exp(lt[:nl]) * np.exp(m / 2) / np.cosh(c / 2) / 2
+    ref = sg / (np.exp(lt[nl]) * 0.5 + sg.sum(1, keepdims=True))
+    rc, got = orc.approx_expected_logisticsoftmax(orc.make_lik(orc.CAT_BIJ, nlatent=nl, logtheta=lt), m, c)
+    assert rc == 0 and np.allclose(got, ref, rtol=1e-13, atol=0)

@@ -105,13 +105,19 @@ def main():
         del beta, gamma
         Ω = A.init_aux_variables(lik, n)
         t_gibbs = timeit(lambda: A.aux_sample_(Ω, lik, y, f), st, reps=3, warm=1)
+        extra = {}
+        if name == "hetero":                       # λ statistics, 40 / 24 B per observation
+            t_l = timeit(lambda: A.hetero_lambda_stats(y, qf), st, reps=args.reps)
+            t_ls = timeit(lambda: A.hetero_lambda_stats_sampled(y, f), st, reps=args.reps)
+            extra = dict(ms_lambda_stats=t_l, gbs_lambda_stats=40 * n / t_l / 1e6, frac_lambda_stats=40 * n / t_l / 1e6 / peak,
+                         ms_lambda_stats_sampled=t_ls, gbs_lambda_stats_sampled=24 * n / t_ls / 1e6)
         key = "cat" if cat else name.split("_")[0]
         units = n * nl if cat else n
         bpo = BYTES[key]
         rows.append(dict(likelihood=name, n=n, nlatent=nl, bytes_per_unit=bpo, ms_cavi_elbo=t_elbo, ms_cavi=t_plain,
                          gbs_cavi_elbo=bpo * units / t_elbo / 1e6, frac_elbo=bpo * units / t_elbo / 1e6 / peak,
                          gbs_cavi=bpo * units / t_plain / 1e6, frac=bpo * units / t_plain / 1e6 / peak,
-                         ms_gibbs=t_gibbs, draws_per_s=units / t_gibbs * 1e3))
+                         ms_gibbs=t_gibbs, draws_per_s=units / t_gibbs * 1e3, **extra))
         print(json.dumps(rows[-1]), flush=True)
         del q, Ω, mu, var, f, y, qf
         torch.cuda.empty_cache()
