@@ -257,4 +257,42 @@ end
 AGPL.logtilt(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::DV) = sampled_terms(lik, Ω, y, f, false)[S_LOGTILT]
 AGPL.aug_loglik(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::DV) = sampled_terms(lik, Ω, y, f, true)[S_AUGLL]
 
+# ---- multi-GPU (one Julia process per GPU, e.g. Distributed / MPI.jl) ------------------------------------------
+# Peer-memory mailbox: the all-reduce of the 64-byte scalar block runs INSIDE the reducing kernels (include/augcuda.h).
+# `allgather(bytes)` is the caller's transport (MPI.Allgather, a Distributed remotecall, ...): it must return the
+# concatenation of every rank's 64-byte handle in rank order, and act as a barrier.
+function init_p2p!(nranks::Integer, rank::Integer, allgather::Function; fused::Bool=true)
+    h = Vector{UInt8}(undef, 64)
+    check(ccall((:aug_comm_p2p_export, lib), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Ptr{Cvoid}}), ctx().h, h, C_NULL))
+    all = allgather(h)::Vector{UInt8}
+    length(all) == 64 * nranks || error("allgather must return nranks × 64 bytes")
+    check(ccall((:aug_comm_p2p_attach, lib), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), ctx().h, nranks, rank, all))
+    allgather(h)                       # barrier: nobody exchanges before everybody has mapped everybody
+    fused && check(ccall((:aug_comm_set_fused, lib), Int32, (Ptr{Cvoid}, Int32), ctx().h, 1))
+    return nothing
+end
+
+# ---- callers on either side of the path (SURVEY §8(f) rows 3-4) --------------------------------------------------
+# opt_lik of examples/heteroscedasticgaussian/script.jl:41-51 for device arguments
+function opt_lik(lik::HeteroscedasticGaussianLikelihood, qfg::DeviceNormals, y::DV; n_total::Integer=length(y))
+    out = AugDeviceVector{Float64}(undef, 1)
+    n = length(y)
+    check(ccall((:aug_hetero_lambda_stats, lib), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                ctx().h, n, y.ptr, qfg.μ.ptr, qfg.σ².ptr, n, out.ptr))
+    s = Array(out)[1]
+    return HeteroscedasticGaussianLikelihood(InvScaledLogistic(max(n_total / (2s), lik.invlink.λ)))
+end
+
+# (l::LogisticSoftMaxLink)(f) row-wise on a device matrix stored class-fastest (categorical.jl:32-35)
+function logisticsoftmax_rows(lik::CategoricalLikelihood, f::DV, n::Integer)
+    K = lik.invlink isa BijectiveSimplexLink ? nlatent(lik) + 1 : nlatent(lik)
+    out = AugDeviceVector{Float64}(undef, n * K)
+    withdesc(lik) do d
+        check(ccall((:aug_logisticsoftmax, lib), Int32, (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Float64}, Ptr{Float64}),
+                    ctx().h, d, n, f.ptr, out.ptr))
+    end
+    return out
+end
+
 end # module
