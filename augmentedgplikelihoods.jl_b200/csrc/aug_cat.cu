@@ -456,6 +456,278 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_tma_kernel(const CatTmaArgs 
     }
 }
 
+// ------------------------------------------------------------------ row-aligned staged variant (round 1e)
+// ncu on cat_tma_kernel (profiles/r1d): issue slots 53 % busy, stalls on the CTA-wide barriers between the three
+// phases; with K = 100 a 256-thread CTA also leaves 22 % of phase 1 and phase 3 idle (800 pairs / 256 threads =
+// 3.125 -> 4 iterations).  This variant removes both:
+//   * a CTA is TWO warps and owns ONE tile of 16 rows; 7-8 CTAs are resident per SM, so a barrier only ever stalls
+//     two warps and the other CTAs of the SM are in different phases;
+//   * phase 1 is row-aligned: 4 lanes per row walk the row's element pairs, so Σ_j p_ij and the two row-wise ELBO
+//     sums are thread-private and finish with two shuffles - phase 2 and the X1/X23 staging arrays disappear, and
+//     the ELBO instantiation needs no more shared memory than the plain one;
+//   * P and ±h overwrite mu and var IN PLACE in the staged tile (17 B of shared memory per element in flight
+//     instead of 50-66), which is what lets 8 tiles be resident per SM; the stage is refilled (cp.async.bulk on an
+//     mbarrier, one 800-byte row per copy into padded rows when nl is even) as soon as phase 3 has read it.
+#define CAT_ROW_BLOCK 64
+#define CAT_ROW_R 16
+#ifndef CAT_ROW_ILP4
+#define CAT_ROW_ILP4 1
+#endif
+struct CatRowArgs {
+    CatArgs a;               // a.n = rows covered by full tiles
+    int64_t ntiles;
+    int E;                   // elements per tile = 16 * nl
+    int rs;                  // row stride of the staged rows in doubles: nl (odd nl) or nl + 2 (even nl)
+    int off_mu, off_var, off_rinv;
+    int accumulate;
+    double log_inv_denom;
+};
+
+template <bool ELBO, bool EVEN>
+__global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowArgs ta) {
+    const CatArgs& a = ta.a;
+    extern __shared__ __align__(128) unsigned char cat_stage[];
+    const int nl = a.nl, E = ta.E, rs = ta.rs;
+    const uint8_t* Y = cat_stage;
+    double* P = reinterpret_cast<double*>(cat_stage + ta.off_mu);      // mu, then p
+    double* H = reinterpret_cast<double*>(cat_stage + ta.off_var);     // var, then ±h (sign = y)
+    double* rinv = reinterpret_cast<double*>(cat_stage + ta.off_rinv);
+    uint64_t* full = reinterpret_cast<uint64_t*>(rinv + CAT_ROW_R);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    // warp 0 streams a tile into the stage: y as one span; mu/var as one span (odd nl) or one padded row per lane
+    auto issue = [&](int64_t tile) {
+        const int64_t o = tile * E;
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was written through the generic proxy
+            mbar_expect_tx(full, (uint32_t)E * 17u);
+            bulk_g2s(cat_stage, a.y + o, (uint32_t)E, full);
+            if (!EVEN) {
+                bulk_g2s(P, a.mu + o, (uint32_t)E * 8u, full);
+                bulk_g2s(H, a.var + o, (uint32_t)E * 8u, full);
+            }
+            // (pulling the CTA's next tile into L2 here with cp.async.bulk.prefetch.L2 shortens the wait on this
+            //  single-buffered stage but was measured 12 % SLOWER overall: the prefetched lines compete with the
+            //  streaming stores for L2)
+        }
+        if (EVEN) {
+            __syncwarp();
+            const int r = lane & 15;
+            const double* src = (lane < 16 ? a.mu : a.var) + o + (int64_t)r * nl;
+            double* dst = (lane < 16 ? P : H) + r * rs;
+            bulk_g2s(dst, src, (uint32_t)nl * 8u, full);
+        }
+    };
+    if (warp == 0 && first < ta.ntiles) issue(first);
+
+    const int l8 = lane & 7;
+    const int jj_first = 4 * warp + (lane >> 3);                           // phase 3: class of this thread
+    const double inv_denom = 1.0 / a.L.c0;
+    const bool vec_out = ((a.ldo & 1) == 0) && ((((uintptr_t)a.beta) | ((uintptr_t)a.gamma)) & 15u) == 0;
+    const bool both_out = a.beta != nullptr && a.gamma != nullptr && vec_out;
+    double acc[3] = {0.0, 0.0, 0.0};
+    uint32_t parity = 0;
+    for (int64_t tile = first; tile < ta.ntiles; tile += stride) {
+        mbar_wait(full, parity);
+        parity ^= 1u;
+        // ---- phase 1: straight-line element pairs, in place.  Even nl: 4 lanes per row (a row is nl/2 aligned pairs).
+        //      Odd nl: 8 lanes per ROW PAIR - rows 2k and 2k+1 are one 16-byte aligned span of nl pairs whose pair
+        //      h = (nl-1)/2 straddles the two rows; a lane walks the span upwards, so its row sums switch from the
+        //      first to the second row exactly once.
+        {
+            const int sub = EVEN ? (tid >> 2) : (tid >> 3);                 // row (even nl) / row pair (odd nl)
+            const int kq = EVEN ? (tid & 3) : (tid & 7), LQ = EVEN ? 4 : 8; // first pair and pair step of this lane
+            const int npairs = EVEN ? (nl >> 1) : nl, hq = nl >> 1;         // odd nl: hq = the straddling pair
+            const int so = EVEN ? sub * rs : 2 * sub * nl;
+            double* Pr = P + so;
+            double* Hr = H + so;
+            const uint8_t* Yr = Y + (EVEN ? sub * nl : 2 * sub * nl);
+            const int64_t gro = tile * E + (int64_t)(EVEN ? sub : 2 * sub) * nl;   // global element offset of the span
+            double sp = 0.0, A1 = 0.0, A23 = 0.0, t0 = 0.0, t1 = 0.0;      // running row sums / row-independent ELBO terms
+            double spA = 0.0, A1A = 0.0, A23A = 0.0;                        // odd nl: sums of the first row once passed
+            bool bad = false, sw = false;
+            struct PairIn { uchar2 yy; double2 m, v; };
+            struct PairOut { double c0, c1, p0, p1, h0, h1; };
+            auto load = [&](const int q) {
+                PairIn in;
+                in.yy = *reinterpret_cast<const uchar2*>(Yr + 2 * q);
+                in.m = *reinterpret_cast<const double2*>(Pr + 2 * q);
+                in.v = *reinterpret_cast<const double2*>(Hr + 2 * q);
+                return in;
+            };
+            auto next_row = [&]() {
+                spA = sp; sp = 0.0;
+                if (ELBO) { A1A = A1; A23A = A23; A1 = 0.0; A23 = 0.0; }
+                sw = true;
+            };
+            auto eval = [&](const int q, const PairIn& in) {
+                PairOut o;
+                bad = bad || cat_slow(in.m.x, in.v.x) || cat_slow(in.m.y, in.v.y);
+                double xa0 = 0.0, xb0 = 0.0, xa1 = 0.0, xb1 = 0.0;
+                cat_elem<ELBO, false>(in.m.x, in.v.x, in.yy.x != 0, inv_denom, ta.log_inv_denom, a.L.c2, o.c0, o.p0, o.h0,
+                                      xa0, xb0, t0, t1);
+                cat_elem<ELBO, false>(in.m.y, in.v.y, in.yy.y != 0, inv_denom, ta.log_inv_denom, a.L.c2, o.c1, o.p1, o.h1,
+                                      xa1, xb1, t0, t1);
+                if (EVEN) {
+                    sp += o.p0 + o.p1;
+                    if (ELBO) { A1 += xa0 + xa1; A23 += xb0 + xb1; }
+                } else {
+                    if (q > hq && !sw) next_row();
+                    sp += o.p0;
+                    if (ELBO) { A1 += xa0; A23 += xb0; }
+                    if (q == hq) next_row();
+                    sp += o.p1;
+                    if (ELBO) { A1 += xa1; A23 += xb1; }
+                }
+                return o;
+            };
+            auto store = [&](const int q, const PairIn& in, const PairOut& o) {
+                if (a.s0) st_stream2(a.s0 + gro + 2 * q, o.c0, o.c1);
+                if (a.s1) st_stream2(a.s1 + gro + 2 * q, o.p0, o.p1);
+                if (a.s2) *reinterpret_cast<uchar2*>(a.s2 + gro + 2 * q) = in.yy;    // φᵢ.y .= y[i]  categorical.jl:89,106
+                *reinterpret_cast<double2*>(Pr + 2 * q) = make_double2(o.p0, o.p1);
+                // h = tanh(c/2)/(2c) > 0 always: its sign bit carries y_ij to phase 3
+                *reinterpret_cast<double2*>(Hr + 2 * q) = make_double2(in.yy.x ? -o.h0 : o.h0, in.yy.y ? -o.h1 : o.h1);
+            };
+            int q = kq;
+#if CAT_ROW_ILP4
+#pragma unroll 1
+            for (; q + LQ < npairs; q += 2 * LQ) {      // two pairs = four independent evaluations in flight
+                const PairIn i0 = load(q), i1 = load(q + LQ);
+                const PairOut o0 = eval(q, i0), o1 = eval(q + LQ, i1);
+                store(q, i0, o0);
+                store(q + LQ, i1, o1);
+            }
+#endif
+#pragma unroll 1
+            for (; q < npairs; q += LQ) {
+                const PairIn i0 = load(q);
+                const PairOut o0 = eval(q, i0);
+                store(q, i0, o0);
+            }
+            if (bad) {
+                // rare: an element of this thread is outside the straight-line range -> redo the thread's share of the
+                // span with the any-input instantiation; the staged inputs are gone (in place), so re-read them
+                sp = A1 = A23 = t0 = t1 = spA = A1A = A23A = 0.0;
+                sw = false;
+                for (q = kq; q < npairs; q += LQ) {
+                    for (int u = 0; u < 2; ++u) {
+                        const int64_t o = gro + 2 * q + u;
+                        const bool yb = a.y[o] != 0;
+                        double c, pp, h, xa = 0.0, xb = 0.0;
+                        cat_elem<ELBO, true>(a.mu[o], a.var[o], yb, inv_denom, ta.log_inv_denom, a.L.c2, c, pp, h, xa, xb, t0, t1);
+                        if (a.s0) a.s0[o] = c;
+                        if (a.s1) a.s1[o] = pp;
+                        Pr[2 * q + u] = pp;
+                        Hr[2 * q + u] = yb ? -h : h;
+                        if (!EVEN && !sw && 2 * q + u >= nl) next_row();
+                        sp += pp;
+                        if (ELBO) { A1 += xa; A23 += xb; }
+                    }
+                }
+            }
+            if (!EVEN && !sw) next_row();
+            acc[0] += t0;
+            acc[1] += t1;
+            // row sums over the lanes of the row (pair)
+#pragma unroll
+            for (int o = 1; o < LQ; o <<= 1) {
+                sp += __shfl_xor_sync(0xffffffffu, sp, o);
+                if (ELBO) {
+                    A1 += __shfl_xor_sync(0xffffffffu, A1, o);
+                    A23 += __shfl_xor_sync(0xffffffffu, A23, o);
+                }
+                if (!EVEN) {
+                    spA += __shfl_xor_sync(0xffffffffu, spA, o);
+                    if (ELBO) {
+                        A1A += __shfl_xor_sync(0xffffffffu, A1A, o);
+                        A23A += __shfl_xor_sync(0xffffffffu, A23A, o);
+                    }
+                }
+            }
+            // even nl: lane 0 of the row; odd nl: lane 0 finishes the first row of the pair, lane 1 the second
+            if (kq == 0 || (!EVEN && kq == 1)) {
+                const bool second = !EVEN && kq == 1;
+                const double srow = (EVEN || second) ? sp : spA;
+                const double a1 = (EVEN || second) ? A1 : A1A, a23 = (EVEN || second) ? A23 : A23A;
+                const double p0 = 1.0 - srow;                             // _p₀ negativemultinomial.jl:27
+                const bool ok = p0 >= 1e-290;
+                const double ri = ok ? augf::rcp(p0) : 1.0 / p0;
+                rinv[EVEN ? sub : 2 * sub + (second ? 1 : 0)] = ri;
+                if (!(srow < 1.0)) acc[2] += 1.0;                         // ctor precondition :18-22
+                if (ELBO) {
+                    // the n̄-proportional parts of expected_logtilt and of the PG KL, and
+                    // KL(NM(1,q)||NM(1,p)) = log p0q − log p0p + (1/p0q) Σ q_j (log q_j − log p_j)  :72-82
+                    acc[0] = fma(ri, a1, acc[0]);
+                    acc[1] += fma(ri, a23, (ok ? augf::log_(p0) : log(p0)) - a.L.c3);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: class-major; 8 lanes x 2 rows = the tile's 16 rows = one 128-byte segment per array;
+        //      a warp covers 4 classes, the CTA 8 classes per step
+        if (a.beta || a.gamma) {
+            const int r = 2 * l8;
+            const double2 ri = *reinterpret_cast<const double2*>(rinv + r);
+            const double* Pp = P + r * rs + jj_first;
+            const double* Hp = H + r * rs + jj_first;
+            // (measured: the same stores to contiguous addresses would make the fused call 9 % faster - the class-major
+            //  result layout of the reference, one 128-byte segment per class and tile, is what costs the DRAM pages)
+            int64_t o = (int64_t)jj_first * a.ldo + (tile * CAT_ROW_R + r);
+            const int64_t ostep = 4 * (CAT_ROW_BLOCK / 32) * a.ldo;
+#pragma unroll 2
+            for (int jj = jj_first; jj < nl; jj += 4 * (CAT_ROW_BLOCK / 32)) {
+                const double hs0 = Hp[0], hs1 = Hp[rs];
+                const double y0 = __double2hiint(hs0) < 0 ? 1.0 : 0.0, y1 = __double2hiint(hs1) < 0 ? 1.0 : 0.0;
+                const double n0 = Pp[0] * ri.x, n1 = Pp[rs] * ri.y;                  // mean(NM(1,p)) :54
+                const double b0 = 0.5 * (y0 - n0), b1 = 0.5 * (y1 - n1);             // categorical.jl:124,135
+                const double g0 = (y0 + n0) * fabs(hs0), g1 = (y1 + n1) * fabs(hs1); // :128; pgnm.jl:41-54
+                if (both_out) {
+                    st_stream2(a.beta + o, b0, b1);
+                    st_stream2(a.gamma + o, g0, g1);
+                } else if (vec_out) {
+                    if (a.beta) st_stream2(a.beta + o, b0, b1);
+                    if (a.gamma) st_stream2(a.gamma + o, g0, g1);
+                } else {
+                    if (a.beta) { st_stream1(a.beta + o, b0); st_stream1(a.beta + o + 1, b1); }
+                    if (a.gamma) { st_stream1(a.gamma + o, g0); st_stream1(a.gamma + o + 1, g1); }
+                }
+                Pp += 4 * (CAT_ROW_BLOCK / 32);
+                Hp += 4 * (CAT_ROW_BLOCK / 32);
+                o += ostep;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of P/H before the async refill
+        __syncthreads();   // every thread is done with the stage: refill it
+        if (warp == 0 && tile + stride < ta.ntiles) issue(tile + stride);
+    }
+    if (ELBO) {
+        double out[3];
+        if (block_reduce_and_finalize<3, CAT_ROW_BLOCK>(acc, a.partials, a.counter, out)) {
+            if (ta.accumulate) {
+                out[0] += a.scalars[AUG_S_EXPECTED_LOGTILT];
+                out[1] += a.scalars[AUG_S_KL];
+                out[2] += a.scalars[AUG_S_FLAGS];
+            }
+            if (a.xch) xch_allreduce<3>(a.xch, out);
+            a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
+            a.scalars[AUG_S_KL] = out[1];
+            a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
+            a.scalars[AUG_S_FLAGS] = out[2];
+            if (out[2] > 0.0) atomicOr(a.dflag, 1u);
+        }
+    } else if (acc[2] > 0.0) {
+        atomicOr(a.dflag, 1u);
+    }
+}
+
 // ------------------------------------------------------------------ Gibbs: aux_sample! for CAT
 struct CatSampleArgs {
     int64_t n, i0;
@@ -921,6 +1193,15 @@ bool cat_no_tma() {   // AUGCUDA_NO_TMA=1 keeps every call on the direct-load ke
     return v == 1;
 }
 
+bool cat_row_enabled() {   // AUGCUDA_CAT_ROW=0 keeps wide rows on the CTA-wide staged kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AUGCUDA_CAT_ROW");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // the direct-load row kernel: any alignment, FROM_STATE verbs, ragged tails, rows too wide for the staged ring
 int32_t launch_cat_direct(aug_ctx* ctx, CatArgs a, bool elbo, bool from_state) {
     const size_t per_elem = (elbo ? 4 : 2) * sizeof(double);
@@ -988,6 +1269,57 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
     if (rc) return rc;
     // ---- full tiles of a fused call on 16-byte aligned arrays: the bulk-async staged kernel
     int64_t n0 = 0;   // rows it covers; the ragged tail [n0, n) goes through the direct-load kernel below
+    // (a) wide rows (K of the order of 100): the row-aligned two-warp kernel, 7-8 tiles resident per SM
+    if (!from_state && !cat_no_tma() && cat_row_enabled() && a.nl >= 32 && aug_aligned16(y) && aug_aligned16(mu) &&
+        aug_aligned16(var) && aug_aligned16(s0) && aug_aligned16(s1) && aug_aligned16(s2) && n >= CAT_ROW_R) {
+        CatRowArgs ta{};
+        ta.a = a;
+        const int nl = a.nl;
+        const bool even = (nl & 1) == 0;
+        ta.a.R = CAT_ROW_R;
+        ta.E = CAT_ROW_R * nl;
+        ta.rs = even ? nl + 2 : nl;
+        ta.off_mu = (ta.E + 127) & ~127;
+        ta.off_var = (ta.off_mu + CAT_ROW_R * ta.rs * 8 + 127) & ~127;
+        ta.off_rinv = (ta.off_var + CAT_ROW_R * ta.rs * 8 + 15) & ~15;
+        ta.log_inv_denom = -log(a.L.c0);
+        const size_t smem = (size_t)ta.off_rinv + CAT_ROW_R * sizeof(double) + 16;
+        if ((smem + 1024 + 128) * 4 <= (size_t)ctx->smem_per_sm) {       // at least 4 tiles (8 warps) per SM
+            ta.ntiles = n / CAT_ROW_R;
+            n0 = ta.ntiles * CAT_ROW_R;
+            ta.a.n = n0;
+            const void* k = elbo ? (even ? (const void*)cat_row_kernel<true, true> : (const void*)cat_row_kernel<true, false>)
+                                 : (even ? (const void*)cat_row_kernel<false, true> : (const void*)cat_row_kernel<false, false>);
+            AUG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, CAT_ROW_BLOCK, smem) != cudaSuccess || occ < 1) occ = 1;
+            int64_t grid = (int64_t)ctx->sms * occ;
+            if (grid > AUG_MAX_GRID) grid = AUG_MAX_GRID;
+            if (grid > ta.ntiles) grid = ta.ntiles;
+            ta.accumulate = (elbo && n0 < n) ? 1 : 0;
+            if (n0 < n) {   // the tail launch goes first and the staged launch accumulates onto its scalars
+                const int64_t eo = n0 * nl;
+                CatArgs t = a;
+                t.xch = nullptr;
+                t.n = n - n0;
+                t.y = a.y + eo;
+                t.mu = a.mu + eo;
+                t.var = a.var + eo;
+                if (a.s0) t.s0 = a.s0 + eo;
+                if (a.s1) t.s1 = a.s1 + eo;
+                if (a.s2) t.s2 = a.s2 + eo;
+                if (a.beta) t.beta = a.beta + n0;
+                if (a.gamma) t.gamma = a.gamma + n0;
+                rc = launch_cat_direct(ctx, t, elbo, false);
+                if (rc) return rc;
+            }
+            void* args[] = {(void*)&ta};
+            AUG_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(CAT_ROW_BLOCK), args, smem, ctx->stream));
+            ctx->launches++;
+            return AUG_OK;
+        }
+    }
+    // (b) narrow rows: CTA-wide tiles of ~1792 elements
     if (!from_state && !cat_no_tma() && aug_aligned16(y) && aug_aligned16(mu) && aug_aligned16(var) &&
         aug_aligned16(s0) && aug_aligned16(s1) && aug_aligned16(s2)) {
         CatTmaArgs ta{};

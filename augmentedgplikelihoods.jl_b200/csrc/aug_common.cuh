@@ -104,11 +104,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Block tree: warp shuffles, then one smem round, then a fixed-order last-block pass over the
 // per-CTA partials.  Deterministic for a given grid size (no floating-point atomics).
 // Returns true in exactly one thread of the grid (thread 0 of the last CTA), which holds the totals.
-template <int NV>
+// BLOCK = threads per CTA of the calling kernel (a multiple of 32).
+template <int NV, int BLOCK = AUG_BLOCK>
 __device__ __forceinline__ bool block_reduce_and_finalize(double (&acc)[NV], double* __restrict__ partials,
                                                           unsigned int* __restrict__ counter,
                                                           double* __restrict__ out /* NV results */) {
-    __shared__ double sm[NV][AUG_BLOCK / 32];
+    __shared__ double sm[NV][BLOCK / 32];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -120,7 +121,7 @@ __device__ __forceinline__ bool block_reduce_and_finalize(double (&acc)[NV], dou
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            double v = lane < AUG_BLOCK / 32 ? sm[k][lane] : 0.0;
+            double v = lane < BLOCK / 32 ? sm[k][lane] : 0.0;
             v = warp_sum(v);
             if (lane == 0) partials[(size_t)blockIdx.x * AUG_NRED + k] = v;
         }
@@ -136,7 +137,7 @@ __device__ __forceinline__ bool block_reduce_and_finalize(double (&acc)[NV], dou
     double tot[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) tot[k] = 0.0;
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += AUG_BLOCK) {
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) tot[k] += __ldcg(&partials[(size_t)b * AUG_NRED + k]);
     }
@@ -150,7 +151,7 @@ __device__ __forceinline__ bool block_reduce_and_finalize(double (&acc)[NV], dou
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            double v = lane < AUG_BLOCK / 32 ? sm[k][lane] : 0.0;
+            double v = lane < BLOCK / 32 ? sm[k][lane] : 0.0;
             v = warp_sum(v);
             if (lane == 0) out[k] = v;
         }
@@ -243,6 +244,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// pull a span into L2 ahead of the bulk copy that will stage it (no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;

@@ -227,7 +227,8 @@ def test_large_n_properties(A):
 
 @pytest.mark.parametrize("nl,bij,n", [(1, True, 5000), (2, False, 3001), (16, True, 700), (31, True, 333),
                                       (99, True, 2000), (100, False, 2000), (130, True, 515), (100, True, 16),
-                                      (257, True, 100)])
+                                      (257, True, 100), (33, True, 100), (64, False, 200), (65, True, 97),
+                                      (200, False, 64), (199, True, 50)])
 def test_categorical_staged_kernel_vs_oracle(A, orc, nl, bij, n):
     """The bulk-async staged kernel (full 16k-row tiles) + the direct-load kernel on the ragged tail, at class
     counts that put rows on every alignment; extreme inputs (|m| beyond the straight-line range, saturation of
@@ -260,10 +261,11 @@ def test_categorical_staged_kernel_vs_oracle(A, orc, nl, bij, n):
         if want_elbo:
             s = host(scal)
             for k in range(3):
-                assert s[k] == pytest.approx(ocomp[k], rel=RTOL, abs=1e-12), (nl, n, k)
+                # (narrow rows: the planted saturated classes make Σp >= 1 in row 0 -> NaN KL on both sides)
+                assert s[k] == pytest.approx(ocomp[k], rel=RTOL, abs=1e-12, nan_ok=True), (nl, n, k)
             # state-only verbs (direct-load kernel) agree with the fused staged kernel
-            assert A.expected_logtilt(lik, q, dev(y), A.Normals(dev(mu), dev(var))) == pytest.approx(s[0], rel=RTOL)
-            assert A.aux_kldivergence(lik, q, dev(y), A.Normals(dev(mu), dev(var))) == pytest.approx(s[1], rel=RTOL)
+            assert A.expected_logtilt(lik, q, dev(y), A.Normals(dev(mu), dev(var))) == pytest.approx(s[0], rel=RTOL, nan_ok=True)
+            assert A.aux_kldivergence(lik, q, dev(y), A.Normals(dev(mu), dev(var))) == pytest.approx(s[1], rel=RTOL, nan_ok=True)
 
 
 def test_categorical_sum_p_precondition_flag(A):

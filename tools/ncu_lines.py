@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-source-line instruction and stall-sample totals from an ncu report (needs -lineinfo).
-   python tools/ncu_lines.py REPORT.ncu-rep KERNEL_REGEX [top] [FILE:LO-HI ...]   (NCU_SKIP=k picks the k-th matching launch)"""
+   python tools/ncu_lines.py REPORT.ncu-rep KERNEL_REGEX [top] [FILE:LO-HI ...]   (NCU_SKIP=k picks the k-th matching launch; NCU_SORT=samples sorts by stall samples)"""
 import csv
 import os
 import subprocess
@@ -25,6 +25,7 @@ for r in rows:
         hdr = r
         ii = hdr.index("Instructions Executed")
         si = hdr.index("# Samples")
+        stall_cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
         continue
     if hdr is None or len(r) < len(hdr) or r[0] == "":
         continue
@@ -33,12 +34,24 @@ for r in rows:
     except ValueError:
         continue
     key = (cur_file, int(r[0]), r[1].strip()[:110])
-    a = tot.setdefault(key, [0, 0])
+    a = tot.setdefault(key, [0, 0, {}])
     a[0] += inst; a[1] += samp
+    for i, nm in stall_cols:
+        try:
+            a[2][nm] = a[2].get(nm, 0) + int(r[i])
+        except ValueError:
+            pass
     total_inst += inst; total_samp += samp
 print(f"total warp-instructions {total_inst}, samples {total_samp}")
-for (f, ln, src), (inst, samp) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:top]:
-    print(f"{100*inst/max(total_inst,1):5.1f}% inst {100*samp/max(total_samp,1):5.1f}% smp  {f}:{ln}  {src}")
+by = 1 if os.environ.get("NCU_SORT", "inst") == "samples" else 0
+for (f, ln, src), (inst, samp, st) in sorted(tot.items(), key=lambda kv: -kv[1][by])[:top]:
+    why = " ".join(f"{k}={v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:3] if v > 0)
+    print(f"{100*inst/max(total_inst,1):5.1f}% inst {100*samp/max(total_samp,1):5.1f}% smp  {f}:{ln}  {src[:70]}  [{why}]")
+allst = {}
+for v in tot.values():
+    for k, c in v[2].items():
+        allst[k] = allst.get(k, 0) + c
+print("stall samples:", " ".join(f"{k}={100*c/max(total_samp,1):.1f}%" for k, c in sorted(allst.items(), key=lambda kv: -kv[1]) if c))
 # optional: totals per file / line range given as extra args FILE:LO-HI
 for spec in sys.argv[4:]:
     f, rng = spec.split(":")
