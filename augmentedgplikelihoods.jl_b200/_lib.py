@@ -71,6 +71,11 @@ SIGNATURES = {
     "aug_hetero_lambda_stats_sampled": [_vp, _i64, _vp, _vp, _i64, _vp],
     "aug_logisticsoftmax": [_vp, C.POINTER(AugLik), _i64, _vp, _vp],
     "aug_approx_expected_logisticsoftmax": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _vp],
+    "aug_sparse_marginals": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "aug_sparse_precision_potential": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "aug_sparse_cavi_sweep": [_vp, C.POINTER(AugLik), _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _vp, _vp, _vp, _vp, _vp, _vp],
+    "aug_dense_precision_potential": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "aug_comm_get_unique_id": [C.c_char * 128],
     "aug_comm_init": [_vp, _i32, _i32, C.c_char * 128],
     "aug_comm_destroy": [_vp],

@@ -712,3 +712,101 @@ def approx_expected_logisticsoftmax(mu, c, lik: CategoricalLikelihood, ctx=None)
                                                       _ptr(_f64(c, "c")), _ptr(out)))
     ctx.leave()
     return out
+
+
+# ----------------------------------------------------------------------------- SURVEY §8(f) rows 1 and 2
+def _kappa(kappa):
+    """κ = K_Z⁻¹ K_{Z,X}: Julia's column-major M×N matrix = a contiguous [n][m] tensor here."""
+    if kappa.dim() != 2:
+        raise ValueError("kappa must be [n][m] (the Julia M×N matrix as stored)")
+    if kappa.shape[1] > 128:
+        raise ValueError("m <= 128 inducing points")
+    return _f64(kappa, "kappa")
+
+
+def sparse_marginals(kappa, mvec, B, kdiag, ctx=None) -> Normals:
+    """marginals(post_u(x)) of the SVGP posterior — examples/bernoulli/script.jl:32-33:
+    μ_t = κ_tᵀ m, σ²_t = k_tt − κ_tᵀ (K_Z − S) κ_t.  B = K_Z − S ([m][m])."""
+    ctx = ctx or default_context()
+    kappa = _kappa(kappa)
+    n, m = kappa.shape
+    ctx.enter()
+    mu, var = ctx.empty((n,)), ctx.empty((n,))
+    check(ctx.lib.aug_sparse_marginals(ctx.h, n, m, _ptr(kappa), _ptr(_f64(mvec, "mvec")), _ptr(_f64(B, "B")),
+                                       _ptr(_f64(kdiag, "kdiag")), _ptr(mu), _ptr(var)))
+    ctx.leave()
+    return Normals(mu, var)
+
+
+def _split_pr(Pr, m):
+    return Pr[: m * m].view(m, m), Pr[m * m:]
+
+
+def _reduce_pr(ctx, Pr):
+    if ctx.comm_ready:              # shards of the observation axis: P and rhs are plain sums (SURVEY §8e)
+        check(ctx.lib.aug_allreduce_scalars(ctx.h, _ptr(Pr), Pr.numel()))
+
+
+def sparse_precision_potential(kappa, gamma, beta, P0=None, r0=None, ctx=None):
+    """docs/src/index.md:156-160: returns (P0 + κ·Diagonal(γ)·κᵀ, r0 + κ·β).  In a sharded run pass P0 / r0 on
+    rank 0 only; the sums over ranks are taken here when a communicator is attached."""
+    ctx = ctx or default_context()
+    kappa = _kappa(kappa)
+    n, m = kappa.shape
+    ctx.enter()
+    Pr = ctx.empty((m * m + m,))
+    check(ctx.lib.aug_sparse_precision_potential(ctx.h, n, m, _ptr(kappa), _ptr(_f64(gamma, "gamma")),
+                                                 _ptr(_f64(beta, "beta")), _ptr(P0), _ptr(r0), _ptr(Pr)))
+    _reduce_pr(ctx, Pr)
+    ctx.leave()
+    return _split_pr(Pr, m)
+
+
+def sparse_cavi_sweep_(qΩ: Optional[AuxPosterior], lik, y, kappa, mvec, B, kdiag, P0=None, r0=None,
+                       want_elbo: bool = True, want_marginals: bool = False, want_potentials: bool = False,
+                       ctx: Optional[Context] = None):
+    """One pass over κ for a whole CAVI iteration of a sparse variational GP (examples/bernoulli/script.jl:29-39 with
+    the sparse update of docs/src/index.md:154-163): marginals → aux_posterior!(qΩ, …) → E[β], E[γ] (+ ELBO sums)
+    → P = P0 + κ·Diagonal(γ)·κᵀ, rhs = r0 + κ·β.  qΩ may be None (state not materialised).
+    Returns (P [m][m], rhs [m], scalars | None, qf | None, (β, γ) | None)."""
+    ctx = ctx or default_context()
+    if lik.kind in (HETERO, CAT, CAT_BIJ):
+        raise ValueError("multi-latent likelihoods: call sparse_marginals / sparse_precision_potential per latent GP")
+    y = _check_y(lik, y)
+    kappa = _kappa(kappa)
+    n, m = kappa.shape
+    d = lik._desc()
+    ctx.enter()
+    Pr = ctx.empty((m * m + m,))
+    scal = ctx.empty((NSCALARS,)) if want_elbo else None
+    if scal is not None:
+        scal.zero_()
+    mu = ctx.empty((n,)) if want_marginals else None
+    var = ctx.empty((n,)) if want_marginals else None
+    beta = ctx.empty((n,)) if want_potentials else None
+    gamma = ctx.empty((n,)) if want_potentials else None
+    s = [qΩ._s(i) if qΩ is not None else None for i in range(3)]
+    check(ctx.lib.aug_sparse_cavi_sweep(ctx.h, C.byref(d), n, m, _ptr(y), _ptr(kappa), _ptr(_f64(mvec, "mvec")),
+                                        _ptr(_f64(B, "B")), _ptr(_f64(kdiag, "kdiag")), _ptr(mu), _ptr(var),
+                                        _ptr(s[0]), _ptr(s[1]), _ptr(s[2]), _ptr(beta), _ptr(gamma), _ptr(P0),
+                                        _ptr(r0), _ptr(Pr), _ptr(scal)))
+    _reduce_pr(ctx, Pr)
+    if scal is not None and ctx.comm_ready:
+        check(ctx.lib.aug_allreduce_scalars(ctx.h, _ptr(scal), NSCALARS))
+    ctx.leave()
+    P, rhs = _split_pr(Pr, m)
+    return (P, rhs, scal, Normals(mu, var) if want_marginals else None,
+            (beta, gamma) if want_potentials else None)
+
+
+def dense_precision_potential(Kinv, gamma, beta, r0=None, out=None, ctx=None):
+    """examples/bernoulli/script.jl:35-36: (inv(K) + Diagonal(γ), β + K \\ mean(fz)); out=Kinv updates in place."""
+    ctx = ctx or default_context()
+    n = gamma.numel()
+    ctx.enter()
+    P = out if out is not None else ctx.empty((n, n))
+    rhs = ctx.empty((n,))
+    check(ctx.lib.aug_dense_precision_potential(ctx.h, n, _ptr(_f64(Kinv, "Kinv")), _ptr(_f64(gamma, "gamma")),
+                                                _ptr(_f64(beta, "beta")), _ptr(r0), _ptr(P), _ptr(rhs)))
+    ctx.leave()
+    return P, rhs

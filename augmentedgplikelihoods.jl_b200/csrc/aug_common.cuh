@@ -72,6 +72,9 @@ struct aug_ctx {
     int xch_ranks, xch_rank;
     int fused;                                     // reducing verbs return globally reduced scalars
     aug_pipe* pipe;
+    // sparse-GP sweep (aug_sparse.cu): per-CTA partial P / rhs / ELBO sums, summed in a fixed order by a finalise launch
+    double* sparse_scratch;
+    size_t sparse_scratch_bytes;
 };
 
 // Likelihood constants precomputed on the host once per call (never per observation)

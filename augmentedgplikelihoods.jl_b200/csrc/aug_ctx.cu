@@ -392,6 +392,7 @@ int32_t aug_ctx_destroy(aug_ctx* c) {
     if (c->table) cudaFree(c->table);
     if (c->pgtab) cudaFree(c->pgtab);
     if (c->dtheta) cudaFree(c->dtheta);
+    if (c->sparse_scratch) cudaFree(c->sparse_scratch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return AUG_OK;

@@ -270,6 +270,40 @@ int32_t aug_logisticsoftmax(aug_ctx* ctx, const aug_lik* lik, int64_t n, const d
 int32_t aug_approx_expected_logisticsoftmax(aug_ctx* ctx, const aug_lik* lik, int64_t n, const double* mu,
                                             const double* c, double* out);
 
+/* ---- the sparse-GP steps either side of the path ----------------------------------
+ * The reference's user loop (examples/bernoulli/script.jl:29-39; sparse form docs/src/index.md:154-163) is
+ *   qf = marginals(post_u(x));  aux_posterior!(qΩ, lik, y, qf);
+ *   S = inv(K_Z⁻¹ + κ·Diagonal(γ)·κᵀ);  m = S·(κ·β + K_Z⁻¹ μ₀(Z)),        κ = K_Z⁻¹ K_{Z,X}  (M×N)
+ * `kappa` is that Julia matrix as stored (column-major M×N) = [n][m], inducing index fastest; m <= 128.
+ * B = K_Z − S (M×M, symmetric; read as given, the quadratic form does not depend on its storage order).
+ * Outputs: Pr = [m*m + m] doubles, Pr[i*m + j] = P0[i*m+j] + Σ_t γ_t κ_it κ_jt (exactly symmetric), Pr[m*m + i] =
+ * r0[i] + Σ_t β_t κ_it;  P0 / r0 may be NULL (zeros).  Sums over observations run in a fixed order for a given
+ * device (bit-reproducible).  Multi-GPU: shard kappa / y by observations, pass P0 / r0 on rank 0 only and
+ * aug_allreduce_scalars(ctx, Pr, m*m + m) (and the scalar block) afterwards.
+ * FP64 tensor-core kernels (DMMA m8n8k4): 3·m² flops per observation for the fused sweep (2·m² producer + m²
+ * consumer, the symmetric half), bound by the FP64 pipe for m >= 32 and by HBM (8·m bytes per observation) below. */
+
+/* row 2 — marginals(post_u(x)), examples/bernoulli/script.jl:32-33 (SVGP posterior with q(u) = N(mvec, S), zero
+ * prior mean): mu_t = κ_tᵀ·mvec, var_t = kdiag_t − κ_tᵀ·B·κ_t. */
+int32_t aug_sparse_marginals(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa, const double* mvec,
+                             const double* B, const double* kdiag, double* mu, double* var);
+/* row 1 — docs/src/index.md:156-160: P = P0 + κ·Diagonal(gamma)·κᵀ, rhs = r0 + κ·beta. */
+int32_t aug_sparse_precision_potential(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa,
+                                       const double* gamma, const double* beta, const double* P0,
+                                       const double* r0, double* Pr);
+/* rows 2 + path + 1 in ONE pass over kappa (scalar-latent likelihoods): marginals → aux_posterior! →
+ * expected_auglik_potential_and_precision (+ expected_logtilt / aux_kldivergence sums) → P, rhs.  mu / var /
+ * s0 / s1 / s2 / beta / gamma are optional per-observation outputs (NULL: not materialised); scalars as in
+ * aug_cavi_step or NULL. */
+int32_t aug_sparse_cavi_sweep(aug_ctx* ctx, const aug_lik* lik, int64_t n, int32_t m, const void* y,
+                              const double* kappa, const double* mvec, const double* B, const double* kdiag,
+                              double* mu, double* var, void* s0, void* s1, void* s2, double* beta,
+                              double* gamma, const double* P0, const double* r0, double* Pr, double* scalars);
+/* dense (non-sparse) form, examples/bernoulli/script.jl:35-36: P = Kinv + Diagonal(gamma) (n×n, P may alias
+ * Kinv), rhs = r0 + beta (r0 = K \ mean(fz) or NULL). */
+int32_t aug_dense_precision_potential(aug_ctx* ctx, int64_t n, const double* Kinv, const double* gamma,
+                                      const double* beta, const double* r0, double* P, double* rhs);
+
 /* ---- multi-GPU: shard over observations, all-reduce only the scalars ---- */
 int32_t aug_comm_get_unique_id(char uid[128]);
 int32_t aug_comm_init(aug_ctx* ctx, int32_t nranks, int32_t rank, const char uid[128]);

@@ -1215,4 +1215,59 @@ int orc_approx_expected_logisticsoftmax(const aug_lik* l, int64_t n, const doubl
     return 0;
 }
 
+// ---- the sparse-GP steps either side of the path ---------------------------------
+// The reference has NO code for these (they live in the user's loop): the formulas are the ones of
+// docs/src/index.md:154-163 and examples/bernoulli/script.jl:29-39 with the SVGP posterior marginals of
+// ApproximateGPs (Centered parametrisation, zero prior mean):
+//   κ = K_Z⁻¹ K_{Z,X} (M×N, Julia column-major = kappa[t*m + i]),   B = K_Z − S
+//   μ_t = κ_tᵀ m,   σ²_t = k_tt − κ_tᵀ B κ_t
+//   P = P0 + κ Diagonal(γ) κᵀ,   rhs = r0 + κ β
+// Straightforward loops in long double (x87 80-bit): the parity target of the GPU tree / tensor-core sums.
+int orc_sparse_marginals(int64_t n, int m, const double* kappa, const double* mvec, const double* B,
+                         const double* kdiag, double* mu, double* var) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int64_t t = 0; t < n; ++t) {
+        const double* k = kappa + t * m;
+        long double a = 0, q = 0;
+        for (int i = 0; i < m; ++i) a += (long double)mvec[i] * k[i];
+        for (int i = 0; i < m; ++i) {
+            long double r = 0;
+            for (int j = 0; j < m; ++j) r += (long double)B[(size_t)i * m + j] * k[j];
+            q += r * k[i];
+        }
+        mu[t] = (double)a;
+        var[t] = (double)((long double)kdiag[t] - q);
+    }
+    return 0;
+}
+int orc_sparse_precision_potential(int64_t n, int m, const double* kappa, const double* gamma, const double* beta,
+                                   const double* P0, const double* r0, double* Pr) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int i = 0; i < m; ++i) {
+        for (int j = 0; j <= i; ++j) {
+            long double a = 0;
+            for (int64_t t = 0; t < n; ++t) a += (long double)gamma[t] * kappa[t * m + i] * kappa[t * m + j];
+            Pr[(size_t)i * m + j] = (double)(a + (P0 ? (long double)P0[(size_t)i * m + j] : 0.0L));
+            Pr[(size_t)j * m + i] = (double)(a + (P0 ? (long double)P0[(size_t)j * m + i] : 0.0L));
+        }
+        long double b = 0;
+        for (int64_t t = 0; t < n; ++t) b += (long double)beta[t] * kappa[t * m + i];
+        Pr[(size_t)m * m + i] = (double)(b + (r0 ? (long double)r0[i] : 0.0L));
+    }
+    return 0;
+}
+// the reference's call sequence for one sparse CAVI iteration, as separate passes with temporaries
+// (marginals → aux_posterior! → expected potential / precision → ELBO terms → P, rhs)
+int orc_sparse_cavi_sweep(const aug_lik* l, int64_t n, int m, const void* y, const double* kappa, const double* mvec,
+                          const double* B, const double* kdiag, double* mu, double* var, void* s0, void* s1, void* s2,
+                          double* beta, double* gamma, const double* P0, const double* r0, double* Pr,
+                          double* scalars, double* scalars_comp) {
+    int rc = orc_sparse_marginals(n, m, kappa, mvec, B, kdiag, mu, var);
+    if (rc) return rc;
+    rc = orc_cavi_step(l, n, y, mu, var, 0, s0, s1, s2, beta, gamma, n, scalars, scalars_comp);
+    if (rc) return rc;
+    return orc_sparse_precision_potential(n, m, kappa, gamma, beta, P0, r0, Pr);
+}
+
 }  // extern "C"
+

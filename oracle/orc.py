@@ -285,3 +285,39 @@ def approx_expected_logisticsoftmax(lik, mu, c):
     rc = lib().orc_approx_expected_logisticsoftmax(C.byref(lik), C.c_int64(n), _p(np.ascontiguousarray(mu)),
                                                    _p(np.ascontiguousarray(c)), _p(out))
     return rc, out
+
+
+# ---- SURVEY §8(f) rows 1 and 2 (sparse-GP producer / consumer) ------------------------------------
+def sparse_marginals(kappa, mvec, B, kdiag):
+    n, m = kappa.shape
+    mu, var = np.zeros(n), np.zeros(n)
+    rc = lib().orc_sparse_marginals(C.c_int64(n), C.c_int(m), _p(np.ascontiguousarray(kappa)),
+                                    _p(np.ascontiguousarray(mvec)), _p(np.ascontiguousarray(B)),
+                                    _p(np.ascontiguousarray(kdiag)), _p(mu), _p(var))
+    assert rc == 0
+    return mu, var
+
+
+def sparse_precision_potential(kappa, gamma, beta, P0=None, r0=None):
+    n, m = kappa.shape
+    Pr = np.zeros(m * m + m)
+    rc = lib().orc_sparse_precision_potential(C.c_int64(n), C.c_int(m), _p(np.ascontiguousarray(kappa)),
+                                              _p(np.ascontiguousarray(gamma)), _p(np.ascontiguousarray(beta)),
+                                              _p(P0), _p(r0), _p(Pr))
+    assert rc == 0
+    return Pr[: m * m].reshape(m, m), Pr[m * m:]
+
+
+def sparse_cavi_sweep(lik, y, kappa, mvec, B, kdiag, P0=None, r0=None, with_y_copy=True):
+    n, m = kappa.shape
+    mu, var = np.zeros(n), np.zeros(n)
+    state = alloc_state(lik, n, with_y_copy)
+    beta, gamma = np.zeros((1, n)), np.zeros((1, n))
+    seq, comp = np.zeros(8), np.zeros(8)
+    Pr = np.zeros(m * m + m)
+    rc = lib().orc_sparse_cavi_sweep(C.byref(lik), C.c_int64(n), C.c_int(m), _p(y), _p(np.ascontiguousarray(kappa)),
+                                     _p(np.ascontiguousarray(mvec)), _p(np.ascontiguousarray(B)),
+                                     _p(np.ascontiguousarray(kdiag)), _p(mu), _p(var), _p(state[0]), _p(state[1]),
+                                     _p(state[2]), _p(beta), _p(gamma), _p(P0), _p(r0), _p(Pr), _p(seq), _p(comp))
+    return rc, dict(mu=mu, var=var, state=state, beta=beta[0], gamma=gamma[0], P=Pr[: m * m].reshape(m, m),
+                    rhs=Pr[m * m:], seq=seq, comp=comp)

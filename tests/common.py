@@ -83,3 +83,18 @@ def synth_inputs(kind, n, seed, params=(), nlatent=1):
     else:
         raise ValueError(kind)
     return y, mu, var, f
+
+
+def synth_sparse(n, m, seed):
+    """Well-conditioned synthetic sparse-GP inputs for SURVEY §8(f) rows 1-2: κ ~ N(0, 1/m) ([n][m], the Julia
+    M×N matrix as stored), B = A Aᵀ scaled so that κᵀBκ ≈ 0.3 (symmetric PSD, like K_Z − S at a CAVI fixed point),
+    k_tt = κᵀBκ + 0.3 + U/2 (so σ² = k_tt − κᵀBκ lies in (0.3, 0.8) as for a valid SVGP posterior), m ~ N(0, 1)."""
+    rng = np.random.default_rng(seed)
+    kappa = rng.standard_normal((n, m)) / np.sqrt(m)
+    A = rng.standard_normal((m, m))
+    B = A @ A.T
+    B *= 0.3 * m / np.trace(B)
+    B = 0.5 * (B + B.T)
+    kdiag = np.einsum("ti,ij,tj->t", kappa, B, kappa) + 0.3 + 0.5 * rng.random(n)
+    mvec = rng.standard_normal(m)
+    return kappa, mvec, B, kdiag

@@ -1,0 +1,175 @@
+"""SURVEY §8(f) rows 1 and 2 on the GPU against the oracle: the sparse-GP producer (marginals of the SVGP posterior,
+examples/bernoulli/script.jl:32-33), the consumer (P = P0 + κ Diagonal(γ) κᵀ, rhs = r0 + κβ, docs/src/index.md:
+154-163) and the fused one-pass CAVI sweep (producer → aux_posterior! → E[β], E[γ], ELBO sums → consumer).
+
+Tolerances (fp64): per-observation arrays 1e-12 relative; sums over observations 1e-12 relative to the sum of the
+absolute values of their terms (P_ij: sqrt(P_ii P_jj) bounds it by Cauchy-Schwarz) — the GPU adds them in a
+different (tree / tensor-core) order than the oracle's long-double loop."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import aug_pkg
+from common import BERNOULLI, LAPLACE, NEGBIN, POISSON, STUDENTT, Y_DTYPE, relerr, synth_inputs, synth_sparse
+from gpu_common import dev, host, make_lik
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+KINDS = [(BERNOULLI, (), {}), (NEGBIN, (10.0,), {"r_is_int": True}), (NEGBIN, (5.5,), {}), (POISSON, (10.0,), {}),
+         (LAPLACE, (1.0,), {}), (STUDENTT, (3.0, 1.5), {})]
+
+
+@pytest.fixture(scope="module")
+def A():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    A = aug_pkg.load_package()
+    ctx = A.Context(0)
+    A.set_default_context(ctx)
+    yield A
+    A.set_default_context(None)
+    ctx.close()
+
+
+def check_P(P, rhs, oP, orhs, kappa, beta):
+    d = np.sqrt(np.abs(np.diag(oP)))
+    tolP = RTOL * np.maximum(np.outer(d, d), 1e-300)
+    assert np.all(np.abs(P - oP) <= tolP), float(np.max(np.abs(P - oP) / tolP)) * RTOL
+    tolr = RTOL * (np.abs(kappa) * np.abs(beta)[:, None]).sum(0)
+    assert np.all(np.abs(rhs - orhs) <= tolr + 1e-300)
+    assert np.array_equal(P, P.T)                       # mirrored from the lower triangle: exactly symmetric
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (5, 8), (100, 16), (4097, 20), (3000, 32), (2049, 33), (5000, 64),
+                                 (1500, 100), (4000, 128), (20000, 128)])
+def test_marginals_and_consumer_vs_oracle(A, orc, n, m):
+    orc.set_threads(8)
+    kappa, mvec, B, kdiag = synth_sparse(n, m, 1000 + m)
+    rng = np.random.default_rng(n + m)
+    gamma, beta = 0.25 * rng.random(n), rng.standard_normal(n)
+    P0 = rng.standard_normal((m, m)); P0 = P0 @ P0.T / m; P0 = 0.5 * (P0 + P0.T)
+    r0 = rng.standard_normal(m)
+    omu, ovar = orc.sparse_marginals(kappa, mvec, B, kdiag)
+    oP, orhs = orc.sparse_precision_potential(kappa, gamma, beta, P0, r0)
+    q = A.sparse_marginals(dev(kappa), dev(mvec), dev(B), dev(kdiag))
+    scale = np.abs(kappa) @ np.abs(mvec)
+    assert np.all(np.abs(host(q.mu) - omu) <= RTOL * scale)
+    assert relerr(host(q.var), ovar) <= RTOL
+    P, rhs = A.sparse_precision_potential(dev(kappa), dev(gamma), dev(beta), dev(P0), dev(r0))
+    check_P(host(P) - P0, host(rhs) - r0, oP - P0, orhs - r0, kappa, beta)
+    np.testing.assert_allclose(host(P), oP, rtol=1e-11, atol=1e-13)
+    orc.set_threads(1)
+
+
+@pytest.mark.parametrize("kind,params,kw", KINDS)
+@pytest.mark.parametrize("n,m", [(3001, 16), (2500, 48), (6000, 128)])
+def test_fused_sweep_vs_oracle(A, orc, kind, params, kw, n, m):
+    orc.set_threads(8)
+    kappa, mvec, B, kdiag = synth_sparse(n, m, 77 + m)
+    y, _, _, _ = synth_inputs(kind, n, 5 + m, params)
+    olik = orc.make_lik(kind, *params, **kw)
+    rc, o = orc.sparse_cavi_sweep(olik, y, kappa, mvec, B, kdiag)
+    assert rc == 0
+    lik = make_lik(kind, params, kw)
+    qO = A.init_aux_posterior(lik, n)
+    P, rhs, scal, qf, bg = A.sparse_cavi_sweep_(qO, lik, dev(y), dev(kappa), dev(mvec), dev(B), dev(kdiag),
+                                                want_elbo=True, want_marginals=True, want_potentials=True)
+    torch.cuda.synchronize()
+    assert relerr(host(qf.var), o["var"]) <= RTOL
+    assert np.all(np.abs(host(qf.mu) - o["mu"]) <= RTOL * (np.abs(kappa) @ np.abs(mvec)))
+    for i in range(3):
+        s = qO._s(i)
+        if s is not None and o["state"][i] is not None:
+            if o["state"][i].dtype == np.float64:
+                assert relerr(host(s), o["state"][i]) <= 4 * RTOL, i
+            else:
+                assert np.array_equal(host(s), o["state"][i])
+    beta, gamma = host(bg[0]), host(bg[1])
+    assert relerr(gamma, o["gamma"]) <= 4 * RTOL
+    assert relerr(beta, o["beta"], floor=1.0) <= 4 * RTOL        # Poisson-type β = (y − λ̂)/2 cancels (see common.relerr)
+    check_P(host(P), host(rhs), o["P"], o["rhs"], kappa, o["beta"])
+    s = host(scal)
+    for k in range(3):
+        assert abs(s[k] - o["comp"][k]) <= 4 * RTOL * max(abs(o["comp"][k]), float(n)), (k, s[k], o["comp"][k])
+    # the fused sweep equals the three verbs called one after the other (the reference's call pattern)
+    q2 = A.sparse_marginals(dev(kappa), dev(mvec), dev(B), dev(kdiag))
+    assert torch.equal(q2.mu, qf.mu) and torch.equal(q2.var, qf.var)
+    P2, rhs2 = A.sparse_precision_potential(dev(kappa), bg[1], bg[0])
+    assert torch.equal(P2, P) and torch.equal(rhs2, rhs)
+    orc.set_threads(1)
+
+
+def test_sweep_is_bit_reproducible_and_optional_outputs(A):
+    n, m = 50_000, 64
+    kappa, mvec, B, kdiag = synth_sparse(n, m, 3)
+    y, _, _, _ = synth_inputs(BERNOULLI, n, 4)
+    lik = A.BernoulliLikelihood()
+    args = (lik, dev(y), dev(kappa), dev(mvec), dev(B), dev(kdiag))
+    P1, r1, s1, _, _ = A.sparse_cavi_sweep_(None, *args)
+    P2, r2, s2, _, _ = A.sparse_cavi_sweep_(A.init_aux_posterior(lik, n), *args, want_marginals=True)
+    assert torch.equal(P1, P2) and torch.equal(r1, r2) and torch.equal(s1, s2)
+    P3, r3, s3, _, _ = A.sparse_cavi_sweep_(None, *args, want_elbo=False)
+    assert s3 is None and torch.equal(P1, P3)
+
+
+def test_unaligned_kappa_and_empty_shard(A, orc):
+    n, m = 777, 24
+    kappa, mvec, B, kdiag = synth_sparse(n, m, 11)
+    rng = np.random.default_rng(12)
+    gamma, beta = rng.random(n), rng.standard_normal(n)
+    oP, orhs = orc.sparse_precision_potential(kappa, gamma, beta)
+    buf = dev(np.r_[0.0, kappa.ravel()])                 # κ at an odd element offset: 8-byte cp.async path
+    ctx = A.default_context()
+    Pr = torch.zeros(m * m + m, dtype=torch.float64, device="cuda")
+    dg, db = dev(gamma), dev(beta)
+    A.check(ctx.lib.aug_sparse_precision_potential(ctx.h, n, m, C.c_void_p(buf.data_ptr() + 8),
+                                                   C.c_void_p(dg.data_ptr()), C.c_void_p(db.data_ptr()),
+                                                   None, None, C.c_void_p(Pr.data_ptr())))
+    ctx.sync()
+    check_P(host(Pr[: m * m]).reshape(m, m), host(Pr[m * m:]), oP, orhs, kappa, beta)
+    # n = 0 (an empty shard): P = P0, rhs = r0
+    P0, r0 = dev(np.eye(m)), dev(np.arange(m, dtype=np.float64))
+    P, rhs = A.sparse_precision_potential(torch.zeros((0, m), dtype=torch.float64, device="cuda"),
+                                          torch.zeros(0, dtype=torch.float64, device="cuda"),
+                                          torch.zeros(0, dtype=torch.float64, device="cuda"), P0, r0)
+    assert torch.equal(P, P0) and torch.equal(rhs, r0)
+    # argument errors mirror the ABI contract
+    with pytest.raises(A.AugError):
+        A.check(ctx.lib.aug_sparse_precision_potential(ctx.h, 10, 129, C.c_void_p(buf.data_ptr()), None, None, None,
+                                                       None, C.c_void_p(Pr.data_ptr())))
+    with pytest.raises(ValueError):
+        A.sparse_cavi_sweep_(None, A.HeteroscedasticGaussianLikelihood(1.0), dev(np.zeros(4)), dev(np.zeros((4, 2))),
+                             dev(np.zeros(2)), dev(np.zeros((2, 2))), dev(np.ones(4)))
+
+
+def test_dense_precision_potential(A):
+    n = 300
+    rng = np.random.default_rng(0)
+    Kinv = rng.standard_normal((n, n)); Kinv = Kinv @ Kinv.T
+    gamma, beta, r0 = rng.random(n), rng.standard_normal(n), rng.standard_normal(n)
+    P, rhs = A.dense_precision_potential(dev(Kinv), dev(gamma), dev(beta), dev(r0))
+    assert np.array_equal(host(P), Kinv + np.diag(gamma))           # inv(K) + Diagonal(γ)  script.jl:35
+    assert np.array_equal(host(rhs), beta + r0)                       # β + K \ mean(fz)       script.jl:36
+    K2 = dev(Kinv)
+    P2, _ = A.dense_precision_potential(K2, dev(gamma), dev(beta), out=K2)
+    assert P2.data_ptr() == K2.data_ptr() and np.array_equal(host(K2), Kinv + np.diag(gamma))
+
+
+def test_one_cavi_iteration_end_to_end(A, orc):
+    """The user's loop of examples/bernoulli/script.jl:29-39 in its sparse form, one iteration on the device:
+    sweep → S = inv(K_Z⁻¹ + κ Diagonal(γ) κᵀ), m = S (κ β)  vs the oracle's separate passes + numpy inverse."""
+    n, m = 8000, 32
+    kappa, mvec, B, kdiag = synth_sparse(n, m, 21)
+    y, _, _, _ = synth_inputs(BERNOULLI, n, 22)
+    KZinv = np.linalg.inv(B + 0.5 * np.eye(m))
+    lik = A.BernoulliLikelihood()
+    P, rhs, scal, _, _ = A.sparse_cavi_sweep_(None, lik, dev(y), dev(kappa), dev(mvec), dev(B), dev(kdiag), P0=dev(KZinv))
+    S = torch.linalg.inv(P)
+    mnew = S @ rhs
+    rc, o = orc.sparse_cavi_sweep(orc.make_lik(orc.BERNOULLI), y, kappa, mvec, B, kdiag, np.ascontiguousarray(KZinv), None)
+    So = np.linalg.inv(o["P"])
+    np.testing.assert_allclose(host(S), So, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(host(mnew), So @ o["rhs"], rtol=1e-9, atol=1e-12)
