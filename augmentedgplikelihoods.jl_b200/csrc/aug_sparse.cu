@@ -40,34 +40,39 @@ enum { SP_FUSED = 0, SP_PRODUCER = 1, SP_CONSUMER = 2 };
 template <int MT>
 struct SpCfg {
     static constexpr int MB = MT / 8;                  // 8-row blocks along the inducing axis
-    static constexpr int RB = MT == 128 ? 1 : 2;       // producer: row-blocks per warp
-    static constexpr int WR = MB / RB;                 // producer: warps along the rows of B
-    static constexpr int WT = SP_GW / WR;              // producer: warps along the observations
-    static constexpr int TO = 16 * WT;                 // observations per tile (2 column blocks of 8 per warp)
-    static constexpr int PAIRS = MB / 2;               // consumer: warp p owns block-rows p and MB-1-p
+    static constexpr int PAIRS = MB / 2;               // warp p owns block-rows p and MB-1-p of a lower block triangle
+    static constexpr int WT = SP_GW / PAIRS;           // producer: warps along the observations
+    static constexpr int TO = 16 * WT;                 // observations per tile (2 column blocks of 8 per producer warp)
     static constexpr int QS = MT == 128 ? 2 : 1;       // consumer: warps sharing one row pair (halves of its MB+1 blocks)
     static constexpr int KG = SP_GW / (PAIRS * QS);    // consumer: groups splitting the observations of a tile
     static constexpr int OG = TO / KG;                 // observations per group and tile (multiple of 4)
     static constexpr int NACC = (MB + QS) / QS;        // 8x8 accumulator blocks per consumer warp (ceil((MB+1)/QS))
-    static constexpr int STRIDE = MT + 4;              // padded row length (doubles): ≡ 4 mod 16
-    static constexpr int EW = TO >= 32 ? TO / 32 : 1;  // evaluation warps
+    static constexpr int STRIDE = MT + 4;              // padded κ row length (doubles): ≡ 4 mod 16
+    static constexpr int EW = TO / 32;                 // evaluation warps: one observation per lane
     static constexpr int NE = EW * 32;
     static constexpr int NT = SP_GW * 32 + NE;         // threads per CTA
-    static constexpr int RPT = MT > NE ? MT / NE : 1;  // rhs rows per evaluation thread
-    static constexpr int RPARTS = NE > MT ? NE / MT : 1;  // evaluation threads sharing one rhs row
+    static constexpr int LPO = SP_GW * 32 / TO;        // GEMM lanes per observation for μ_t = κ_tᵀ m (= MB)
+    static constexpr int NR = QS == 1 ? 2 : 1;         // consumer: block-rows whose rhs = κβ slice this warp accumulates
+    // B' = block-lower-triangular half of the symmetrised B (diagonal blocks halved): κᵀBκ = 2 κᵀB'κ.
+    // Packed by block-rows: the 8 rows of block-row I hold 8(I+1) columns + 4 pad (row stride ≡ ±4 mod 16).
+    __host__ __device__ static constexpr int brs(int I) { return 8 * (I + 1) + 4; }
+    __host__ __device__ static constexpr int boff(int I) { return 32 * I * I + 64 * I; }   // Σ_{J<I} 8·brs(J)
+    static constexpr int B_DOUBLES = 32 * MB * MB + 64 * MB;
     // shared memory (doubles)
     static constexpr int OFF_B = 0;
-    static constexpr int OFF_K = OFF_B + MT * STRIDE;
+    static constexpr int OFF_K = OFF_B + B_DOUBLES;
     static constexpr int OFF_M = OFF_K + SP_STAGES * TO * STRIDE;
-    static constexpr int OFF_Q = OFF_M + MT;                       // q partials [2][WR][TO]
-    static constexpr int OFF_G = OFF_Q + 2 * WR * TO;              // γ_t [TO]
+    static constexpr int OFF_Q = OFF_M + MT;                       // q partials [2][PAIRS][TO]
+    static constexpr int OFF_MU = OFF_Q + 2 * PAIRS * TO;          // μ_t [2][TO]
+    static constexpr int OFF_G = OFF_MU + 2 * TO;                  // γ_t [TO]
     static constexpr int OFF_BE = OFF_G + TO;                      // β_t [TO]
-    static constexpr int OFF_RED = OFF_BE + TO;                    // end-of-kernel reductions [NE]
+    static constexpr int OFF_RED = OFF_BE + TO;                    // end-of-kernel reductions [2 NE]
     static constexpr int SMEM_DOUBLES = OFF_RED + NE * 2;
     static constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;
     static_assert(OG % 4 == 0 && OG >= 4, "consumer k-steps cover 4 observations");
-    static_assert(WR * WT == SP_GW && PAIRS * QS * KG == SP_GW, "warp grids");
+    static_assert(PAIRS * WT == SP_GW && PAIRS * QS * KG == SP_GW, "warp grids");
     static_assert(STRIDE % 16 == 4, "bank-conflict-free padding");
+    static_assert(LPO * TO == SP_GW * 32 && MT % LPO == 0, "μ lanes");
 };
 
 struct SparseArgs {
@@ -88,9 +93,9 @@ struct SparseArgs {
     void* s2;
     double* beta;
     double* gamma;
-    double* scratch;          // [grid*KG][MT*MT] P partials, then [grid][MT] rhs partials, then [grid][2] ELBO partials
+    double* scratch;          // [grid*KG][MT*MT] P partials, then [grid*KG][MT] rhs partials, then [grid][2] ELBO partials
     int vec16;                // kappa is 16-byte aligned and m is even: 16-byte cp.async
-    int elbo;
+    int elbo;                 // ELBO sums requested
     LikConst L;
 };
 
@@ -120,10 +125,17 @@ __device__ __forceinline__ void sp_issue_tile(const SparseArgs& a, int64_t tile,
         const unsigned um = (unsigned)a.m;
         if (a.vec16) {
             const unsigned tot = (unsigned)rows * um / 2u;
-            for (unsigned e2 = threadIdx.x; e2 < tot; e2 += C::NT) {
-                const unsigned e = 2u * e2;
-                const unsigned row = e / um, col = e - row * um;
-                cp_async16(stage + row * C::STRIDE + col, src + e);
+            if (um == (unsigned)MT) {                       // full width: row / column are shifts
+                for (unsigned e2 = threadIdx.x; e2 < tot; e2 += C::NT) {
+                    const unsigned e = 2u * e2;
+                    cp_async16(stage + (e / MT) * C::STRIDE + (e % MT), src + e);
+                }
+            } else {
+                for (unsigned e2 = threadIdx.x; e2 < tot; e2 += C::NT) {
+                    const unsigned e = 2u * e2;
+                    const unsigned row = e / um, col = e - row * um;
+                    cp_async16(stage + row * C::STRIDE + col, src + e);
+                }
             }
         } else {
             const unsigned tot = (unsigned)rows * um;
@@ -136,63 +148,101 @@ __device__ __forceinline__ void sp_issue_tile(const SparseArgs& a, int64_t tile,
     cp_async_commit();   // always: keeps the group count uniform across threads and iterations
 }
 
-// producer GEMM of one tile: q partial of this warp's row-blocks for its 16 observations → qp[wr][t]
+// producer of one tile (GEMM warps): half quadratic forms q'_t = Σ_i κ_it (B'κ)_it over this warp's two block-rows
+// for its 16 observations → qp[p][t], and μ_t = κ_tᵀ m (LPO lanes per observation) → mus[t]
 template <int MT>
 __device__ __forceinline__ void sp_producer(const double* __restrict__ Bs, const double* __restrict__ kap,
-                                            double* __restrict__ qp, int warp, int lane, int kend) {
+                                            const double* __restrict__ ms, double* __restrict__ qp,
+                                            double* __restrict__ mus, int warp, int lane, int kend) {
     typedef SpCfg<MT> C;
-    const int wr = warp % C::WR, wt = warp / C::WR;
+    const int p = warp % C::PAIRS, wt = warp / C::PAIRS;
     const int r = lane >> 2, k = lane & 3;
-    double c[C::RB][2][2];
+    const int ra = p, rb = C::MB - 1 - p;                                  // block-rows: ra has ra+1 k-blocks, rb has rb+1 > ra+1
+    double c[2][2][2];
 #pragma unroll
-    for (int rb = 0; rb < C::RB; ++rb)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int tb = 0; tb < 2; ++tb) c[rb][tb][0] = c[rb][tb][1] = 0.0;
-    const double* ap = Bs + (8 * (wr * C::RB) + r) * C::STRIDE + k;       // A[row = r][k]     = B[8I + r][k0 + k]
-    const double* bp = kap + (8 * (wt * 2) + r) * C::STRIDE + k;          // B[k][col = r]     = κ[k0 + k][t0 + r]
+        for (int tb = 0; tb < 2; ++tb) c[i][tb][0] = c[i][tb][1] = 0.0;
+    const double* apa = Bs + C::boff(ra) + r * C::brs(ra) + k;             // A[row r][k] = B'[8I + r][k0 + k]
+    const double* apb = Bs + C::boff(rb) + r * C::brs(rb) + k;
+    const double* bp = kap + (8 * (wt * 2) + r) * C::STRIDE + k;           // B[k][col r] = κ[k0 + k][t0 + r]
+    const int ka = min(8 * (ra + 1), kend), kb = min(8 * (rb + 1), kend);
+    int k0 = 0;
 #pragma unroll 4
-    for (int k0 = 0; k0 < kend; k0 += 4) {
-        double av[C::RB], bv[2];
-#pragma unroll
-        for (int rb = 0; rb < C::RB; ++rb) av[rb] = ap[rb * 8 * C::STRIDE + k0];
-#pragma unroll
-        for (int tb = 0; tb < 2; ++tb) bv[tb] = bp[tb * 8 * C::STRIDE + k0];
-#pragma unroll
-        for (int rb = 0; rb < C::RB; ++rb)
-#pragma unroll
-            for (int tb = 0; tb < 2; ++tb) dmma8x8x4(c[rb][tb][0], c[rb][tb][1], av[rb], bv[tb]);
+    for (; k0 < ka; k0 += 4) {
+        const double a0 = apa[k0], a1 = apb[k0];
+        const double b0 = bp[k0], b1 = bp[8 * C::STRIDE + k0];
+        dmma8x8x4(c[0][0][0], c[0][0][1], a0, b0);
+        dmma8x8x4(c[0][1][0], c[0][1][1], a0, b1);
+        dmma8x8x4(c[1][0][0], c[1][0][1], a1, b0);
+        dmma8x8x4(c[1][1][0], c[1][1][1], a1, b1);
     }
-    // C[row r][col 2k + e] = (Bκ)[8I + r][t]; q_t = Σ_i κ[i][t] (Bκ)[i][t]: own rows, then the 8 lanes sharing k
+#pragma unroll 4
+    for (; k0 < kb; k0 += 4) {
+        const double a1 = apb[k0];
+        const double b0 = bp[k0], b1 = bp[8 * C::STRIDE + k0];
+        dmma8x8x4(c[1][0][0], c[1][0][1], a1, b0);
+        dmma8x8x4(c[1][1][0], c[1][1][1], a1, b1);
+    }
+    // C[row r][col 2k + e] = (B'κ)[8I + r][t]: own rows, then the 8 lanes sharing k
+    double s[4];
 #pragma unroll
     for (int tb = 0; tb < 2; ++tb)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int t = 8 * (wt * 2 + tb) + 2 * k + e;
-            double s = 0.0;
-#pragma unroll
-            for (int rb = 0; rb < C::RB; ++rb)
-                s = fma(c[rb][tb][e], kap[t * C::STRIDE + 8 * (wr * C::RB + rb) + r], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 8);
-            s += __shfl_xor_sync(0xffffffffu, s, 16);
-            if (r == 0) qp[wr * C::TO + t] = s;
+            const double* row = kap + (8 * (wt * 2 + tb) + 2 * k + e) * C::STRIDE + r;
+            s[tb * 2 + e] = fma(c[0][tb][e], row[8 * ra], c[1][tb][e] * row[8 * rb]);
         }
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+    if (r == 0) {
+#pragma unroll
+        for (int tb = 0; tb < 2; ++tb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) qp[p * C::TO + 8 * (wt * 2 + tb) + 2 * k + e] = s[tb * 2 + e];
+    }
+    // μ_t: LPO consecutive lanes per observation, MT / LPO elements each
+    {
+        const int idx = warp * 32 + lane;
+        const int t = idx / C::LPO, sidx = idx % C::LPO;
+        const double* row = kap + t * C::STRIDE + sidx;
+        double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < MT / C::LPO; j += 2) {
+            m0 = fma(ms[sidx + C::LPO * j], row[C::LPO * j], m0);
+            m1 = fma(ms[sidx + C::LPO * (j + 1)], row[C::LPO * (j + 1)], m1);
+        }
+        double mu = m0 + m1;
+#pragma unroll
+        for (int o = 1; o < C::LPO; o <<= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
+        if (sidx == 0) mus[t] = mu;
+    }
 }
 
-// consumer SYRK of one tile into this warp's accumulators
+// consumer of one tile into this warp's accumulators: SYRK blocks P_IJ += Σ_t γ_t κ_It κ_Jtᵀ, and the rhs slice
+// (κβ)_I as one more DMMA per block-row whose B operand carries β_t in column 0 — a plain DFMA loop in the
+// evaluation warp would starve behind the DMMA stream on the shared FP64 pipe (measured: ~64 clk per issue).
 template <int MT>
 __device__ __forceinline__ void sp_consumer(const double* __restrict__ kap, const double* __restrict__ gs,
-                                            double (&acc)[SpCfg<MT>::NACC][2], int warp, int lane) {
+                                            const double* __restrict__ bs, double (&acc)[SpCfg<MT>::NACC][2],
+                                            double (&racc)[SpCfg<MT>::NR][2], int warp, int lane) {
     typedef SpCfg<MT> C;
     const int p = warp % C::PAIRS, h = (warp / C::PAIRS) % C::QS, g = warp / (C::PAIRS * C::QS);
     const int r = lane >> 2, k = lane & 3;
-#pragma unroll
+#pragma unroll 2
     for (int ks = 0; ks < C::OG / 4; ++ks) {
         const int t = g * C::OG + 4 * ks + k;
         const double* row = kap + t * C::STRIDE + r;
         const double gm = gs[t];
-        const double aP = row[8 * p] * gm;                       // A[row r][k] = γ_t κ[8I + r][t]
-        const double aQ = row[8 * (C::MB - 1 - p)] * gm;
+        const double bt = r == 0 ? bs[t] : 0.0;                  // B[k][col 0] = β_t, other columns 0
+        const double rawP = row[8 * p], rawQ = row[8 * (C::MB - 1 - p)];
+        double aP = rawP * gm;                                   // A[row r][k] = γ_t κ[8I + r][t]
+        double aQ = rawQ * gm;
+        // keep the two products where they are: sunk below the per-block select they become one DMUL per DMMA,
+        // each queueing behind the other warps' DMMAs on the FP64 pipe (ncu: 17 % of all stall samples)
+        asm volatile("" : "+d"(aP), "+d"(aQ));
 #pragma unroll
         for (int qi = 0; qi < C::NACC; ++qi) {
             const int q = h * C::NACC + qi;                       // block index in the concatenated rows p, MB-1-p
@@ -202,6 +252,12 @@ __device__ __forceinline__ void sp_consumer(const double* __restrict__ kap, cons
                 const double b = row[8 * J];                      // B[k][col r] = κ[8J + r][t]
                 dmma8x8x4(acc[qi][0], acc[qi][1], first ? aP : aQ, b);
             }
+        }
+        if (C::QS == 1) {
+            dmma8x8x4(racc[0][0], racc[0][1], rawP, bt);
+            dmma8x8x4(racc[C::NR - 1][0], racc[C::NR - 1][1], rawQ, bt);
+        } else {
+            dmma8x8x4(racc[0][0], racc[0][1], h == 0 ? rawP : rawQ, bt);
         }
     }
 }
@@ -219,6 +275,7 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
     double* ring = sm + C::OFF_K;
     double* ms = sm + C::OFF_M;
     double* qs = sm + C::OFF_Q;
+    double* mus = sm + C::OFF_MU;
     double* gs = sm + C::OFF_G;
     double* bs = sm + C::OFF_BE;
     double* red = sm + C::OFF_RED;
@@ -228,12 +285,22 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
     const int m = a.m;
     const int kend = (m + 3) & ~3;
 
-    // ---- one-time staging: zero the ring (pad columns / rows stay zero or finite for ever), B, m
+    // ---- one-time staging: zero the ring (pad columns / rows stay zero or finite for ever), B', m
     for (int e = tid; e < SP_STAGES * C::TO * C::STRIDE; e += C::NT) ring[e] = 0.0;
     if (PROD) {
-        for (int e = tid; e < MT * C::STRIDE; e += C::NT) {
-            const int i = e / C::STRIDE, j = e - i * C::STRIDE;
-            Bs[e] = (i < m && j < m) ? __ldg(a.B + (size_t)i * m + j) : 0.0;
+        for (int I = 0; I < C::MB; ++I) {
+            const int rs = C::brs(I);
+            double* dst = Bs + C::boff(I);
+            for (int e = tid; e < 8 * rs; e += C::NT) {
+                const int rr = e / rs, j = e - rr * rs;
+                const int i = 8 * I + rr;
+                double v = 0.0;
+                if (j < 8 * (I + 1) && i < m && j < m) {
+                    v = 0.5 * (__ldg(a.B + (size_t)i * m + j) + __ldg(a.B + (size_t)j * m + i));   // symmetrised
+                    if (j >= 8 * I) v *= 0.5;                                                        // diagonal block: half
+                }
+                dst[e] = v;
+            }
         }
         for (int e = tid; e < MT; e += C::NT) ms[e] = e < m ? __ldg(a.mvec + e) : 0.0;
     }
@@ -248,10 +315,29 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
     double acc[C::NACC][2];
 #pragma unroll
     for (int q = 0; q < C::NACC; ++q) acc[q][0] = acc[q][1] = 0.0;
-    double racc[C::RPT];
+    double racc[C::NR][2];
 #pragma unroll
-    for (int i = 0; i < C::RPT; ++i) racc[i] = 0.0;
+    for (int i = 0; i < C::NR; ++i) racc[i][0] = racc[i][1] = 0.0;
     double e_elt = 0.0, e_kl = 0.0;
+    double ev_mu = 0.0, ev_var = 1.0, ev_y = 0.0;   // evaluation lane: inputs of tile l kept for the ELBO pass of phase B
+    bool ev_valid = false;
+
+    // per-observation scalars of the evaluation lanes, fetched one tile ahead (latency hidden behind a whole phase)
+    double pf0 = 0.0, pf1 = 0.0;       // FUSED / PRODUCER: k_tt, y   CONSUMER: γ, β
+    auto prefetch = [&](int64_t l, double& x0, double& x1) {
+        x0 = 0.0; x1 = 0.0;
+        if (l < nloc) {
+            const int64_t i = gtile(l) * C::TO + et;
+            if (i < a.n) {
+                if (MODE == SP_CONSUMER) { x0 = __ldg(a.gamma_in + i); x1 = __ldg(a.beta_in + i); }
+                else {
+                    x0 = __ldg(a.kdiag + i);
+                    if (MODE == SP_FUSED) x1 = (double)__ldg(reinterpret_cast<const yt*>(a.y) + i);
+                }
+            }
+        }
+    };
+    if (!gemm_warp) prefetch(0, pf0, pf1);
 
     // ---- prologue
     sp_issue_tile<MT>(a, gtile(0), stage(0));
@@ -259,50 +345,45 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
     cp_async_wait<1>();
     __syncthreads();                                   // tile 0 visible
     sp_issue_tile<MT>(a, gtile(2), stage(2));
-    if (PROD && gemm_warp && nloc > 0) sp_producer<MT>(Bs, stage(0), qs, warp, lane, kend);
+    if (PROD && gemm_warp && nloc > 0) sp_producer<MT>(Bs, stage(0), ms, qs, mus, warp, lane, kend);
     cp_async_wait<1>();
-    __syncthreads();                                   // q(0) and tile 1 visible; tile 2 may be in flight
+    __syncthreads();                                   // q(0), μ(0) and tile 1 visible; tile 2 may be in flight
 
     for (int64_t l = 0; l < nloc; ++l) {
         const double* kap = stage(l);
         // ================= phase A: producer(l+1) ‖ evaluation(l)
         if (gemm_warp) {
-            if (PROD && l + 1 < nloc)
-                sp_producer<MT>(Bs, stage(l + 1), qs + (int)((l + 1) & 1) * (C::WR * C::TO), warp, lane, kend);
-        } else if (et < C::TO) {
+            if (PROD && l + 1 < nloc) {
+                const int nb = (int)((l + 1) & 1);
+                sp_producer<MT>(Bs, stage(l + 1), ms, qs + nb * (C::PAIRS * C::TO), mus + nb * C::TO, warp, lane, kend);
+            }
+        } else {
             const int t = et;
             const int64_t i = gtile(l) * C::TO + t;
             const bool valid = i < a.n;
+            const double c0 = pf0, c1 = pf1;
+            prefetch(l + 1, pf0, pf1);                 // next tile's scalars: in flight during this phase
             double g0 = 0.0, b0 = 0.0;
             if (MODE == SP_CONSUMER) {
-                if (valid) { g0 = __ldg(a.gamma_in + i); b0 = __ldg(a.beta_in + i); }
+                g0 = c0; b0 = c1;
             } else {
-                double kd = 0.0, yv = 0.0;
-                if (valid) {
-                    kd = __ldg(a.kdiag + i);
-                    if (MODE == SP_FUSED) yv = (double)__ldg(reinterpret_cast<const yt*>(a.y) + i);
-                }
-                const double* row = kap + t * C::STRIDE;
-                double mu0 = 0.0, mu1 = 0.0;
-                for (int j = 0; j < kend; j += 2) {
-                    mu0 = fma(ms[j], row[j], mu0);
-                    mu1 = fma(ms[j + 1], row[j + 1], mu1);
-                }
-                const double mu = mu0 + mu1;
-                const double* qp = qs + (int)(l & 1) * (C::WR * C::TO) + t;
+                const int cb = (int)(l & 1);
+                const double mu = mus[cb * C::TO + t];
+                const double* qp = qs + cb * (C::PAIRS * C::TO) + t;
                 double q = 0.0;
 #pragma unroll
-                for (int w = 0; w < C::WR; ++w) q += qp[w * C::TO];
-                const double var = kd - q;
+                for (int w = 0; w < C::PAIRS; ++w) q += qp[w * C::TO];
+                const double var = fma(-2.0, q, c0);   // k_tt − κᵀBκ,  κᵀBκ = 2 κᵀB'κ
                 if (valid) {
                     if (a.mu) a.mu[i] = mu;
                     if (a.var) a.var[i] = var;
                     if (MODE == SP_FUSED) {
+                        // part 1 (phase A): what the consumer and the caller need; the ELBO terms follow in phase B
                         Obs o;
-                        o.y = yv; o.ys = yv;
+                        o.y = c1; o.ys = c1;
                         o.m = mu; o.v = var; o.mg = 0.0; o.vg = 0.0;
                         o.s0 = o.s1 = o.s2 = 0.0;
-                        if (a.elbo) eval<KIND, false, true, true>(a.L, o);
+                        if (fast_ok<KIND, false, false>(o)) eval<KIND, false, false, false>(a.L, o);
                         else eval<KIND, false, false, true>(a.L, o);
                         if (a.s0) a.s0[i] = o.s0;
                         if (KIND == AUG_POISSON && a.s1) a.s1[i] = o.s1;
@@ -310,9 +391,9 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
                         if (a.beta) a.beta[i] = o.b0;
                         if (a.gamma) a.gamma[i] = o.g0;
                         g0 = o.g0; b0 = o.b0;
-                        e_elt += o.elt; e_kl += o.kl;
                     }
                 }
+                ev_mu = mu; ev_var = var; ev_y = c1; ev_valid = valid;
             }
             if (CONS) { gs[t] = g0; bs[t] = b0; }
         }
@@ -320,16 +401,16 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
         // ================= phase B: consumer(l) ‖ rhs(l)
         if (CONS) {
             if (gemm_warp) {
-                sp_consumer<MT>(kap, gs, acc, warp, lane);
-            } else {
-                const int part = C::RPARTS > 1 ? et / MT : 0;
-                const int i0 = C::RPARTS > 1 ? et - part * MT : et;
-#pragma unroll 4
-                for (int t = part; t < C::TO; t += C::RPARTS) {
-                    const double bt = bs[t];
-#pragma unroll
-                    for (int rr = 0; rr < C::RPT; ++rr) racc[rr] = fma(bt, kap[t * C::STRIDE + i0 + rr * C::NE], racc[rr]);
-                }
+                sp_consumer<MT>(kap, gs, bs, acc, racc, warp, lane);
+            } else if (MODE == SP_FUSED && a.elbo && ev_valid) {
+                // part 2: expected_logtilt / aux_kldivergence terms of tile l (nothing waits for them)
+                Obs o;
+                o.y = ev_y; o.ys = ev_y;
+                o.m = ev_mu; o.v = ev_var; o.mg = 0.0; o.vg = 0.0;
+                o.s0 = o.s1 = o.s2 = 0.0;
+                if (fast_ok<KIND, false, true>(o)) eval<KIND, false, true, false>(a.L, o);
+                else eval<KIND, false, true, true>(a.L, o);
+                e_elt += o.elt; e_kl += o.kl;
             }
         }
         cp_async_wait<0>();                            // tile l+2 landed (the only group in flight)
@@ -341,42 +422,30 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
     // ---- epilogue: partials to scratch
     double* Ppart = a.scratch;
     double* rpart = a.scratch + (size_t)gridDim.x * C::KG * (MT * MT);
-    double* spart = rpart + (size_t)gridDim.x * MT;
-    if (CONS) {
-        if (gemm_warp) {
-            const int p = warp % C::PAIRS, h = (warp / C::PAIRS) % C::QS, g = warp / (C::PAIRS * C::QS);
-            const int r = lane >> 2, k = lane & 3;
-            double* dst = Ppart + ((size_t)blockIdx.x * C::KG + g) * (MT * MT);
+    double* spart = rpart + (size_t)gridDim.x * C::KG * MT;
+    if (CONS && gemm_warp) {
+        const int p = warp % C::PAIRS, h = (warp / C::PAIRS) % C::QS, g = warp / (C::PAIRS * C::QS);
+        const int r = lane >> 2, k = lane & 3;
+        double* dst = Ppart + ((size_t)blockIdx.x * C::KG + g) * (MT * MT);
 #pragma unroll
-            for (int qi = 0; qi < C::NACC; ++qi) {
-                const int q = h * C::NACC + qi;
-                if (q <= C::MB) {
-                    const bool first = q <= p;
-                    const int I = first ? p : C::MB - 1 - p;
-                    const int J = first ? q : q - p - 1;
-                    double2 v = make_double2(acc[qi][0], acc[qi][1]);
-                    *reinterpret_cast<double2*>(dst + (size_t)(8 * I + r) * MT + 8 * J + 2 * k) = v;
-                }
-            }
-        } else {
-            // rhs: sum the RPARTS evaluation threads that share a row (fixed order), then one value per row
-            if (C::RPARTS > 1) {
-                red[et] = racc[0];
+        for (int qi = 0; qi < C::NACC; ++qi) {
+            const int q = h * C::NACC + qi;
+            if (q <= C::MB) {
+                const bool first = q <= p;
+                const int I = first ? p : C::MB - 1 - p;
+                const int J = first ? q : q - p - 1;
+                double2 v = make_double2(acc[qi][0], acc[qi][1]);
+                *reinterpret_cast<double2*>(dst + (size_t)(8 * I + r) * MT + 8 * J + 2 * k) = v;
             }
         }
-    }
-    __syncthreads();
-    if (CONS && !gemm_warp) {
-        if (C::RPARTS > 1) {
-            if (et < MT) {
-                double s = 0.0;
-#pragma unroll
-                for (int pp = 0; pp < C::RPARTS; ++pp) s += red[pp * MT + et];
-                rpart[(size_t)blockIdx.x * MT + et] = s;
+        if (k == 0) {                                  // column 0 of the rhs blocks
+            double* rd = rpart + ((size_t)blockIdx.x * C::KG + g) * MT;
+            if (C::QS == 1) {
+                rd[8 * p + r] = racc[0][0];
+                rd[8 * (C::MB - 1 - p) + r] = racc[C::NR - 1][0];
+            } else {
+                rd[8 * (h == 0 ? p : C::MB - 1 - p) + r] = racc[0][0];
             }
-        } else {
-#pragma unroll
-            for (int rr = 0; rr < C::RPT; ++rr) rpart[(size_t)blockIdx.x * MT + et + rr * C::NE] = racc[rr];
         }
     }
     __syncthreads();
@@ -406,7 +475,7 @@ __global__ void __launch_bounds__(256) sparse_finalize_kernel(const double* __re
     __shared__ double part[2][32][8];
     const double* Ppart = scratch;
     const double* rpart = scratch + (size_t)grid * C::KG * (MT * MT);
-    const double* spart = rpart + (size_t)grid * MT;
+    const double* spart = rpart + (size_t)grid * C::KG * MT;
     const int ex = threadIdx.x & 7, sl = threadIdx.x >> 3;
     if (blockIdx.x == gridDim.x - 1) {                        // scalar block
         if (scalars == nullptr) return;
@@ -435,7 +504,7 @@ __global__ void __launch_bounds__(256) sparse_finalize_kernel(const double* __re
         for (int b = sl; b < grid * C::KG; b += 32) s += __ldg(src + (size_t)b * (MT * MT));
     } else if (e < m * m + m) {
         const int i = e - m * m;
-        for (int b = sl; b < grid; b += 32) s += __ldg(rpart + (size_t)b * MT + i);
+        for (int b = sl; b < grid * C::KG; b += 32) s += __ldg(rpart + (size_t)b * MT + i);
     }
     part[0][sl][ex] = s;
     __syncthreads();
@@ -477,7 +546,7 @@ int32_t sp_launch(aug_ctx* ctx, SparseArgs& a, const double* P0, const double* r
     int64_t grid = ctx->sms;
     if (grid > a.ntiles) grid = a.ntiles;
     if (grid < 1) grid = 1;
-    const size_t need = ((size_t)grid * C::KG * (MT * MT) + (size_t)grid * MT + (size_t)grid * 2) * sizeof(double);
+    const size_t need = ((size_t)grid * C::KG * (MT * MT) + (size_t)grid * C::KG * MT + (size_t)grid * 2) * sizeof(double);
     if (ctx->sparse_scratch_bytes < need) {
         if (ctx->sparse_scratch) {
             AUG_CUDA(cudaStreamSynchronize(ctx->stream));
