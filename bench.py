@@ -168,6 +168,120 @@ def run_reference(args):
     emit(line)
 
 
+def fp64_peak():
+    """Measured FP64 tensor (DMMA m8n8k4) peak of this GPU: tools/fp64_peak (built by build()) run live, else the
+    number recorded on this pool (profiles/fp64_peak_r1f.jsonl)."""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    if os.path.exists(exe):
+        try:
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+            best = max(json.loads(l)["tflops"] for l in out.splitlines() if '"dmma' in l)
+            return best, "measured live (tools/fp64_peak: mma.sync.m8n8k4.f64, all SMs)"
+        except Exception:
+            pass
+    return 37.1, "recorded (profiles/fp64_peak_r1f.jsonl)"
+
+
+def sparse_leg(A, ctx, torch, dist, world, dev, args, rank):
+    """aug_sparse_cavi_sweep on m inducing points: marginals -> aux_posterior! -> E[beta], E[gamma], ELBO sums ->
+    P = kappa Diag(gamma) kappa^T, rhs = kappa beta, next to the library composition (cuBLAS DGEMMs through torch +
+    our streaming CAVI kernel).  FP64-pipe bound: roofline against the measured DMMA peak."""
+    m, n = args.sparse_m, args.sparse_n
+    g = torch.Generator(device=dev)
+    g.manual_seed(100 + rank)
+    kappa = torch.randn(n, m, dtype=torch.float64, device=dev, generator=g) / m ** 0.5
+    Aq = torch.randn(m, m, dtype=torch.float64, device=dev, generator=g)
+    B = Aq @ Aq.T
+    B = B * (0.3 * m / torch.trace(B))
+    B = 0.5 * (B + B.T)
+    kdiag = ((kappa @ B) * kappa).sum(1) + 0.3 + 0.5 * torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+    mvec = torch.randn(m, dtype=torch.float64, device=dev, generator=g)
+    y = (torch.rand(n, device=dev, generator=g) < 0.5).to(torch.uint8)
+    lik = A.BernoulliLikelihood()
+    q = A.init_aux_posterior(lik, n)
+    st = ctx.stream
+    res = {}
+
+    def fused():
+        res["f"] = A.sparse_cavi_sweep_(q, lik, y, kappa, mvec, B, kdiag, want_elbo=True, want_potentials=True)
+
+    def library():
+        mu = kappa @ mvec
+        var = kdiag - ((kappa @ B) * kappa).sum(1)
+        _, b, gm, sc = A.cavi_step_(q, lik, y, A.Normals(mu, var))
+        res["l"] = ((kappa * gm[0][:, None]).T @ kappa, kappa.T @ b[0], sc)
+
+    def timed(fn, k):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), (ctx.launches() - l0) // k
+
+    k = max(3, min(args.steps, 20))
+    ms_f, launches = timed(fused, k)
+    ms_l, _ = timed(library, max(2, k // 4))
+    Pf, rf, sf = res["f"][0], res["f"][1], res["f"][2]
+    Pl, rl, sl = res["l"]
+    agree = {"P": float(((Pf - Pl).abs().max() / Pl.abs().max()).item()),
+             "rhs": float(((rf - rl).abs().max() / rl.abs().max()).item()),
+             "elbo": float(((sf[2] - sl[2]).abs() / sl[2].abs()).item())}
+    flops = 2.0 * m * m + 6.0 * m            # symmetric quadratic form + symmetric rank-1 update + mu + rhs, per obs
+    peak, src = fp64_peak() if rank == 0 else (37.1, "")
+    ach = flops * n / (ms_f * 1e-3) / 1e12
+    return {"workload": f"sparse-GP CAVI iteration (Bernoulli), m={m} inducing points, {n} observations per GPU: "
+                        "aug_sparse_cavi_sweep = SVGP marginals + aux_posterior! + E[beta],E[gamma] + ELBO sums + "
+                        "P = kappa Diag(gamma) kappa^T, rhs = kappa beta in one pass over kappa",
+            "m": m, "obs_per_gpu": n, "ms_per_sweep": ms_f, "obs_per_s": n * world / (ms_f * 1e-3),
+            "gpu_launches_per_sweep": int(launches),
+            "roofline": {"kernel": "sparse_sweep_kernel<128, FUSED, BERNOULLI> (DMMA m8n8k4)", "bound": "tensor",
+                         "note": "fp64 tensor pipe (tcgen05 has no f64 kind); HBM traffic 8m B/obs is 10% of the HBM roofline",
+                         "achieved": ach, "peak": peak, "peak_source": src, "unit": "TFLOP/s", "frac": ach / peak,
+                         "flops_per_obs": flops, "traffic": None},
+            "library_composition": {"what": "torch (cuBLAS DGEMM) kappa@m, kappa@B, row dots, (kappa*gamma)^T@kappa, "
+                                            "kappa^T@beta + aug_cavi_step", "ms": ms_l, "speedup": ms_l / ms_f,
+                                    "max_rel_diff": agree}}
+
+
+def sparse_cpu(m, n=20000):
+    """the oracle's separate-pass restatement of the same iteration on the host cores (bounded sample)"""
+    import numpy as np
+    from oracle import orc
+    orc.lib()
+    threads = orc.max_threads()
+    orc.set_threads(threads)
+    rng = np.random.default_rng(0)
+    kappa = rng.standard_normal((n, m)) / np.sqrt(m)
+    Aq = rng.standard_normal((m, m))
+    B = Aq @ Aq.T
+    B *= 0.3 * m / np.trace(B)
+    B = 0.5 * (B + B.T)
+    kdiag = np.einsum("ti,ij,tj->t", kappa, B, kappa) + 0.3 + 0.5 * rng.random(n)
+    mvec = rng.standard_normal(m)
+    y = (rng.random(n) < 0.5).astype(np.uint8)
+    lik = orc.make_lik(orc.BERNOULLI)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        rc, _ = orc.sparse_cavi_sweep(lik, y, kappa, mvec, B, kdiag)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": n / best, "unit": "obs/s", "cores": threads, "kind": "port",
+            "sample": f"{n} observations, m={m}: separate passes (marginals, aux_posterior!, potentials, ELBO, P/rhs) in "
+                      f"long double, OpenMP {threads} threads, best of 2"}
+
+
 def main():
     # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner under
     # NCCL_DEBUG, torchrun notices) is sent to stderr; the result line is written to the saved descriptor.
@@ -187,6 +301,9 @@ def main():
                     help="N>1: all-reduce of the scalar block fused into the CAVI kernel over peer memory (p2p) or "
                          "a separate ncclAllReduce (nccl)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the secondary sparse-GP sweep measurement")
+    ap.add_argument("--sparse-m", type=int, default=128)
+    ap.add_argument("--sparse-n", type=int, default=2_000_000, help="observations per GPU of the sparse sweep leg")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -329,6 +446,11 @@ def main():
                "path": "aug_cavi_step_host + aug_aux_sample_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"}
         del hy, hmu, hvar, hf, hc, hb, hg, hw
 
+    # ---------------- secondary leg: one sparse-GP CAVI iteration as one pass over κ
+    sparse = None
+    if not args.no_sparse:
+        sparse = sparse_leg(A, ctx, torch, dist, world, dev, args, rank)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -388,6 +510,10 @@ def main():
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "elbo_check": elbo,
     }
+    if sparse:
+        if not args.no_cpu:
+            sparse["cpu_baseline"] = sparse_cpu(args.sparse_m)
+        line["sparse_sweep"] = sparse
     if cpu:
         line["speedup_vs_cpu"] = {"value_vs_all_threads": line["value"] / cpu["value"],
                                   "pg_draws_vs_single_thread": line["parts"]["pg_draws_per_s"] /

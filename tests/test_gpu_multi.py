@@ -221,3 +221,64 @@ def test_mailbox_timeout_raises_flag_instead_of_hanging():
             c.close()
     finally:
         del os.environ["AUGCUDA_XCH_TIMEOUT_MS"]
+
+
+def _sparse_worker(rank, world, port, qu):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from common import synth_sparse
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    A = aug_pkg.load_package()
+    ctx = A.Context(rank)
+    A.set_default_context(ctx)
+    A.dist.init_comm(ctx)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.tdev)
+    n, m = 30_001, 64
+    kappa, mvec, B, kdiag = synth_sparse(n, m, 5)
+    y, _, _, _ = synth_inputs(BERNOULLI, n, 6)
+    P0 = np.eye(m) * 0.5
+    lo, hi = A.dist.shard_bounds(n, world, rank)
+    lik = A.BernoulliLikelihood()
+    P, rhs, scal, _, _ = A.sparse_cavi_sweep_(None, lik, dev(y[lo:hi]), dev(kappa[lo:hi]), dev(mvec), dev(B),
+                                              dev(kdiag[lo:hi]), P0=dev(P0) if rank == 0 else None)
+    ctx.sync()
+    qu.put((rank, P.cpu().numpy().copy(), rhs.cpu().numpy().copy(), scal.cpu().numpy().copy()))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sparse_sweep_matches_single_gpu(orc):
+    """SURVEY §8(f) rows 1-2 sharded over 2 GPUs: the exchange is one ncclAllReduce of m*m + m doubles (and the
+    scalar block); every rank ends with the P, rhs and ELBO sums of the whole data set."""
+    _need2()
+    import torch.multiprocessing as mp
+    from common import synth_sparse
+    A = aug_pkg.load_package()
+    n, m = 30_001, 64
+    kappa, mvec, B, kdiag = synth_sparse(n, m, 5)
+    y, _, _, _ = synth_inputs(BERNOULLI, n, 6)
+    P0 = np.eye(m) * 0.5
+    orc.set_threads(8)
+    rc, o = orc.sparse_cavi_sweep(orc.make_lik(orc.BERNOULLI), y, kappa, mvec, B, kdiag, P0, None)
+    orc.set_threads(1)
+    mpc = mp.get_context("spawn")
+    qu = mpc.Queue()
+    port = _free_port()
+    procs = [mpc.Process(target=_sparse_worker, args=(r, 2, port, qu)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        rank, P, rhs, scal = qu.get(timeout=300)
+        got[rank] = (P, rhs, scal)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    d = np.sqrt(np.diag(o["P"]))
+    assert np.all(np.abs(got[0][0] - o["P"]) <= 1e-12 * np.outer(d, d))
+    assert np.all(np.abs(got[0][1] - o["rhs"]) <= 1e-12 * (np.abs(kappa) * np.abs(o["beta"])[:, None]).sum(0))
+    for k in range(3):
+        assert got[0][2][k] == pytest.approx(o["comp"][k], rel=1e-12)

@@ -92,3 +92,60 @@ def test_two_rank_scalar_allreduce_matches_single_rank():
         gg = np.concatenate([np.array(part[2]) for part in sorted(gathered)], axis=1)
         assert np.array_equal(gg, g)
         assert D.combine_scalars_host([block])[0] == block[0]
+
+
+def _sparse_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from common import synth_sparse
+    from oracle import orc
+    orc.set_threads(1)
+    D = aug_pkg.load_package().dist
+    n, m = 1501, 12
+    kappa, mvec, B, kdiag = synth_sparse(n, m, 5)
+    y, _, _, _ = synth_inputs(BERNOULLI, n, 6)
+    rng = np.random.default_rng(1)
+    P0 = rng.standard_normal((m, m)); P0 = P0 @ P0.T
+    r0 = rng.standard_normal(m)
+    lo, hi = D.shard_bounds(n, world, rank)
+    # P0 / r0 enter on rank 0 only (include/augcuda.h, "Multi-GPU"); every other rank contributes its shard's sums
+    rc, o = orc.sparse_cavi_sweep(orc.make_lik(orc.BERNOULLI), np.ascontiguousarray(y[lo:hi]),
+                                  np.ascontiguousarray(kappa[lo:hi]), mvec, B, np.ascontiguousarray(kdiag[lo:hi]),
+                                  P0 if rank == 0 else None, r0 if rank == 0 else None)
+    assert rc == 0
+    Pr = torch.from_numpy(np.concatenate([o["P"].ravel(), o["rhs"]]))
+    dist.all_reduce(Pr, op=dist.ReduceOp.SUM)              # the exchange of the sparse rows: m*m + m doubles
+    sc = torch.from_numpy(o["comp"].copy())
+    dist.all_reduce(sc, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        out.put((Pr.numpy().tolist(), sc.numpy().tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sparse_sweep_matches_single_rank():
+    """SURVEY §8(f) rows 1-2 under sharding: P, rhs and the ELBO sums are plain sums over observation shards."""
+    from common import synth_sparse
+    from oracle import orc
+    orc.set_threads(1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sparse_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    Pr, sc = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n, m = 1501, 12
+    kappa, mvec, B, kdiag = synth_sparse(n, m, 5)
+    y, _, _, _ = synth_inputs(BERNOULLI, n, 6)
+    rng = np.random.default_rng(1)
+    P0 = rng.standard_normal((m, m)); P0 = P0 @ P0.T
+    r0 = rng.standard_normal(m)
+    rc, o = orc.sparse_cavi_sweep(orc.make_lik(orc.BERNOULLI), y, kappa, mvec, B, kdiag, P0, r0)
+    np.testing.assert_allclose(np.array(Pr[: m * m]).reshape(m, m), o["P"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(np.array(Pr[m * m:]), o["rhs"], rtol=0, atol=1e-12)
+    for k in range(3):
+        assert sc[k] == pytest.approx(o["comp"][k], rel=1e-12)
