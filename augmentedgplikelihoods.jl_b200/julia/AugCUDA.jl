@@ -295,4 +295,44 @@ function logisticsoftmax_rows(lik::CategoricalLikelihood, f::DV, n::Integer)
     return out
 end
 
+# ---- the sparse-GP steps either side of the path (SURVEY §8(f) rows 1-2) ---------------------------------------
+# κ = K_Z \ K_ZX is an M×N device matrix stored column-major (what `AugDeviceVector` of length M*N holds), B = K_Z − S.
+# marginals(post_u(x)) of examples/bernoulli/script.jl:32-33 for a device κ:
+function sparse_marginals(κ::DV, M::Integer, m::DV, B::DV, kdiag::DV)
+    N = length(κ) ÷ M
+    μ = AugDeviceVector{Float64}(undef, N); σ² = AugDeviceVector{Float64}(undef, N)
+    check(ccall((:aug_sparse_marginals, lib), Int32,
+                (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx().h, N, M, κ.ptr, m.ptr, B.ptr, kdiag.ptr, μ.ptr, σ².ptr))
+    return DeviceNormals(μ, σ²)
+end
+# docs/src/index.md:156-160: (K_Z⁻¹ + κ Diagonal(γ) κᵀ, κβ + K_Z⁻¹μ₀) as one [M*M + M] device vector
+function sparse_precision_potential(κ::DV, M::Integer, γ::DV, β::DV; P0=nothing, r0=nothing)
+    N = length(κ) ÷ M
+    Pr = AugDeviceVector{Float64}(undef, M * M + M)
+    check(ccall((:aug_sparse_precision_potential, lib), Int32,
+                (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx().h, N, M, κ.ptr, γ.ptr, β.ptr, ptr(P0), ptr(r0), Pr.ptr))
+    return Pr
+end
+# one CAVI iteration of cavi!(…) (examples/bernoulli/script.jl:29-39, sparse update) in ONE pass over κ:
+# marginals → aux_posterior!(qΩ, lik, y, ·) → E[β], E[γ] (+ ELBO sums) → P, rhs.  Returns (Pr, scalars).
+function sparse_cavi_sweep!(qΩ, lik::AbstractLikelihood, y::DV, κ::DV, M::Integer, m::DV, B::DV, kdiag::DV;
+                            P0=nothing, r0=nothing)
+    N = length(y)
+    Pr = AugDeviceVector{Float64}(undef, M * M + M)
+    sc = AugDeviceVector{Float64}(undef, 8)
+    φ = state(qΩ)
+    s = (ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ)))   # C_NULL where the likelihood has no such field
+    withdesc(lik) do d
+        check(ccall((:aug_sparse_cavi_sweep, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64},
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    ctx().h, d, N, M, y.ptr, κ.ptr, m.ptr, B.ptr, kdiag.ptr, C_NULL, C_NULL, s[1], s[2], s[3],
+                    C_NULL, C_NULL, ptr(P0), ptr(r0), Pr.ptr, sc.ptr))
+    end
+    return Pr, Array(sc)
+end
+
 end # module
