@@ -32,47 +32,52 @@
 
 namespace {
 
-constexpr int SP_GW = 16;        // GEMM warps per CTA
-constexpr int SP_STAGES = 3;     // κ ring depth: tile j (consumer), j+1 (producer), j+2 (in flight)
+constexpr int SP_GW = 16;        // GEMM warps per CTA: warps 0-7 = producer group X, warps 8-15 = consumer group Y
+constexpr int SP_XW = 8;         // warps per group
+constexpr int SP_STAGES = 4;     // κ ring: tile k-2 (consumer), k-1 (between), k (producer), k+1 (in flight)
 
 enum { SP_FUSED = 0, SP_PRODUCER = 1, SP_CONSUMER = 2 };
 
+// Both GEMMs walk the symmetric M×M block structure by CYCLIC BLOCK DIAGONALS: the owner of block-row I handles the
+// blocks (I, (I+d) mod MB) for d = 0 .. MB/2 (the half diagonal d = MB/2 only for I < MB/2 in the consumer, with
+// weight ½ from both sides in the producer).  Every unordered pair of block-rows is met exactly once, every owner has
+// the same amount of work, one of the two operands of every block is the owner's own κ rows, and all block offsets
+// are (I + d) & (MB-1) with a compile-time d: no selects, no variable trip counts.
 template <int MT>
 struct SpCfg {
     static constexpr int MB = MT / 8;                  // 8-row blocks along the inducing axis
-    static constexpr int PAIRS = MB / 2;               // warp p owns block-rows p and MB-1-p of a lower block triangle
-    static constexpr int WT = SP_GW / PAIRS;           // producer: warps along the observations
-    static constexpr int TO = 16 * WT;                 // observations per tile (2 column blocks of 8 per producer warp)
-    static constexpr int QS = MT == 128 ? 2 : 1;       // consumer: warps sharing one row pair (halves of its MB+1 blocks)
-    static constexpr int KG = SP_GW / (PAIRS * QS);    // consumer: groups splitting the observations of a tile
-    static constexpr int OG = TO / KG;                 // observations per group and tile (multiple of 4)
-    static constexpr int NACC = (MB + QS) / QS;        // 8x8 accumulator blocks per consumer warp (ceil((MB+1)/QS))
+    static constexpr int ND = MB / 2 + 1;              // block diagonals per owner (d = 0 .. MB/2)
+    static constexpr int OPW = MB > SP_XW ? MB / SP_XW : 1;   // owners (block-rows) per warp of a group
+    static constexpr int SPL = MB > SP_XW ? 1 : SP_XW / MB;   // warps of a group sharing one owner (split over observations)
+    static constexpr int TO = MT == 128 ? 32 : (MT == 64 ? 64 : (MT == 32 ? 128 : 256));   // observations per tile
+    static constexpr int TBW = TO / 8 / SPL;           // producer: 8-observation column blocks per warp
+    static constexpr int OG = TO / SPL;                // consumer: observations per warp and tile
+    static constexpr int KG = SPL;                     // partial P / rhs copies per CTA
+    static constexpr int NSLOT = SP_XW / SPL;          // producer: partial quadratic forms per observation
     static constexpr int STRIDE = MT + 4;              // padded κ row length (doubles): ≡ 4 mod 16
-    static constexpr int EW = TO / 32;                 // evaluation warps: one observation per lane
-    static constexpr int NE = EW * 32;
-    static constexpr int NT = SP_GW * 32 + NE;         // threads per CTA
-    static constexpr int LPO = SP_GW * 32 / TO;        // GEMM lanes per observation for μ_t = κ_tᵀ m (= MB)
-    static constexpr int NR = QS == 1 ? 2 : 1;         // consumer: block-rows whose rhs = κβ slice this warp accumulates
-    // B' = block-lower-triangular half of the symmetrised B (diagonal blocks halved): κᵀBκ = 2 κᵀB'κ.
-    // Packed by block-rows: the 8 rows of block-row I hold 8(I+1) columns + 4 pad (row stride ≡ ±4 mod 16).
-    __host__ __device__ static constexpr int brs(int I) { return 8 * (I + 1) + 4; }
-    __host__ __device__ static constexpr int boff(int I) { return 32 * I * I + 64 * I; }   // Σ_{J<I} 8·brs(J)
-    static constexpr int B_DOUBLES = 32 * MB * MB + 64 * MB;
+    static constexpr int BRS = ND * 8 + 4;             // padded row length of the staged B' (≡ 4 or 12 mod 16)
+    static constexpr int EW = TO / 32;                 // evaluating warps: one observation per lane
+    // MT = 128: the evaluator is warp 0 of group X (16 warps per CTA keep 128 registers per thread for the 17
+    // accumulator blocks of a consumer warp); smaller MT: EW dedicated warps after the GEMM warps
+    static constexpr bool EVAL_IN_X = MT == 128;
+    static constexpr int NT = SP_GW * 32 + (EVAL_IN_X ? 0 : EW * 32);   // threads per CTA
+    static constexpr int LPO = SP_XW * 32 / TO;        // producer lanes per observation for μ_t = κ_tᵀ m
     // shared memory (doubles)
     static constexpr int OFF_B = 0;
-    static constexpr int OFF_K = OFF_B + B_DOUBLES;
+    static constexpr int OFF_K = OFF_B + MT * BRS;
     static constexpr int OFF_M = OFF_K + SP_STAGES * TO * STRIDE;
-    static constexpr int OFF_Q = OFF_M + MT;                       // q partials [2][PAIRS][TO]
-    static constexpr int OFF_MU = OFF_Q + 2 * PAIRS * TO;          // μ_t [2][TO]
-    static constexpr int OFF_G = OFF_MU + 2 * TO;                  // γ_t [TO]
-    static constexpr int OFF_BE = OFF_G + TO;                      // β_t [TO]
-    static constexpr int OFF_RED = OFF_BE + TO;                    // end-of-kernel reductions [2 NE]
-    static constexpr int SMEM_DOUBLES = OFF_RED + NE * 2;
+    static constexpr int OFF_Q = OFF_M + MT;                       // half quadratic forms [2][NSLOT][TO]
+    static constexpr int OFF_MU = OFF_Q + 2 * NSLOT * TO;          // μ_t [2][TO]
+    static constexpr int OFF_G = OFF_MU + 2 * TO;                  // γ_t [2][TO]
+    static constexpr int OFF_BE = OFF_G + 2 * TO;                  // β_t [2][TO]
+    static constexpr int OFF_RED = OFF_BE + 2 * TO;                // end-of-kernel reductions [2 EW]
+    static constexpr int SMEM_DOUBLES = OFF_RED + 2 * EW + 2;
     static constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;
     static_assert(OG % 4 == 0 && OG >= 4, "consumer k-steps cover 4 observations");
-    static_assert(PAIRS * WT == SP_GW && PAIRS * QS * KG == SP_GW, "warp grids");
-    static_assert(STRIDE % 16 == 4, "bank-conflict-free padding");
-    static_assert(LPO * TO == SP_GW * 32 && MT % LPO == 0, "μ lanes");
+    static_assert(STRIDE % 16 == 4 && (BRS % 16 == 4 || BRS % 16 == 12), "bank-conflict-free padding");
+    static_assert(LPO >= 1 && MT / LPO == 16, "μ lanes");
+    static_assert(OPW * SP_XW == MB * SPL && (OPW == 1 || SPL == 1), "owner grid");
+    static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
 struct SparseArgs {
@@ -148,71 +153,75 @@ __device__ __forceinline__ void sp_issue_tile(const SparseArgs& a, int64_t tile,
     cp_async_commit();   // always: keeps the group count uniform across threads and iterations
 }
 
-// producer of one tile (GEMM warps): half quadratic forms q'_t = Σ_i κ_it (B'κ)_it over this warp's two block-rows
-// for its 16 observations → qp[p][t], and μ_t = κ_tᵀ m (LPO lanes per observation) → mus[t]
+// producer of one tile (group X, gw = 0..7): half quadratic forms q'_t = Σ_{i ∈ own rows} κ_it (B'κ)_it for this
+// warp's TBW column blocks → qp[slot][t]  (κᵀBκ = 2 Σ_slots q'), and μ_t = κ_tᵀ m (LPO lanes per observation) → mus[t]
 template <int MT>
 __device__ __forceinline__ void sp_producer(const double* __restrict__ Bs, const double* __restrict__ kap,
                                             const double* __restrict__ ms, double* __restrict__ qp,
-                                            double* __restrict__ mus, int warp, int lane, int kend) {
+                                            double* __restrict__ mus, int gw, int lane) {
     typedef SpCfg<MT> C;
-    const int p = warp % C::PAIRS, wt = warp / C::PAIRS;
     const int r = lane >> 2, k = lane & 3;
-    const int ra = p, rb = C::MB - 1 - p;                                  // block-rows: ra has ra+1 k-blocks, rb has rb+1 > ra+1
-    double c[2][2][2];
+    const int sp = C::OPW == 1 ? gw / C::MB : 0;                            // which share of the observations
+    const int ow0 = C::OPW == 1 ? gw % C::MB : gw;                          // owners: ow0 (+ 8 when OPW == 2)
+    const int tb0 = sp * C::TBW;
+    double c[C::OPW][C::TBW][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int o = 0; o < C::OPW; ++o)
 #pragma unroll
-        for (int tb = 0; tb < 2; ++tb) c[i][tb][0] = c[i][tb][1] = 0.0;
-    const double* apa = Bs + C::boff(ra) + r * C::brs(ra) + k;             // A[row r][k] = B'[8I + r][k0 + k]
-    const double* apb = Bs + C::boff(rb) + r * C::brs(rb) + k;
-    const double* bp = kap + (8 * (wt * 2) + r) * C::STRIDE + k;           // B[k][col r] = κ[k0 + k][t0 + r]
-    const int ka = min(8 * (ra + 1), kend), kb = min(8 * (rb + 1), kend);
-    int k0 = 0;
-#pragma unroll 4
-    for (; k0 < ka; k0 += 4) {
-        const double a0 = apa[k0], a1 = apb[k0];
-        const double b0 = bp[k0], b1 = bp[8 * C::STRIDE + k0];
-        dmma8x8x4(c[0][0][0], c[0][0][1], a0, b0);
-        dmma8x8x4(c[0][1][0], c[0][1][1], a0, b1);
-        dmma8x8x4(c[1][0][0], c[1][0][1], a1, b0);
-        dmma8x8x4(c[1][1][0], c[1][1][1], a1, b1);
+        for (int tb = 0; tb < C::TBW; ++tb) c[o][tb][0] = c[o][tb][1] = 0.0;
+    const double* ap = Bs + (8 * ow0 + r) * C::BRS + k;                     // A[row r][k] = B'[8 I + r][4 ks + k]
+    const double* bp = kap + (8 * tb0 + r) * C::STRIDE + k;                 // B[k][col r] = κ[8 x + 4 half + k][t0 + r]
+#pragma unroll
+    for (int ks = 0; ks < 2 * C::ND; ++ks) {
+        const int d = ks >> 1, half = ks & 1;
+#pragma unroll
+        for (int o = 0; o < C::OPW; ++o) {
+            const double av = ap[o * (8 * SP_XW) * C::BRS + 4 * ks];
+            const int xb = (ow0 + o * SP_XW + d) & (C::MB - 1);
+            const double* bq = bp + 8 * xb + 4 * half;
+#pragma unroll
+            for (int tb = 0; tb < C::TBW; ++tb) dmma8x8x4(c[o][tb][0], c[o][tb][1], av, bq[tb * 8 * C::STRIDE]);
+        }
     }
-#pragma unroll 4
-    for (; k0 < kb; k0 += 4) {
-        const double a1 = apb[k0];
-        const double b0 = bp[k0], b1 = bp[8 * C::STRIDE + k0];
-        dmma8x8x4(c[1][0][0], c[1][0][1], a1, b0);
-        dmma8x8x4(c[1][1][0], c[1][1][1], a1, b1);
-    }
-    // C[row r][col 2k + e] = (B'κ)[8I + r][t]: own rows, then the 8 lanes sharing k
-    double s[4];
+    // C[row r][col 2k + e] = (B'κ)[8 I + r][t]: times κ[8 I + r][t], summed over own rows, then over the 8 lanes sharing k
+    double s[C::TBW][2];
 #pragma unroll
-    for (int tb = 0; tb < 2; ++tb)
+    for (int tb = 0; tb < C::TBW; ++tb)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const double* row = kap + (8 * (wt * 2 + tb) + 2 * k + e) * C::STRIDE + r;
-            s[tb * 2 + e] = fma(c[0][tb][e], row[8 * ra], c[1][tb][e] * row[8 * rb]);
+            const double* row = kap + (8 * (tb0 + tb) + 2 * k + e) * C::STRIDE + r;
+            double v = c[0][tb][e] * row[8 * ow0];
+            if (C::OPW == 2) v = fma(c[C::OPW - 1][tb][e], row[8 * (ow0 + SP_XW)], v);
+            s[tb][e] = v;
         }
 #pragma unroll
     for (int o = 4; o <= 16; o <<= 1)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+        for (int tb = 0; tb < C::TBW; ++tb) {
+            s[tb][0] += __shfl_xor_sync(0xffffffffu, s[tb][0], o);
+            s[tb][1] += __shfl_xor_sync(0xffffffffu, s[tb][1], o);
+        }
     if (r == 0) {
 #pragma unroll
-        for (int tb = 0; tb < 2; ++tb)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) qp[p * C::TO + 8 * (wt * 2 + tb) + 2 * k + e] = s[tb * 2 + e];
+        for (int tb = 0; tb < C::TBW; ++tb) {
+            double* dst = qp + ow0 * C::TO + 8 * (tb0 + tb) + 2 * k;       // slot = ow0 (0 .. NSLOT-1)
+            dst[0] = s[tb][0];
+            dst[1] = s[tb][1];
+        }
     }
-    // μ_t: LPO consecutive lanes per observation, MT / LPO elements each
+    // μ_t: LPO consecutive lanes per observation, 16 elements each (start rotated by t when one lane owns a row:
+    // 32 rows at stride ≡ 4 mod 16 would otherwise hit 4 banks)
     {
-        const int idx = warp * 32 + lane;
+        const int idx = gw * 32 + lane;
         const int t = idx / C::LPO, sidx = idx % C::LPO;
-        const double* row = kap + t * C::STRIDE + sidx;
+        const double* row = kap + t * C::STRIDE;
+        const int rot = C::LPO == 1 ? t : 0;
         double m0 = 0.0, m1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < MT / C::LPO; j += 2) {
-            m0 = fma(ms[sidx + C::LPO * j], row[C::LPO * j], m0);
-            m1 = fma(ms[sidx + C::LPO * (j + 1)], row[C::LPO * (j + 1)], m1);
+        for (int j = 0; j < 16; j += 2) {
+            const int i0 = sidx + C::LPO * ((j + rot) & 15), i1 = sidx + C::LPO * ((j + 1 + rot) & 15);
+            m0 = fma(ms[i0], row[i0], m0);
+            m1 = fma(ms[i1], row[i1], m1);
         }
         double mu = m0 + m1;
 #pragma unroll
@@ -221,44 +230,64 @@ __device__ __forceinline__ void sp_producer(const double* __restrict__ Bs, const
     }
 }
 
-// consumer of one tile into this warp's accumulators: SYRK blocks P_IJ += Σ_t γ_t κ_It κ_Jtᵀ, and the rhs slice
-// (κβ)_I as one more DMMA per block-row whose B operand carries β_t in column 0 — a plain DFMA loop in the
-// evaluation warp would starve behind the DMMA stream on the shared FP64 pipe (measured: ~64 clk per issue).
+// consumer of one tile (group Y, gw = 0..7) into this warp's accumulators: blocks P_{I,x} += Σ_t γ_t κ_It κ_xtᵀ for
+// x = (I + d) mod MB, and the rhs slice (κβ)_I as one more DMMA whose B operand carries β_t in column 0 — a plain
+// DFMA loop would starve behind the DMMA stream on the shared FP64 pipe.
 template <int MT>
 __device__ __forceinline__ void sp_consumer(const double* __restrict__ kap, const double* __restrict__ gs,
-                                            const double* __restrict__ bs, double (&acc)[SpCfg<MT>::NACC][2],
-                                            double (&racc)[SpCfg<MT>::NR][2], int warp, int lane) {
+                                            const double* __restrict__ bs, double (&acc)[SpCfg<MT>::OPW][SpCfg<MT>::ND][2],
+                                            double (&racc)[SpCfg<MT>::OPW][2], int gw, int lane) {
     typedef SpCfg<MT> C;
-    const int p = warp % C::PAIRS, h = (warp / C::PAIRS) % C::QS, g = warp / (C::PAIRS * C::QS);
     const int r = lane >> 2, k = lane & 3;
+    const int g = C::OPW == 1 ? gw / C::MB : 0;
+    const int ow0 = C::OPW == 1 ? gw % C::MB : gw;
+    // the γ_t scaling of step ks+1 is issued before the DMMAs of step ks: the DMUL only has to find a slot on the
+    // FP64 pipe between the DMMAs of all warps, nothing waits for its result for a whole step
+    double raw[C::OPW], av[C::OPW], bt;
+    {
+        const int t = g * C::OG + k;
+        const double gm = gs[t];
+        bt = r == 0 ? bs[t] : 0.0;                               // B[k][col 0] = β_t, other columns 0
+#pragma unroll
+        for (int o = 0; o < C::OPW; ++o) {
+            raw[o] = kap[t * C::STRIDE + r + 8 * (ow0 + o * SP_XW)];
+            av[o] = raw[o] * gm;                                 // A[row r][k] = γ_t κ[8 I + r][t]
+        }
+    }
 #pragma unroll 2
     for (int ks = 0; ks < C::OG / 4; ++ks) {
         const int t = g * C::OG + 4 * ks + k;
         const double* row = kap + t * C::STRIDE + r;
-        const double gm = gs[t];
-        const double bt = r == 0 ? bs[t] : 0.0;                  // B[k][col 0] = β_t, other columns 0
-        const double rawP = row[8 * p], rawQ = row[8 * (C::MB - 1 - p)];
-        double aP = rawP * gm;                                   // A[row r][k] = γ_t κ[8I + r][t]
-        double aQ = rawQ * gm;
-        // keep the two products where they are: sunk below the per-block select they become one DMUL per DMMA,
-        // each queueing behind the other warps' DMMAs on the FP64 pipe (ncu: 17 % of all stall samples)
-        asm volatile("" : "+d"(aP), "+d"(aQ));
+        double rawn[C::OPW], avn[C::OPW], btn = 0.0;
+        if (ks + 1 < C::OG / 4) {
+            const double gm = gs[t + 4];
+            btn = r == 0 ? bs[t + 4] : 0.0;
 #pragma unroll
-        for (int qi = 0; qi < C::NACC; ++qi) {
-            const int q = h * C::NACC + qi;                       // block index in the concatenated rows p, MB-1-p
-            if (C::QS == 1 || q <= C::MB) {
-                const bool first = q <= p;
-                const int J = first ? q : q - p - 1;
-                const double b = row[8 * J];                      // B[k][col r] = κ[8J + r][t]
-                dmma8x8x4(acc[qi][0], acc[qi][1], first ? aP : aQ, b);
+            for (int o = 0; o < C::OPW; ++o) {
+                rawn[o] = row[4 * C::STRIDE + 8 * (ow0 + o * SP_XW)];
+                avn[o] = rawn[o] * gm;
+                asm volatile("" : "+d"(avn[o]));                 // keep the product here (one per owner and step)
             }
-        }
-        if (C::QS == 1) {
-            dmma8x8x4(racc[0][0], racc[0][1], rawP, bt);
-            dmma8x8x4(racc[C::NR - 1][0], racc[C::NR - 1][1], rawQ, bt);
         } else {
-            dmma8x8x4(racc[0][0], racc[0][1], h == 0 ? rawP : rawQ, bt);
+#pragma unroll
+            for (int o = 0; o < C::OPW; ++o) rawn[o] = avn[o] = 0.0;
         }
+#pragma unroll
+        for (int o = 0; o < C::OPW; ++o) {
+            const int own = ow0 + o * SP_XW;
+            const bool has_half = C::OPW == 2 ? (o == 0) : (own < C::MB / 2);
+#pragma unroll
+            for (int d = 0; d < C::ND; ++d) {
+                if (d < C::ND - 1 || has_half) {
+                    const double b = row[8 * ((own + d) & (C::MB - 1))];   // B[k][col r] = κ[8 x + r][t]
+                    dmma8x8x4(acc[o][d][0], acc[o][d][1], av[o], b);
+                }
+            }
+            dmma8x8x4(racc[o][0], racc[o][1], raw[o], bt);
+        }
+#pragma unroll
+        for (int o = 0; o < C::OPW; ++o) { raw[o] = rawn[o]; av[o] = avn[o]; }
+        bt = btn;
     }
 }
 
@@ -280,50 +309,39 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
     double* bs = sm + C::OFF_BE;
     double* red = sm + C::OFF_RED;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool gemm_warp = warp < SP_GW;
-    const int et = tid - SP_GW * 32;                 // evaluation thread index (>= 0 for evaluation warps)
+    const int role = warp < SP_XW ? 0 : (warp < SP_GW ? 1 : 2);   // 0 = producer group X, 1 = consumer group Y, 2 = evaluation E
+    const bool evaluator = C::EVAL_IN_X ? warp < C::EW : role == 2;
+    const int et = C::EVAL_IN_X ? tid : tid - SP_GW * 32;         // evaluation lane index: one observation each
     const int m = a.m;
-    const int kend = (m + 3) & ~3;
 
     // ---- one-time staging: zero the ring (pad columns / rows stay zero or finite for ever), B', m
     for (int e = tid; e < SP_STAGES * C::TO * C::STRIDE; e += C::NT) ring[e] = 0.0;
     if (PROD) {
-        for (int I = 0; I < C::MB; ++I) {
-            const int rs = C::brs(I);
-            double* dst = Bs + C::boff(I);
-            for (int e = tid; e < 8 * rs; e += C::NT) {
-                const int rr = e / rs, j = e - rr * rs;
-                const int i = 8 * I + rr;
-                double v = 0.0;
-                if (j < 8 * (I + 1) && i < m && j < m) {
+        // B' row (8 I + rr), column 8 d + cc  =  w_d · sym(B)[8 I + rr][8 ((I + d) mod MB) + cc],  w_0 = w_{MB/2} = ½
+        for (int e = tid; e < MT * C::BRS; e += C::NT) {
+            const int i = e / C::BRS, c = e - i * C::BRS;
+            double v = 0.0;
+            if (c < 8 * C::ND) {
+                const int I = i >> 3, d = c >> 3;
+                const int j = 8 * ((I + d) & (C::MB - 1)) + (c & 7);
+                if (i < m && j < m) {
                     v = 0.5 * (__ldg(a.B + (size_t)i * m + j) + __ldg(a.B + (size_t)j * m + i));   // symmetrised
-                    if (j >= 8 * I) v *= 0.5;                                                        // diagonal block: half
+                    if (d == 0 || d == C::MB / 2) v *= 0.5;
                 }
-                dst[e] = v;
             }
+            Bs[e] = v;
         }
         for (int e = tid; e < MT; e += C::NT) ms[e] = e < m ? __ldg(a.mvec + e) : 0.0;
     }
-    for (int e = tid; e < C::TO; e += C::NT) { gs[e] = 0.0; bs[e] = 0.0; }
+    for (int e = tid; e < 2 * C::TO; e += C::NT) { gs[e] = 0.0; bs[e] = 0.0; }
     __syncthreads();
 
     // local tile l ↔ global tile blockIdx.x + l * gridDim.x
     const int64_t nloc = a.ntiles > (int64_t)blockIdx.x ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto gtile = [&](int64_t l) -> int64_t { return l < nloc ? (int64_t)blockIdx.x + l * gridDim.x : a.ntiles; };
-    auto stage = [&](int64_t l) -> double* { return ring + (int)(l % SP_STAGES) * (C::TO * C::STRIDE); };
+    auto stage = [&](int64_t l) -> double* { return ring + (int)(l & (SP_STAGES - 1)) * (C::TO * C::STRIDE); };
 
-    double acc[C::NACC][2];
-#pragma unroll
-    for (int q = 0; q < C::NACC; ++q) acc[q][0] = acc[q][1] = 0.0;
-    double racc[C::NR][2];
-#pragma unroll
-    for (int i = 0; i < C::NR; ++i) racc[i][0] = racc[i][1] = 0.0;
-    double e_elt = 0.0, e_kl = 0.0;
-    double ev_mu = 0.0, ev_var = 1.0, ev_y = 0.0;   // evaluation lane: inputs of tile l kept for the ELBO pass of phase B
-    bool ev_valid = false;
-
-    // per-observation scalars of the evaluation lanes, fetched one tile ahead (latency hidden behind a whole phase)
-    double pf0 = 0.0, pf1 = 0.0;       // FUSED / PRODUCER: k_tt, y   CONSUMER: γ, β
+    // per-observation scalars of the evaluation lanes, fetched one tile ahead (latency hidden behind a whole iteration)
     auto prefetch = [&](int64_t l, double& x0, double& x1) {
         x0 = 0.0; x1 = 0.0;
         if (l < nloc) {
@@ -337,123 +355,149 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
             }
         }
     };
-    if (!gemm_warp) prefetch(0, pf0, pf1);
 
-    // ---- prologue
+    // ---- prologue: tiles 0 and 1 land before the first iteration
     sp_issue_tile<MT>(a, gtile(0), stage(0));
     sp_issue_tile<MT>(a, gtile(1), stage(1));
-    cp_async_wait<1>();
-    __syncthreads();                                   // tile 0 visible
-    sp_issue_tile<MT>(a, gtile(2), stage(2));
-    if (PROD && gemm_warp && nloc > 0) sp_producer<MT>(Bs, stage(0), ms, qs, mus, warp, lane, kend);
-    cp_async_wait<1>();
-    __syncthreads();                                   // q(0), μ(0) and tile 1 visible; tile 2 may be in flight
-
-    for (int64_t l = 0; l < nloc; ++l) {
-        const double* kap = stage(l);
-        // ================= phase A: producer(l+1) ‖ evaluation(l)
-        if (gemm_warp) {
-            if (PROD && l + 1 < nloc) {
-                const int nb = (int)((l + 1) & 1);
-                sp_producer<MT>(Bs, stage(l + 1), ms, qs + nb * (C::PAIRS * C::TO), mus + nb * C::TO, warp, lane, kend);
-            }
-        } else {
-            const int t = et;
-            const int64_t i = gtile(l) * C::TO + t;
-            const bool valid = i < a.n;
-            const double c0 = pf0, c1 = pf1;
-            prefetch(l + 1, pf0, pf1);                 // next tile's scalars: in flight during this phase
-            double g0 = 0.0, b0 = 0.0;
-            if (MODE == SP_CONSUMER) {
-                g0 = c0; b0 = c1;
-            } else {
-                const int cb = (int)(l & 1);
-                const double mu = mus[cb * C::TO + t];
-                const double* qp = qs + cb * (C::PAIRS * C::TO) + t;
-                double q = 0.0;
-#pragma unroll
-                for (int w = 0; w < C::PAIRS; ++w) q += qp[w * C::TO];
-                const double var = fma(-2.0, q, c0);   // k_tt − κᵀBκ,  κᵀBκ = 2 κᵀB'κ
-                if (valid) {
-                    if (a.mu) a.mu[i] = mu;
-                    if (a.var) a.var[i] = var;
-                    if (MODE == SP_FUSED) {
-                        // part 1 (phase A): what the consumer and the caller need; the ELBO terms follow in phase B
-                        Obs o;
-                        o.y = c1; o.ys = c1;
-                        o.m = mu; o.v = var; o.mg = 0.0; o.vg = 0.0;
-                        o.s0 = o.s1 = o.s2 = 0.0;
-                        if (fast_ok<KIND, false, false>(o)) eval<KIND, false, false, false>(a.L, o);
-                        else eval<KIND, false, false, true>(a.L, o);
-                        if (a.s0) a.s0[i] = o.s0;
-                        if (KIND == AUG_POISSON && a.s1) a.s1[i] = o.s1;
-                        if (YSTATE && a.s2) reinterpret_cast<s2t*>(a.s2)[i] = (s2t)o.y;
-                        if (a.beta) a.beta[i] = o.b0;
-                        if (a.gamma) a.gamma[i] = o.g0;
-                        g0 = o.g0; b0 = o.b0;
-                    }
-                }
-                ev_mu = mu; ev_var = var; ev_y = c1; ev_valid = valid;
-            }
-            if (CONS) { gs[t] = g0; bs[t] = b0; }
-        }
-        __syncthreads();
-        // ================= phase B: consumer(l) ‖ rhs(l)
-        if (CONS) {
-            if (gemm_warp) {
-                sp_consumer<MT>(kap, gs, bs, acc, racc, warp, lane);
-            } else if (MODE == SP_FUSED && a.elbo && ev_valid) {
-                // part 2: expected_logtilt / aux_kldivergence terms of tile l (nothing waits for them)
-                Obs o;
-                o.y = ev_y; o.ys = ev_y;
-                o.m = ev_mu; o.v = ev_var; o.mg = 0.0; o.vg = 0.0;
-                o.s0 = o.s1 = o.s2 = 0.0;
-                if (fast_ok<KIND, false, true>(o)) eval<KIND, false, true, false>(a.L, o);
-                else eval<KIND, false, true, true>(a.L, o);
-                e_elt += o.elt; e_kl += o.kl;
-            }
-        }
-        cp_async_wait<0>();                            // tile l+2 landed (the only group in flight)
-        __syncthreads();                               // everyone is done with tile l: its stage is free
-        sp_issue_tile<MT>(a, gtile(l + 3), stage(l + 3));
-    }
     cp_async_wait<0>();
+    __syncthreads();
 
-    // ---- epilogue: partials to scratch
+    // ---- software pipeline, one CTA barrier per tile:  iteration k = producer(k) ‖ evaluation(k-1) ‖ consumer(k-2).
+    // The two GEMM groups share the FP64 tensor pipe: the shuffle / reduction epilogue of the producer group and the
+    // scalar math of the evaluation warps run while the other group keeps the pipe busy.  Each role runs its own
+    // copy of the loop (so the consumer's accumulators are live in the consumer warps only); every copy executes
+    // the same nloc + 2 barriers.
+    auto tail = [&](int64_t k) {
+        cp_async_wait<0>();                            // tile k+1 landed (the only group in flight)
+        asm volatile("bar.sync 0, %0;" ::"n"(C::NT) : "memory");   // tile k-2 is free; q(k), μ(k), γ(k-1), β(k-1) visible
+        sp_issue_tile<MT>(a, gtile(k + 2), stage(k + 2));
+    };
     double* Ppart = a.scratch;
     double* rpart = a.scratch + (size_t)gridDim.x * C::KG * (MT * MT);
     double* spart = rpart + (size_t)gridDim.x * C::KG * MT;
-    if (CONS && gemm_warp) {
-        const int p = warp % C::PAIRS, h = (warp / C::PAIRS) % C::QS, g = warp / (C::PAIRS * C::QS);
-        const int r = lane >> 2, k = lane & 3;
-        double* dst = Ppart + ((size_t)blockIdx.x * C::KG + g) * (MT * MT);
+
+    double e_elt = 0.0, e_kl = 0.0;
+    double pf0 = 0.0, pf1 = 0.0;                       // FUSED / PRODUCER: k_tt, y   CONSUMER: γ, β
+    auto evaluate = [&](int64_t k) {
+    if (k >= 1 && k - 1 < nloc) {
+        const int64_t l = k - 1;
+        const int t = et;
+        const int64_t i = gtile(l) * C::TO + t;
+        const bool valid = i < a.n;
+        const double c0 = pf0, c1 = pf1;
+        prefetch(l + 1, pf0, pf1);             // next tile's scalars: in flight during this iteration
+        double g0 = 0.0, b0 = 0.0;
+        const int cb = (int)(l & 1);
+        if (MODE == SP_CONSUMER) {
+            g0 = c0; b0 = c1;
+        } else {
+            const double mu = mus[cb * C::TO + t];
+            const double* qp = qs + cb * (C::NSLOT * C::TO) + t;
+            double q = 0.0;
 #pragma unroll
-        for (int qi = 0; qi < C::NACC; ++qi) {
-            const int q = h * C::NACC + qi;
-            if (q <= C::MB) {
-                const bool first = q <= p;
-                const int I = first ? p : C::MB - 1 - p;
-                const int J = first ? q : q - p - 1;
-                double2 v = make_double2(acc[qi][0], acc[qi][1]);
-                *reinterpret_cast<double2*>(dst + (size_t)(8 * I + r) * MT + 8 * J + 2 * k) = v;
+            for (int w = 0; w < C::NSLOT; ++w) q += qp[w * C::TO];
+            const double var = fma(-2.0, q, c0);   // k_tt − κᵀBκ,  κᵀBκ = 2 κᵀB'κ
+            if (valid) {
+                if (a.mu) a.mu[i] = mu;
+                if (a.var) a.var[i] = var;
+                if (MODE == SP_FUSED) {
+                    Obs o;
+                    o.y = c1; o.ys = c1;
+                    o.m = mu; o.v = var; o.mg = 0.0; o.vg = 0.0;
+                    o.s0 = o.s1 = o.s2 = 0.0;
+                    if (a.elbo) {
+                        if (fast_ok<KIND, false, true>(o)) eval<KIND, false, true, false>(a.L, o);
+                        else eval<KIND, false, true, true>(a.L, o);
+                        e_elt += o.elt; e_kl += o.kl;
+                    } else {
+                        if (fast_ok<KIND, false, false>(o)) eval<KIND, false, false, false>(a.L, o);
+                        else eval<KIND, false, false, true>(a.L, o);
+                    }
+                    if (a.s0) a.s0[i] = o.s0;
+                    if (KIND == AUG_POISSON && a.s1) a.s1[i] = o.s1;
+                    if (YSTATE && a.s2) reinterpret_cast<s2t*>(a.s2)[i] = (s2t)o.y;
+                    if (a.beta) a.beta[i] = o.b0;
+                    if (a.gamma) a.gamma[i] = o.g0;
+                    g0 = o.g0; b0 = o.b0;
+                }
             }
         }
-        if (k == 0) {                                  // column 0 of the rhs blocks
+        if (CONS) { gs[cb * C::TO + t] = g0; bs[cb * C::TO + t] = b0; }
+    }
+    };
+    if (evaluator) prefetch(0, pf0, pf1);
+
+    if (role == 0) {
+        // ================= producer group X (+ evaluation of the previous tile in its first EW warps)
+        for (int64_t k = 0; k < nloc + 2; ++k) {
+            if (PROD && k < nloc) {
+                const int nb = (int)(k & 1);
+                sp_producer<MT>(Bs, stage(k), ms, qs + nb * (C::NSLOT * C::TO), mus + nb * C::TO, warp, lane);
+            }
+            if (C::EVAL_IN_X && evaluator) evaluate(k);
+            tail(k);
+        }
+    } else if (role == 1) {
+        // ================= consumer group Y
+        double acc[C::OPW][C::ND][2];
+        double racc[C::OPW][2];
+#pragma unroll
+        for (int o = 0; o < C::OPW; ++o) {
+            racc[o][0] = racc[o][1] = 0.0;
+#pragma unroll
+            for (int d = 0; d < C::ND; ++d) acc[o][d][0] = acc[o][d][1] = 0.0;
+        }
+        const int gw = warp - SP_XW;
+        for (int64_t k = 0; k < nloc + 2; ++k) {
+            if (CONS && k >= 2) {
+                const int cb = (int)(k & 1);           // (k-2) & 1
+                sp_consumer<MT>(stage(k - 2), gs + cb * C::TO, bs + cb * C::TO, acc, racc, gw, lane);
+            }
+            tail(k);
+        }
+        if (CONS) {
+            const int r = lane >> 2, k = lane & 3;
+            const int g = C::OPW == 1 ? gw / C::MB : 0;
+            const int ow0 = C::OPW == 1 ? gw % C::MB : gw;
+            double* dst = Ppart + ((size_t)blockIdx.x * C::KG + g) * (MT * MT);
             double* rd = rpart + ((size_t)blockIdx.x * C::KG + g) * MT;
-            if (C::QS == 1) {
-                rd[8 * p + r] = racc[0][0];
-                rd[8 * (C::MB - 1 - p) + r] = racc[C::NR - 1][0];
-            } else {
-                rd[8 * (h == 0 ? p : C::MB - 1 - p) + r] = racc[0][0];
+#pragma unroll
+            for (int o = 0; o < C::OPW; ++o) {
+                const int own = ow0 + o * SP_XW;
+                const bool has_half = C::OPW == 2 ? (o == 0) : (own < C::MB / 2);
+#pragma unroll
+                for (int d = 0; d < C::ND; ++d) {
+                    if (d < C::ND - 1 || has_half) {
+                        const int x = (own + d) & (C::MB - 1);
+                        // C[r][2k + e] = P[8 own + r][8 x + 2k + e]: the lower-triangle copy is this block (x <= own)
+                        // or its transpose (x > own)
+                        if (x <= own) {
+                            *reinterpret_cast<double2*>(dst + (size_t)(8 * own + r) * MT + 8 * x + 2 * k) =
+                                make_double2(acc[o][d][0], acc[o][d][1]);
+                        } else {
+                            dst[(size_t)(8 * x + 2 * k) * MT + 8 * own + r] = acc[o][d][0];
+                            dst[(size_t)(8 * x + 2 * k + 1) * MT + 8 * own + r] = acc[o][d][1];
+                        }
+                    }
+                }
+                if (k == 0) rd[8 * own + r] = racc[o][0];   // column 0 of the rhs block
             }
         }
     }
-    __syncthreads();
-    if (MODE == SP_FUSED && !gemm_warp) {
-        // ELBO partials: evaluation threads → warp shuffles → shared → one pair per CTA
-        const double s0 = warp_sum(e_elt), s1 = warp_sum(e_kl);
-        if (lane == 0) { red[(warp - SP_GW) * 2] = s0; red[(warp - SP_GW) * 2 + 1] = s1; }
+    else {
+        // ================= dedicated evaluation warps (MT < 128)
+        for (int64_t k = 0; k < nloc + 2; ++k) {
+            evaluate(k);
+            tail(k);
+        }
     }
+    if (MODE == SP_FUSED && evaluator) {
+        // ELBO partials: evaluation lanes → warp shuffles → shared → one pair per CTA
+        const int ew = et >> 5;
+        const double s0 = warp_sum(e_elt), s1 = warp_sum(e_kl);
+        if (lane == 0) { red[ew * 2] = s0; red[ew * 2 + 1] = s1; }
+    }
+    cp_async_wait<0>();
     __syncthreads();
     if (MODE == SP_FUSED && tid == 0) {
         double s0 = 0.0, s1 = 0.0;
