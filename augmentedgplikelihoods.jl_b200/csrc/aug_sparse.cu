@@ -194,19 +194,58 @@ __device__ __forceinline__ void sp_producer(const double* __restrict__ Bs, const
             if (C::OPW == 2) v = fma(c[C::OPW - 1][tb][e], row[8 * (ow0 + SP_XW)], v);
             s[tb][e] = v;
         }
+    // Σ over the 8 lanes r = 0..7 that share k.  With NV = 2 TBW >= 8 values per lane the butterfly keeps half of the
+    // values per round (NV - NV/8 adds and shuffles instead of 3 NV): scalar FP64 instructions are served only in the
+    // gaps of the DMMA stream (tools/fp64_peak.cu: a dependent DFMA takes 87 clk next to ONE streaming DMMA warp of the
+    // same sub-partition and starves next to three), so every one of them counts.  Lane r ends with the sum of value
+    // v = r (+ 8 j for NV > 8).
+    constexpr int NV = 2 * C::TBW;
+    double* sv = &s[0][0];
+    if (NV % 8 == 0) {
 #pragma unroll
-    for (int o = 4; o <= 16; o <<= 1)
+        for (int j = 0; j < NV / 8; ++j) {
+            double* v = sv + 8 * j;
+            // round 1 (lanes r, r^1 ↔ xor 4): keep v[0..3] if bit0(r) == 0 else v[4..7]
+            const bool b0 = r & 1, b1 = r & 2, b2 = r & 4;
+            double w4[4], w2[2];
 #pragma unroll
-        for (int tb = 0; tb < C::TBW; ++tb) {
-            s[tb][0] += __shfl_xor_sync(0xffffffffu, s[tb][0], o);
-            s[tb][1] += __shfl_xor_sync(0xffffffffu, s[tb][1], o);
+            for (int i = 0; i < 4; ++i) {
+                const double send = b0 ? v[i] : v[i + 4];
+                const double keep = b0 ? v[i + 4] : v[i];
+                w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double send = b1 ? w4[i] : w4[i + 2];
+                const double keep = b1 ? w4[i + 2] : w4[i];
+                w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            const double send = b2 ? w2[0] : w2[1];
+            const double keep = b2 ? w2[1] : w2[0];
+            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 16);   // value index 4 b0 + 2 b1 + b2 (+ 8 j)
         }
-    if (r == 0) {
+        // lane (r, k) holds the total of value vi = 4 b0 + 2 b1 + b2 of group j: tb = (8 j + vi) / 2, e = vi & 1
 #pragma unroll
-        for (int tb = 0; tb < C::TBW; ++tb) {
-            double* dst = qp + ow0 * C::TO + 8 * (tb0 + tb) + 2 * k;       // slot = ow0 (0 .. NSLOT-1)
-            dst[0] = s[tb][0];
-            dst[1] = s[tb][1];
+        for (int j = 0; j < NV / 8; ++j) {
+            const int vi = ((r & 1) << 2) | (r & 2) | ((r >> 2) & 1);
+            const int tb = (8 * j + vi) >> 1, e = vi & 1;
+            qp[ow0 * C::TO + 8 * (tb0 + tb) + 2 * k + e] = sv[8 * j];
+        }
+    } else {
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+            for (int tb = 0; tb < C::TBW; ++tb) {
+                s[tb][0] += __shfl_xor_sync(0xffffffffu, s[tb][0], o);
+                s[tb][1] += __shfl_xor_sync(0xffffffffu, s[tb][1], o);
+            }
+        if (r == 0) {
+#pragma unroll
+            for (int tb = 0; tb < C::TBW; ++tb) {
+                double* dst = qp + ow0 * C::TO + 8 * (tb0 + tb) + 2 * k;       // slot = ow0 (0 .. NSLOT-1)
+                dst[0] = s[tb][0];
+                dst[1] = s[tb][1];
+            }
         }
     }
     // μ_t: LPO consecutive lanes per observation, 16 elements each (start rotated by t when one lane owns a row:

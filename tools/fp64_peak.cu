@@ -41,6 +41,34 @@ __global__ void __launch_bounds__(512, 1) k_dfma(double* out, int iters, double 
     if (s == 12345.678) out[0] = s;
 }
 
+
+// How long does a scalar FP64 instruction of one warp wait while the other warps of the SM stream DMMAs?
+// warp 0: `iters` dependent DFMAs (clock64 around them); warps 1..: DMMA streams until warp 0 is done (flag in smem).
+__global__ void __launch_bounds__(512, 1) k_mix(double* out, long long* cyc, int iters, int dmma_warps, double a0) {
+    __shared__ volatile int done;
+    if (threadIdx.x == 0) done = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        double c = a0;
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) c = fma(c, 1.0000001, 1e-9);
+        long long t1 = clock64();
+        if (c == 12345.678) out[0] = c;
+        if (threadIdx.x == 0) { cyc[blockIdx.x] = t1 - t0; done = 1; }
+    } else if (warp <= dmma_warps) {
+        double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        double a = a0 + threadIdx.x * 1e-9, b = 1.0;
+        while (!done) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dmma(c[i][0], c[i][1], a, b);
+        }
+        if (c[0][0] + c[1][0] + c[2][1] + c[3][1] == 12345.678) out[1] = c[0][0];
+    }
+}
+
 template <typename F>
 float time_ms(F f) {
     cudaEvent_t e0, e1;
@@ -78,6 +106,16 @@ int main() {
         float ms = time_ms([&] { k_dfma<8><<<sms, warps * 32, 0>>>(out, iters, 1.0000001, 1e-9); });
         double flops = 2.0 * 32 * 8 * (double)iters * warps * sms;
         printf("{\"kernel\": \"dfma\", \"warps_per_sm\": %d, \"chains\": 8, \"ms\": %.4f, \"tflops\": %.3f}\n", warps, ms, flops / ms * 1e-9);
+    }
+    {
+        long long* cyc; cudaMalloc(&cyc, sizeof(long long) * sms);
+        for (int dw = 0; dw <= 15; dw = dw == 0 ? 3 : (dw == 3 ? 7 : (dw == 7 ? 15 : 16))) {
+            k_mix<<<sms, 512>>>(out, cyc, 2000, dw, 1.0);
+            cudaDeviceSynchronize();
+            long long h[256]; cudaMemcpy(h, cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+            double avg = 0; for (int i = 0; i < sms; ++i) avg += (double)h[i];
+            printf("{\"kernel\": \"dependent_dfma_next_to_dmma\", \"dmma_warps_per_sm\": %d, \"clk_per_dfma\": %.1f}\n", dw, avg / sms / 2000.0);
+        }
     }
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", p.name, sms, p.clockRate);
     return 0;
