@@ -99,6 +99,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def host_threads(orc):
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: the oracle's num_threads clause overrides it)"""
+    try:
+        return max(orc.max_threads(), len(os.sched_getaffinity(0)))
+    except Exception:
+        return orc.max_threads()
+
+
 def cpu_inputs(n, seed=1):
     import numpy as np
     rng = np.random.default_rng(seed)
@@ -138,7 +146,7 @@ def run_reference(args):
         return
     from oracle import orc
     orc.lib()
-    threads = orc.max_threads()
+    threads = host_threads(orc)
     probe = cpu_inputs(1_000_000)
     for _ in range(max(1, args.warmup)):
         tp = cpu_reference(1_000_000, threads, inputs=probe)[0]
@@ -259,7 +267,7 @@ def sparse_cpu(m, n=20000):
     import numpy as np
     from oracle import orc
     orc.lib()
-    threads = orc.max_threads()
+    threads = host_threads(orc)
     orc.set_threads(threads)
     rng = np.random.default_rng(0)
     kappa = rng.standard_normal((n, m)) / np.sqrt(m)
@@ -462,7 +470,7 @@ def main():
     if not args.no_cpu:
         from oracle import orc
         orc.lib()
-        threads = orc.max_threads()
+        threads = host_threads(orc)
         t1, c1, g1 = cpu_reference(min(args.cpu_n // 10, 2_000_000), 1)
         n1 = min(args.cpu_n // 10, 2_000_000)
         tt, tc, tg = cpu_reference(args.cpu_n, threads, repeats=2)
