@@ -190,6 +190,15 @@ def fp64_peak():
     return 37.1, "recorded (profiles/fp64_peak_r1f.jsonl)"
 
 
+def sparse_traffic(m, n):
+    """dram bytes per launch from the ncu --set full capture recorded in profiles/traffic.json (m = 128 only)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["sparse_sweep_kernel_m128_fused"]
+        return t["bytes_per_obs"] * n if m == 128 else None
+    except Exception:
+        return None
+
+
 def sparse_leg(A, ctx, torch, dist, world, dev, args, rank):
     """aug_sparse_cavi_sweep on m inducing points: marginals -> aux_posterior! -> E[beta], E[gamma], ELBO sums ->
     P = kappa Diag(gamma) kappa^T, rhs = kappa beta, next to the library composition (cuBLAS DGEMMs through torch +
@@ -256,7 +265,7 @@ def sparse_leg(A, ctx, torch, dist, world, dev, args, rank):
             "roofline": {"kernel": "sparse_sweep_kernel<128, FUSED, BERNOULLI> (DMMA m8n8k4)", "bound": "tensor",
                          "note": "fp64 tensor pipe (tcgen05 has no f64 kind); HBM traffic 8m B/obs is 10% of the HBM roofline",
                          "achieved": ach, "peak": peak, "peak_source": src, "unit": "TFLOP/s", "frac": ach / peak,
-                         "flops_per_obs": flops, "traffic": None},
+                         "flops_per_obs": flops, "traffic": sparse_traffic(m, n)},
             "library_composition": {"what": "torch (cuBLAS DGEMM) kappa@m, kappa@B, row dots, (kappa*gamma)^T@kappa, "
                                             "kappa^T@beta + aug_cavi_step", "ms": ms_l, "speedup": ms_l / ms_f,
                                     "max_rel_diff": agree}}
