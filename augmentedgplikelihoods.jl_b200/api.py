@@ -719,8 +719,6 @@ def _kappa(kappa):
     """κ = K_Z⁻¹ K_{Z,X}: Julia's column-major M×N matrix = a contiguous [n][m] tensor here."""
     if kappa.dim() != 2:
         raise ValueError("kappa must be [n][m] (the Julia M×N matrix as stored)")
-    if kappa.shape[1] > 128:
-        raise ValueError("m <= 128 inducing points")
     return _f64(kappa, "kappa")
 
 

@@ -467,7 +467,8 @@ template <int KIND, bool ELBO>
 int32_t launch_tma(aug_ctx* ctx, const CaviArgs& a, int64_t ntiles) {
     typedef TileLayout<KIND> TL;
     const void* k = (const void*)cavi_tma_kernel<KIND, ELBO>;
-    static bool configured = false;
+    static bool configured_dev[64] = {false};   // the attribute is per device: one flag per ordinal
+    bool& configured = configured_dev[ctx->device & 63];
     static int occ = 1;
     if (!configured) {
         AUG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::SMEM_BYTES));

@@ -75,6 +75,7 @@ struct aug_ctx {
     // sparse-GP sweep (aug_sparse.cu): per-CTA partial P / rhs / ELBO sums, summed in a fixed order by a finalise launch
     double* sparse_scratch;
     size_t sparse_scratch_bytes;
+    void* cublas;          // cublasHandle_t for the m > 128 composition (created on first use)
 };
 
 // Likelihood constants precomputed on the host once per call (never per observation)

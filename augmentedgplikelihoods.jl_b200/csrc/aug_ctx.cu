@@ -10,6 +10,8 @@
 
 #include "aug_common.cuh"
 
+void aug_cublas_destroy(aug_ctx* c);   // aug_sparse.cu: releases the cuBLAS handle of the m > 128 composition
+
 // kernels implemented in the other translation units
 int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void* y, const double* mu,
                           const double* var, int64_t ld, void* s0, void* s1, void* s2, const void* rs0,
@@ -324,8 +326,10 @@ const char* aug_strerror(int32_t rc) {
         case AUG_ERR_NOT_INIT: return "context or communicator not initialised";
         case AUG_ERR_NO_NCCL: return "libnccl.so.2 could not be loaded";
         case AUG_ERR_DEVICE_FLAG: return "a kernel raised the device-side error flag";
+        case AUG_ERR_NO_CUBLAS: return "libcublas.so.12 could not be loaded (needed for m > 128 inducing points)";
         default: break;
     }
+    if (rc >= 2000) return "cuBLAS error (cublasStatus_t = rc - 2000)";
     if (rc >= 1000) return "NCCL error (ncclResult_t = rc - 1000)";
     if (rc > 0) return cudaGetErrorString((cudaError_t)rc);
     return "unknown error";
@@ -393,6 +397,7 @@ int32_t aug_ctx_destroy(aug_ctx* c) {
     if (c->pgtab) cudaFree(c->pgtab);
     if (c->dtheta) cudaFree(c->dtheta);
     if (c->sparse_scratch) cudaFree(c->sparse_scratch);
+    aug_cublas_destroy(c);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return AUG_OK;

@@ -26,9 +26,16 @@
 //     so the latency-bound scalar math of tile j hides behind the DMMA stream of tile j+1.
 //   * P / rhs / ELBO partials of every CTA (and k-group) go to a scratch buffer; a second launch adds them in a
 //     fixed order (bit-reproducible, no floating-point atomics), mirrors the lower triangle and adds P0 / r0.
+#include <dlfcn.h>
+
 #include "aug_common.cuh"
 #include "aug_math.cuh"
 #include "aug_cavi_eval.cuh"
+
+int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void* y, const double* mu,
+                          const double* var, int64_t ld, void* s0, void* s1, void* s2, const void* rs0,
+                          const void* rs1, const void* rs2, double* beta, double* gamma, int64_t ldo,
+                          double* scalars, bool from_state);
 
 namespace {
 
@@ -620,7 +627,8 @@ template <int MT, int MODE, int KIND>
 int32_t sp_launch(aug_ctx* ctx, SparseArgs& a, const double* P0, const double* r0, double* Pr, double* scalars) {
     typedef SpCfg<MT> C;
     const void* k = (const void*)sparse_sweep_kernel<MT, MODE, KIND>;
-    static bool configured = false;
+    static bool configured_dev[64] = {false};   // the attribute is per device: one flag per ordinal
+    bool& configured = configured_dev[ctx->device & 63];
     if (!configured) {
         AUG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
@@ -664,14 +672,194 @@ int32_t sp_dispatch_m(aug_ctx* ctx, SparseArgs& a, const double* P0, const doubl
     return sp_launch<128, MODE, KIND>(ctx, a, P0, r0, Pr, scalars);
 }
 
+// ================================================================== m > 128: chunked library composition
+// Same three steps with cuBLAS doing the GEMM-shaped parts (plain library GEMMs, bound with dlopen so that
+// libaugcuda.so has no link-time dependency): per chunk of observations
+//   T = sym(B)·κ_chunkᵀ (DGEMM) → μ_t, σ²_t = k_tt − κ_t·T_t (row kernel)      [producer]
+//   aug_cavi_dispatch over all n (the streaming kernel of §3.1)                  [path]
+//   W = κ_chunk scaled by γ_t (row kernel) → Pacc += W·κ_chunkᵀ (DGEMM), racc += κ_chunk·β (DGEMV)   [consumer]
+typedef int (*fn_cublas_create)(void**);
+typedef int (*fn_cublas_destroy)(void*);
+typedef int (*fn_cublas_setstream)(void*, cudaStream_t);
+typedef int (*fn_cublas_dgemm)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int,
+                               const double*, double*, int);
+typedef int (*fn_cublas_dgemv)(void*, int, int, int, const double*, const double*, int, const double*, int,
+                               const double*, double*, int);
+struct CublasApi {
+    void* lib = nullptr;
+    fn_cublas_create create = nullptr;
+    fn_cublas_destroy destroy = nullptr;
+    fn_cublas_setstream setstream = nullptr;
+    fn_cublas_dgemm dgemm = nullptr;
+    fn_cublas_dgemv dgemv = nullptr;
+} g_cublas;
+
+int32_t cublas_load() {
+    if (g_cublas.lib) return AUG_OK;
+    void* h = dlopen("libcublas.so.12", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the one the process already holds
+    if (!h) h = dlopen("libcublas.so.12", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libcublas.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return AUG_ERR_NO_CUBLAS;
+    g_cublas.create = (fn_cublas_create)dlsym(h, "cublasCreate_v2");
+    g_cublas.destroy = (fn_cublas_destroy)dlsym(h, "cublasDestroy_v2");
+    g_cublas.setstream = (fn_cublas_setstream)dlsym(h, "cublasSetStream_v2");
+    g_cublas.dgemm = (fn_cublas_dgemm)dlsym(h, "cublasDgemm_v2");
+    g_cublas.dgemv = (fn_cublas_dgemv)dlsym(h, "cublasDgemv_v2");
+    if (!g_cublas.create || !g_cublas.destroy || !g_cublas.setstream || !g_cublas.dgemm || !g_cublas.dgemv)
+        return AUG_ERR_NO_CUBLAS;
+    g_cublas.lib = h;
+    return AUG_OK;
+}
+#define AUG_CUBLAS(x)                          \
+    do {                                       \
+        int s__ = (x);                         \
+        if (s__ != 0) return 2000 + s__;       \
+    } while (0)
+
+// Bs[i*m + j] = (B[i*m + j] + B[j*m + i]) / 2
+__global__ void gen_sym_kernel(int m, const double* __restrict__ B, double* __restrict__ Bs) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < m * m) {
+        const int i = e / m, j = e - i * m;
+        Bs[e] = 0.5 * (B[e] + B[(size_t)j * m + i]);
+    }
+}
+// one warp per observation: μ_t = κ_t·m, σ²_t = k_tt − κ_t·T_t
+__global__ void gen_rowdot_kernel(int64_t rows, int m, const double* __restrict__ kap, const double* __restrict__ T,
+                                  const double* __restrict__ mvec, const double* __restrict__ kdiag,
+                                  double* __restrict__ mu, double* __restrict__ var) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = w0; t < rows; t += nw) {
+        const double* k = kap + t * m;
+        const double* tt = T + t * m;
+        double q = 0.0, a = 0.0;
+        for (int i = lane; i < m; i += 32) {
+            const double kv = k[i];
+            q = fma(kv, tt[i], q);
+            a = fma(kv, __ldg(mvec + i), a);
+        }
+        q = warp_sum(q);
+        a = warp_sum(a);
+        if (lane == 0) {
+            if (mu) mu[t] = a;
+            if (var) var[t] = kdiag[t] - q;
+        }
+    }
+}
+// W[t][i] = γ_t κ[t][i]
+__global__ void gen_scale_kernel(int64_t rows, int m, const double* __restrict__ kap, const double* __restrict__ gamma,
+                                 double* __restrict__ W) {
+    const int64_t tot = rows * m, nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += nth) W[e] = kap[e] * gamma[e / m];
+}
+// Pr[i*m + j] = Pacc(max(i,j), min(i,j)) + P0, Pr[m*m + i] = racc[i] + r0   (Pacc column-major, lower triangle used)
+__global__ void gen_finalize_kernel(int m, const double* __restrict__ Pacc, const double* __restrict__ racc,
+                                    const double* __restrict__ P0, const double* __restrict__ r0, double* __restrict__ Pr) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < m * m) {
+        const int i = e / m, j = e - i * m;
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        Pr[e] = Pacc[(size_t)lo * m + hi] + (P0 ? P0[e] : 0.0);
+    } else if (e < m * m + m) {
+        const int i = e - m * m;
+        Pr[e] = racc[i] + (r0 ? r0[i] : 0.0);
+    }
+}
+
+// mode: SP_PRODUCER / SP_CONSUMER / SP_FUSED.  All per-observation outputs may be null (kept in scratch when a later
+// step needs them).
+int32_t sparse_general(aug_ctx* ctx, int mode, const aug_lik* lik, int64_t n, int m, const void* y, const double* kappa,
+                       const double* mvec, const double* B, const double* kdiag, const double* gamma_in,
+                       const double* beta_in, double* mu, double* var, void* s0, void* s1, void* s2, double* beta,
+                       double* gamma, const double* P0, const double* r0, double* Pr, double* scalars) {
+    int32_t rc = cublas_load();
+    if (rc) return rc;
+    if (!ctx->cublas) AUG_CUBLAS(g_cublas.create(&ctx->cublas));
+    AUG_CUBLAS(g_cublas.setstream(ctx->cublas, ctx->stream));
+    const bool prod = mode != SP_CONSUMER, cons = mode != SP_PRODUCER, fused = mode == SP_FUSED;
+    int64_t ch = ((int64_t)1 << 25) / m;             // chunk: 256 MB of T
+    if (ch < 1024) ch = 1024;
+    if (ch > n) ch = n > 0 ? n : 1;
+    // scratch: Bs | Pacc | racc | T[ch*m] | mu[n] var[n] beta[n] gamma[n] (only what the caller did not provide)
+    size_t off = 0;
+    auto take = [&](size_t doubles) { size_t o = off; off += (doubles + 1) & ~(size_t)1; return o; };
+    const size_t o_bs = take((size_t)m * m), o_pacc = take((size_t)m * m), o_racc = take((size_t)m);
+    const size_t o_t = take((size_t)ch * m);
+    const size_t o_mu = (fused && !mu) ? take((size_t)n) : 0, o_var = (fused && !var) ? take((size_t)n) : 0;
+    const size_t o_be = (fused && !beta) ? take((size_t)n) : 0, o_ga = (fused && !gamma) ? take((size_t)n) : 0;
+    const size_t need = off * sizeof(double);
+    if (ctx->sparse_scratch_bytes < need) {
+        if (ctx->sparse_scratch) {
+            AUG_CUDA(cudaStreamSynchronize(ctx->stream));
+            AUG_CUDA(cudaFree(ctx->sparse_scratch));
+            ctx->sparse_scratch = nullptr;
+            ctx->sparse_scratch_bytes = 0;
+        }
+        AUG_CUDA(cudaMalloc(&ctx->sparse_scratch, need));
+        ctx->sparse_scratch_bytes = need;
+    }
+    double* S = ctx->sparse_scratch;
+    double *Bs = S + o_bs, *Pacc = S + o_pacc, *racc = S + o_racc, *T = S + o_t;
+    double* mu_w = mu ? mu : (fused ? S + o_mu : nullptr);
+    double* var_w = var ? var : (fused ? S + o_var : nullptr);
+    double* be_w = fused ? (beta ? beta : S + o_be) : nullptr;
+    double* ga_w = fused ? (gamma ? gamma : S + o_ga) : nullptr;
+    const double one = 1.0, zero = 0.0;
+    const int grid = ctx->sms * 8;
+    if (prod && n > 0) {
+        gen_sym_kernel<<<(m * m + 255) / 256, 256, 0, ctx->stream>>>(m, B, Bs);
+        ctx->launches++;
+        for (int64_t r0i = 0; r0i < n; r0i += ch) {
+            const int64_t rows = n - r0i < ch ? n - r0i : ch;
+            const double* kc = kappa + r0i * m;
+            // column-major view: κ_chunkᵀ is m × rows (ld m); T = Bs · κ_chunkᵀ
+            AUG_CUBLAS(g_cublas.dgemm(ctx->cublas, 0, 0, m, (int)rows, m, &one, Bs, m, kc, m, &zero, T, m));
+            gen_rowdot_kernel<<<grid, 256, 0, ctx->stream>>>(rows, m, kc, T, mvec, kdiag + r0i, mu_w ? mu_w + r0i : nullptr,
+                                                             var_w ? var_w + r0i : nullptr);
+            ctx->launches++;
+        }
+        AUG_CUDA(cudaGetLastError());
+    }
+    if (fused) {
+        rc = aug_cavi_dispatch(ctx, lik, n, y, mu_w, var_w, 0, s0, s1, s2, nullptr, nullptr, nullptr, be_w, ga_w, n, scalars,
+                               false);
+        if (rc) return rc;
+    }
+    if (cons) {
+        const double* g = fused ? ga_w : gamma_in;
+        const double* b = fused ? be_w : beta_in;
+        AUG_CUDA(cudaMemsetAsync(Pacc, 0, sizeof(double) * ((size_t)m * m), ctx->stream));
+        AUG_CUDA(cudaMemsetAsync(racc, 0, sizeof(double) * (size_t)m, ctx->stream));
+        for (int64_t r0i = 0; r0i < n; r0i += ch) {
+            const int64_t rows = n - r0i < ch ? n - r0i : ch;
+            const double* kc = kappa + r0i * m;
+            gen_scale_kernel<<<grid, 256, 0, ctx->stream>>>(rows, m, kc, g + r0i, T);
+            ctx->launches++;
+            // Pacc (m × m, column-major) += W · κ_chunk  with W = T viewed as m × rows
+            AUG_CUBLAS(g_cublas.dgemm(ctx->cublas, 0, 1, m, m, (int)rows, &one, T, m, kc, m, &one, Pacc, m));
+            AUG_CUBLAS(g_cublas.dgemv(ctx->cublas, 0, m, (int)rows, &one, kc, m, b + r0i, 1, &one, racc, 1));
+        }
+        gen_finalize_kernel<<<(m * m + m + 255) / 256, 256, 0, ctx->stream>>>(m, Pacc, racc, P0, r0, Pr);
+        ctx->launches++;
+        AUG_CUDA(cudaGetLastError());
+    }
+    return AUG_OK;
+}
+
 int32_t sp_check(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa) {
     if (!ctx) return AUG_ERR_NOT_INIT;
-    if (n < 0 || m < 1 || m > 128) return AUG_ERR_BAD_ARG;
+    if (n < 0 || m < 1) return AUG_ERR_BAD_ARG;
     if (n > 0 && kappa == nullptr) return AUG_ERR_BAD_ARG;
     return AUG_OK;
 }
 
 }  // namespace
+
+void aug_cublas_destroy(aug_ctx* c) {
+    if (c->cublas && g_cublas.destroy) g_cublas.destroy(c->cublas);
+    c->cublas = nullptr;
+}
 
 extern "C" {
 
@@ -682,6 +870,9 @@ int32_t aug_sparse_marginals(aug_ctx* ctx, int64_t n, int32_t m, const double* k
     if (n == 0) return AUG_OK;
     if (!mvec || !B || !kdiag || (!mu && !var)) return AUG_ERR_BAD_ARG;
     AUG_CUDA(cudaSetDevice(ctx->device));
+    if (m > 128)
+        return sparse_general(ctx, SP_PRODUCER, nullptr, n, m, nullptr, kappa, mvec, B, kdiag, nullptr, nullptr, mu, var,
+                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     SparseArgs a{};
     a.n = n; a.m = m; a.kappa = kappa; a.mvec = mvec; a.B = B; a.kdiag = kdiag; a.mu = mu; a.var = var;
     a.vec16 = (aug_aligned16(kappa) && (m % 2 == 0)) ? 1 : 0;
@@ -695,6 +886,9 @@ int32_t aug_sparse_precision_potential(aug_ctx* ctx, int64_t n, int32_t m, const
     if (rc) return rc;
     if (!Pr || (n > 0 && (!gamma || !beta))) return AUG_ERR_BAD_ARG;
     AUG_CUDA(cudaSetDevice(ctx->device));
+    if (m > 128)
+        return sparse_general(ctx, SP_CONSUMER, nullptr, n, m, nullptr, kappa, nullptr, nullptr, nullptr, gamma, beta, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, P0, r0, Pr, nullptr);
     SparseArgs a{};
     a.n = n; a.m = m; a.kappa = kappa; a.gamma_in = gamma; a.beta_in = beta;
     a.vec16 = (aug_aligned16(kappa) && (m % 2 == 0)) ? 1 : 0;
@@ -710,6 +904,11 @@ int32_t aug_sparse_cavi_sweep(aug_ctx* ctx, const aug_lik* lik, int64_t n, int32
     if (!lik || !Pr || !mvec || !B) return AUG_ERR_BAD_ARG;
     if (n > 0 && (!y || !kdiag)) return AUG_ERR_BAD_ARG;
     AUG_CUDA(cudaSetDevice(ctx->device));
+    if (m > 128) {
+        if (lik->kind == AUG_HETERO || lik->kind == AUG_CAT || lik->kind == AUG_CAT_BIJ) return AUG_ERR_BAD_KIND;
+        return sparse_general(ctx, SP_FUSED, lik, n, m, y, kappa, mvec, B, kdiag, nullptr, nullptr, mu, var, s0, s1, s2, beta,
+                              gamma, P0, r0, Pr, scalars);
+    }
     SparseArgs a{};
     a.n = n; a.m = m; a.y = y; a.kappa = kappa; a.mvec = mvec; a.B = B; a.kdiag = kdiag;
     a.mu = mu; a.var = var; a.s0 = (double*)s0; a.s1 = (double*)s1; a.s2 = s2; a.beta = beta; a.gamma = gamma;

@@ -66,7 +66,8 @@ enum aug_status {
                                   sum(p) >= 1 (negativemultinomial.jl:18-22) */
     AUG_ERR_NOT_INIT     = -4,
     AUG_ERR_NO_NCCL      = -5,
-    AUG_ERR_DEVICE_FLAG  = -6  /* a kernel raised the device-side error flag */
+    AUG_ERR_DEVICE_FLAG  = -6, /* a kernel raised the device-side error flag */
+    AUG_ERR_NO_CUBLAS    = -7  /* m > 128 needs libcublas.so.12 (dlopen), which could not be loaded */
 };
 
 /*
@@ -274,7 +275,9 @@ int32_t aug_approx_expected_logisticsoftmax(aug_ctx* ctx, const aug_lik* lik, in
  * The reference's user loop (examples/bernoulli/script.jl:29-39; sparse form docs/src/index.md:154-163) is
  *   qf = marginals(post_u(x));  aux_posterior!(qΩ, lik, y, qf);
  *   S = inv(K_Z⁻¹ + κ·Diagonal(γ)·κᵀ);  m = S·(κ·β + K_Z⁻¹ μ₀(Z)),        κ = K_Z⁻¹ K_{Z,X}  (M×N)
- * `kappa` is that Julia matrix as stored (column-major M×N) = [n][m], inducing index fastest; m <= 128.
+ * `kappa` is that Julia matrix as stored (column-major M×N) = [n][m], inducing index fastest.  m <= 128 runs the
+ * fused tensor-core kernels below; m > 128 runs the same steps as a chunked composition of cuBLAS DGEMM / DGEMV calls
+ * (libcublas.so.12 bound with dlopen, like NCCL) around the library's own kernels — same results, more passes over kappa.
  * B = K_Z − S (M×M, symmetric; read as given, the quadratic form does not depend on its storage order).
  * Outputs: Pr = [m*m + m] doubles, Pr[i*m + j] = P0[i*m+j] + Σ_t γ_t κ_it κ_jt (exactly symmetric), Pr[m*m + i] =
  * r0[i] + Σ_t β_t κ_it;  P0 / r0 may be NULL (zeros).  Sums over observations run in a fixed order for a given
