@@ -4,6 +4,7 @@
 // the kernel and D2H copies of consecutive chunks overlap on three streams (copy-in, the ctx
 // stream, copy-out) ordered by events.  Per-chunk scalars land in pinned host memory and are
 // added in chunk order, so the result does not depend on timing.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -83,6 +84,16 @@ int32_t pipe_get(aug_ctx* ctx, size_t slot_bytes, size_t chunks) {
 }
 
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+// elements per staged chunk (AUGCUDA_HOST_CHUNK_LOG2 = 18..26 overrides the default 2^22 for tuning runs)
+inline int64_t host_chunk_elems() {
+    static int lg = -1;
+    if (lg < 0) {
+        const char* e = getenv("AUGCUDA_HOST_CHUNK_LOG2");
+        int v = e ? atoi(e) : 22;
+        lg = (v >= 18 && v <= 26) ? v : 22;
+    }
+    return (int64_t)1 << lg;
+}
 inline bool is_cat(int k) { return k == AUG_CAT || k == AUG_CAT_BIJ; }
 inline size_t y_size(int kind) {
     return (kind == AUG_BERNOULLI || is_cat(kind)) ? 1 : 8;
@@ -123,7 +134,7 @@ int32_t aug_cavi_step_host(aug_ctx* c, const aug_lik* lik, int64_t n, const void
         ~FusedOff() { c->fused = was; }
     } fused_off(c);
 
-    int64_t chunk = ((int64_t)1 << 22) / per;
+    int64_t chunk = host_chunk_elems() / per;
     if (chunk < 2) chunk = 2;
     chunk &= ~(int64_t)1;
     if (chunk > n) chunk = n;
@@ -227,7 +238,7 @@ int32_t aug_aux_sample_host(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i
     if ((needs_y && !y) || (needs_n && !nvar) || (het && ld < n)) return AUG_ERR_BAD_ARG;
     const uint64_t offset = c->offset++;   // one RNG tick for the whole call, whatever the chunking
     if (n == 0) return AUG_OK;
-    int64_t chunk = ((int64_t)1 << 22) / per;
+    int64_t chunk = host_chunk_elems() / per;
     if (chunk < 2) chunk = 2;
     chunk &= ~(int64_t)1;
     if (chunk > n) chunk = n;

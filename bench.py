@@ -460,7 +460,10 @@ def main():
         assert abs(hs[2] - elbo) <= 1e-9 * abs(elbo) or world > 1, (hs[2], elbo)
         e2e = {"value": n * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * (1 + 8 + 8 + 1 + 8),
                "d2h_bytes_per_step": n * (24 + 8) + 64, "ms_per_step": 1e3 * e2e_s, "steps": ksteps,
-               "path": "aug_cavi_step_host + aug_aux_sample_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"}
+               "path": "aug_cavi_step_host + aug_aux_sample_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)",
+               "pcie_GBs": (n * (1 + 8 + 8 + 1 + 8) + n * (24 + 8) + 64) / e2e_s * 1e-9,
+               "pcie_bound": "measured on this pool (tools/pcie_probe.py, profiles/e2e_pcie_probe_r1k.txt): 55.5 GB/s H2D, "
+                             "57.0 D2H, 49.8 each way when both run: the D2H side (32 B/obs) bounds the step at ~64 ms"}
         del hy, hmu, hvar, hf, hc, hb, hg, hw
 
     # ---------------- secondary leg: one sparse-GP CAVI iteration as one pass over κ
