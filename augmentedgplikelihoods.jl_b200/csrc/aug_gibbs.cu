@@ -89,7 +89,10 @@ __device__ __noinline__ double pg1_finish_sequential(uint64_t seed, uint64_t off
 #define PG1_QCAP 64
 #define PG1_MAXCTR 255u
 
-__global__ void __launch_bounds__(AUG_BLOCK, 3) pg1_compact_kernel(const Pg1Args a) {
+#ifndef PG1_MIN_BLOCKS
+#define PG1_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(const Pg1Args a) {
     __shared__ __align__(16) double tab_s[AUG_PGTAB_N * AUG_PGTAB_DEG];   // r(z) table: 10 KB, read by every fresh step
     __shared__ uint32_t qel_s[AUG_BLOCK / 32][PG1_QCAP];
     __shared__ uint32_t qra_s[AUG_BLOCK / 32][PG1_QCAP];

@@ -192,6 +192,24 @@ AGPL.expected_aug_loglik(lik::AbstractLikelihood, qΩ::For, y::DV, qf::DeviceNor
 # aux_kldivergence(lik, qΩ, y) has no qf in the reference; the KL kernels only read the state and y, so a
 # zero qf of the right length is passed (the heteroscedastic prior needs the real qf: use elbo_terms).
 
+# The fused call of a CAVI iteration (examples/bernoulli/script.jl:29-39): aux_posterior!(qΩ, lik, y, qf) +
+# expected_auglik_potential_and_precision + the expected_logtilt / aux_kldivergence sums in ONE pass -> aug_cavi_step
+function cavi_step!(qΩ::For, lik::AbstractLikelihood, y::DV, qf::DeviceNormals)
+    n, nl = length(qΩ), AGPL.nlatent(lik)
+    β, γ = DV{Float64}(undef, n * nl), DV{Float64}(undef, n * nl)
+    sc = DV{Float64}(undef, 8)
+    φ = state(qΩ)
+    withdesc(lik) do d
+        check(ccall((:aug_cavi_step, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Cvoid}, Ptr{Cvoid},
+                     Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                    ctx().h, d, n, y.ptr, qf.μ.ptr, qf.σ².ptr, qf.ld, ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ)), β.ptr, γ.ptr, n,
+                    sc.ptr))
+    end
+    split(v) = ntuple(j -> DV{Float64}(v.ptr + (j - 1) * n * 8, n, false), nl)
+    return qΩ, split(β), split(γ), Array(sc)      # sc[S_ELT], sc[S_KL], sc[S_EAUGLL]
+end
+
 # ---------------------------------------------------------------- sampling verbs
 # aux_sample!(rng, Ω, lik, y, f)                      -> aug_aux_sample                 (a14-a19)
 function AGPL.aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::AbstractLikelihood, y::DV, f::DV; i0::Integer=0)

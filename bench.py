@@ -294,9 +294,25 @@ def sparse_cpu(m, n=20000):
         rc, _ = orc.sparse_cavi_sweep(lik, y, kappa, mvec, B, kdiag)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": n / best, "unit": "obs/s", "cores": threads, "kind": "port",
-            "sample": f"{n} observations, m={m}: separate passes (marginals, aux_posterior!, potentials, ELBO, P/rhs) in "
-                      f"long double, OpenMP {threads} threads, best of 2"}
+    # what the user's Julia loop would run: BLAS for the matrix products (numpy -> OpenBLAS / MKL, all cores) around
+    # the per-observation passes of the oracle (double precision throughout)
+    nb = 20 * n
+    kb = np.tile(kappa, (20, 1)); yb = np.tile(y, 20); kdb = np.tile(kdiag, 20)
+    bestb = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        mu = kb @ mvec
+        var = kdb - np.einsum("ti,ti->t", kb @ B, kb)
+        rc, st, be, ga, seq, comp = orc.cavi_step(lik, yb, mu, var)
+        P = (kb * ga[0][:, None]).T @ kb
+        rhs = kb.T @ be[0]
+        dt = time.perf_counter() - t0
+        bestb = dt if bestb is None else min(bestb, dt)
+    return {"value": nb / bestb, "unit": "obs/s", "cores": threads, "kind": "port",
+            "sample": f"{nb} observations, m={m}: BLAS (numpy) matrix products + the oracle's separate per-observation passes, "
+                      f"double precision, {threads} threads, best of 2",
+            "long_double_oracle": {"value": n / best, "unit": "obs/s",
+                                   "sample": f"{n} observations, the parity oracle itself (long double loops, OpenMP {threads})"}}
 
 
 def main():

@@ -71,3 +71,49 @@ def test_likelihood_descriptors():
     assert pkg.nlatent(pkg.CategoricalLikelihood(100, bijective=False)) == 100
     assert pkg.nlatent(pkg.HeteroscedasticGaussianLikelihood(5.0)) == 2
     assert pkg.nlatent(pkg.BernoulliLikelihood()) == 1
+
+
+def test_julia_glue_binds_only_declared_symbols_with_matching_arity():
+    """AugCUDA.jl cannot be executed here (no Julia): check statically that every ccall names a function the header
+    declares and passes as many arguments as the C prototype (= the ctypes signature table) has."""
+    pkg = aug_pkg.load_package()
+    src = open(os.path.join(ROOT, "augmentedgplikelihoods.jl_b200", "julia", "AugCUDA.jl")).read()
+    syms = set(header_symbols())
+    calls = list(re.finditer(r"ccall\(\(:(aug_[a-z0-9_]+),\s*lib\),\s*(\w+),\s*\(", src))
+    assert len(calls) >= 20
+    seen = set()
+    for m in calls:
+        name, ret = m.group(1), m.group(2)
+        assert name in syms, f"{name} is not declared in include/augcuda.h"
+        seen.add(name)
+        # the argument-type tuple: balanced parentheses from the opening "(" of the tuple
+        i = m.end()
+        depth, j = 1, i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[j], 0)
+            j += 1
+        types = src[i:j - 1]
+        # split on top-level commas
+        parts, d, cur = [], 0, ""
+        for ch in types:
+            if ch in "({[":
+                d += 1
+            elif ch in ")}]":
+                d -= 1
+            if ch == "," and d == 0:
+                parts.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            parts.append(cur)
+        nargs = len([p for p in parts if p.strip()])
+        if name == "aug_strerror":
+            assert ret == "Cstring" and nargs == 1
+            continue
+        assert ret == "Int32", (name, ret)
+        assert nargs == len(pkg._lib.SIGNATURES[name]), (name, nargs, len(pkg._lib.SIGNATURES[name]))
+    # the verbs of the path and of the rows either side of it are all bound
+    for must in ("aug_cavi_step", "aug_aux_sample", "aug_expected_elbo_terms", "aug_sampled_loglik_terms",
+                 "aug_sparse_cavi_sweep", "aug_sparse_marginals", "aug_sparse_precision_potential"):
+        assert must in seen, must
