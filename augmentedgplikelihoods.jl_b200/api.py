@@ -741,18 +741,29 @@ def _split_pr(Pr, m):
 
 
 def _reduce_pr(ctx, Pr):
+    if ctx.fused:                   # exchanged inside the verb's finalise launch over peer memory
+        return
     if ctx.comm_ready:              # shards of the observation axis: P and rhs are plain sums
         check(ctx.lib.aug_allreduce_scalars(ctx.h, _ptr(Pr), Pr.numel()))
 
 
+def _prior_terms(ctx, P0, r0):
+    """P0 / r0 are given on every rank.  NCCL mode adds them once (rank 0) before the sum over ranks; fused mode adds
+    them on every rank after the in-kernel exchange (include/augcuda.h)."""
+    if ctx.comm_ready and not ctx.fused and getattr(ctx, "rank", 0) != 0:
+        return None, None
+    return P0, r0
+
+
 def sparse_precision_potential(kappa, gamma, beta, P0=None, r0=None, ctx=None):
-    """docs/src/index.md:156-160: returns (P0 + κ·Diagonal(γ)·κᵀ, r0 + κ·β).  In a sharded run pass P0 / r0 on
-    rank 0 only; the sums over ranks are taken here when a communicator is attached."""
+    """docs/src/index.md:156-160: returns (P0 + κ·Diagonal(γ)·κᵀ, r0 + κ·β).  In a sharded run pass the same P0 / r0
+    on every rank; the sums over ranks are taken here (NCCL) or inside the verb (fused mailbox mode)."""
     ctx = ctx or default_context()
     kappa = _kappa(kappa)
     n, m = kappa.shape
     ctx.enter()
     Pr = ctx.empty((m * m + m,))
+    P0, r0 = _prior_terms(ctx, P0, r0)
     check(ctx.lib.aug_sparse_precision_potential(ctx.h, n, m, _ptr(kappa), _ptr(_f64(gamma, "gamma")),
                                                  _ptr(_f64(beta, "beta")), _ptr(P0), _ptr(r0), _ptr(Pr)))
     _reduce_pr(ctx, Pr)
@@ -784,12 +795,13 @@ def sparse_cavi_sweep_(qΩ: Optional[AuxPosterior], lik, y, kappa, mvec, B, kdia
     beta = ctx.empty((n,)) if want_potentials else None
     gamma = ctx.empty((n,)) if want_potentials else None
     s = [qΩ._s(i) if qΩ is not None else None for i in range(3)]
+    P0, r0 = _prior_terms(ctx, P0, r0)
     check(ctx.lib.aug_sparse_cavi_sweep(ctx.h, C.byref(d), n, m, _ptr(y), _ptr(kappa), _ptr(_f64(mvec, "mvec")),
                                         _ptr(_f64(B, "B")), _ptr(_f64(kdiag, "kdiag")), _ptr(mu), _ptr(var),
                                         _ptr(s[0]), _ptr(s[1]), _ptr(s[2]), _ptr(beta), _ptr(gamma), _ptr(P0),
                                         _ptr(r0), _ptr(Pr), _ptr(scal)))
     _reduce_pr(ctx, Pr)
-    if scal is not None and ctx.comm_ready:
+    if scal is not None and ctx.comm_ready and not ctx.fused:
         check(ctx.lib.aug_allreduce_scalars(ctx.h, _ptr(scal), NSCALARS))
     ctx.leave()
     P, rhs = _split_pr(Pr, m)

@@ -15,6 +15,10 @@
 #define AUG_MAX_RANKS 8        // GPUs of one NVSwitch box that can share a peer-memory mailbox
 #define AUG_XCH_SLOT 8         // 64-bit words per mailbox slot: 7 values + 1 epoch flag
 #define AUG_XCH_WORDS (2 * AUG_MAX_RANKS * AUG_XCH_SLOT)   // [parity][source rank][slot]
+// bulk area behind the slots: [parity][source rank][AUG_XCH_BULK doubles] — the P / rhs sums of the sparse-GP sweep
+// (m*m + m <= 128*128 + 128 doubles), pushed by the finalise kernel and published with the slot's epoch flag
+#define AUG_XCH_BULK (128 * 128 + 128 + 8)
+#define AUG_XCH_TOTAL_WORDS (AUG_XCH_WORDS + 2 * AUG_MAX_RANKS * AUG_XCH_BULK)
 
 #define AUG_CUDA(x)                                   \
     do {                                              \

@@ -583,8 +583,8 @@ int32_t aug_comm_p2p_export(aug_ctx* c, char handle[64], void** local_ptr) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     AUG_CUDA(cudaSetDevice(c->device));
     if (!c->mailbox) {
-        AUG_CUDA(cudaMalloc(&c->mailbox, sizeof(unsigned long long) * AUG_XCH_WORDS));
-        AUG_CUDA(cudaMemset(c->mailbox, 0, sizeof(unsigned long long) * AUG_XCH_WORDS));
+        AUG_CUDA(cudaMalloc(&c->mailbox, sizeof(unsigned long long) * AUG_XCH_TOTAL_WORDS));
+        AUG_CUDA(cudaMemset(c->mailbox, 0, sizeof(unsigned long long) * AUG_XCH_TOTAL_WORDS));
     }
     if (handle) {
         cudaIpcMemHandle_t h;

@@ -607,6 +607,87 @@ __global__ void __launch_bounds__(256) sparse_finalize_kernel(const double* __re
     }
 }
 
+// Fused multi-GPU mode: the same fixed-order sums, then the all-reduce over ranks INSIDE this launch.  Every block
+// pushes its 8 outputs into the bulk area [epoch parity][this rank] of EVERY rank's mailbox (peer stores over NVLink),
+// the last block to arrive exchanges the two ELBO sums through the slot protocol (xch_allreduce: its release / acquire
+// of the epoch flag also publishes the bulk data pushed before it), then adds the ranks' bulk entries in rank order
+// (bit-identical on all ranks) plus P0 / r0 and writes Pr.
+template <int MT>
+__global__ void __launch_bounds__(256) sparse_finalize_xch_kernel(const double* __restrict__ scratch, int grid, int m,
+                                                                  const double* __restrict__ P0, const double* __restrict__ r0,
+                                                                  double* __restrict__ Pr, double* __restrict__ scalars,
+                                                                  int kge, AugXchDev* __restrict__ x,
+                                                                  unsigned int* __restrict__ counter) {
+    __shared__ double part[32][8];
+    __shared__ int s_last, s_ok;
+    const double* Ppart = scratch;
+    const double* rpart = scratch + (size_t)grid * kge * (MT * MT);
+    const double* spart = rpart + (size_t)grid * kge * MT;
+    const int ex = threadIdx.x & 7, sl = threadIdx.x >> 3;
+    const int nr = x->nranks, me = x->rank;
+    const unsigned long long ep = x->epoch + 1ull;            // the epoch this launch will publish (read before anyone bumps it)
+    const size_t half = (size_t)(ep & 1ull) * AUG_MAX_RANKS * AUG_XCH_BULK;
+    const int nout = m * m + m;
+    const int e = blockIdx.x * 8 + ex;
+    double s = 0.0;
+    if (e < m * m) {
+        const int i = e / m, j = e - i * m;
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        const double* src = Ppart + hi * MT + lo;
+        for (int b = sl; b < grid * kge; b += 32) s += __ldg(src + (size_t)b * (MT * MT));
+    } else if (e < nout) {
+        const int i = e - m * m;
+        for (int b = sl; b < grid * kge; b += 32) s += __ldg(rpart + (size_t)b * MT + i);
+    }
+    part[sl][ex] = s;
+    __syncthreads();
+    if (sl == 0 && e < nout) {
+        double t = 0.0;
+        for (int q = 0; q < 32; ++q) t += part[q][ex];
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
+        for (int r = 0; r < nr; ++r)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(x->box[r] + AUG_XCH_WORDS + half + (size_t)me * AUG_XCH_BULK + e),
+                         "l"(bits)
+                         : "memory");
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicInc(counter, gridDim.x - 1);   // wraps to 0: graph-replayable
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        double v[2] = {0.0, 0.0};
+        if (scalars != nullptr)
+            for (int b = 0; b < grid; ++b) { v[0] += __ldcg(spart + 2 * b); v[1] += __ldcg(spart + 2 * b + 1); }
+        xch_allreduce<2>(x, v);                               // publishes epoch ep, waits for every rank's flag
+        s_ok = !(v[0] != v[0]);                               // NaN = a peer did not arrive (error flag bit 1 is set)
+        if (scalars != nullptr) {
+            scalars[AUG_S_EXPECTED_LOGTILT] = v[0];
+            scalars[AUG_S_KL] = v[1];
+            scalars[AUG_S_EXPECTED_AUGLL] = v[0] + v[1];      // generic.jl:52-54 ("+")
+        }
+    }
+    __syncthreads();
+    const bool ok = s_ok != 0;
+    const unsigned long long* mine = x->box[me] + AUG_XCH_WORDS + half;
+    for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+        double t = 0.0;
+        for (int r = 0; r < nr; ++r) {                        // rank order: identical bits on every rank
+            unsigned long long w;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(mine + (size_t)r * AUG_XCH_BULK + o) : "memory");
+            t += __longlong_as_double((long long)w);
+        }
+        if (o < m * m) t += P0 ? P0[o] : 0.0;
+        else t += r0 ? r0[o - m * m] : 0.0;
+        Pr[o] = ok ? t : __longlong_as_double(0x7ff8000000000000ll);
+    }
+}
+
 __global__ void dense_diag_kernel(int64_t n, const double* __restrict__ Kinv, const double* __restrict__ gamma,
                                   const double* __restrict__ beta, const double* __restrict__ r0, double* __restrict__ P,
                                   double* __restrict__ rhs) {
@@ -654,7 +735,15 @@ int32_t sp_launch(aug_ctx* ctx, SparseArgs& a, const double* P0, const double* r
     AUG_CUDA(cudaGetLastError());
     const bool want_P = MODE != SP_PRODUCER;
     const bool want_s = MODE == SP_FUSED && scalars != nullptr;
-    if (want_P || want_s) {
+    AugXchDev* xch = want_P ? aug_xch_for(ctx) : nullptr;    // fused multi-GPU mode: the verb is collective
+    if (xch) {
+        const int nout = a.m * a.m + a.m;
+        sparse_finalize_xch_kernel<MT><<<(nout + 7) / 8, 256, 0, ctx->stream>>>(a.scratch, (int)grid, a.m, P0, r0, Pr,
+                                                                               want_s ? scalars : nullptr, C::KG, xch,
+                                                                               ctx->counter + 1);
+        ctx->launches++;
+        AUG_CUDA(cudaGetLastError());
+    } else if (want_P || want_s) {
         const int nout = want_P ? a.m * a.m + a.m : 0;
         sparse_finalize_kernel<MT><<<(nout + 7) / 8 + 1, 256, 0, ctx->stream>>>(a.scratch, (int)grid, a.m, P0, r0, Pr,
                                                                              want_s ? scalars : nullptr, want_P ? 1 : 0);
@@ -773,6 +862,7 @@ int32_t sparse_general(aug_ctx* ctx, int mode, const aug_lik* lik, int64_t n, in
                        const double* mvec, const double* B, const double* kdiag, const double* gamma_in,
                        const double* beta_in, double* mu, double* var, void* s0, void* s1, void* s2, double* beta,
                        double* gamma, const double* P0, const double* r0, double* Pr, double* scalars) {
+    if (mode != SP_PRODUCER && aug_xch_for(ctx)) return AUG_ERR_PRECONDITION;   // the in-kernel exchange covers m <= 128
     int32_t rc = cublas_load();
     if (rc) return rc;
     if (!ctx->cublas) AUG_CUBLAS(g_cublas.create(&ctx->cublas));

@@ -281,8 +281,11 @@ int32_t aug_approx_expected_logisticsoftmax(aug_ctx* ctx, const aug_lik* lik, in
  * B = K_Z − S (M×M, symmetric; read as given, the quadratic form does not depend on its storage order).
  * Outputs: Pr = [m*m + m] doubles, Pr[i*m + j] = P0[i*m+j] + Σ_t γ_t κ_it κ_jt (exactly symmetric), Pr[m*m + i] =
  * r0[i] + Σ_t β_t κ_it;  P0 / r0 may be NULL (zeros).  Sums over observations run in a fixed order for a given
- * device (bit-reproducible).  Multi-GPU: shard kappa / y by observations, pass P0 / r0 on rank 0 only and
- * aug_allreduce_scalars(ctx, Pr, m*m + m) (and the scalar block) afterwards.
+ * device (bit-reproducible).  Multi-GPU: shard kappa / y by observations, then either pass P0 / r0 on rank 0 only and
+ * aug_allreduce_scalars(ctx, Pr, m*m + m) (and the scalar block) afterwards, or — in fused mode (aug_comm_set_fused,
+ * m <= 128) — do nothing: the finalise launch of the verb pushes its sums into every rank's mailbox over NVLink, publishes
+ * the epoch flag, adds the ranks' sums in rank order and only then adds P0 / r0 (pass the same P0 / r0 on every rank)
+ * and writes Pr and the scalars: kernel and collective are one launch, every rank ends with identical bits.
  * FP64 tensor-core kernels (DMMA m8n8k4): 3·m² flops per observation for the fused sweep (2·m² producer + m²
  * consumer, the symmetric half), bound by the FP64 pipe for m >= 32 and by HBM (8·m bytes per observation) below. */
 

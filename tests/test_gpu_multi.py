@@ -223,7 +223,7 @@ def test_mailbox_timeout_raises_flag_instead_of_hanging():
         del os.environ["AUGCUDA_XCH_TIMEOUT_MS"]
 
 
-def _sparse_worker(rank, world, port, qu):
+def _sparse_worker(rank, world, port, mode, qu):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
     from common import synth_sparse
@@ -232,7 +232,10 @@ def _sparse_worker(rank, world, port, qu):
     A = aug_pkg.load_package()
     ctx = A.Context(rank)
     A.set_default_context(ctx)
-    A.dist.init_comm(ctx)
+    if mode == "nccl":
+        A.dist.init_comm(ctx)
+    else:
+        A.dist.init_p2p(ctx, fused=True)
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.tdev)
     n, m = 30_001, 64
     kappa, mvec, B, kdiag = synth_sparse(n, m, 5)
@@ -240,16 +243,25 @@ def _sparse_worker(rank, world, port, qu):
     P0 = np.eye(m) * 0.5
     lo, hi = A.dist.shard_bounds(n, world, rank)
     lik = A.BernoulliLikelihood()
-    P, rhs, scal, _, _ = A.sparse_cavi_sweep_(None, lik, dev(y[lo:hi]), dev(kappa[lo:hi]), dev(mvec), dev(B),
-                                              dev(kdiag[lo:hi]), P0=dev(P0) if rank == 0 else None)
-    ctx.sync()
-    qu.put((rank, P.cpu().numpy().copy(), rhs.cpu().numpy().copy(), scal.cpu().numpy().copy()))
+    res = []
+    for rep in range(3):                                   # epochs advance on the device: repeat the collective verb
+        P, rhs, scal, _, bg = A.sparse_cavi_sweep_(None, lik, dev(y[lo:hi]), dev(kappa[lo:hi]), dev(mvec), dev(B),
+                                                   dev(kdiag[lo:hi]), P0=dev(P0), want_potentials=True)
+        P2, rhs2 = A.sparse_precision_potential(dev(kappa[lo:hi]), bg[1], bg[0], P0=dev(P0))   # the stand-alone verb too
+        ctx.sync()
+        res.append((P.cpu().numpy().copy(), rhs.cpu().numpy().copy(), scal.cpu().numpy().copy(),
+                    P2.cpu().numpy().copy(), rhs2.cpu().numpy().copy()))
+    for r in res[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(r, res[0]))
+    assert ctx.error_flag() == 0
+    qu.put((rank,) + res[0])
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
 
 
-def test_two_rank_sparse_sweep_matches_single_gpu(orc):
+@pytest.mark.parametrize("mode", ["nccl", "p2p_fused"])
+def test_two_rank_sparse_sweep_matches_single_gpu(orc, mode):
     """SURVEY §8(f) rows 1-2 sharded over 2 GPUs: the exchange is one ncclAllReduce of m*m + m doubles (and the
     scalar block); every rank ends with the P, rhs and ELBO sums of the whole data set."""
     _need2()
@@ -266,13 +278,14 @@ def test_two_rank_sparse_sweep_matches_single_gpu(orc):
     mpc = mp.get_context("spawn")
     qu = mpc.Queue()
     port = _free_port()
-    procs = [mpc.Process(target=_sparse_worker, args=(r, 2, port, qu)) for r in range(2)]
+    procs = [mpc.Process(target=_sparse_worker, args=(r, 2, port, mode, qu)) for r in range(2)]
     for p in procs:
         p.start()
     got = {}
     for _ in range(2):
-        rank, P, rhs, scal = qu.get(timeout=300)
+        rank, P, rhs, scal, P2, rhs2 = qu.get(timeout=300)
         got[rank] = (P, rhs, scal)
+        assert np.all(np.abs(P2 - P) <= 1e-12 * np.abs(P).max()) and np.all(np.abs(rhs2 - rhs) <= 1e-12 * np.abs(rhs).max())
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
