@@ -659,11 +659,21 @@ __global__ void __launch_bounds__(256) sparse_finalize_xch_kernel(const double* 
     }
     __syncthreads();
     if (!s_last) return;
-    if (threadIdx.x == 0) {
-        __threadfence();
-        double v[2] = {0.0, 0.0};
+    __threadfence();
+    // ELBO partials of the CTAs: one load pair per thread (in flight together), then a fixed-order sum by thread 0
+    __shared__ double se[2][256];
+    {
+        double a0 = 0.0, a1 = 0.0;
         if (scalars != nullptr)
-            for (int b = 0; b < grid; ++b) { v[0] += __ldcg(spart + 2 * b); v[1] += __ldcg(spart + 2 * b + 1); }
+            for (int b = threadIdx.x; b < grid; b += 256) { a0 += __ldcg(spart + 2 * b); a1 += __ldcg(spart + 2 * b + 1); }
+        se[0][threadIdx.x] = a0;
+        se[1][threadIdx.x] = a1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v[2] = {0.0, 0.0};
+        const int nb = grid < 256 ? grid : 256;
+        for (int b = 0; b < nb; ++b) { v[0] += se[0][b]; v[1] += se[1][b]; }
         xch_allreduce<2>(x, v);                               // publishes epoch ep, waits for every rank's flag
         s_ok = !(v[0] != v[0]);                               // NaN = a peer did not arrive (error flag bit 1 is set)
         if (scalars != nullptr) {
@@ -675,16 +685,35 @@ __global__ void __launch_bounds__(256) sparse_finalize_xch_kernel(const double* 
     __syncthreads();
     const bool ok = s_ok != 0;
     const unsigned long long* mine = x->box[me] + AUG_XCH_WORDS + half;
-    for (int o = threadIdx.x; o < nout; o += blockDim.x) {
-        double t = 0.0;
+    // gather: 8 outputs per thread and step, all their loads in flight before the first add (system-scope loads are
+    // not cached: one dependent load per add would cost ~1 µs each)
+    constexpr int GU = 8;
+    for (int o0 = threadIdx.x; o0 < nout; o0 += blockDim.x * GU) {
+        double t[GU];
+#pragma unroll
+        for (int u = 0; u < GU; ++u) t[u] = 0.0;
         for (int r = 0; r < nr; ++r) {                        // rank order: identical bits on every rank
-            unsigned long long w;
-            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(mine + (size_t)r * AUG_XCH_BULK + o) : "memory");
-            t += __longlong_as_double((long long)w);
+            unsigned long long w[GU];
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                const int o = o0 + u * blockDim.x;
+                w[u] = 0ull;
+                if (o < nout)
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w[u]) : "l"(mine + (size_t)r * AUG_XCH_BULK + o) : "memory");
+            }
+#pragma unroll
+            for (int u = 0; u < GU; ++u) t[u] += __longlong_as_double((long long)w[u]);
         }
-        if (o < m * m) t += P0 ? P0[o] : 0.0;
-        else t += r0 ? r0[o - m * m] : 0.0;
-        Pr[o] = ok ? t : __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            const int o = o0 + u * blockDim.x;
+            if (o < nout) {
+                double v = t[u];
+                if (o < m * m) v += P0 ? P0[o] : 0.0;
+                else v += r0 ? r0[o - m * m] : 0.0;
+                Pr[o] = ok ? v : __longlong_as_double(0x7ff8000000000000ll);
+            }
+        }
     }
 }
 
