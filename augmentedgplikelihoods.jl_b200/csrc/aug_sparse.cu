@@ -126,6 +126,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// The CTA-wide barrier of the role loops.  The three roles run separate copies of the tile loop; the barrier itself is
+// ONE instruction (not inlined) that all of them call, so every thread of the CTA meets the same barrier at the same
+// address (what compute-sanitizer's synccheck verifies).
+template <int NT>
+__device__ __noinline__ void sp_role_barrier() {
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+
 // issue the copies of one κ tile (rows of observations [t0, t0 + TO) ∩ [0, n), m doubles each) into a ring stage
 template <int MT>
 __device__ __forceinline__ void sp_issue_tile(const SparseArgs& a, int64_t tile, double* stage) {
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
     // the same nloc + 2 barriers.
     auto tail = [&](int64_t k) {
         cp_async_wait<0>();                            // tile k+1 landed (the only group in flight)
-        asm volatile("bar.sync 0, %0;" ::"n"(C::NT) : "memory");   // tile k-2 is free; q(k), μ(k), γ(k-1), β(k-1) visible
+        sp_role_barrier<C::NT>();                      // tile k-2 is free; q(k), μ(k), γ(k-1), β(k-1) are visible
         sp_issue_tile<MT>(a, gtile(k + 2), stage(k + 2));
     };
     double* Ppart = a.scratch;
