@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Small invocations of every kernel family of the path for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import aug_pkg  # noqa: E402
+from common import BERNOULLI, CAT, CAT_BIJ, HETERO, LAPLACE, NEGBIN, POISSON, STUDENTT, synth_inputs  # noqa: E402
+from gpu_common import make_lik  # noqa: E402
+
+A = aug_pkg.load_package()
+ctx = A.Context(0)
+A.set_default_context(ctx)
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+n = int(os.environ.get("SAN_N", "20000"))
+for kind, params, kw in [(BERNOULLI, (), {}), (NEGBIN, (10,), dict(r_is_int=True)), (NEGBIN, (5.5,), {}), (POISSON, (10.0,), {}),
+                         (LAPLACE, (1.0,), {}), (STUDENTT, (3.0, 1.5), {}), (HETERO, (5.0,), dict(nlatent=2)),
+                         (CAT_BIJ, (), dict(nlatent=99)), (CAT, (), dict(nlatent=10))]:
+    nl = kw.get("nlatent", 1)
+    nn = n // 10 if kind in (CAT, CAT_BIJ) else n
+    y, mu, var, f = synth_inputs(kind, nn, 1, params, nl)
+    lik = make_lik(kind, params, kw)
+    q = A.init_aux_posterior(lik, nn)
+    q, beta, gamma, scal = A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)), want_elbo=(kind != CAT))
+    if kind != CAT:
+        A.expected_logtilt(lik, q, dev(y), A.Normals(dev(mu), dev(var)))
+    Om = A.aux_sample(A.AugPhilox(3, 0), lik, dev(y), dev(f))
+    A.auglik_potential_and_precision(lik, Om, dev(y), dev(f))
+    if kind != CAT:
+        A.logtilt(lik, Om, dev(y), dev(f))
+    torch.cuda.synchronize()
+    print("ok", kind, nn, flush=True)
+assert ctx.error_flag() == 0
+ctx.close()
