@@ -62,7 +62,11 @@ def main():
             def prod():
                 res["p"] = A.sparse_marginals(kappa, mvec, B, kdiag)
 
+            def fused_noelbo():
+                res["fn"] = A.sparse_cavi_sweep_(q, lik, y, kappa, mvec, B, kdiag, want_elbo=False)
+
             t_f = timeit(fused, a.reps)
+            t_fn = timeit(fused_noelbo, a.reps)
             t_p = timeit(prod, a.reps)
             beta, gamma = res["f"][4]
 
@@ -70,7 +74,7 @@ def main():
                 res["c"] = A.sparse_precision_potential(kappa, gamma, beta)
 
             t_c = timeit(cons, a.reps)
-            line = {"m": m, "n": n, "ms_fused": t_f, "ms_producer": t_p, "ms_consumer": t_c,
+            line = {"m": m, "n": n, "ms_fused": t_f, "ms_fused_no_elbo": t_fn, "ms_producer": t_p, "ms_consumer": t_c,
                     "obs_per_s": n / t_f * 1e3, "tflops_fused": 3.0 * m * m * n / t_f * 1e-9,
                     "frac_fp64_peak": 3.0 * m * m * n / t_f * 1e-9 / a.peak_tflops,
                     "tflops_producer": 2.0 * m * m * n / t_p * 1e-9, "tflops_consumer": 1.0 * m * m * n / t_c * 1e-9,
