@@ -9,23 +9,26 @@
 //   path       aux_posterior! + E[β_t], E[γ_t] + ELBO terms                  (aug_cavi_eval.cuh)
 //   consumer   P += γ_t κ_t κ_tᵀ (lower block triangle),  rhs += β_t κ_t
 //
-// This IS GEMM-shaped work, in fp64: 2M² + M² flops per observation against 8M bytes, so for M >= 32 the bound is
-// the FP64 pipe (measured 37.1 TFLOP/s for DMMA and for DFMA on B200, tools/fp64_peak.cu), not HBM.  tcgen05 has
-// no f64 kind; the fp64 tensor path of sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), which is what the GEMM
-// warps issue: same peak as DFMA but 1 operand fetch per 256 FMAs instead of per 32.
+// This IS GEMM-shaped work, in fp64: the symmetric forms need 2M² (+O(M)) flops per observation against 8M bytes, so for
+// M >= 32 the bound is the FP64 pipe (measured 37.1 TFLOP/s for DMMA and for DFMA on B200, tools/fp64_peak.cu), not
+// HBM.  tcgen05 has no f64 kind; the fp64 tensor path of sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), which is
+// what the GEMM warps issue: same peak as DFMA but 1 operand fetch per 256 FMAs instead of per 32.
 //
-// One persistent CTA per SM: 16 GEMM warps + TO/32 evaluation warps.
-//   * κ tiles of TO observations stream through a 3-stage shared-memory ring (cp.async 16 B, rows padded to
-//     MT + 4 doubles so that every fragment load below is bank-conflict-free); B is staged once, padded alike.
-//   * iteration j:  phase A   GEMM warps: producer GEMM of tile j+1 (C = B·κ_tile, then q_t = Σ_i κ_it C_it by
-//                             in-register products + 3 shuffles)  ‖  evaluation warps: μ_t, σ²_t, CAVI closed
-//                             forms of tile j, global stores, γ_t / β_t into shared memory
-//                   phase B   GEMM warps: consumer SYRK of tile j into register accumulators (warp p of a k-group
-//                             owns block-rows p and MB−1−p of the lower triangle: MB+1 blocks each)
-//                             ‖  evaluation warps: rhs += β_t κ_t
-//     so the latency-bound scalar math of tile j hides behind the DMMA stream of tile j+1.
-//   * P / rhs / ELBO partials of every CTA (and k-group) go to a scratch buffer; a second launch adds them in a
-//     fixed order (bit-reproducible, no floating-point atomics), mirrors the lower triangle and adds P0 / r0.
+// One persistent CTA per SM (M <= 128; larger M: sparse_general below):
+//   * κ tiles of TO observations stream through a 4-stage shared-memory ring (cp.async 16 B, rows padded to MT + 4
+//     doubles so that every fragment load is bank-conflict-free); B' = the symmetrised B arranged by cyclic block
+//     diagonals (diagonal and half-diagonal blocks halved: κᵀBκ = 2 Σ_I κ_Iᵀ Σ_d B'_{I,d} κ_{(I+d) mod MB}) is staged once.
+//   * warp roles: group X (8 warps) = producer GEMM of tile k (C = B'κ_tile by DMMA, q_t by in-register products and
+//     a butterfly over the 8 lanes of a row group, μ_t by 16-element dot products); evaluator (warp 0 of X at
+//     M = 128, dedicated warps below) = σ²_t and the CAVI closed forms of tile k-1, global stores, γ_t / β_t into shared
+//     memory; group Y (8 warps) = consumer SYRK of tile k-2 into register accumulators (the owner of block-row I holds
+//     the blocks (I, (I+d) mod MB), d = 0..MB/2) with rhs = κβ as one more DMMA per block-row.  ONE CTA barrier per
+//     tile (sp_role_barrier): the two groups share the tensor pipe, so one group's scalar epilogue overlaps the other's
+//     DMMA stream.
+//   * P / rhs / ELBO partials of every CTA go to a scratch buffer; a second launch adds them in a fixed order
+//     (bit-reproducible, no floating-point atomics), mirrors the lower triangle and adds P0 / r0 — and, in fused
+//     multi-GPU mode, all-reduces them over the peer-memory mailbox inside that same launch.
+// Measured behaviour, dropped variants and what bounds the kernel: DESIGN.md §3.6.
 #include <dlfcn.h>
 
 #include "aug_common.cuh"
