@@ -175,3 +175,27 @@ def test_one_cavi_iteration_end_to_end(A, orc):
     So = np.linalg.inv(o["P"])
     np.testing.assert_allclose(host(S), So, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(host(mnew), So @ o["rhs"], rtol=1e-9, atol=1e-12)
+
+
+def test_call_sequence_with_scratch_regrowth_and_second_context(A, orc):
+    """Different M (fused kernels and the cuBLAS composition) and n back to back on one context — the scratch buffer is
+    re-grown in between — interleaved with path verbs, then the same on a second context with its own stream."""
+    orc.set_threads(8)
+    lik = A.BernoulliLikelihood()
+    olik = orc.make_lik(orc.BERNOULLI)
+    ctx2 = A.Context(0)
+    try:
+        for rep, (n, m) in enumerate([(5000, 128), (70000, 16), (3000, 200), (9000, 64), (200, 8), (4000, 136), (5000, 128)]):
+            kappa, mvec, B, kdiag = synth_sparse(n, m, 300 + rep)
+            y, mu, var, _ = synth_inputs(BERNOULLI, n, 400 + rep)
+            rc, o = orc.sparse_cavi_sweep(olik, y, kappa, mvec, B, kdiag)
+            assert rc == 0
+            for ctx in (None, ctx2):
+                P, rhs, scal, _, _ = A.sparse_cavi_sweep_(None, lik, dev(y), dev(kappa), dev(mvec), dev(B), dev(kdiag), ctx=ctx)
+                q = A.init_aux_posterior(lik, n, ctx=ctx)
+                A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)), ctx=ctx)      # a path verb in between
+                check_P(host(P), host(rhs), o["P"], o["rhs"], kappa, o["beta"])
+                assert abs(float(scal[2]) - o["comp"][2]) <= 4 * RTOL * max(abs(o["comp"][2]), float(n))
+    finally:
+        ctx2.close()
+        orc.set_threads(1)
