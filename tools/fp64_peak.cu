@@ -25,6 +25,23 @@ __global__ void __launch_bounds__(512, 1) k_dmma(double* out, int iters, double 
     if (s == 12345.678) out[0] = s;
 }
 
+
+// the same stream with DISTINCT A / B operand registers per chain (the real kernels never reuse an operand register pair)
+template <int CHAINS>
+__global__ void __launch_bounds__(512, 1) k_dmma_distinct(double* out, int iters, double a0, double b0) {
+    double c[CHAINS][2], a[CHAINS], b[CHAINS];
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) { c[i][0] = c[i][1] = 0.0; a[i] = a0 + (threadIdx.x + 7 * i) * 1e-9; b[i] = b0 + i * 1e-7; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < CHAINS; ++i) dmma(c[i][0], c[i][1], a[i], b[i]);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
 template <int CHAINS>
 __global__ void __launch_bounds__(512, 1) k_dfma(double* out, int iters, double a0, double b0) {
     double c[CHAINS];
@@ -101,6 +118,11 @@ int main() {
         float ms = time_ms([&] { k_dmma<2><<<sms, 512, 0>>>(out, iters, 1.0, 1.0); });
         double flops = 2.0 * 256 * 2 * (double)iters * 16 * sms;
         printf("{\"kernel\": \"dmma_m8n8k4\", \"warps_per_sm\": 16, \"chains\": 2, \"ms\": %.4f, \"tflops\": %.3f}\n", ms, flops / ms * 1e-9);
+    }
+    for (int warps = 4; warps <= 16; warps *= 2) {
+        float ms = time_ms([&] { k_dmma_distinct<8><<<sms, warps * 32, 0>>>(out, iters, 1.0, 1.0); });
+        double flops = 2.0 * 256 * 8 * (double)iters * warps * sms;
+        printf("{\"kernel\": \"dmma_m8n8k4_distinct_operands\", \"warps_per_sm\": %d, \"chains\": 8, \"ms\": %.4f, \"tflops\": %.3f}\n", warps, ms, flops / ms * 1e-9);
     }
     for (int warps = 8; warps <= 16; warps *= 2) {
         float ms = time_ms([&] { k_dfma<8><<<sms, warps * 32, 0>>>(out, iters, 1.0000001, 1e-9); });
