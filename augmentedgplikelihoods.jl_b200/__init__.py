@@ -15,3 +15,4 @@ from .api import (AugPhilox, AuxPosterior, AuxSamples, BernoulliLikelihood, Cate
                   Context, HeteroscedasticGaussianLikelihood, LaplaceLikelihood, NegativeBinomialLikelihood,
                   Normals, PoissonLikelihood, StudentTLikelihood, default_context, set_default_context)
 from . import dist  # noqa: E402,F401
+from . import testutils  # noqa: E402,F401
