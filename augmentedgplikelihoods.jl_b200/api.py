@@ -571,6 +571,63 @@ def aug_loglik(lik, Ω, y, f, ctx=None) -> float:
 
 
 # ----------------------------------------------------------------------------- SpecialDistributions
+# ----------------------------------------------------------------------------- the two auxiliary-variable laws as objects
+class AuxPrior:
+    """aux_prior(lik, y) (a10): the prior p(Ω) of the augmentation — PolyaGamma(1, 0) / PolyaGamma(y + r, 0) /
+    PolyaGammaPoisson / InverseGamma / Gamma / PolyaGammaNegativeMultinomial per likelihood.  The device
+    implementation never materialises per-observation distribution objects: this handle carries (lik, y) and
+    evaluates the log-density on the device."""
+
+    def __init__(self, lik, y):
+        if lik.kind == HETERO:
+            raise TypeError("the heteroscedastic likelihood has no explicit prior / tilt split (can_split == false)")
+        self.lik, self.y = lik, y
+
+    def __len__(self):
+        return _nobs(self.lik, self.y)
+
+    def logdensity(self, Ω: AuxSamples, ctx=None) -> float:
+        """logdensity_def(aux_prior(lik, y), Ω) — generic.jl:49; the prior does not depend on f."""
+        ctx = ctx or default_context()
+        n = len(self)
+        shape = (n, self.lik.nlatent) if _is_cat(self.lik) else (n,)
+        f0 = torch.zeros(shape, dtype=torch.float64, device=ctx.tdev)
+        return float(_sampled_terms(self.lik, Ω, self.y, f0, True, ctx)[_lib.S_LOGPRIOR].item())
+
+
+class AuxFullConditional:
+    """aux_full_conditional(lik, y, f) (a14): p(Ω | y, f), the law aux_sample! draws from."""
+
+    def __init__(self, lik, y, f):
+        self.lik, self.y, self.f = lik, y, f
+
+    def __len__(self):
+        return _nobs(self.lik, self.y)
+
+    def rand(self, rng: Optional[AugPhilox] = None, ctx=None, i0: int = 0) -> AuxSamples:
+        """tvrand(rng, aux_full_conditional(lik, y, f)) == aux_sample(rng, lik, y, f) — generic.jl:14-20"""
+        args = ([rng] if rng is not None else []) + [self.lik, self.y, self.f]
+        return aux_sample(*args, ctx=ctx, i0=i0)
+
+
+def aux_prior(lik, y) -> AuxPrior:
+    return AuxPrior(lik, y)
+
+
+def aux_full_conditional(lik, y, f) -> AuxFullConditional:
+    return AuxFullConditional(lik, y, f)
+
+
+def logdensity_def(dist: AuxPrior, Ω: AuxSamples, ctx=None) -> float:
+    return dist.logdensity(Ω, ctx=ctx)
+
+
+def tvrand(*args, ctx=None, i0: int = 0) -> AuxSamples:
+    """tvrand([rng,] dist) for dist = aux_full_conditional(lik, y, f) — TestUtils.jl:108-110"""
+    rng, dist = (args[0], args[1]) if isinstance(args[0], AugPhilox) else (None, args[0])
+    return dist.rand(rng, ctx=ctx, i0=i0)
+
+
 def pg_rand(b, c, n=None, b_is_int=None, rng: Optional[AugPhilox] = None, ctx=None, i0=0):
     """rand(PolyaGamma(b, c)[, n]) — SpecialDistributions/polyagamma.jl:121-164"""
     ctx = ctx or default_context()

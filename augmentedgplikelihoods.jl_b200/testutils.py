@@ -103,6 +103,14 @@ def test_auglik(lik, n: int = 10, seed: int = 0, ctx=None, atol: float = 1e-5):
     if lik.kind != CAT:                                    # the non-bijective prior NM(1, 1/nl) is improper
         out["aug_loglik"] = A.aug_loglik(lik, Om, dy, df, ctx=ctx)
         assert finite(out["aug_loglik"])
+        if can_split(lik):                                 # aug_loglik = logtilt + logdensity(aux_prior(lik, y), Ω)  generic.jl:48-50
+            pO = A.aux_prior(lik, dy)
+            lp = A.logdensity_def(pO, Om, ctx=ctx)
+            assert finite(lp) and len(pO) == n
+            assert abs(out["logtilt"] + lp - out["aug_loglik"]) <= 1e-9 * max(1.0, abs(out["aug_loglik"]))
+        pc = A.aux_full_conditional(lik, dy, df)           # two more draws through the distribution handle
+        Om_a, Om_b = A.tvrand(prng, pc, ctx=ctx), A.tvrand(prng, pc, ctx=ctx)
+        assert len(Om_a) == n and not torch.equal(Om_a.omega, Om_b.omega)
 
     # Full conditional Ω: C = p(f, y) = p(y | Ω, f) p(Ω) / p(Ω | y, f) does not depend on Ω
     if lik.kind in (BERNOULLI, NEGBIN):
