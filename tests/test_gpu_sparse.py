@@ -219,3 +219,29 @@ def test_cavi_loop_on_a_sparse_gp_never_decreases_the_elbo(A):
         assert np.all(d >= -1e-7 * np.abs(elbos[:-1])), elbos
         assert d[0] > 0 and abs(d[-1]) <= 1e-6 * abs(elbos[-1]) + 1e-3          # it moved, then converged
         assert np.all(np.linalg.eigvalsh(S) > 0)
+
+
+def test_gibbs_and_cavi_agree_on_the_sparse_posterior(A):
+    """examples/sparse_bernoulli_gibbs.py = gibbs_sample of examples/bernoulli/script.jl:76-87 in sparse form (aux_sample! +
+    the consumer verb with the sampled ω).  Both inference schemes of the reference target the same posterior over the
+    inducing values: the Gibbs mean (fixed seeds) lies within a few posterior standard deviations / Monte-Carlo errors
+    of the CAVI mean, and the Gibbs spread is not smaller than the (mean-field) CAVI spread by more than noise."""
+    import importlib.util
+    import os
+    import sys
+    exdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples")
+    sys.path.insert(0, exdir)
+    try:
+        spec = importlib.util.spec_from_file_location("sparse_bernoulli_gibbs", os.path.join(exdir, "sparse_bernoulli_gibbs.py"))
+        ex = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ex)
+    finally:
+        sys.path.remove(exdir)
+    prob = ex.make_problem(20_000, 12, seed=5)
+    us = ex.gibbs(A, *prob, nsamples=400, seed=1)[100:]
+    m_cavi, S_cavi, _ = ex.cavi(A, *prob, iters=10, verbose=False)
+    sd_cavi = np.sqrt(np.diag(S_cavi))
+    sd_gibbs = us.std(0)
+    z = (us.mean(0) - m_cavi) / np.maximum(sd_gibbs, sd_cavi)
+    assert np.all(np.abs(z) < 1.0), z                       # same posterior mean up to a fraction of its own spread
+    assert np.all(sd_gibbs > 0.5 * sd_cavi) and np.all(sd_gibbs < 4.0 * sd_cavi), (sd_gibbs, sd_cavi)
