@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 import aug_pkg  # noqa: E402
 
 
-def make_problem(n, m, seed=0, lengthscale=2.0):
+def make_problem(n, m, seed=0, lengthscale=2.0, lik=None, gen_y=None):
     """x sorted in [-10, 10] (script.jl:12), SqExponential kernel with lengthscale 2 (:13), f ~ GP, y ~ Bernoulli(σ(f));
     inducing points on a grid.  Returns y, κ ([n][m], the Julia M×N matrix as stored), k_tt, K_Z, K_Z⁻¹."""
     rng = np.random.default_rng(seed)
@@ -33,7 +33,10 @@ def make_problem(n, m, seed=0, lengthscale=2.0):
     KZinv = 0.5 * (KZinv + KZinv.T)
     u = L @ rng.standard_normal(m)                                        # a draw of the inducing values
     f = kappa @ u
-    y = (rng.random(n) < 1.0 / (1.0 + np.exp(-f))).astype(np.uint8)
+    if lik is None:
+        y = (rng.random(n) < 1.0 / (1.0 + np.exp(-f))).astype(np.uint8)
+    else:                                                                 # any scalar-latent likelihood: y ~ lik(f)
+        y = gen_y(rng, lik, f)
     kdiag = np.ones(n) + 1e-6
     return y, kappa, kdiag, KZ, KZinv
 
@@ -44,10 +47,10 @@ def kl_mvn(m, S, K, Kinv):
     return 0.5 * (np.trace(Kinv @ S) + m @ Kinv @ m - M + np.linalg.slogdet(K)[1] - np.linalg.slogdet(S)[1])
 
 
-def cavi(A, y, kappa, kdiag, KZ, KZinv, iters=8, verbose=True):
+def cavi(A, y, kappa, kdiag, KZ, KZinv, iters=8, verbose=True, lik=None):
     ctx = A.default_context()
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.tdev)
-    lik = A.BernoulliLikelihood()
+    lik = lik or A.BernoulliLikelihood()
     n, M = kappa.shape
     dy, dk, dkd, dP0 = dev(y), dev(kappa), dev(kdiag), dev(KZinv)
     q = A.init_aux_posterior(lik, n)                                      # qΩ = init_aux_posterior(lik, N)   script.jl:43
