@@ -269,3 +269,26 @@ def test_cavi_loop_elbo_is_monotone_for_every_scalar_latent_likelihood(A, name):
     assert np.all(np.isfinite(elbos))
     assert np.all(d >= -1e-7 * np.abs(elbos[:-1])), elbos
     assert d[0] > 0
+
+
+def test_fused_sweep_vs_mpmath_golden(A):
+    """The GPU sweep against tests/golden/golden_sparse.json (mpmath, 50 digits) directly — no oracle in between."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_sparse.json")) as fh:
+        G = json.load(fh)
+    lik = A.BernoulliLikelihood()
+    for c in G["cases"]:
+        N = lambda k, dt=np.float64: np.ascontiguousarray(c[k], dtype=dt)
+        n = c["n"]
+        q = A.init_aux_posterior(lik, n)
+        P, rhs, scal, qf, bg = A.sparse_cavi_sweep_(q, lik, dev(N("y", np.uint8)), dev(N("kappa")), dev(N("mvec")), dev(N("B")),
+                                                    dev(N("kdiag")), P0=dev(N("P0")), r0=dev(N("r0")),
+                                                    want_marginals=True, want_potentials=True)
+        assert relerr(host(qf.var), N("var")) <= RTOL and np.all(np.abs(host(qf.mu) - N("mu")) <= 1e-14)
+        assert relerr(host(q.c), N("c")) <= RTOL and relerr(host(bg[1]), N("gamma")) <= RTOL
+        assert np.array_equal(host(bg[0]), N("beta"))
+        np.testing.assert_allclose(host(P), N("P"), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(host(rhs), N("rhs"), rtol=0, atol=1e-12)
+        s = host(scal)
+        assert s[0] == pytest.approx(c["expected_logtilt"], rel=1e-12) and s[1] == pytest.approx(c["kl"], rel=1e-11)

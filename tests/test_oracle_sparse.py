@@ -73,3 +73,26 @@ def test_oracle_sparse_p0_r0_and_sweep_composition(orc):
     # S = inv(K_Z⁻¹ + κ Diagonal(γ) κᵀ) is what the user forms next: P must be symmetric positive definite
     assert np.array_equal(out["P"], out["P"].T)
     assert np.all(np.linalg.eigvalsh(out["P"]) > 0)
+
+
+def test_oracle_sparse_sweep_vs_mpmath_golden(orc):
+    """tests/golden/golden_sparse.json (mpmath, 50 digits; make_golden_sparse.py): the whole sweep of the oracle —
+    marginals, Bernoulli path, P, rhs, ELBO sums — against an evaluation that shares no code with it."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_sparse.json")) as fh:
+        G = json.load(fh)
+    for c in G["cases"]:
+        A = lambda k, dt=np.float64: np.ascontiguousarray(c[k], dtype=dt)
+        rc, o = orc.sparse_cavi_sweep(orc.make_lik(orc.BERNOULLI), A("y", np.uint8), A("kappa"), A("mvec"), A("B"),
+                                      A("kdiag"), A("P0"), A("r0"))
+        assert rc == 0
+        np.testing.assert_allclose(o["mu"], A("mu"), rtol=0, atol=2e-15)
+        np.testing.assert_allclose(o["var"], A("var"), rtol=1e-14)
+        np.testing.assert_allclose(o["state"][0], A("c"), rtol=1e-14)
+        np.testing.assert_allclose(o["gamma"], A("gamma"), rtol=1e-14)
+        assert np.array_equal(o["beta"], A("beta"))
+        np.testing.assert_allclose(o["P"], A("P"), rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(o["rhs"], A("rhs"), rtol=0, atol=1e-13)
+        assert o["comp"][0] == pytest.approx(c["expected_logtilt"], rel=1e-13)
+        assert o["comp"][1] == pytest.approx(c["kl"], rel=1e-12)
