@@ -72,6 +72,7 @@ SIGNATURES = {
     "aug_logisticsoftmax": [_vp, C.POINTER(AugLik), _i64, _vp, _vp],
     "aug_approx_expected_logisticsoftmax": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _vp],
     "aug_sparse_marginals": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "aug_sparse_marginals_strided": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64],
     "aug_sparse_precision_potential": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "aug_sparse_cavi_sweep": [_vp, C.POINTER(AugLik), _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp, _vp, _vp, _vp],

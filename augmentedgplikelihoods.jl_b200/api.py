@@ -793,6 +793,28 @@ def sparse_marginals(kappa, mvec, B, kdiag, ctx=None) -> Normals:
     return Normals(mu, var)
 
 
+def sparse_marginals_into_(qf: Normals, j: int, kappa, mvec, B, kdiag, ctx=None) -> Normals:
+    """Latent j of a multi-latent qf in place: qf.mu[:, j], qf.var[:, j] for the class-fastest [n][nl] layout of the
+    Categorical likelihood (one call per latent GP; κ may be shared), qf.mu[j], qf.var[j] for the latent-major [2][n]
+    layout of the heteroscedastic one."""
+    ctx = ctx or default_context()
+    kappa = _kappa(kappa)
+    n, m = kappa.shape
+    mu, var = _f64(qf.mu, "mu"), _f64(qf.var, "var")
+    if mu.dim() != 2 or not mu.is_contiguous() or not var.is_contiguous():
+        raise ValueError("qf must hold contiguous 2-d mu / var")
+    if mu.shape[0] == n and mu.shape[1] != n:              # [n][nl]: class fastest
+        off, stride = j * 8, mu.shape[1]
+    else:                                                  # [nl][n]: latent major
+        off, stride = j * n * 8, 1
+    ctx.enter()
+    check(ctx.lib.aug_sparse_marginals_strided(ctx.h, n, m, _ptr(kappa), _ptr(_f64(mvec, "mvec")), _ptr(_f64(B, "B")),
+                                               _ptr(_f64(kdiag, "kdiag")), C.c_void_p(mu.data_ptr() + off),
+                                               C.c_void_p(var.data_ptr() + off), stride))
+    ctx.leave()
+    return qf
+
+
 def _split_pr(Pr, m):
     return Pr[: m * m].view(m, m), Pr[m * m:]
 

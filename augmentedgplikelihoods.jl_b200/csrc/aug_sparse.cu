@@ -94,6 +94,7 @@ struct SparseArgs {
     int64_t n;
     int m;
     int64_t ntiles;
+    int64_t ostride;          // element stride of the mu / var outputs (1, or nlatent for class-fastest [n][nl] arrays)
     const void* y;
     const double* kappa;
     const double* mvec;
@@ -466,8 +467,8 @@ __global__ void __launch_bounds__(SpCfg<MT>::NT, 1) sparse_sweep_kernel(const Sp
             for (int w = 0; w < C::NSLOT; ++w) q += qp[w * C::TO];
             const double var = fma(-2.0, q, c0);   // k_tt − κᵀBκ,  κᵀBκ = 2 κᵀB'κ
             if (valid) {
-                if (a.mu) a.mu[i] = mu;
-                if (a.var) a.var[i] = var;
+                if (a.mu) a.mu[i * a.ostride] = mu;
+                if (a.var) a.var[i * a.ostride] = var;
                 if (MODE == SP_FUSED) {
                     Obs o;
                     o.y = c1; o.ys = c1;
@@ -871,7 +872,7 @@ __global__ void gen_sym_kernel(int m, const double* __restrict__ B, double* __re
 // one warp per observation: μ_t = κ_t·m, σ²_t = k_tt − κ_t·T_t
 __global__ void gen_rowdot_kernel(int64_t rows, int m, const double* __restrict__ kap, const double* __restrict__ T,
                                   const double* __restrict__ mvec, const double* __restrict__ kdiag,
-                                  double* __restrict__ mu, double* __restrict__ var) {
+                                  double* __restrict__ mu, double* __restrict__ var, int64_t ostride) {
     const int lane = threadIdx.x & 31;
     const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t t = w0; t < rows; t += nw) {
@@ -886,8 +887,8 @@ __global__ void gen_rowdot_kernel(int64_t rows, int m, const double* __restrict_
         q = warp_sum(q);
         a = warp_sum(a);
         if (lane == 0) {
-            if (mu) mu[t] = a;
-            if (var) var[t] = kdiag[t] - q;
+            if (mu) mu[t * ostride] = a;
+            if (var) var[t * ostride] = kdiag[t] - q;
         }
     }
 }
@@ -916,7 +917,8 @@ __global__ void gen_finalize_kernel(int m, const double* __restrict__ Pacc, cons
 int32_t sparse_general(aug_ctx* ctx, int mode, const aug_lik* lik, int64_t n, int m, const void* y, const double* kappa,
                        const double* mvec, const double* B, const double* kdiag, const double* gamma_in,
                        const double* beta_in, double* mu, double* var, void* s0, void* s1, void* s2, double* beta,
-                       double* gamma, const double* P0, const double* r0, double* Pr, double* scalars) {
+                       double* gamma, const double* P0, const double* r0, double* Pr, double* scalars,
+                       int64_t ostride = 1) {
     if (mode != SP_PRODUCER && aug_xch_for(ctx)) return AUG_ERR_PRECONDITION;   // the in-kernel exchange covers m <= 128
     int32_t rc = cublas_load();
     if (rc) return rc;
@@ -960,8 +962,9 @@ int32_t sparse_general(aug_ctx* ctx, int mode, const aug_lik* lik, int64_t n, in
             const double* kc = kappa + r0i * m;
             // column-major view: κ_chunkᵀ is m × rows (ld m); T = Bs · κ_chunkᵀ
             AUG_CUBLAS(g_cublas.dgemm(ctx->cublas, 0, 0, m, (int)rows, m, &one, Bs, m, kc, m, &zero, T, m));
-            gen_rowdot_kernel<<<grid, 256, 0, ctx->stream>>>(rows, m, kc, T, mvec, kdiag + r0i, mu_w ? mu_w + r0i : nullptr,
-                                                             var_w ? var_w + r0i : nullptr);
+            gen_rowdot_kernel<<<grid, 256, 0, ctx->stream>>>(rows, m, kc, T, mvec, kdiag + r0i,
+                                                             mu_w ? mu_w + r0i * ostride : nullptr,
+                                                             var_w ? var_w + r0i * ostride : nullptr, ostride);
             ctx->launches++;
         }
         AUG_CUDA(cudaGetLastError());
@@ -1008,20 +1011,26 @@ void aug_cublas_destroy(aug_ctx* c) {
 
 extern "C" {
 
-int32_t aug_sparse_marginals(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa, const double* mvec,
-                             const double* B, const double* kdiag, double* mu, double* var) {
+int32_t aug_sparse_marginals_strided(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa, const double* mvec,
+                                     const double* B, const double* kdiag, double* mu, double* var, int64_t stride) {
     int32_t rc = sp_check(ctx, n, m, kappa);
     if (rc) return rc;
     if (n == 0) return AUG_OK;
-    if (!mvec || !B || !kdiag || (!mu && !var)) return AUG_ERR_BAD_ARG;
+    if (!mvec || !B || !kdiag || (!mu && !var) || stride < 1) return AUG_ERR_BAD_ARG;
     AUG_CUDA(cudaSetDevice(ctx->device));
     if (m > 128)
         return sparse_general(ctx, SP_PRODUCER, nullptr, n, m, nullptr, kappa, mvec, B, kdiag, nullptr, nullptr, mu, var,
-                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stride);
     SparseArgs a{};
     a.n = n; a.m = m; a.kappa = kappa; a.mvec = mvec; a.B = B; a.kdiag = kdiag; a.mu = mu; a.var = var;
+    a.ostride = stride;
     a.vec16 = (aug_aligned16(kappa) && (m % 2 == 0)) ? 1 : 0;
     return sp_dispatch_m<SP_PRODUCER, AUG_BERNOULLI>(ctx, a, nullptr, nullptr, nullptr, nullptr);
+}
+
+int32_t aug_sparse_marginals(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa, const double* mvec,
+                             const double* B, const double* kdiag, double* mu, double* var) {
+    return aug_sparse_marginals_strided(ctx, n, m, kappa, mvec, B, kdiag, mu, var, 1);
 }
 
 int32_t aug_sparse_precision_potential(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa,
@@ -1036,6 +1045,7 @@ int32_t aug_sparse_precision_potential(aug_ctx* ctx, int64_t n, int32_t m, const
                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, P0, r0, Pr, nullptr);
     SparseArgs a{};
     a.n = n; a.m = m; a.kappa = kappa; a.gamma_in = gamma; a.beta_in = beta;
+    a.ostride = 1;
     a.vec16 = (aug_aligned16(kappa) && (m % 2 == 0)) ? 1 : 0;
     return sp_dispatch_m<SP_CONSUMER, AUG_BERNOULLI>(ctx, a, P0, r0, Pr, nullptr);
 }
@@ -1057,6 +1067,7 @@ int32_t aug_sparse_cavi_sweep(aug_ctx* ctx, const aug_lik* lik, int64_t n, int32
     SparseArgs a{};
     a.n = n; a.m = m; a.y = y; a.kappa = kappa; a.mvec = mvec; a.B = B; a.kdiag = kdiag;
     a.mu = mu; a.var = var; a.s0 = (double*)s0; a.s1 = (double*)s1; a.s2 = s2; a.beta = beta; a.gamma = gamma;
+    a.ostride = 1;
     a.vec16 = (aug_aligned16(kappa) && (m % 2 == 0)) ? 1 : 0;
     a.elbo = scalars != nullptr ? 1 : 0;
     rc = aug_lik_const(ctx, lik, &a.L, scalars != nullptr, false);

@@ -293,6 +293,11 @@ int32_t aug_approx_expected_logisticsoftmax(aug_ctx* ctx, const aug_lik* lik, in
  * prior mean): mu_t = κ_tᵀ·mvec, var_t = kdiag_t − κ_tᵀ·B·κ_t. */
 int32_t aug_sparse_marginals(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa, const double* mvec,
                              const double* B, const double* kdiag, double* mu, double* var);
+/* the same with an element stride on the outputs: mu[t*stride], var[t*stride].  stride = nlatent writes latent j of the
+ * class-fastest [n][nl] marginals of the Categorical likelihood (categorical.jl:63,84) in place, one call per latent GP
+ * (pass mu + j, var + j). */
+int32_t aug_sparse_marginals_strided(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa, const double* mvec,
+                                     const double* B, const double* kdiag, double* mu, double* var, int64_t stride);
 /* row 1 — docs/src/index.md:156-160: P = P0 + κ·Diagonal(gamma)·κᵀ, rhs = r0 + κ·beta. */
 int32_t aug_sparse_precision_potential(aug_ctx* ctx, int64_t n, int32_t m, const double* kappa,
                                        const double* gamma, const double* beta, const double* P0,

@@ -101,3 +101,56 @@ def test_reference_quirk_categorical_update_ignores_theta(A):
     d = np.diff(elbos)
     assert np.all(np.isfinite(elbos)) and elbos[-1] > elbos[0] + 10.0
     assert d.min() > -0.1                                  # the dips stay two orders of magnitude below the first gain
+
+
+@pytest.mark.parametrize("K,M", [(4, 16), (6, 40)])
+def test_sparse_categorical_cavi_with_shared_kappa(A, K, M):
+    """Multi-class sparse GP on the device: the nl = K − 1 latent GPs share κ; per latent one strided marginals call
+    writes its column of the class-fastest [n][nl] qf in place, the categorical CAVI kernel does the path, and one
+    consumer call per latent (β, γ are class-major) forms P_j, rhs_j.  logθ = 0 (see quirk Q8): the augmented ELBO
+    never decreases."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "sparse_bernoulli_cavi", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples",
+                                              "sparse_bernoulli_cavi.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    n = 6000
+    lik = A.CategoricalLikelihood(K, bijective=True)
+    nl = lik.nlatent
+    _, kappa, kdiag, KZ, KZinv = ex.make_problem(n, M, seed=K)
+    rng = np.random.default_rng(K)
+    Lz = np.linalg.cholesky(KZ)
+    f = np.stack([kappa @ (Lz @ rng.standard_normal(M)) for _ in range(nl)], axis=1)
+    y = A.testutils.gen_y(rng, lik, f)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dk, dkd, dy, dP0 = dev(kappa), dev(kdiag), dev(y), dev(KZinv)
+    m = [np.zeros(M) for _ in range(nl)]
+    S = [KZ.copy() for _ in range(nl)]
+    qf = A.Normals(torch.empty((n, nl), dtype=torch.float64, device="cuda"),
+                   torch.empty((n, nl), dtype=torch.float64, device="cuda"))
+    q = A.init_aux_posterior(lik, n)
+    elbos = []
+    for _ in range(10):
+        for j in range(nl):
+            Bj = KZ - S[j]
+            A.sparse_marginals_into_(qf, j, dk, dev(m[j]), dev(0.5 * (Bj + Bj.T)), dkd)
+        q, beta, gamma, scal = A.cavi_step_(q, lik, dy, qf)
+        s = scal.cpu().numpy()
+        elbos.append(s[0] - s[1] - sum(kl_mvn(mj, Sj, KZ, KZinv) for mj, Sj in zip(m, S)))
+        for j in range(nl):
+            P, rhs = A.sparse_precision_potential(dk, gamma[j], beta[j], P0=dP0)
+            Sj = np.linalg.inv(P.cpu().numpy())
+            S[j] = 0.5 * (Sj + Sj.T)
+            m[j] = S[j] @ rhs.cpu().numpy()
+    elbos = np.array(elbos)
+    d = np.diff(elbos)
+    assert np.all(np.isfinite(elbos)) and A.default_context().error_flag() == 0
+    assert np.all(d >= -1e-8 * np.abs(elbos[:-1])), elbos
+    assert d[0] > 0
+    # the strided marginals equal the contiguous verb's
+    q0 = A.sparse_marginals(dk, dev(m[0]), dev(0.5 * ((KZ - S[0]) + (KZ - S[0]).T)), dkd)
+    qchk = A.Normals(torch.zeros((n, nl), dtype=torch.float64, device="cuda"), torch.zeros((n, nl), dtype=torch.float64, device="cuda"))
+    A.sparse_marginals_into_(qchk, 0, dk, dev(m[0]), dev(0.5 * ((KZ - S[0]) + (KZ - S[0]).T)), dkd)
+    assert torch.equal(qchk.mu[:, 0], q0.mu) and torch.equal(qchk.var[:, 0], q0.var) and float(qchk.mu[:, 1:].abs().sum()) == 0.0
