@@ -66,7 +66,7 @@ def allreduce_scalars_(ctx, scal: torch.Tensor):
 
 
 def init_p2p(ctx, group=None, fused=True):
-    """Attach the peer-memory mailbox (NVLink / NVSwitch): every rank exports a cudaIpc handle of its 1 KiB mailbox,
+    """Attach the peer-memory mailbox (NVLink / NVSwitch): every rank exports a cudaIpc handle of its mailbox (slots + bulk area),
     torch.distributed all-gathers the handles, every rank maps its peers.  With fused=True the scalar-producing
     verbs (cavi_step_ with want_elbo, expected_elbo_terms, sampled_loglik_terms) return the sums over ALL ranks,
     exchanged inside their own reducing kernel — no separate all-reduce launch (include/augcuda.h)."""
