@@ -260,7 +260,8 @@ def sparse_leg(A, ctx, torch, dist, world, dev, args, rank):
     return {"workload": f"sparse-GP CAVI iteration (Bernoulli), m={m} inducing points, {n} observations per GPU: "
                         "aug_sparse_cavi_sweep = SVGP marginals + aux_posterior! + E[beta],E[gamma] + ELBO sums + "
                         "P = kappa Diag(gamma) kappa^T, rhs = kappa beta in one pass over kappa",
-            "m": m, "obs_per_gpu": n, "ms_per_sweep": ms_f, "obs_per_s": n * world / (ms_f * 1e-3),
+            "m": m, "obs_per_gpu": n, "l2": f"kappa is {8.0 * m * n / 1e9:.1f} GB per sweep >> 126 MB L2 (no flush needed)",
+            "ms_per_sweep": ms_f, "obs_per_s": n * world / (ms_f * 1e-3),
             "gpu_launches_per_sweep": int(launches),
             "roofline": {"kernel": "sparse_sweep_kernel<128, FUSED, BERNOULLI> (DMMA m8n8k4)", "bound": "tensor",
                          "note": "fp64 tensor pipe (tcgen05 has no f64 kind); HBM traffic 8m B/obs is 10% of the HBM roofline",
