@@ -90,6 +90,14 @@ SIGNATURES = {
     "aug_allreduce_scalars_p2p": [_vp, _vp, _i32],
     "aug_cavi_step_host": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "aug_aux_sample_host": [_vp, C.POINTER(AugLik), _i64, _i64, _vp, _vp, _i64, _vp, _vp],
+    "aug_init_aux_posterior_host": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _vp],
+    "aug_aux_posterior_host": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "aug_expected_potential_precision_host": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp,
+                                              _vp, _i64],
+    "aug_expected_elbo_terms_host": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    "aug_init_aux_variables_host": [_vp, C.POINTER(AugLik), _i64, _i64, _vp, _vp],
+    "aug_potential_precision_host": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64],
+    "aug_sampled_loglik_terms_host": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _i64, _vp, _vp, _i32, _vp],
 }
 
 _lib = None

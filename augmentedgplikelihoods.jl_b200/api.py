@@ -154,6 +154,9 @@ class Normals:
     mu: torch.Tensor
     var: torch.Tensor
 
+    def __post_init__(self):
+        self.mu, self.var = _t(self.mu), _t(self.var)
+
     def __len__(self):
         return self.mu.shape[-1] if self.mu.dim() == 1 else self.mu.shape[0]
 
@@ -162,6 +165,9 @@ class Normals:
 class AuxSamples:
     omega: torch.Tensor
     n: Optional[torch.Tensor] = None
+
+    def __post_init__(self):
+        self.omega, self.n = _t(self.omega), _t(self.n)
 
     @property
     def ω(self):
@@ -291,6 +297,50 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+# ---- host-array dispatch.  The reference's verbs take plain host Vectors (src/generic.jl:1-88); here a verb whose
+# array arguments are HOST tensors (torch CPU tensors or numpy arrays) goes through the *_host entry points of the
+# C ABI (chunked H2D / kernel / D2H pipeline inside the library) and returns host tensors; device tensors go through
+# the device-pointer entry points.  Mixing the two in one call is an error.  Either way the arithmetic runs on the GPU.
+def _t(a):
+    """numpy array -> torch view of the same memory; tensors pass through"""
+    if a is None or torch.is_tensor(a):
+        return a
+    return torch.as_tensor(a)
+
+
+def _is_host(*ts) -> bool:
+    flags = {bool(t.is_cuda) for t in ts if t is not None}
+    if len(flags) > 1:
+        raise ValueError("host and device arrays mixed in one call")
+    return flags == {False}
+
+
+def _hptr(t):
+    if t is None:
+        return None
+    if t.is_cuda:
+        raise ValueError("host tensor expected")
+    if not t.is_contiguous():
+        raise ValueError("contiguous tensor expected")
+    return C.c_void_p(t.data_ptr())
+
+
+def _hempty(shape, dtype=torch.float64, pin=True):
+    """host output buffer (pinned: the D2H copies of the staging pipeline then run at full PCIe speed)"""
+    try:
+        return torch.empty(shape, dtype=dtype, pin_memory=pin)
+    except RuntimeError:
+        return torch.empty(shape, dtype=dtype)
+
+
+def _hscal():
+    return (C.c_double * NSCALARS)()
+
+
+def _scal_tensor(hs):
+    return torch.tensor(list(hs), dtype=torch.float64)
+
+
 def _check_y(lik, y):
     want = _Y_DTYPE[lik.kind]
     if y.dtype == torch.bool and want == torch.uint8:
@@ -315,13 +365,16 @@ def _f64(t, name):
 
 
 # ----------------------------------------------------------------------------- variational verbs
-def init_aux_posterior(lik: Likelihood, n: int, ctx: Optional[Context] = None, with_y_copy: bool = True):
-    """init_aux_posterior(lik, n) — zero-filled state (bernoulli.jl:7-11 ... categorical.jl:59-70)."""
+def init_aux_posterior(lik: Likelihood, n: int, ctx: Optional[Context] = None, with_y_copy: bool = True,
+                       host: bool = False):
+    """init_aux_posterior(lik, n) — zero-filled state (bernoulli.jl:7-11 ... categorical.jl:59-70).
+    host=True: the state lives in (pinned) host memory and the verbs take the host-buffer path."""
     ctx = ctx or default_context()
     names = _FIELDS[lik.kind]
     shape = (n, lik.nlatent) if _is_cat(lik) else (n,)
     fields = {}
-    ctx.enter()
+    if not host:
+        ctx.enter()
     for i, name in enumerate(names):
         if name is None:
             continue
@@ -331,9 +384,13 @@ def init_aux_posterior(lik: Likelihood, n: int, ctx: Optional[Context] = None, w
             dt = torch.uint8 if _is_cat(lik) else torch.int64
         else:
             dt = torch.float64
-        fields[name] = ctx.empty(shape, dt)
+        fields[name] = _hempty(shape, dt) if host else ctx.empty(shape, dt)
     q = AuxPosterior(lik, fields)
     d = lik._desc()
+    if host:
+        check(ctx.lib.aug_init_aux_posterior_host(ctx.h, C.byref(d), n, _hptr(q._s(0)), _hptr(q._s(1)),
+                                                  _hptr(q._s(2))))
+        return q
     check(ctx.lib.aug_init_aux_posterior(ctx.h, C.byref(d), n, _ptr(q._s(0)), _ptr(q._s(1)), _ptr(q._s(2))))
     ctx.leave()
     return q
@@ -342,8 +399,13 @@ def init_aux_posterior(lik: Likelihood, n: int, ctx: Optional[Context] = None, w
 def aux_posterior_(qΩ: AuxPosterior, lik: Likelihood, y, qf: Normals, ctx: Optional[Context] = None):
     """aux_posterior!(qΩ, lik, y, qf) — updates the variational parameters in place, returns qΩ."""
     ctx = ctx or default_context()
-    y = _check_y(lik, y)
+    y = _check_y(lik, _t(y))
     d = lik._desc()
+    if _is_host(y, qf.mu, qf.var, qΩ._s(0)):
+        check(ctx.lib.aug_aux_posterior_host(ctx.h, C.byref(d), _nobs(lik, y), _hptr(y), _hptr(_f64(qf.mu, "mu")),
+                                             _hptr(_f64(qf.var, "var")), _ld(lik, qf.mu), _hptr(qΩ._s(0)),
+                                             _hptr(qΩ._s(1)), _hptr(qΩ._s(2))))
+        return qΩ
     ctx.enter()
     check(ctx.lib.aug_aux_posterior(ctx.h, C.byref(d), _nobs(lik, y), _ptr(y), _ptr(_f64(qf.mu, "mu")),
                                     _ptr(_f64(qf.var, "var")), _ld(lik, qf.mu), _ptr(qΩ._s(0)), _ptr(qΩ._s(1)),
@@ -355,7 +417,8 @@ def aux_posterior_(qΩ: AuxPosterior, lik: Likelihood, y, qf: Normals, ctx: Opti
 def aux_posterior(lik: Likelihood, y, qf: Normals, ctx: Optional[Context] = None):
     """aux_posterior(lik, y, qf) — generic.jl:22-24"""
     ctx = ctx or default_context()
-    return aux_posterior_(init_aux_posterior(lik, _nobs(lik, y), ctx), lik, y, qf, ctx)
+    y = _t(y)
+    return aux_posterior_(init_aux_posterior(lik, _nobs(lik, y), ctx, host=not y.is_cuda), lik, y, qf, ctx)
 
 
 def _alloc_bg(ctx, lik, n, want_beta=True, want_gamma=True):
@@ -372,14 +435,21 @@ def expected_auglik_potential_and_precision(lik, qΩ: AuxPosterior, y, qf: Optio
                                             ctx: Optional[Context] = None, _b=True, _g=True):
     """expected_auglik_potential_and_precision(lik, qΩ, y[, qf]) -> (β tuple, γ tuple)  (a7)"""
     ctx = ctx or default_context()
-    y = _check_y(lik, y)
+    y = _check_y(lik, _t(y))
     n = _nobs(lik, y)
     if lik.kind == HETERO and qf is None:
         raise TypeError("the heteroscedastic likelihood needs qf (heteroscedasticgaussian.jl:68-104)")
     d = lik._desc()
+    mu = qf.mu if (qf is not None and lik.kind == HETERO) else None
+    if _is_host(y, mu, qΩ._s(0)):
+        beta = _hempty((lik.nlatent, n)) if _b else None
+        gamma = _hempty((lik.nlatent, n)) if _g else None
+        check(ctx.lib.aug_expected_potential_precision_host(ctx.h, C.byref(d), n, _hptr(y), _hptr(mu), _ld(lik, mu),
+                                                            _hptr(qΩ._s(0)), _hptr(qΩ._s(1)), _hptr(qΩ._s(2)),
+                                                            _hptr(beta), _hptr(gamma), n))
+        return (_tuple(beta) if _b else None), (_tuple(gamma) if _g else None)
     ctx.enter()
     beta, gamma = _alloc_bg(ctx, lik, n, _b, _g)
-    mu = qf.mu if (qf is not None and lik.kind == HETERO) else None
     check(ctx.lib.aug_expected_potential_precision(ctx.h, C.byref(d), n, _ptr(y), _ptr(mu), _ld(lik, mu),
                                                    _ptr(qΩ._s(0)), _ptr(qΩ._s(1)), _ptr(qΩ._s(2)), _ptr(beta),
                                                    _ptr(gamma), n))
@@ -396,14 +466,28 @@ def expected_auglik_precision(lik, qΩ, y, qf=None, ctx=None):
 
 
 def cavi_step_(qΩ: AuxPosterior, lik, y, qf: Normals, want_elbo: bool = True, ctx: Optional[Context] = None,
-               out=None):
+               out=None, want_beta: bool = True):
     """Fused call pattern of examples/bernoulli/script.jl:29-39: aux_posterior! +
     expected_auglik_potential_and_precision (+ expected_logtilt, aux_kldivergence, expected_aug_loglik).
     Returns (qΩ, β tuple, γ tuple, scalars) with scalars a device tensor of 8 doubles (or None)."""
     ctx = ctx or default_context()
-    y = _check_y(lik, y)
+    y = _check_y(lik, _t(y))
     n = _nobs(lik, y)
     d = lik._desc()
+    if _is_host(y, qf.mu, qf.var, qΩ._s(0) if qΩ is not None else None):
+        # host-buffer path; optional outputs: qΩ=None skips the state, want_beta=False skips β (D2H bytes saved)
+        if out is None:
+            beta = _hempty((lik.nlatent, n)) if want_beta else None
+            gamma = _hempty((lik.nlatent, n))
+        else:
+            beta, gamma = out[0], out[1]
+        hs = _hscal() if want_elbo else None
+        s_ = [qΩ._s(i) if qΩ is not None else None for i in range(3)]
+        check(ctx.lib.aug_cavi_step_host(ctx.h, C.byref(d), n, _hptr(y), _hptr(_f64(qf.mu, "mu")),
+                                         _hptr(_f64(qf.var, "var")), _ld(lik, qf.mu), _hptr(s_[0]), _hptr(s_[1]),
+                                         _hptr(s_[2]), _hptr(beta), _hptr(gamma), n, hs))
+        return (qΩ, _tuple(beta) if beta is not None else None, _tuple(gamma),
+                _scal_tensor(hs) if want_elbo else None)
     ctx.enter()
     if out is None:
         beta, gamma = _alloc_bg(ctx, lik, n)
@@ -419,11 +503,17 @@ def cavi_step_(qΩ: AuxPosterior, lik, y, qf: Normals, want_elbo: bool = True, c
 
 def _elbo_terms(lik, qΩ, y, qf, ctx):
     ctx = ctx or default_context()
-    y = _check_y(lik, y)
+    y = _check_y(lik, _t(y))
     d = lik._desc()
+    if _is_host(y, qf.mu, qf.var, qΩ._s(0)):
+        hs = _hscal()
+        check(ctx.lib.aug_expected_elbo_terms_host(ctx.h, C.byref(d), _nobs(lik, y), _hptr(y),
+                                                   _hptr(_f64(qf.mu, "mu")), _hptr(_f64(qf.var, "var")),
+                                                   _ld(lik, qf.mu), _hptr(qΩ._s(0)), _hptr(qΩ._s(1)),
+                                                   _hptr(qΩ._s(2)), hs))
+        return _scal_tensor(hs)
     ctx.enter()
-    scal = ctx.empty((NSCALARS,))
-    scal.zero_()
+    scal = ctx.empty((NSCALARS,))      # the verb writes all 8 slots (its own + zeros): nothing to clear here
     check(ctx.lib.aug_expected_elbo_terms(ctx.h, C.byref(d), _nobs(lik, y), _ptr(y), _ptr(_f64(qf.mu, "mu")),
                                           _ptr(_f64(qf.var, "var")), _ld(lik, qf.mu), _ptr(qΩ._s(0)),
                                           _ptr(qΩ._s(1)), _ptr(qΩ._s(2)), _ptr(scal)))
@@ -434,6 +524,8 @@ def _elbo_terms(lik, qΩ, y, qf, ctx):
 def _reduce(ctx, scal):
     """sum the scalar block over ranks when a communicator is attached"""
     ctx = ctx or default_context()
+    if not scal.is_cuda:            # host-buffer verbs are rank-local (include/augcuda.h)
+        return scal
     if ctx.fused:                   # exchanged inside the reducing kernel over peer memory
         return scal
     if ctx.comm_ready:
@@ -456,7 +548,7 @@ def aux_kldivergence(lik, qΩ, y, qf=None, ctx=None) -> float:
         n = len(qΩ)
         ctx = ctx or default_context()
         shape = (n, lik.nlatent) if _is_cat(lik) else (n,)
-        z = torch.zeros(shape, dtype=torch.float64, device=ctx.tdev)
+        z = torch.zeros(shape, dtype=torch.float64, device=ctx.tdev if _t(y).is_cuda else "cpu")
         qf = Normals(z, z)
     return float(_reduce(ctx, _elbo_terms(lik, qΩ, y, qf, ctx))[_lib.S_KL].item())
 
@@ -477,12 +569,19 @@ def _store_rng(ctx, rng):
         rng.offset = ctx.offset()
 
 
-def init_aux_variables(*args, ctx: Optional[Context] = None, i0: int = 0):
+def init_aux_variables(*args, ctx: Optional[Context] = None, i0: int = 0, host: bool = False):
     """init_aux_variables([rng,] lik, n) — generic.jl:32-34 and the per-likelihood methods"""
     rng, (lik, n) = (args[0], args[1:]) if isinstance(args[0], AugPhilox) else (None, args)
     ctx = ctx or default_context()
     _apply_rng(ctx, rng)
     shape = (n, lik.nlatent) if _is_cat(lik) else (n,)
+    if host:
+        omega = _hempty(shape)
+        nv = _hempty(shape, torch.int64) if (lik.kind in (POISSON, HETERO) or _is_cat(lik)) else None
+        d = lik._desc()
+        check(ctx.lib.aug_init_aux_variables_host(ctx.h, C.byref(d), n, i0, _hptr(omega), _hptr(nv)))
+        _store_rng(ctx, rng)
+        return AuxSamples(omega, nv)
     ctx.enter()
     omega = ctx.empty(shape)
     nv = ctx.empty(shape, torch.int64) if (lik.kind in (POISSON, HETERO) or _is_cat(lik)) else None
@@ -498,8 +597,14 @@ def aux_sample_(*args, ctx: Optional[Context] = None, i0: int = 0):
     rng, (Ω, lik, y, f) = (args[0], args[1:]) if isinstance(args[0], AugPhilox) else (None, args)
     ctx = ctx or default_context()
     _apply_rng(ctx, rng)
-    y = _check_y(lik, y)
+    y = _check_y(lik, _t(y))
+    f = _t(f)
     d = lik._desc()
+    if _is_host(y, f, Ω.omega, Ω.n):
+        check(ctx.lib.aug_aux_sample_host(ctx.h, C.byref(d), _nobs(lik, y), i0, _hptr(y), _hptr(_f64(f, "f")),
+                                          _ld(lik, f), _hptr(Ω.omega), _hptr(Ω.n)))
+        _store_rng(ctx, rng)
+        return Ω
     ctx.enter()
     check(ctx.lib.aug_aux_sample(ctx.h, C.byref(d), _nobs(lik, y), i0, _ptr(y), _ptr(_f64(f, "f")), _ld(lik, f),
                                  _ptr(Ω.omega), _ptr(Ω.n)))
@@ -512,12 +617,17 @@ def aux_sample(*args, ctx: Optional[Context] = None, i0: int = 0):
     """aux_sample([rng,] lik, y, f) — generic.jl:14-20"""
     rng, (lik, y, f) = (args[0], args[1:]) if isinstance(args[0], AugPhilox) else (None, args)
     ctx = ctx or default_context()
+    y = _t(y)
     n = _nobs(lik, y)
     shape = (n, lik.nlatent) if _is_cat(lik) else (n,)
-    ctx.enter()
-    omega = ctx.empty(shape)
-    nv = ctx.empty(shape, torch.int64) if (lik.kind in (POISSON, HETERO) or _is_cat(lik)) else None
-    ctx.leave()
+    needs_n = lik.kind in (POISSON, HETERO) or _is_cat(lik)
+    if not y.is_cuda:
+        omega, nv = _hempty(shape), (_hempty(shape, torch.int64) if needs_n else None)
+    else:
+        ctx.enter()
+        omega = ctx.empty(shape)
+        nv = ctx.empty(shape, torch.int64) if needs_n else None
+        ctx.leave()
     Ω = AuxSamples(omega, nv)
     return aux_sample_(*(([rng] if rng else []) + [Ω, lik, y, f]), ctx=ctx, i0=i0)
 
@@ -525,14 +635,20 @@ def aux_sample(*args, ctx: Optional[Context] = None, i0: int = 0):
 def auglik_potential_and_precision(lik, Ω: AuxSamples, y, f=None, ctx=None, _b=True, _g=True):
     """auglik_potential_and_precision(lik, Ω, y[, f]) (a20)"""
     ctx = ctx or default_context()
-    y = _check_y(lik, y)
+    y = _check_y(lik, _t(y))
     n = _nobs(lik, y)
     if lik.kind == HETERO and f is None:
         raise TypeError("the heteroscedastic likelihood needs f (heteroscedasticgaussian.jl:48-66)")
     d = lik._desc()
+    ff = _t(f) if lik.kind == HETERO else None
+    if _is_host(y, ff, Ω.omega, Ω.n):
+        beta = _hempty((lik.nlatent, n)) if _b else None
+        gamma = _hempty((lik.nlatent, n)) if _g else None
+        check(ctx.lib.aug_potential_precision_host(ctx.h, C.byref(d), n, _hptr(y), _hptr(ff), _ld(lik, ff),
+                                                   _hptr(Ω.omega), _hptr(Ω.n), _hptr(beta), _hptr(gamma), n))
+        return (_tuple(beta) if _b else None), (_tuple(gamma) if _g else None)
     ctx.enter()
     beta, gamma = _alloc_bg(ctx, lik, n, _b, _g)
-    ff = f if lik.kind == HETERO else None
     check(ctx.lib.aug_potential_precision(ctx.h, C.byref(d), n, _ptr(y), _ptr(ff), _ld(lik, ff), _ptr(Ω.omega),
                                           _ptr(Ω.n), _ptr(beta), _ptr(gamma), n))
     ctx.leave()
@@ -549,11 +665,16 @@ def auglik_precision(lik, Ω, y, f=None, ctx=None):
 
 def _sampled_terms(lik, Ω, y, f, with_prior, ctx):
     ctx = ctx or default_context()
-    y = _check_y(lik, y)
+    y = _check_y(lik, _t(y))
+    f = _t(f)
     d = lik._desc()
+    if _is_host(y, f, Ω.omega, Ω.n):
+        hs = _hscal()
+        check(ctx.lib.aug_sampled_loglik_terms_host(ctx.h, C.byref(d), _nobs(lik, y), _hptr(y), _hptr(_f64(f, "f")),
+                                                    _ld(lik, f), _hptr(Ω.omega), _hptr(Ω.n), int(with_prior), hs))
+        return _scal_tensor(hs)
     ctx.enter()
-    scal = ctx.empty((NSCALARS,))
-    scal.zero_()
+    scal = ctx.empty((NSCALARS,))      # the verb writes all 8 slots (its own + zeros): nothing to clear here
     check(ctx.lib.aug_sampled_loglik_terms(ctx.h, C.byref(d), _nobs(lik, y), _ptr(y), _ptr(_f64(f, "f")),
                                            _ld(lik, f), _ptr(Ω.omega), _ptr(Ω.n), int(with_prior), _ptr(scal)))
     ctx.leave()
@@ -591,7 +712,7 @@ class AuxPrior:
         ctx = ctx or default_context()
         n = len(self)
         shape = (n, self.lik.nlatent) if _is_cat(self.lik) else (n,)
-        f0 = torch.zeros(shape, dtype=torch.float64, device=ctx.tdev)
+        f0 = torch.zeros(shape, dtype=torch.float64, device=ctx.tdev if Ω.omega.is_cuda else "cpu")
         return float(_sampled_terms(self.lik, Ω, self.y, f0, True, ctx)[_lib.S_LOGPRIOR].item())
 
 
@@ -867,8 +988,6 @@ def sparse_cavi_sweep_(qΩ: Optional[AuxPosterior], lik, y, kappa, mvec, B, kdia
     ctx.enter()
     Pr = ctx.empty((m * m + m,))
     scal = ctx.empty((NSCALARS,)) if want_elbo else None
-    if scal is not None:
-        scal.zero_()
     mu = ctx.empty((n,)) if want_marginals else None
     var = ctx.empty((n,)) if want_marginals else None
     beta = ctx.empty((n,)) if want_potentials else None

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_cavi_kernel(const CatArgs a) {
             a.scalars[AUG_S_KL] = out[1];
             a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
             a.scalars[AUG_S_FLAGS] = out[2];
+            scal_zero_except(a.scalars, 0x47u);
             if (out[2] > 0.0) atomicOr(a.dflag, 1u);
         }
     } else if (acc[2] > 0.0) {
@@ -449,6 +450,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_tma_kernel(const CatTmaArgs 
             a.scalars[AUG_S_KL] = out[1];
             a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
             a.scalars[AUG_S_FLAGS] = out[2];
+            scal_zero_except(a.scalars, 0x47u);
             if (out[2] > 0.0) atomicOr(a.dflag, 1u);
         }
     } else if (acc[2] > 0.0) {
@@ -721,6 +723,7 @@ __global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowA
             a.scalars[AUG_S_KL] = out[1];
             a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
             a.scalars[AUG_S_FLAGS] = out[2];
+            scal_zero_except(a.scalars, 0x47u);
             if (out[2] > 0.0) atomicOr(a.dflag, 1u);
         }
     } else if (acc[2] > 0.0) {

@@ -116,6 +116,7 @@ __device__ __forceinline__ void write_scalars(const CaviArgs& a, const double (&
     a.scalars[AUG_S_EXPECTED_LOGTILT] = e;
     a.scalars[AUG_S_KL] = k;
     a.scalars[AUG_S_EXPECTED_AUGLL] = e + k;   // generic.jl:52-54 ("+")
+    scal_zero_except(a.scalars, 0x07u);
 }
 
 template <int KIND, bool FROM_STATE, bool ELBO, bool VEC>
@@ -527,7 +528,7 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
     if (n < 0) return AUG_ERR_BAD_ARG;
     if (n == 0) {
         if (scalars) {
-            AUG_CUDA(cudaMemsetAsync(scalars, 0, 3 * sizeof(double), ctx->stream));
+            AUG_CUDA(cudaMemsetAsync(scalars, 0, AUG_NSCALARS * sizeof(double), ctx->stream));
             if (aug_xch_for(ctx)) return aug_xch_zero_contribution(ctx, scalars, AUG_S_EXPECTED_LOGTILT, 2);
         }
         return AUG_OK;

@@ -44,7 +44,7 @@ __device__ __forceinline__ bool fast_ok(const Obs& o) {
             // approx_expected_logistic evaluates exp_((-m-c)/2): s2 <= 2.4e5 keeps |m|, c <= 490
             if (KIND == AUG_POISSON) ok = ok && s2 <= 2.4e5;
         }
-        if (ELBO && KIND != AUG_BERNOULLI) ok = ok && o.y < (double)AUG_TABLE_N;
+        if (ELBO && KIND != AUG_BERNOULLI) ok = ok && o.y >= 0.0 && o.y < (double)AUG_TABLE_N;   // y < 0: DomainError in the reference -> NaN on the SAFE path
         if (KIND == AUG_POISSON && FROM_STATE) ok = ok && o.s1 >= 0.0 && o.s1 <= 1e290;
     } else if (KIND == AUG_LAPLACE || KIND == AUG_STUDENTT) {
         const double d = o.m - o.y;
@@ -88,6 +88,7 @@ __device__ __forceinline__ void eval(const LikConst& L, Obs& o) {
         if (ELBO) {
             double lc;                                          // negbin_logconst :51-52
             if (!SAFE) lc = __ldg(&L.table[(int)fmin(fmax(o.y, 0.0), (double)(AUG_TABLE_N - 1))]);
+            else if (o.y < 0.0) lc = __longlong_as_double(0x7ff8000000000000ll);   // loggamma / binomial of a negative count
             else if (o.y < (double)AUG_TABLE_N) lc = __ldg(&L.table[(int)o.y]);
             else lc = lgamma(o.y + r) - lgamma(o.y + 1.0) - L.c0;
             o.elt = lc - (o.y + r) * LN2 + 0.5 * fma(o.m, o.y - r, -s2m * th);   // :62-64

@@ -222,6 +222,14 @@ __device__ __forceinline__ void xch_allreduce(AugXchDev* __restrict__ x, double 
     for (int k = 0; k < NV; ++k) v[k] = tot[k];
 }
 
+// Every scalar-producing verb owns the WHOLE 8-slot block of its call: the finaliser writes the verb's slots and zeroes
+// the rest, so a caller never has to clear the block (and an 8-slot all-reduce never sums stale values).
+__device__ __forceinline__ void scal_zero_except(double* __restrict__ s, unsigned keep_mask) {
+#pragma unroll
+    for (int k = 0; k < AUG_NSCALARS; ++k)
+        if (!((keep_mask >> k) & 1u)) s[k] = 0.0;
+}
+
 // 128-bit streaming loads/stores (read-once / write-once data: keep it out of L1)
 __device__ __forceinline__ double2 ld_stream2(const double* p) {
     double2 r;

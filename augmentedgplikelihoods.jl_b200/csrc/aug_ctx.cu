@@ -582,10 +582,11 @@ int32_t aug_comm_p2p_export(aug_ctx* c, char handle[64], void** local_ptr) {
     if (!c) return AUG_ERR_NOT_INIT;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     AUG_CUDA(cudaSetDevice(c->device));
-    if (!c->mailbox) {
-        AUG_CUDA(cudaMalloc(&c->mailbox, sizeof(unsigned long long) * AUG_XCH_TOTAL_WORDS));
-        AUG_CUDA(cudaMemset(c->mailbox, 0, sizeof(unsigned long long) * AUG_XCH_TOTAL_WORDS));
-    }
+    if (!c->mailbox) AUG_CUDA(cudaMalloc(&c->mailbox, sizeof(unsigned long long) * AUG_XCH_TOTAL_WORDS));
+    // an export opens a SESSION: every rank exports before any rank attaches and the device epoch restarts at 0 in
+    // p2p_finish_attach, so flags a previous session left behind (epoch 1, 2, ...) must not survive into this one
+    AUG_CUDA(cudaStreamSynchronize(c->stream));
+    AUG_CUDA(cudaMemset(c->mailbox, 0, sizeof(unsigned long long) * AUG_XCH_TOTAL_WORDS));
     if (handle) {
         cudaIpcMemHandle_t h;
         AUG_CUDA(cudaIpcGetMemHandle(&h, c->mailbox));
@@ -596,6 +597,7 @@ int32_t aug_comm_p2p_export(aug_ctx* c, char handle[64], void** local_ptr) {
 }
 
 static void p2p_close(aug_ctx* c) {
+    cudaStreamSynchronize(c->stream);   // no exchanging kernel may still be polling / pushing when the maps go away
     for (int r = 0; r < AUG_MAX_RANKS; ++r) {
         if (c->peer_ipc[r] && c->peer_box[r]) cudaIpcCloseMemHandle(c->peer_box[r]);
         c->peer_box[r] = nullptr;

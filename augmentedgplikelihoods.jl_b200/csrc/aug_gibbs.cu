@@ -389,6 +389,21 @@ int32_t aug_aux_sample_dev(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i0
     }
 }
 
+// device-pointer implementation of init_aux_variables with an explicit RNG tick (shared with the host-buffer pipeline)
+int32_t aug_init_aux_variables_dev(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i0, double* omega,
+                                   int64_t* nvar, uint64_t off) {
+    if (n == 0) return AUG_OK;
+    const bool needs_n = lik->kind == AUG_POISSON || lik->kind == AUG_HETERO || is_cat(lik->kind);
+    if (needs_n && !nvar) return AUG_ERR_BAD_ARG;
+    const int64_t per = is_cat(lik->kind) ? lik->nlatent : 1;
+    const int64_t m = n * per;
+    const int grid = aug_grid_for(c, (const void*)init_aux_kernel, m, AUG_BLOCK);
+    init_aux_kernel<<<grid, AUG_BLOCK, 0, c->stream>>>(lik->kind, m, i0 * per, c->seed, off, omega,
+                                                        needs_n ? nvar : nullptr, c->pgtab);
+    c->launches++;
+    return (int32_t)cudaGetLastError();
+}
+
 extern "C" {
 
 int32_t aug_aux_sample(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i0, const void* y, const double* f,
@@ -408,16 +423,7 @@ int32_t aug_init_aux_variables(aug_ctx* c, const aug_lik* lik, int64_t n, int64_
     if (lik->kind < 0 || lik->kind >= AUG_NKINDS) return AUG_ERR_BAD_KIND;
     AUG_CUDA(cudaSetDevice(c->device));
     const uint64_t off = c->offset++;
-    if (n == 0) return AUG_OK;
-    const bool needs_n = lik->kind == AUG_POISSON || lik->kind == AUG_HETERO || is_cat(lik->kind);
-    if (needs_n && !nvar) return AUG_ERR_BAD_ARG;
-    const int64_t per = is_cat(lik->kind) ? lik->nlatent : 1;
-    const int64_t m = n * per;
-    const int grid = aug_grid_for(c, (const void*)init_aux_kernel, m, AUG_BLOCK);
-    init_aux_kernel<<<grid, AUG_BLOCK, 0, c->stream>>>(lik->kind, m, i0 * per, c->seed, off, omega,
-                                                        needs_n ? nvar : nullptr, c->pgtab);
-    c->launches++;
-    return (int32_t)cudaGetLastError();
+    return aug_init_aux_variables_dev(c, lik, n, i0, omega, nvar, off);
 }
 
 static int32_t pg_rand_common(aug_ctx* c, int64_t n, int64_t i0, const double* b, const double* cc, double bs,

@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(AUG_BLOCK) loglik_kernel(const LLArgs a) {
         } else if (KIND == AUG_NEGBIN) {                      // negativebinomial.jl:54-57,73
             const double y = (double)reinterpret_cast<const int64_t*>(a.y)[i], r = a.L.p0;
             double lc;
-            if (y < (double)AUG_TABLE_N) lc = __ldg(&a.L.table[(int)y]);
+            if (y < 0.0) lc = __longlong_as_double(0x7ff8000000000000ll);
+            else if (y < (double)AUG_TABLE_N) lc = __ldg(&a.L.table[(int)y]);
             else lc = lgamma(y + r) - lgamma(y + 1.0) - a.L.c0;
             lt = lc - (y + r) * LN2 + 0.5 * (f * (y - r) - f * f * w);
             if (a.with_prior) lp = pg_logpdf_dev(r + y, 0.0, w);
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) loglik_kernel(const LLArgs a) {
         a.scalars[AUG_S_LOGTILT] = out[0];
         a.scalars[AUG_S_LOGPRIOR] = out[1];
         a.scalars[AUG_S_AUGLL] = out[0] + out[1];             // generic.jl:48-50
+        scal_zero_except(a.scalars, 0x38u);
     }
 }
 
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_loglik_kernel(const CatLLArgs a
         a.scalars[AUG_S_LOGTILT] = out[0];
         a.scalars[AUG_S_LOGPRIOR] = out[1];
         a.scalars[AUG_S_AUGLL] = out[0] + out[1];
+        scal_zero_except(a.scalars, 0x38u);
     }
 }
 
@@ -243,7 +246,7 @@ int32_t aug_sampled_loglik_terms(aug_ctx* c, const aug_lik* lik, int64_t n, cons
     if (!lik || n < 0 || !y || !f || !omega || !scalars) return AUG_ERR_BAD_ARG;
     AUG_CUDA(cudaSetDevice(c->device));
     if (n == 0) {
-        AUG_CUDA(cudaMemsetAsync(scalars + AUG_S_LOGTILT, 0, 3 * sizeof(double), c->stream));
+        AUG_CUDA(cudaMemsetAsync(scalars, 0, AUG_NSCALARS * sizeof(double), c->stream));
         if (aug_xch_for(c)) return aug_xch_zero_contribution(c, scalars, AUG_S_LOGTILT, 2);
         return AUG_OK;
     }

@@ -109,6 +109,7 @@ __device__ __forceinline__ double logistic(double x) {
 
 // log y! / negbin log-constant with a table for small integer y (device lgamma beyond it)
 __device__ __forceinline__ double lfact(double y, const double* __restrict__ table) {
+    if (y < 0.0) return __longlong_as_double(0x7ff8000000000000ll);   // logfactorial(y < 0): DomainError in the reference
     if (table != nullptr && y < (double)AUG_TABLE_N) return __ldg(&table[(int)y]);
     return lgamma(y + 1.0);
 }

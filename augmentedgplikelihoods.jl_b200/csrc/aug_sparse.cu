@@ -608,6 +608,7 @@ __global__ void __launch_bounds__(256) sparse_finalize_kernel(const double* __re
             scalars[AUG_S_EXPECTED_LOGTILT] = t0;
             scalars[AUG_S_KL] = t1;
             scalars[AUG_S_EXPECTED_AUGLL] = t0 + t1;          // generic.jl:52-54 ("+")
+            scal_zero_except(scalars, 0x07u);
         }
         return;
     }
@@ -707,6 +708,7 @@ __global__ void __launch_bounds__(256) sparse_finalize_xch_kernel(const double* 
             scalars[AUG_S_EXPECTED_LOGTILT] = v[0];
             scalars[AUG_S_KL] = v[1];
             scalars[AUG_S_EXPECTED_AUGLL] = v[0] + v[1];      // generic.jl:52-54 ("+")
+            scal_zero_except(scalars, 0x07u);
         }
     }
     __syncthreads();

@@ -3,7 +3,9 @@
 #
 # STATUS: written to the C ABI of include/augcuda.h, NOT executed: there is no Julia in the build image
 # (INTEGRATION.md).  Everything the tests and bench.py exercise goes through the same ABI from Python
-# (augmentedgplikelihoods.jl_b200/api.py), function for function.
+# (augmentedgplikelihoods.jl_b200/api.py), function for function.  What CAN be checked without Julia is checked
+# statically by tests/test_abi_cpu.py: every ccall names a declared symbol and its argument-type tuple agrees,
+# type class by type class, with the C prototype in include/augcuda.h and with the ctypes table.
 #
 # Design: Julia multiple dispatch is the reference's plugin mechanism (src/AugmentedGPLikelihoods.jl:18-30),
 # so the "plugin" is a set of METHODS of the reference's generic functions, specialised on a device array
@@ -16,7 +18,7 @@ using AugmentedGPLikelihoods: AbstractLikelihood, BijectiveSimplexLink, Logistic
     ScaledLogistic, InvScaledLogistic, LaplaceLikelihood, StudentTLikelihood
 using GPLikelihoods: BernoulliLikelihood, PoissonLikelihood, NegativeBinomialLikelihood, NBParamFailure,
     HeteroscedasticGaussianLikelihood, CategoricalLikelihood, LogisticLink
-using Distributions: Normal
+using Distributions: Normal, mean, var
 using MeasureTheory: For
 using TupleVectors: TupleVector
 using Random: AbstractRNG
@@ -66,7 +68,15 @@ mutable struct AugDeviceVector{T} <: AbstractVector{T}
     ptr::Ptr{T}
     len::Int
     owner::Bool
+    parent::Any      # views keep the owning vector reachable (its finalizer frees the allocation)
 end
+AugDeviceVector{T}(ptr::Ptr{T}, len::Integer, owner::Bool) where {T} = AugDeviceVector{T}(ptr, len, owner, nothing)
+"non-owning view of `n` elements of `v` starting at element offset `off`; keeps `v` alive"
+subvector(v::AugDeviceVector{T}, off::Integer, n::Integer) where {T} =
+    AugDeviceVector{T}(v.ptr + off * sizeof(T), n, false, v)
+"one vector per latent out of a latent-major [nl][n] block (the tuple the reference's verbs return)"
+split_latents(v::AugDeviceVector, n::Integer, nl::Integer) = ntuple(j -> subvector(v, (j - 1) * n, n), nl)
+split_latents(v::Vector, n::Integer, nl::Integer) = ntuple(j -> view(v, (j - 1) * n + 1:j * n), nl)
 Base.size(v::AugDeviceVector) = (v.len,)
 Base.getindex(::AugDeviceVector, ::Int) = error("scalar indexing of a device vector: copy it with Array(v)")
 Base.pointer(v::AugDeviceVector) = v.ptr
@@ -74,7 +84,7 @@ Base.pointer(v::AugDeviceVector) = v.ptr
 function AugDeviceVector{T}(::UndefInitializer, n::Integer) where {T}
     p = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:aug_malloc, lib), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Csize_t), ctx().h, p, n * sizeof(T)))
-    v = AugDeviceVector{T}(Ptr{T}(p[]), n, true)
+    v = AugDeviceVector{T}(Ptr{T}(p[]), n, true, nothing)
     finalizer(x -> x.owner && ccall((:aug_free, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx().h, x.ptr), v)
     return v
 end
@@ -97,6 +107,7 @@ struct DeviceNormals <: AbstractVector{Normal{Float64}}
     σ²::AugDeviceVector{Float64}
     ld::Int                       # leading dimension for the 2-latent heteroscedastic layout, else 0
 end
+DeviceNormals(μ::AugDeviceVector{Float64}, σ²::AugDeviceVector{Float64}) = DeviceNormals(μ, σ², 0)
 Base.size(q::DeviceNormals) = (q.ld == 0 ? q.μ.len : q.ld,)
 
 "rng argument: counter-based Philox4x32-10 stream (seed, offset); every sampling verb consumes one tick."
@@ -167,8 +178,7 @@ function AGPL.expected_auglik_potential_and_precision(lik::AbstractLikelihood, q
                     ctx().h, d, n, y.ptr, qf === nothing ? C_NULL : qf.μ.ptr, qf === nothing ? 0 : qf.ld,
                     ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ)), β.ptr, γ.ptr, n))
     end
-    split(v) = ntuple(j -> DV{Float64}(v.ptr + (j - 1) * n * 8, n, false), nl)   # one vector per latent
-    return split(β), split(γ)
+    return split_latents(β, n, nl), split_latents(γ, n, nl)
 end
 AGPL.expected_auglik_potential(lik::AbstractLikelihood, qΩ::For, y::DV, qf=nothing) =
     first(AGPL.expected_auglik_potential_and_precision(lik, qΩ, y, qf))
@@ -206,8 +216,7 @@ function cavi_step!(qΩ::For, lik::AbstractLikelihood, y::DV, qf::DeviceNormals)
                     ctx().h, d, n, y.ptr, qf.μ.ptr, qf.σ².ptr, qf.ld, ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ)), β.ptr, γ.ptr, n,
                     sc.ptr))
     end
-    split(v) = ntuple(j -> DV{Float64}(v.ptr + (j - 1) * n * 8, n, false), nl)
-    return qΩ, split(β), split(γ), Array(sc)      # sc[S_ELT], sc[S_KL], sc[S_EAUGLL]
+    return qΩ, split_latents(β, n, nl), split_latents(γ, n, nl), Array(sc)      # sc[S_ELT], sc[S_KL], sc[S_EAUGLL]
 end
 
 # ---------------------------------------------------------------- sampling verbs
@@ -254,8 +263,7 @@ function AGPL.auglik_potential_and_precision(lik::AbstractLikelihood, Ω::TupleV
                     ctx().h, d, n, y.ptr, f === nothing ? C_NULL : f.ptr, f === nothing ? 0 : length(f) ÷ 2,
                     Ω.ω.ptr, ptr(nv), β.ptr, γ.ptr, n))
     end
-    split(v) = ntuple(j -> DV{Float64}(v.ptr + (j - 1) * n * 8, n, false), nl)
-    return split(β), split(γ)
+    return split_latents(β, n, nl), split_latents(γ, n, nl)
 end
 
 # logtilt / aug_loglik                                -> aug_sampled_loglik_terms         (a21-a24)
@@ -274,6 +282,134 @@ function sampled_terms(lik, Ω::TupleVector, y::DV, f::DV, with_prior::Bool)
 end
 AGPL.logtilt(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::DV) = sampled_terms(lik, Ω, y, f, false)[S_LOGTILT]
 AGPL.aug_loglik(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::DV) = sampled_terms(lik, Ω, y, f, true)[S_AUGLL]
+
+# ---------------------------------------------------------------- host `Vector` methods (the reference's own argument types)
+# src/generic.jl:1-88 dispatches every verb on plain host vectors.  These methods keep those signatures — y::Vector,
+# qf::AbstractVector{<:Normal}, f::Vector, Ω / qΩ with Vector fields — and bind to the *_host entry points: the
+# library stages chunks through the GPU (H2D, kernel, D2H overlapped) and the results come back in host vectors.
+# The only host-side work is the AoS → SoA split of qf (mean.(qf), var.(qf)): the ABI takes struct-of-arrays.
+const HV = Vector
+hptr(::Nothing) = C_NULL
+hptr(v::Vector) = Ptr{Cvoid}(pointer(v))
+moments(qf::AbstractVector{<:Normal}) = (convert(Vector{Float64}, mean.(qf)), convert(Vector{Float64}, var.(qf)))
+# two-latent heteroscedastic qfg = (qf, qg) (heteroscedasticgaussian.jl:38): latent-major [2][n]
+moments(qfg::Tuple) = (vcat((mean.(q) for q in qfg)...), vcat((var.(q) for q in qfg)...))
+ldof(lik, n) = lik isa HeteroscedasticGaussianLikelihood ? n : 0
+
+function AGPL.aux_posterior!(qΩ::For, lik::AbstractLikelihood, y::HV, qf)
+    φ = state(qΩ); μ, σ² = moments(qf); n = length(qΩ)
+    withdesc(lik) do d
+        GC.@preserve y μ σ² φ check(ccall((:aug_aux_posterior_host, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64,
+                     Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    ctx().h, d, n, hptr(y), μ, σ², ldof(lik, n), hptr(s0(φ)), hptr(s1(φ)), hptr(s2(φ))))
+    end
+    return qΩ
+end
+
+function AGPL.expected_auglik_potential_and_precision(lik::AbstractLikelihood, qΩ::For, y::HV, qf=nothing)
+    n, nl = length(qΩ), AGPL.nlatent(lik)
+    β, γ = Vector{Float64}(undef, n * nl), Vector{Float64}(undef, n * nl)
+    φ = state(qΩ)
+    μ = qf === nothing ? nothing : first(moments(qf))
+    withdesc(lik) do d
+        GC.@preserve y μ φ β γ check(ccall((:aug_expected_potential_precision_host, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Cvoid}, Ptr{Cvoid},
+                     Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64),
+                    ctx().h, d, n, hptr(y), μ === nothing ? C_NULL : pointer(μ), ldof(lik, n),
+                    hptr(s0(φ)), hptr(s1(φ)), hptr(s2(φ)), β, γ, n))
+    end
+    return split_latents(β, n, nl), split_latents(γ, n, nl)
+end
+
+function elbo_terms(lik, qΩ::For, y::HV, qf)
+    sc = zeros(Float64, 8); φ = state(qΩ); μ, σ² = moments(qf); n = length(qΩ)
+    withdesc(lik) do d
+        GC.@preserve y μ σ² φ check(ccall((:aug_expected_elbo_terms_host, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Cvoid},
+                     Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
+                    ctx().h, d, n, hptr(y), μ, σ², ldof(lik, n), hptr(s0(φ)), hptr(s1(φ)), hptr(s2(φ)), sc))
+    end
+    return sc
+end
+AGPL.expected_logtilt(lik::AbstractLikelihood, qΩ::For, y::HV, qf) = elbo_terms(lik, qΩ, y, qf)[S_ELT]
+AGPL.expected_aug_loglik(lik::AbstractLikelihood, qΩ::For, y::HV, qf) = elbo_terms(lik, qΩ, y, qf)[S_EAUGLL]
+
+"fused CAVI iteration on host vectors; `want_state = false` / `want_β = false` skip those outputs (and their D2H bytes)"
+function cavi_step!(qΩ::For, lik::AbstractLikelihood, y::HV, qf; want_state::Bool=true, want_β::Bool=true)
+    n, nl = length(qΩ), AGPL.nlatent(lik)
+    β = want_β ? Vector{Float64}(undef, n * nl) : nothing
+    γ = Vector{Float64}(undef, n * nl)
+    sc = zeros(Float64, 8); φ = state(qΩ); μ, σ² = moments(qf)
+    st = want_state ? (hptr(s0(φ)), hptr(s1(φ)), hptr(s2(φ))) : (C_NULL, C_NULL, C_NULL)
+    withdesc(lik) do d
+        GC.@preserve y μ σ² φ β γ check(ccall((:aug_cavi_step_host, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Cvoid}, Ptr{Cvoid},
+                     Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                    ctx().h, d, n, hptr(y), μ, σ², ldof(lik, n), st[1], st[2], st[3],
+                    β === nothing ? C_NULL : pointer(β), γ, n, sc))
+    end
+    return qΩ, (β === nothing ? nothing : split_latents(β, n, nl)), split_latents(γ, n, nl), sc
+end
+
+function AGPL.aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::AbstractLikelihood, y::HV, f::HV; i0::Integer=0)
+    seed!(rng)
+    nv = hasproperty(Ω, :n) ? Ω.n : nothing
+    n = lik isa CategoricalLikelihood ? length(Ω.ω) ÷ AGPL.nlatent(lik) : length(Ω.ω)
+    withdesc(lik) do d
+        GC.@preserve y f Ω check(ccall((:aug_aux_sample_host, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}),
+                    ctx().h, d, n, i0, hptr(y), f, ldof(lik, n), Ω.ω, nv === nothing ? C_NULL : pointer(nv)))
+    end
+    sync_offset!(rng)
+    return Ω
+end
+
+function init_aux_variables_host(rng::AugPhilox, lik::AbstractLikelihood, n::Int; i0::Integer=0)
+    seed!(rng)
+    m = lik isa CategoricalLikelihood ? n * AGPL.nlatent(lik) : n
+    ω = Vector{Float64}(undef, m)
+    needs_n = lik isa Union{PoissonLikelihood,HeteroscedasticGaussianLikelihood,CategoricalLikelihood}
+    nv = needs_n ? Vector{Int64}(undef, m) : nothing
+    withdesc(lik) do d
+        GC.@preserve ω nv check(ccall((:aug_init_aux_variables_host, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Int64, Ptr{Float64}, Ptr{Int64}),
+                    ctx().h, d, n, i0, ω, nv === nothing ? C_NULL : pointer(nv)))
+    end
+    sync_offset!(rng)
+    return needs_n ? TupleVector((; ω, n=nv)) : TupleVector((; ω))
+end
+
+function AGPL.auglik_potential_and_precision(lik::AbstractLikelihood, Ω::TupleVector, y::HV, f::Union{Nothing,HV}=nothing)
+    nl = AGPL.nlatent(lik)
+    n = length(Ω.ω) ÷ (lik isa CategoricalLikelihood ? nl : 1)
+    β, γ = Vector{Float64}(undef, n * nl), Vector{Float64}(undef, n * nl)
+    nv = hasproperty(Ω, :n) ? Ω.n : nothing
+    withdesc(lik) do d
+        GC.@preserve y f Ω β γ check(ccall((:aug_potential_precision_host, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64},
+                     Ptr{Float64}, Ptr{Float64}, Int64),
+                    ctx().h, d, n, hptr(y), f === nothing ? C_NULL : pointer(f), ldof(lik, n),
+                    Ω.ω, nv === nothing ? C_NULL : pointer(nv), β, γ, n))
+    end
+    return split_latents(β, n, nl), split_latents(γ, n, nl)
+end
+
+function sampled_terms(lik, Ω::TupleVector, y::HV, f::HV, with_prior::Bool)
+    sc = zeros(Float64, 8)
+    nv = hasproperty(Ω, :n) ? Ω.n : nothing
+    n = lik isa CategoricalLikelihood ? length(Ω.ω) ÷ AGPL.nlatent(lik) : length(Ω.ω)
+    withdesc(lik) do d
+        GC.@preserve y f Ω check(ccall((:aug_sampled_loglik_terms_host, lib), Int32,
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}, Int32,
+                     Ptr{Float64}),
+                    ctx().h, d, n, hptr(y), f, ldof(lik, n), Ω.ω, nv === nothing ? C_NULL : pointer(nv),
+                    with_prior, sc))
+    end
+    return sc
+end
+AGPL.logtilt(lik::AbstractLikelihood, Ω::TupleVector, y::HV, f::HV) = sampled_terms(lik, Ω, y, f, false)[S_LOGTILT]
+AGPL.aug_loglik(lik::AbstractLikelihood, Ω::TupleVector, y::HV, f::HV) = sampled_terms(lik, Ω, y, f, true)[S_AUGLL]
 
 # ---- multi-GPU (one Julia process per GPU, e.g. Distributed / MPI.jl) ------------------------------------------
 # Peer-memory mailbox: the all-reduce of the 64-byte scalar block runs INSIDE the reducing kernels (include/augcuda.h).

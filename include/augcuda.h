@@ -92,7 +92,8 @@ typedef struct aug_lik {
     const double* logtheta;
 } aug_lik;
 
-/* Slots of the device scalar block written by the reducing verbs */
+/* Slots of the device scalar block written by the reducing verbs.  A verb owns the WHOLE block of its call: it
+ * writes its own slots and zeroes the others, so the caller never has to clear it. */
 enum aug_scalar_slot {
     AUG_S_EXPECTED_LOGTILT = 0, /* api.jl:219-223 and per-likelihood methods */
     AUG_S_KL               = 1, /* generic.jl:56-62, laplace.jl:98-104 */
@@ -345,20 +346,57 @@ int32_t aug_comm_get_fused(aug_ctx* ctx, int32_t* on);
 /* in-place sum over ranks of count <= 7 device doubles through the mailbox (one 32-thread kernel, no NCCL) */
 int32_t aug_allreduce_scalars_p2p(aug_ctx* ctx, double* dev, int32_t count);
 
-/* ---- host-buffer plugin call (end-to-end path) --------------------------- */
-/* Same as aug_cavi_step but every data pointer is a HOST buffer (pinned for
- * full speed); the library stages chunks through device memory, overlapping
- * H2D, kernel and D2H on internal streams, and returns after the results and
- * scalars_host[AUG_NSCALARS] are on the host. */
+/* ---- host-buffer plugin calls (end-to-end path) ------------------------------
+ * The reference's verbs take plain host `Vector`s (src/generic.jl:1-88); these are the entry points a method
+ * specialised on `Vector` arguments binds to.  Same arguments as the device verbs above, but EVERY data pointer
+ * is a HOST buffer (pinned for full speed; pageable works) and scalars come back in a host block of
+ * AUG_NSCALARS doubles.  The library stages chunks of the observation axis (2^22 elements) through device
+ * memory, overlapping H2D, kernel and D2H on internal streams, and returns when the outputs are on the host.
+ * The arithmetic is done by the same kernels as the device verbs: arrays are bit-identical to theirs, samples are
+ * bit-identical for the same (seed, offset, i0), scalars are the per-chunk sums added in chunk order.
+ * Optional outputs (NULL = not computed / not copied back): s0, s1, s2, beta, gamma, scalars_host — e.g. a
+ * Bernoulli caller that already holds beta = sign(y - 1/2)/2 (bernoulli.jl:28) passes beta = NULL and saves
+ * 8 B/observation of D2H.  In fused multi-GPU mode these calls stay rank-local (no in-kernel exchange). */
+
+/* init_aux_posterior(T, lik, n): zero-fills host arrays (bernoulli.jl:7-11 ... categorical.jl:59-70) */
+int32_t aug_init_aux_posterior_host(aug_ctx* ctx, const aug_lik* lik, int64_t n, void* s0, void* s1, void* s2);
+/* aux_posterior!(qΩ, lik, y, qf) — see aug_aux_posterior */
+int32_t aug_aux_posterior_host(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                               const void* y, const double* mu, const double* var, int64_t ld,
+                               void* s0, void* s1, void* s2);
+/* expected_auglik_potential_and_precision(lik, qΩ, y[, qf]) — see aug_expected_potential_precision */
+int32_t aug_expected_potential_precision_host(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                                              const void* y, const double* mu, int64_t ld,
+                                              const void* s0, const void* s1, const void* s2,
+                                              double* beta, double* gamma, int64_t ldo);
+/* fused CAVI step — see aug_cavi_step (examples/bernoulli/script.jl:29-39) */
 int32_t aug_cavi_step_host(aug_ctx* ctx, const aug_lik* lik, int64_t n,
                            const void* y, const double* mu, const double* var, int64_t ld,
                            void* s0, void* s1, void* s2,
                            double* beta, double* gamma, int64_t ldo,
                            double* scalars_host);
-/* Same for aux_sample! */
+/* expected_logtilt / aux_kldivergence / expected_aug_loglik — see aug_expected_elbo_terms */
+int32_t aug_expected_elbo_terms_host(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                                     const void* y, const double* mu, const double* var, int64_t ld,
+                                     const void* s0, const void* s1, const void* s2,
+                                     double* scalars_host);
+/* init_aux_variables(rng, lik, n) — see aug_init_aux_variables */
+int32_t aug_init_aux_variables_host(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0,
+                                    double* omega, int64_t* nvar);
+/* aux_sample!(rng, Ω, lik, y, f) — see aug_aux_sample (generic.jl:1-12) */
 int32_t aug_aux_sample_host(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0,
                             const void* y, const double* f, int64_t ld,
                             double* omega, int64_t* nvar);
+/* auglik_potential_and_precision(lik, Ω, y[, f]) — see aug_potential_precision */
+int32_t aug_potential_precision_host(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                                     const void* y, const double* f, int64_t ld,
+                                     const double* omega, const int64_t* nvar,
+                                     double* beta, double* gamma, int64_t ldo);
+/* logtilt / logdensity(aux_prior) / aug_loglik — see aug_sampled_loglik_terms */
+int32_t aug_sampled_loglik_terms_host(aug_ctx* ctx, const aug_lik* lik, int64_t n,
+                                      const void* y, const double* f, int64_t ld,
+                                      const double* omega, const int64_t* nvar,
+                                      int32_t with_prior, double* scalars_host);
 
 #ifdef __cplusplus
 }

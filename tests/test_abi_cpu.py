@@ -17,6 +17,83 @@ def header_symbols():
     return sorted(set(re.findall(r"\b(aug_[a-z0-9_]+)\s*\(", src)))
 
 
+def header_prototypes():
+    """name -> list of C argument-type classes parsed from include/augcuda.h (ptr / i32 / i64 / u64 / size / f64)"""
+    src = open(os.path.join(ROOT, "include", "augcuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int32_t|const char\s*\*)\s+(aug_[a-z0-9_]+)\s*\(([^;{]*)\)\s*;", src):
+        name, args = m.group(1), " ".join(m.group(2).split())
+        classes = []
+        if args not in ("", "void"):
+            for a in args.split(","):
+                if "*" in a or "[" in a:
+                    classes.append("ptr")
+                elif "uint64_t" in a:
+                    classes.append("u64")
+                elif "int64_t" in a:
+                    classes.append("i64")
+                elif "int32_t" in a:
+                    classes.append("i32")
+                elif "size_t" in a:
+                    classes.append("u64")      # size_t == uint64_t on LP64 (ctypes aliases them)
+                elif "double" in a:
+                    classes.append("f64")
+                else:
+                    raise AssertionError(f"unclassified C argument {a!r} of {name}")
+        protos[name] = classes
+    return protos
+
+
+def ctypes_class(t):
+    if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or hasattr(t, "_length_"):
+        return "ptr"
+    return {C.c_int32: "i32", C.c_int64: "i64", C.c_uint64: "u64", C.c_double: "f64", C.c_uint32: "u32"}[t]
+
+
+def julia_class(t):
+    t = t.strip()
+    if t.startswith(("Ptr{", "Ref{")) or t == "Cstring":
+        return "ptr"
+    return {"Int32": "i32", "Int64": "i64", "UInt64": "u64", "Csize_t": "u64", "Float64": "f64", "Cint": "i32"}[t]
+
+
+def test_header_compiles_as_c_and_a_c_client_links(tmp_path):
+    """include/augcuda.h is a C header: it must compile as C99 (not only parse with a regex), and a plain C client
+    must link against libaugcuda.so and call through it without a GPU (version + strerror + a failing ctx_create)."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "augcuda.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "client.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "augcuda.h"\n'
+        "int main(void) {\n"
+        "    aug_lik lik; memset(&lik, 0, sizeof lik); lik.kind = AUG_POISSON; lik.nlatent = 1; lik.p[0] = 10.0;\n"
+        "    if (aug_version() != AUGCUDA_VERSION) return 1;\n"
+        '    if (strcmp(aug_strerror(AUG_OK), "ok") != 0) return 2;\n'
+        "    if (sizeof(aug_lik) != 56) return 3;\n"
+        "    /* NULL ctx: every verb must refuse without touching a device */\n"
+        "    if (aug_cavi_step(NULL, &lik, 0, NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL, NULL, 0, NULL) != AUG_ERR_NOT_INIT) return 4;\n"
+        "    if (aug_cavi_step_host(NULL, &lik, 0, NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL, NULL, 0, NULL) != AUG_ERR_NOT_INIT) return 5;\n"
+        "    if (aug_aux_sample_host(NULL, &lik, 0, 0, NULL, NULL, 0, NULL, NULL) != AUG_ERR_NOT_INIT) return 6;\n"
+        '    printf("c client ok\\n");\n    return 0;\n}\n')
+    exe = tmp_path / "client"
+    libdir = os.path.join(ROOT, "augmentedgplikelihoods.jl_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libaugcuda.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "c client ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
+def test_ctypes_table_matches_the_c_prototypes_type_by_type():
+    pkg = aug_pkg.load_package()
+    protos = header_prototypes()
+    assert set(protos) == set(pkg._lib.SIGNATURES) | {"aug_strerror"}
+    for name, argtypes in pkg._lib.SIGNATURES.items():
+        got = [ctypes_class(t) for t in argtypes]
+        assert got == protos[name], (name, got, protos[name])
+
+
 def test_library_exports_every_declared_symbol():
     pkg = aug_pkg.load_package()
     lib = pkg.load()
@@ -80,7 +157,8 @@ def test_julia_glue_binds_only_declared_symbols_with_matching_arity():
     src = open(os.path.join(ROOT, "augmentedgplikelihoods.jl_b200", "julia", "AugCUDA.jl")).read()
     syms = set(header_symbols())
     calls = list(re.finditer(r"ccall\(\(:(aug_[a-z0-9_]+),\s*lib\),\s*(\w+),\s*\(", src))
-    assert len(calls) >= 20
+    assert len(calls) >= 30
+    protos = header_prototypes()
     seen = set()
     for m in calls:
         name, ret = m.group(1), m.group(2)
@@ -113,7 +191,14 @@ def test_julia_glue_binds_only_declared_symbols_with_matching_arity():
             continue
         assert ret == "Int32", (name, ret)
         assert nargs == len(pkg._lib.SIGNATURES[name]), (name, nargs, len(pkg._lib.SIGNATURES[name]))
+        # type class by type class against the C prototype (pointer / Int32 / Int64 / UInt64 / Csize_t / Float64)
+        got = [julia_class(p) for p in parts if p.strip()]
+        assert got == protos[name], (name, got, protos[name])
     # the verbs of the path and of the rows either side of it are all bound
     for must in ("aug_cavi_step", "aug_aux_sample", "aug_expected_elbo_terms", "aug_sampled_loglik_terms",
-                 "aug_sparse_cavi_sweep", "aug_sparse_marginals", "aug_sparse_precision_potential"):
+                 "aug_sparse_cavi_sweep", "aug_sparse_marginals", "aug_sparse_precision_potential",
+                 # the host-Vector methods (generic.jl:1-88 dispatches on plain vectors)
+                 "aug_cavi_step_host", "aug_aux_posterior_host", "aug_expected_potential_precision_host",
+                 "aug_expected_elbo_terms_host", "aug_aux_sample_host", "aug_init_aux_variables_host",
+                 "aug_potential_precision_host", "aug_sampled_loglik_terms_host"):
         assert must in seen, must
