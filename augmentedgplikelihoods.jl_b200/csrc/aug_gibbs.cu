@@ -12,6 +12,7 @@
 #include "aug_common.cuh"
 #include "aug_math.cuh"
 #include "aug_pg.cuh"
+#include "aug_pgb.cuh"
 
 namespace {
 
@@ -93,12 +94,12 @@ __device__ __noinline__ double pg1_finish_sequential(uint64_t seed, uint64_t off
 #define PG1_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(const Pg1Args a) {
-    __shared__ __align__(16) double tab_s[AUG_PGTAB_N * AUG_PGTAB_DEG];   // r(z) table: 10 KB, read by every fresh step
+    __shared__ __align__(16) double tab_s[AUG_PGTAB_N * AUG_PGTAB_DEG];   // r(z) table, coefficient-major: 10 KB, read by every fresh step
     __shared__ uint32_t qel_s[AUG_BLOCK / 32][PG1_QCAP];
     __shared__ uint32_t qra_s[AUG_BLOCK / 32][PG1_QCAP];
     __shared__ uint32_t quacc_s[AUG_BLOCK / 32][PG1_QCAP];
     __shared__ double qz_s[AUG_BLOCK / 32][PG1_QCAP];
-    for (int t = threadIdx.x; t < AUG_PGTAB_N * AUG_PGTAB_DEG; t += AUG_BLOCK) tab_s[t] = __ldg(a.tab + t);
+    augp::pg1_load_table_cm(tab_s, a.tab, AUG_BLOCK);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* qel = qel_s[warp];
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
             const bool valid = el < a.n;
             const double c = c_next;
             c_next = load_c(ch + W);
-            const augp::PG1 s = augp::pg1_setup<true>(c, tab_s);
+            const augp::PG1 s = augp::pg1_setup_cm(c, tab_s);
             const uint64_t gi = (uint64_t)a.i0 + el;
             const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
             uint32_t w[4];
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
                 }
             } else if (attempt == 0 && round < PG1_MAXCTR) {
                 // rare: a new round after a rejected proposal
-                const augp::PG1 s = augp::pg1_setup<true>(2.0 * z, tab_s);
+                const augp::PG1 s = augp::pg1_setup_cm(2.0 * z, tab_s);
                 uint32_t w[4];
                 augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(0u, round, 0u), c3, w);
                 uacc = w[3];
@@ -215,6 +216,314 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
             }
         }
         push(again, el, ra, uacc, z);
+    }
+}
+
+
+// ------------------------------------------------------------------ PG(b, c), general b: warp-compacted sampler
+// aux_sample! of the NegBin / Poisson / heteroscedastic likelihoods (negativebinomial.jl:20-22, poisson.jl:26-28 +
+// polyagammapoisson.jl:23-27, heteroscedasticgaussian.jl:28-32) and the raw rand(PolyaGamma(b, c)).  Design notes
+// and the three pieces of the law (Devroye sum / exact fractional piece / certified Gamma convolution) in
+// aug_pgb.cuh.  Like pg1_compact_kernel, a draw is a sequence of uniform STEPS; what cannot finish in the
+// straight-line FRESH step of its element is parked in one of two per-warp shared-memory queues — QG: Marsaglia-Tsang
+// retries and extra terms of the convolution, QX: Devroye rounds / truncated-IG attempts / fractional-piece attempts —
+// and a work step pops up to 32 items of ONE queue, so all lanes of a step run the same code.  An element has at
+// most one item in flight and its partial sum travels with the item, so the additions happen in a fixed order:
+// the output depends on (seed, offset, global element index) only.
+enum { PGB_RAW = 100 };
+struct PgbArgs {
+    int64_t n, i0;
+    uint64_t seed, offset;
+    const void* y;
+    const double* f;
+    const double* g;      // HETERO second latent
+    const double* b;      // RAW: per-element b (or nullptr -> bs)
+    const double* c;      // RAW: per-element c (or nullptr -> cs)
+    double bs, cs;
+    int b_is_int;
+    double p0;            // r | lambda
+    double* omega;
+    int64_t* nvar;
+    const double* tab;
+};
+
+#define PGB_T_DEV 0u
+#define PGB_T_GAM 1u
+#define PGB_T_FRAC 2u
+#define PGB_QCAP 64
+
+#ifndef PGB_MIN_BLOCKS
+#define PGB_MIN_BLOCKS 2
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const PgbArgs a) {
+    __shared__ __align__(16) double tab_s[AUG_PGTAB_N * AUG_PGTAB_DEG];
+    __shared__ __align__(16) double2 qx_lo[AUG_BLOCK / 32][PGB_QCAP], qx_hi[AUG_BLOCK / 32][PGB_QCAP];
+    __shared__ __align__(16) double2 qg_lo[AUG_BLOCK / 32][PGB_QCAP], qg_hi[AUG_BLOCK / 32][PGB_QCAP];
+    augp::pg1_load_table_cm(tab_s, a.tab, AUG_BLOCK);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t nchunks = (uint32_t)((a.n + 31) >> 5);
+    const uint32_t W = gridDim.x * (AUG_BLOCK / 32);
+    augb::Key key;
+    key.k0 = (uint32_t)a.seed;
+    key.k1 = (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32);
+    key.c3 = (uint32_t)a.offset;
+    constexpr double SCALE = 0.5 / (augp::PI * augp::PI);
+    int nx = 0, ng = 0;
+
+    auto push = [&](double2* lo, double2* hi, int& qn, bool want, uint32_t el, uint32_t st, double acc, double b, double c) {
+        const uint32_t m = __ballot_sync(0xffffffffu, want);
+        if (want) {
+            const int pos = qn + __popc(m & lt_mask);
+            lo[pos] = make_double2(__hiloint2double((int)st, (int)el), acc);
+            hi[pos] = make_double2(b, c);
+        }
+        qn += __popc(m);
+        __syncwarp();
+    };
+    auto finish = [&](uint32_t el, double v) { st_stream1(a.omega + el, v); };
+
+    uint32_t ch = blockIdx.x * (AUG_BLOCK / 32) + warp;
+    for (;;) {
+        const bool can_fresh = ch < nchunks;
+        int mode;                                   // 0 fresh, 1 exact queue, 2 gamma queue
+        if (nx >= 32) mode = 1;
+        else if (ng >= 32) mode = 2;
+        else if (can_fresh) mode = 0;
+        else if (nx > 0) mode = 1;
+        else if (ng > 0) mode = 2;
+        else break;
+
+        if (mode == 0) {
+            // ---------------------------------------------------------------- fresh step: 32 consecutive elements
+            const uint32_t el = (ch << 5) + lane;
+            ch += W;
+            const bool valid = el < a.n;
+            const uint64_t gi = (uint64_t)a.i0 + el;
+            const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
+            double b = 0.0, c = 0.0;
+            bool isint = true;
+            if (valid) {
+                if (KIND == AUG_NEGBIN) {                               // PG(y + r, |f|)  negativebinomial.jl:20-22
+                    c = ld_stream1(a.f + el);
+                    b = (double)__ldg(reinterpret_cast<const int64_t*>(a.y) + el) + a.p0;
+                    isint = a.b_is_int != 0;
+                } else if (KIND == AUG_POISSON) {                       // poisson.jl:26-28, polyagammapoisson.jl:23-27
+                    c = ld_stream1(a.f + el);
+                    const int64_t y = __ldg(reinterpret_cast<const int64_t*>(a.y) + el);
+                    augr::Philox g;
+                    g.init(a.seed, a.offset, gi, 192u);                 // tag 6
+                    const int64_t nn = augr::poisson_rand(g, a.p0 * augm::logistic(-c));
+                    a.nvar[el] = nn;
+                    b = (double)(nn + y);
+                } else if (KIND == AUG_HETERO) {                        // heteroscedasticgaussian.jl:28-32
+                    const double f = ld_stream1(a.f + el);
+                    c = ld_stream1(a.g + el);
+                    const double d = f - ld_stream1(reinterpret_cast<const double*>(a.y) + el);
+                    augr::Philox g;
+                    g.init(a.seed, a.offset, gi, 192u);
+                    const int64_t nn = augr::poisson_rand(g, a.p0 * augm::logistic(-c) * d * d * 0.5);
+                    a.nvar[el] = nn;
+                    b = (double)nn + 0.5;
+                    isint = false;
+                } else {                                                // rand(PolyaGamma(b, c))
+                    b = a.b ? __ldg(a.b + el) : a.bs;
+                    c = a.c ? __ldg(a.c + el) : a.cs;
+                    isint = a.b_is_int != 0;
+                }
+            }
+            if (isint) b = rint(b);
+            bool live = valid;
+            if (live && !(b > 0.0)) {                                   // Dirac at 0  polyagamma.jl:122-124
+                finish(el, 0.0);
+                live = false;
+            }
+            const bool conv = live && b > PGB_BX;
+            uint32_t gst = 0;
+            double gacc = 0.0;
+            bool gpush = false;
+            if (__any_sync(0xffffffffu, conv)) {
+                if (conv) {
+                    // first attempt of the two leading terms and of the tail in line (3 independent Philox blocks)
+                    const augb::Conv s = augb::conv_setup(b, c);
+                    uint32_t w1[4], w2[4], w0[4];
+                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 1u, 0u, 0u), key.c3, w1);
+                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 2u, 0u, 0u), key.c3, w2);
+                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 0u, 0u, 0u), key.c3, w0);
+                    const double v1 = augb::gamma_attempt(w1, b);
+                    const double v2 = augb::gamma_attempt(w2, b);
+                    const double v0 = augb::gamma_attempt(w0, s.shape);
+                    uint32_t mask = 0;
+                    gacc = s.loc;
+                    if (v1 >= 0.0) gacc = fma(v1, 1.0 / (0.25 + s.w), gacc); else mask |= 1u;
+                    if (v2 >= 0.0) gacc = fma(v2, 1.0 / (2.25 + s.w), gacc); else mask |= 2u;
+                    if (v0 >= 0.0) gacc = fma(v0, s.theta, gacc); else mask |= 4u;
+                    const uint32_t extra = s.kt > 2 ? 3u : 0u;
+                    if (mask == 0u && extra == 0u) {
+                        finish(el, gacc * SCALE);
+                    } else {
+                        gpush = true;
+                        gst = PGB_T_GAM | (mask << 2) | (extra << 5) | ((uint32_t)s.kt << 11) | ((mask ? 1u : 0u) << 17);
+                    }
+                }
+            }
+            push(qg_lo[warp], qg_hi[warp], ng, gpush, el, gst, gacc, b, c);
+            // exact pieces: fractional part first (if any), then floor(b) Devroye draws
+            const bool exact = live && !conv;
+            const double fl = floor(b);
+            const double e = b - fl;
+            const uint32_t rem = (uint32_t)fl;
+            const uint32_t xst = e > 0.0 ? (PGB_T_FRAC | (rem << 2)) : (PGB_T_DEV | (rem << 2));
+            push(qx_lo[warp], qx_hi[warp], nx, exact, el, xst, 0.0, e > 0.0 ? e : 0.0, c);
+            continue;
+        }
+
+        if (mode == 2) {
+            // ---------------------------------------------------------------- gamma step: one Marsaglia-Tsang attempt per item
+            const int cnt = ng < 32 ? ng : 32;
+            const bool active = lane < cnt;
+            uint32_t el = 0, st = 0;
+            double acc = 0.0, b = 1.0, c = 0.0;
+            if (active) {
+                const double2 lo = qg_lo[warp][ng - cnt + lane], hi = qg_hi[warp][ng - cnt + lane];
+                el = (uint32_t)__double2loint(lo.x);
+                st = (uint32_t)__double2hiint(lo.x);
+                acc = lo.y;
+                b = hi.x;
+                c = hi.y;
+            }
+            __syncwarp();
+            ng -= cnt;
+            bool again = false;
+            if (active) {
+                uint32_t mask = (st >> 2) & 7u, extra = (st >> 5) & 63u, att = (st >> 17) & 0x3fffu;
+                const uint32_t kt = (st >> 11) & 63u;
+                const uint32_t k = mask ? ((mask & 1u) ? 1u : ((mask & 2u) ? 2u : 0u)) : extra;
+                const uint64_t gi = (uint64_t)a.i0 + el;
+                const double xp = 0.5 * fabs(c) * (1.0 / augp::PI);
+                double shape = b, wt;
+                if (k == 0u) {
+                    const augb::Conv s = augb::conv_setup(b, c);
+                    shape = s.shape;
+                    wt = s.theta;
+                } else {
+                    const double km = (double)k - 0.5;
+                    wt = 1.0 / fma(km, km, xp * xp);
+                }
+                uint32_t w[4];
+                augr::philox4x32_10(key.k0, key.k1, (uint32_t)gi, (uint32_t)(gi >> 32), augb::ctr(3u, k, 0u, att), key.c3, w);
+                const double v = augb::gamma_attempt(w, shape);
+                again = true;
+                if (v >= 0.0) {
+                    acc = fma(v, wt, acc);
+                    if (mask) {
+                        mask &= mask - 1u;                         // clear the lowest pending bit (k = 1, then 2, then tail)
+                        att = mask ? 1u : 0u;
+                    } else {
+                        extra = extra < kt ? extra + 1u : 0u;
+                        att = 0u;
+                    }
+                    if (mask == 0u && extra == 0u) {
+                        finish(el, acc * SCALE);
+                        again = false;
+                    }
+                } else if (++att > PGB_MAXATT) {
+                    finish(el, augb::pgb_sequential(a.seed, a.offset, gi, b, false, c, a.tab));
+                    again = false;
+                }
+                st = PGB_T_GAM | (mask << 2) | (extra << 5) | (kt << 11) | (att << 17);
+            }
+            push(qg_lo[warp], qg_hi[warp], ng, again, el, st, acc, b, c);
+            continue;
+        }
+
+        // -------------------------------------------------------------------- exact step: Devroye round / IG attempt / fractional attempt
+        const int cnt = nx < 32 ? nx : 32;
+        const bool active = lane < cnt;
+        uint32_t el = 0, st = 0;
+        double acc = 0.0, bb = 0.0, c = 0.0;
+        if (active) {
+            const double2 lo = qx_lo[warp][nx - cnt + lane], hi = qx_hi[warp][nx - cnt + lane];
+            el = (uint32_t)__double2loint(lo.x);
+            st = (uint32_t)__double2hiint(lo.x);
+            acc = lo.y;
+            bb = hi.x;                 // FRAC: e;  DEV: the round's accept uniform in the low word
+            c = hi.y;
+        }
+        __syncwarp();
+        nx -= cnt;
+        bool again = false;
+        if (active) {
+            const uint64_t gi = (uint64_t)a.i0 + el;
+            const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
+            const double z = 0.5 * fabs(c);
+            uint32_t rem = (st >> 2) & 7u;
+            again = true;
+            if ((st & 3u) == PGB_T_FRAC) {
+                uint32_t att = (st >> 16) & 0x3fffu;
+                uint32_t w1[4], w2[4];
+                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(4u, 0u, 0u, att), key.c3, w1);
+                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(5u, 0u, 0u, att), key.c3, w2);
+                const double x = augb::frac_propose(w1, bb, z);
+                if (augb::frac_accept(x, bb, augr::u53_open0(w2[0], w2[1]))) {
+                    acc = 0.25 * x;
+                    if (rem == 0u) {
+                        finish(el, acc);
+                        again = false;
+                    } else {
+                        st = PGB_T_DEV | (rem << 2);                  // sub 0, round 0, attempt 0
+                    }
+                } else if (++att > PGB_MAXATT) {
+                    finish(el, augb::pgb_sequential(a.seed, a.offset, gi, bb + (double)rem, false, c, a.tab));
+                    again = false;
+                } else {
+                    st = PGB_T_FRAC | (rem << 2) | (att << 16);
+                }
+            } else {
+                uint32_t sub = (st >> 5) & 7u, round = (st >> 8) & 0xffu, att = (st >> 16) & 0x3fffu;
+                uint32_t uacc = (uint32_t)__double2loint(bb);
+                double x = -1.0;
+                bool exhausted = false;
+                if (att == 0u) {                                       // round start (sample_pg1, polyagamma.jl:225-257)
+                    const augp::PG1 s = augp::pg1_setup_cm(c, tab_s);
+                    uint32_t w[4];
+                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(0u, sub, round, 0u), key.c3, w);
+                    uacc = w[3];
+                    if (augr::u32_mid(w[0]) < s.r) x = fma(-augf::log_(augr::u53_open0(w[1], w[2])), s.invK, augp::T);
+                    else att = 1u;
+                } else {
+                    uint32_t w[4];
+                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(1u, sub, round, att), key.c3, w);
+                    x = augp::trunc_ig_attempt_w(w, z);
+                    if (x < 0.0 && ++att > PGB_MAXATT) exhausted = true;
+                }
+                if (x > 0.0) {
+                    if (augb::dev_accept(x, uacc, key, e_lo, e_hi, sub, round)) {
+                        acc += 0.25 * x;
+                        rem -= 1u;
+                        sub += 1u;
+                        round = 0u;
+                        att = 0u;
+                        if (rem == 0u) {
+                            finish(el, acc);
+                            again = false;
+                        }
+                    } else {
+                        att = 0u;
+                        if (++round > PGB_MAXROUND) exhausted = true;
+                    }
+                }
+                if (exhausted) {       // restart the remaining draws on a private sequential stream (probability < 1e-70)
+                    finish(el, acc + augb::pgb_sequential(a.seed, a.offset ^ 0x5bd1e995u, gi, (double)rem, true, c, a.tab));
+                    again = false;
+                }
+                st = PGB_T_DEV | (rem << 2) | (sub << 5) | (round << 8) | (att << 16);
+                bb = __hiloint2double(0, (int)uacc);
+            }
+        }
+        push(qx_lo[warp], qx_hi[warp], nx, again, el, st, acc, bb, c);
     }
 }
 
@@ -332,6 +641,25 @@ bool launch_pg1_compact(aug_ctx* ctx, int64_t n, int64_t i0, uint64_t off, const
     return true;
 }
 
+
+// PG(b, c) for n elements through the warp-compacted general-b kernel
+template <int KIND>
+int32_t launch_pgb(aug_ctx* ctx, const PgbArgs& a) {
+    static int occ = 0;
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgb_kernel<KIND>, AUG_BLOCK, 0) != cudaSuccess || occ < 1)
+            occ = 1;
+    }
+    int64_t grid = (int64_t)ctx->sms * occ;
+    const int64_t nchunks = (a.n + 31) / 32;
+    const int64_t need = (nchunks + (AUG_BLOCK / 32) - 1) / (AUG_BLOCK / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    pgb_kernel<KIND><<<(unsigned)grid, AUG_BLOCK, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    return (int32_t)cudaGetLastError();
+}
+
 bool is_cat(int k) { return k == AUG_CAT || k == AUG_CAT_BIJ; }
 
 bool pg1_no_compact() {   // AUGCUDA_NO_COMPACT=1 keeps PG(1) draws on the one-thread-one-draw kernel (A/B measurements)
@@ -377,6 +705,25 @@ int32_t aug_aux_sample_dev(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i0
     if (lik->kind == AUG_BERNOULLI && !pg1_no_compact()) {      // PG(1, |f|)  bernoulli.jl:13-15
         int32_t r2 = 0;
         if (launch_pg1_compact(c, n, i0, off, f, 0.0, omega, &r2)) return r2;
+    }
+    if (!pg1_no_compact() && n < ((int64_t)1 << 32) - 64 &&
+        (lik->kind == AUG_NEGBIN || lik->kind == AUG_POISSON || lik->kind == AUG_HETERO)) {
+        PgbArgs p{};
+        p.n = n;
+        p.i0 = i0;
+        p.seed = c->seed;
+        p.offset = off;
+        p.y = y;
+        p.f = f;
+        p.g = a.g;
+        p.b_is_int = a.L.r_is_int;
+        p.p0 = a.L.p0;
+        p.omega = omega;
+        p.nvar = nvar;
+        p.tab = c->pgtab;
+        if (lik->kind == AUG_NEGBIN) return launch_pgb<AUG_NEGBIN>(c, p);
+        if (lik->kind == AUG_POISSON) return launch_pgb<AUG_POISSON>(c, p);
+        return launch_pgb<AUG_HETERO>(c, p);
     }
     switch (lik->kind) {
         case AUG_BERNOULLI: return launch_map(c, aux_sample_kernel<AUG_BERNOULLI>, a, n);
@@ -436,6 +783,21 @@ static int32_t pg_rand_common(aug_ctx* c, int64_t n, int64_t i0, const double* b
     if (!b && b_is_int && bs == 1.0 && !pg1_no_compact()) {     // all draws are PG(1, c)
         int32_t r2 = 0;
         if (launch_pg1_compact(c, n, i0, off, cc, cs, out, &r2)) return r2;
+    }
+    if (!pg1_no_compact() && n < ((int64_t)1 << 32) - 64) {
+        PgbArgs p{};
+        p.n = n;
+        p.i0 = i0;
+        p.seed = c->seed;
+        p.offset = off;
+        p.b = b;
+        p.c = cc;
+        p.bs = bs;
+        p.cs = cs;
+        p.b_is_int = b_is_int;
+        p.omega = out;
+        p.tab = c->pgtab;
+        return launch_pgb<PGB_RAW>(c, p);
     }
     const int grid = aug_grid_for(c, (const void*)pg_rand_kernel, n, AUG_BLOCK);
     pg_rand_kernel<<<grid, AUG_BLOCK, 0, c->stream>>>(n, i0, c->seed, off, b, cc, bs, cs, b_is_int, out, c->pgtab);

@@ -61,6 +61,37 @@ __device__ __forceinline__ PG1 pg1_setup(double c, const double* __restrict__ ta
     return s;
 }
 
+// The same from a COEFFICIENT-major copy of the table in shared memory: tabT[j * AUG_PGTAB_N + k].  Lanes of a warp
+// hold different intervals k (z = |f|/2 spreads over ~12 of them): with the row-major layout their 16-byte loads hit
+// the same banks (rows are 64 bytes apart: ncu counted 1.1e8 bank conflicts per 1e8 draws in pg1_compact_kernel),
+// here lane addresses differ by 8 bytes per unit of k and the eight LDS.64 are conflict-free.
+__device__ __forceinline__ PG1 pg1_setup_cm(double c, const double* __restrict__ tabT) {
+    PG1 s;
+    s.z = 0.5 * fabs(c);
+    s.K = fma(0.5 * s.z, s.z, PI2_8);
+    s.invK = s.K < 1e290 ? augf::rcp(s.K) : 0.0;
+    if (s.z >= AUG_PGTAB_N * AUG_PGTAB_H) {
+        s.r = 0.0;
+    } else {
+        const double u = s.z * (1.0 / AUG_PGTAB_H);
+        const int k = (int)u;
+        const double x = fma(2.0, u - (double)k, -1.0);
+        const double* col = tabT + k;
+        double p = fma(col[0], x, col[AUG_PGTAB_N]);
+#pragma unroll
+        for (int j = 2; j < AUG_PGTAB_DEG; ++j) p = fma(p, x, col[j * AUG_PGTAB_N]);
+        s.r = p;
+    }
+    return s;
+}
+// cooperative load of the table into shared memory, transposed to coefficient-major
+__device__ __forceinline__ void pg1_load_table_cm(double* __restrict__ tabT, const double* __restrict__ tab, int nthreads) {
+    for (int t = threadIdx.x; t < AUG_PGTAB_N * AUG_PGTAB_DEG; t += nthreads) {
+        const int k = t / AUG_PGTAB_DEG, j = t - k * AUG_PGTAB_DEG;
+        tabT[j * AUG_PGTAB_N + k] = __ldg(tab + t);
+    }
+}
+
 // one proposal from the truncated inverse Gaussian IG(1/z, 1) on (0, t]  (polyagamma.jl:195-221)
 // returns x > 0 when the proposal stage accepted, a negative value to ask for another attempt
 __device__ __forceinline__ double trunc_ig_attempt(augr::Philox& g, double z) {
