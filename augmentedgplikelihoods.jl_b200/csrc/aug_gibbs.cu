@@ -251,27 +251,33 @@ struct PgbArgs {
 #define PGB_T_GAM 1u
 #define PGB_T_FRAC 2u
 #define PGB_QCAP 64
+#define PGB_WARPS (AUG_BLOCK / 32)
+// dynamic shared memory: r(z) table | per warp 3 queues (Devroye, Gamma, fractional) x { lo[QCAP], hi[QCAP] } double2
+#define PGB_SMEM_BYTES (AUG_PGTAB_N * AUG_PGTAB_DEG * 8 + PGB_WARPS * 3 * 2 * PGB_QCAP * 16)
 
 #ifndef PGB_MIN_BLOCKS
 #define PGB_MIN_BLOCKS 2
 #endif
 template <int KIND>
 __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const PgbArgs a) {
-    __shared__ __align__(16) double tab_s[AUG_PGTAB_N * AUG_PGTAB_DEG];
-    __shared__ __align__(16) double2 qx_lo[AUG_BLOCK / 32][PGB_QCAP], qx_hi[AUG_BLOCK / 32][PGB_QCAP];
-    __shared__ __align__(16) double2 qg_lo[AUG_BLOCK / 32][PGB_QCAP], qg_hi[AUG_BLOCK / 32][PGB_QCAP];
+    extern __shared__ __align__(16) unsigned char pgb_smem[];
+    double* tab_s = reinterpret_cast<double*>(pgb_smem);
     augp::pg1_load_table_cm(tab_s, a.tab, AUG_BLOCK);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2* qbase = reinterpret_cast<double2*>(pgb_smem + AUG_PGTAB_N * AUG_PGTAB_DEG * 8) + (size_t)warp * 3 * 2 * PGB_QCAP;
+    double2 *qd_lo = qbase, *qd_hi = qbase + PGB_QCAP;                       // Devroye rounds / truncated-IG attempts
+    double2 *qg_lo = qbase + 2 * PGB_QCAP, *qg_hi = qbase + 3 * PGB_QCAP;    // Marsaglia-Tsang attempts of the convolution
+    double2 *qf_lo = qbase + 4 * PGB_QCAP, *qf_hi = qbase + 5 * PGB_QCAP;    // fractional-piece attempts
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t nchunks = (uint32_t)((a.n + 31) >> 5);
-    const uint32_t W = gridDim.x * (AUG_BLOCK / 32);
+    const uint32_t W = gridDim.x * PGB_WARPS;
     augb::Key key;
     key.k0 = (uint32_t)a.seed;
     key.k1 = (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32);
     key.c3 = (uint32_t)a.offset;
     constexpr double SCALE = 0.5 / (augp::PI * augp::PI);
-    int nx = 0, ng = 0;
+    int nd = 0, ng = 0, nf = 0;
 
     auto push = [&](double2* lo, double2* hi, int& qn, bool want, uint32_t el, uint32_t st, double acc, double b, double c) {
         const uint32_t m = __ballot_sync(0xffffffffu, want);
@@ -283,16 +289,31 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
         qn += __popc(m);
         __syncwarp();
     };
+    auto pop = [&](double2* lo, double2* hi, int& qn, bool& active, uint32_t& el, uint32_t& st, double& acc, double& b, double& c) {
+        const int cnt = qn < 32 ? qn : 32;
+        active = lane < cnt;
+        if (active) {
+            const double2 l = lo[qn - cnt + lane], h = hi[qn - cnt + lane];
+            el = (uint32_t)__double2loint(l.x);
+            st = (uint32_t)__double2hiint(l.x);
+            acc = l.y;
+            b = h.x;
+            c = h.y;
+        }
+        __syncwarp();
+        qn -= cnt;
+    };
     auto finish = [&](uint32_t el, double v) { st_stream1(a.omega + el, v); };
 
-    uint32_t ch = blockIdx.x * (AUG_BLOCK / 32) + warp;
+    uint32_t ch = blockIdx.x * PGB_WARPS + warp;
     for (;;) {
-        const bool can_fresh = ch < nchunks;
-        int mode;                                   // 0 fresh, 1 exact queue, 2 gamma queue
-        if (nx >= 32) mode = 1;
+        int mode;                                   // 0 fresh, 1 Devroye queue, 2 gamma queue, 3 fractional queue
+        if (nf >= 32) mode = 3;
+        else if (nd >= 32) mode = 1;
         else if (ng >= 32) mode = 2;
-        else if (can_fresh) mode = 0;
-        else if (nx > 0) mode = 1;
+        else if (ch < nchunks) mode = 0;
+        else if (nf > 0) mode = 3;
+        else if (nd > 0) mode = 1;
         else if (ng > 0) mode = 2;
         else break;
 
@@ -336,7 +357,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
             }
             if (isint) b = rint(b);
             bool live = valid;
-            if (live && !(b > 0.0)) {                                   // Dirac at 0  polyagamma.jl:122-124
+            if (live && !(b > 1e-250)) {                                // Dirac at 0  polyagamma.jl:122-124 (and b below 1e-250)
                 finish(el, 0.0);
                 live = false;
             }
@@ -357,8 +378,8 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                     const double v0 = augb::gamma_attempt(w0, s.shape);
                     uint32_t mask = 0;
                     gacc = s.loc;
-                    if (v1 >= 0.0) gacc = fma(v1, 1.0 / (0.25 + s.w), gacc); else mask |= 1u;
-                    if (v2 >= 0.0) gacc = fma(v2, 1.0 / (2.25 + s.w), gacc); else mask |= 2u;
+                    if (v1 >= 0.0) gacc = fma(v1, augf::rcp(0.25 + s.w), gacc); else mask |= 1u;
+                    if (v2 >= 0.0) gacc = fma(v2, augf::rcp(2.25 + s.w), gacc); else mask |= 2u;
                     if (v0 >= 0.0) gacc = fma(v0, s.theta, gacc); else mask |= 4u;
                     const uint32_t extra = s.kt > 2 ? 3u : 0u;
                     if (mask == 0u && extra == 0u) {
@@ -369,33 +390,24 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                     }
                 }
             }
-            push(qg_lo[warp], qg_hi[warp], ng, gpush, el, gst, gacc, b, c);
+            push(qg_lo, qg_hi, ng, gpush, el, gst, gacc, b, c);
             // exact pieces: fractional part first (if any), then floor(b) Devroye draws
             const bool exact = live && !conv;
             const double fl = floor(b);
-            const double e = b - fl;
+            double e = b - fl;
+            if (e < 1e-250) e = 0.0;
             const uint32_t rem = (uint32_t)fl;
-            const uint32_t xst = e > 0.0 ? (PGB_T_FRAC | (rem << 2)) : (PGB_T_DEV | (rem << 2));
-            push(qx_lo[warp], qx_hi[warp], nx, exact, el, xst, 0.0, e > 0.0 ? e : 0.0, c);
+            push(qf_lo, qf_hi, nf, exact && e > 0.0, el, PGB_T_FRAC | (rem << 2), 0.0, e, c);
+            push(qd_lo, qd_hi, nd, exact && e == 0.0, el, PGB_T_DEV | (rem << 2), 0.0, 0.0, c);
             continue;
         }
 
         if (mode == 2) {
             // ---------------------------------------------------------------- gamma step: one Marsaglia-Tsang attempt per item
-            const int cnt = ng < 32 ? ng : 32;
-            const bool active = lane < cnt;
+            bool active;
             uint32_t el = 0, st = 0;
             double acc = 0.0, b = 1.0, c = 0.0;
-            if (active) {
-                const double2 lo = qg_lo[warp][ng - cnt + lane], hi = qg_hi[warp][ng - cnt + lane];
-                el = (uint32_t)__double2loint(lo.x);
-                st = (uint32_t)__double2hiint(lo.x);
-                acc = lo.y;
-                b = hi.x;
-                c = hi.y;
-            }
-            __syncwarp();
-            ng -= cnt;
+            pop(qg_lo, qg_hi, ng, active, el, st, acc, b, c);
             bool again = false;
             if (active) {
                 uint32_t mask = (st >> 2) & 7u, extra = (st >> 5) & 63u, att = (st >> 17) & 0x3fffu;
@@ -410,7 +422,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                     wt = s.theta;
                 } else {
                     const double km = (double)k - 0.5;
-                    wt = 1.0 / fma(km, km, xp * xp);
+                    wt = augf::rcp(fma(km, km, xp * xp));
                 }
                 uint32_t w[4];
                 augr::philox4x32_10(key.k0, key.k1, (uint32_t)gi, (uint32_t)(gi >> 32), augb::ctr(3u, k, 0u, att), key.c3, w);
@@ -435,95 +447,94 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                 }
                 st = PGB_T_GAM | (mask << 2) | (extra << 5) | (kt << 11) | (att << 17);
             }
-            push(qg_lo[warp], qg_hi[warp], ng, again, el, st, acc, b, c);
+            push(qg_lo, qg_hi, ng, again, el, st, acc, b, c);
             continue;
         }
 
-        // -------------------------------------------------------------------- exact step: Devroye round / IG attempt / fractional attempt
-        const int cnt = nx < 32 ? nx : 32;
-        const bool active = lane < cnt;
+        if (mode == 3) {
+            // ---------------------------------------------------------------- fractional step: one IG proposal + series test per item
+            bool active;
+            uint32_t el = 0, st = 0;
+            double acc = 0.0, e = 0.5, c = 0.0;
+            pop(qf_lo, qf_hi, nf, active, el, st, acc, e, c);
+            bool again = false, to_dev = false;
+            const uint32_t rem = (st >> 2) & 7u;
+            if (active) {
+                const uint64_t gi = (uint64_t)a.i0 + el;
+                const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
+                uint32_t att = (st >> 16) & 0x3fffu;
+                uint32_t w1[4], w2[4];
+                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(4u, 0u, 0u, att), key.c3, w1);
+                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(5u, 0u, 0u, att), key.c3, w2);
+                const double x = augb::frac_propose(w1, e, 0.5 * fabs(c));
+                if (augb::frac_accept(x, e, augr::u53_open0(w2[0], w2[1]))) {
+                    acc = 0.25 * x;
+                    if (rem == 0u) finish(el, acc);
+                    else to_dev = true;
+                } else if (++att > PGB_MAXATT) {
+                    finish(el, augb::pgb_sequential(a.seed, a.offset, gi, e + (double)rem, false, c, a.tab));
+                } else {
+                    again = true;
+                    st = PGB_T_FRAC | (rem << 2) | (att << 16);
+                }
+            }
+            push(qf_lo, qf_hi, nf, again, el, st, acc, e, c);
+            push(qd_lo, qd_hi, nd, to_dev, el, PGB_T_DEV | (rem << 2), acc, 0.0, c);
+            continue;
+        }
+
+        // -------------------------------------------------------------------- Devroye step: round start or one truncated-IG attempt
+        bool active;
         uint32_t el = 0, st = 0;
         double acc = 0.0, bb = 0.0, c = 0.0;
-        if (active) {
-            const double2 lo = qx_lo[warp][nx - cnt + lane], hi = qx_hi[warp][nx - cnt + lane];
-            el = (uint32_t)__double2loint(lo.x);
-            st = (uint32_t)__double2hiint(lo.x);
-            acc = lo.y;
-            bb = hi.x;                 // FRAC: e;  DEV: the round's accept uniform in the low word
-            c = hi.y;
-        }
-        __syncwarp();
-        nx -= cnt;
+        pop(qd_lo, qd_hi, nd, active, el, st, acc, bb, c);          // bb: the round's accept uniform in the low word
         bool again = false;
         if (active) {
             const uint64_t gi = (uint64_t)a.i0 + el;
             const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
             const double z = 0.5 * fabs(c);
-            uint32_t rem = (st >> 2) & 7u;
+            uint32_t rem = (st >> 2) & 7u, sub = (st >> 5) & 7u, round = (st >> 8) & 0xffu, att = (st >> 16) & 0x3fffu;
+            uint32_t uacc = (uint32_t)__double2loint(bb);
+            double x = -1.0;
+            bool exhausted = false;
             again = true;
-            if ((st & 3u) == PGB_T_FRAC) {
-                uint32_t att = (st >> 16) & 0x3fffu;
-                uint32_t w1[4], w2[4];
-                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(4u, 0u, 0u, att), key.c3, w1);
-                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(5u, 0u, 0u, att), key.c3, w2);
-                const double x = augb::frac_propose(w1, bb, z);
-                if (augb::frac_accept(x, bb, augr::u53_open0(w2[0], w2[1]))) {
-                    acc = 0.25 * x;
+            if (att == 0u) {                                       // round start (sample_pg1, polyagamma.jl:225-257)
+                const augp::PG1 s = augp::pg1_setup_cm(c, tab_s);
+                uint32_t w[4];
+                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(0u, sub, round, 0u), key.c3, w);
+                uacc = w[3];
+                if (augr::u32_mid(w[0]) < s.r) x = fma(-augf::log_(augr::u53_open0(w[1], w[2])), s.invK, augp::T);
+                else att = 1u;
+            } else {
+                uint32_t w[4];
+                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(1u, sub, round, att), key.c3, w);
+                x = augp::trunc_ig_attempt_w(w, z);
+                if (x < 0.0 && ++att > PGB_MAXATT) exhausted = true;
+            }
+            if (x > 0.0) {
+                if (augb::dev_accept(x, uacc, key, e_lo, e_hi, sub, round)) {
+                    acc += 0.25 * x;
+                    rem -= 1u;
+                    sub += 1u;
+                    round = 0u;
+                    att = 0u;
                     if (rem == 0u) {
                         finish(el, acc);
                         again = false;
-                    } else {
-                        st = PGB_T_DEV | (rem << 2);                  // sub 0, round 0, attempt 0
                     }
-                } else if (++att > PGB_MAXATT) {
-                    finish(el, augb::pgb_sequential(a.seed, a.offset, gi, bb + (double)rem, false, c, a.tab));
-                    again = false;
                 } else {
-                    st = PGB_T_FRAC | (rem << 2) | (att << 16);
+                    att = 0u;
+                    if (++round > PGB_MAXROUND) exhausted = true;
                 }
-            } else {
-                uint32_t sub = (st >> 5) & 7u, round = (st >> 8) & 0xffu, att = (st >> 16) & 0x3fffu;
-                uint32_t uacc = (uint32_t)__double2loint(bb);
-                double x = -1.0;
-                bool exhausted = false;
-                if (att == 0u) {                                       // round start (sample_pg1, polyagamma.jl:225-257)
-                    const augp::PG1 s = augp::pg1_setup_cm(c, tab_s);
-                    uint32_t w[4];
-                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(0u, sub, round, 0u), key.c3, w);
-                    uacc = w[3];
-                    if (augr::u32_mid(w[0]) < s.r) x = fma(-augf::log_(augr::u53_open0(w[1], w[2])), s.invK, augp::T);
-                    else att = 1u;
-                } else {
-                    uint32_t w[4];
-                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(1u, sub, round, att), key.c3, w);
-                    x = augp::trunc_ig_attempt_w(w, z);
-                    if (x < 0.0 && ++att > PGB_MAXATT) exhausted = true;
-                }
-                if (x > 0.0) {
-                    if (augb::dev_accept(x, uacc, key, e_lo, e_hi, sub, round)) {
-                        acc += 0.25 * x;
-                        rem -= 1u;
-                        sub += 1u;
-                        round = 0u;
-                        att = 0u;
-                        if (rem == 0u) {
-                            finish(el, acc);
-                            again = false;
-                        }
-                    } else {
-                        att = 0u;
-                        if (++round > PGB_MAXROUND) exhausted = true;
-                    }
-                }
-                if (exhausted) {       // restart the remaining draws on a private sequential stream (probability < 1e-70)
-                    finish(el, acc + augb::pgb_sequential(a.seed, a.offset ^ 0x5bd1e995u, gi, (double)rem, true, c, a.tab));
-                    again = false;
-                }
-                st = PGB_T_DEV | (rem << 2) | (sub << 5) | (round << 8) | (att << 16);
-                bb = __hiloint2double(0, (int)uacc);
             }
+            if (exhausted) {           // finish the remaining draws on a private sequential stream (probability < 1e-70)
+                finish(el, acc + augb::pgb_sequential(a.seed, a.offset ^ 0x5bd1e995u, gi, (double)rem, true, c, a.tab));
+                again = false;
+            }
+            st = PGB_T_DEV | (rem << 2) | (sub << 5) | (round << 8) | (att << 16);
+            bb = __hiloint2double(0, (int)uacc);
         }
-        push(qx_lo[warp], qx_hi[warp], nx, again, el, st, acc, bb, c);
+        push(qd_lo, qd_hi, nd, again, el, st, acc, bb, c);
     }
 }
 
@@ -647,7 +658,9 @@ template <int KIND>
 int32_t launch_pgb(aug_ctx* ctx, const PgbArgs& a) {
     static int occ = 0;
     if (occ == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgb_kernel<KIND>, AUG_BLOCK, 0) != cudaSuccess || occ < 1)
+        if (cudaFuncSetAttribute(pgb_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGB_SMEM_BYTES) != cudaSuccess)
+            return (int32_t)cudaGetLastError();
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgb_kernel<KIND>, AUG_BLOCK, PGB_SMEM_BYTES) != cudaSuccess || occ < 1)
             occ = 1;
     }
     int64_t grid = (int64_t)ctx->sms * occ;
@@ -655,7 +668,7 @@ int32_t launch_pgb(aug_ctx* ctx, const PgbArgs& a) {
     const int64_t need = (nchunks + (AUG_BLOCK / 32) - 1) / (AUG_BLOCK / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    pgb_kernel<KIND><<<(unsigned)grid, AUG_BLOCK, 0, ctx->stream>>>(a);
+    pgb_kernel<KIND><<<(unsigned)grid, AUG_BLOCK, PGB_SMEM_BYTES, ctx->stream>>>(a);
     ctx->launches++;
     return (int32_t)cudaGetLastError();
 }

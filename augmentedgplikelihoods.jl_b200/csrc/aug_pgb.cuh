@@ -69,6 +69,18 @@ static __constant__ double TAIL3[11] = {
     1.9287031163436497807e-6,  -9.0616187123527674494e-6, 0.000040639139692003646051, -0.00017089167198843548335,
     0.00065295505241211784929, -0.0021221644955494829475, 0.0048214098213931957046};
 
+// For KT = 2 (|c| <= 3) the tail parameters themselves as polynomials in w (degree 8, 2e-16 relative on w <= 0.41):
+// theta(w) = T3/T2 and kappa(w) = T2^3/T3^2 (shape = b kappa); loc = b (T1 - theta kappa) is formed from the SAME
+// theta and kappa that are sampled with, so the mean b T1 of the tail is exact whatever their rounding.
+static __constant__ double THETA2[9] = {
+    5.28127610569258015e-8, -4.31455767197214569e-7, 2.80415742473835293e-6, -0.000017721113520866235,
+    0.000110869988004362895, -0.000682087731559447308, 0.00408207521761980359, -0.023482722238011115,
+    0.129199210655591495};
+static __constant__ double KAPPA2[9] = {
+    3.01471237519757539e-9, -4.83814298092573481e-8, 6.34800672867450131e-7, -7.06935670734417957e-6,
+    0.0000628052840369596483, -0.000341645633489901802, -0.00256658071170994153, 0.234991786141717408,
+    2.23560188539702316};
+
 struct Conv {
     double w;            // (c / 2pi)^2
     double loc, theta, shape;   // tail = loc + theta * Gamma(shape)
@@ -88,12 +100,23 @@ __device__ __forceinline__ Conv conv_setup(double b, double c) {
     const double xp = x * (1.0 / PI);
     s.w = xp * xp;
     s.kt = conv_kt(fabs(c));
-    double t1, t2, t3;
-    if (x <= 2.0) {
-        double p = TAIL1[0], q = TAIL2[0], r = TAIL3[0];
+    if (s.kt == 2) {                                           // |c| <= 3: straight-line, no division
+        double p = TAIL1[0], th = THETA2[0], ka = KAPPA2[0];
 #pragma unroll
         for (int m = 1; m < 14; ++m) p = fma(p, s.w, TAIL1[m]);
 #pragma unroll
+        for (int m = 1; m < 9; ++m) { th = fma(th, s.w, THETA2[m]); ka = fma(ka, s.w, KAPPA2[m]); }
+        s.theta = th;
+        s.shape = b * ka;
+        s.loc = b * fma(-th, ka, p);
+        return s;
+    }
+    double t1, t2, t3;
+    if (x <= 2.0) {
+        double p = TAIL1[0], q = TAIL2[0], r = TAIL3[0];
+#pragma unroll 1
+        for (int m = 1; m < 14; ++m) p = fma(p, s.w, TAIL1[m]);
+#pragma unroll 1
         for (int m = 1; m < 11; ++m) { q = fma(q, s.w, TAIL2[m]); r = fma(r, s.w, TAIL3[m]); }
         t1 = p; t2 = q; t3 = r;
     } else {
@@ -112,6 +135,7 @@ __device__ __forceinline__ Conv conv_setup(double b, double c) {
         t2 = s2 - i1 * i1 - i2 * i2;
         t3 = s3 - i1 * i1 * i1 - i2 * i2 * i2;
     }
+#pragma unroll 1
     for (int k = 3; k <= s.kt; ++k) {                          // |c| > 3 only
         const double km = (double)k - 0.5;
         const double id = 1.0 / fma(km, km, s.w);
@@ -120,9 +144,16 @@ __device__ __forceinline__ Conv conv_setup(double b, double c) {
         t3 -= id * id * id;
     }
     s.theta = t3 / t2;
-    s.shape = b * t2 * t2 * t2 / (t3 * t3);
-    s.loc = b * (t1 - t2 * t2 / t3);
+    const double ka = t2 * t2 * t2 / (t3 * t3);
+    s.shape = b * ka;
+    s.loc = b * fma(-s.theta, ka, t1);
     return s;
+}
+
+// sqrt of a non-negative normal-range number without the IEEE slow path
+__device__ __forceinline__ double sqrt_pos(double v) {
+    v = fmax(v, 1e-290);
+    return v * augf::rsqrt_(v);
 }
 
 // one Marsaglia-Tsang attempt for Gamma(shape >= 1, 1) out of one Philox block; < 0: rejected
@@ -131,7 +162,7 @@ __device__ __forceinline__ double gamma_attempt(const uint32_t (&w)[4], double s
     const double d = shape - (1.0 / 3.0);
     const double ci = augf::rsqrt_(9.0 * d);
     const double rad2 = -2.0 * augf::log_(augr::u53_open0(w[0], w[1]));
-    const double x = sqrt(rad2) * cospi(2.0 * augr::u32_mid(w[2]));
+    const double x = sqrt_pos(rad2) * cospi(2.0 * augr::u32_mid(w[2]));
     double v = fma(ci, x, 1.0);
     if (v <= 1e-90) return -1.0;
     v = v * v * v;
@@ -147,9 +178,9 @@ __device__ __forceinline__ double gamma_attempt(const uint32_t (&w)[4], double s
 __device__ __forceinline__ double frac_propose(const uint32_t (&w)[4], double e, double z) {
     const double rad2 = -2.0 * augf::log_(augr::u53_open0(w[0], w[1]));
     const double cs = cospi(2.0 * augr::u32_mid(w[2]));
-    const double y = fmax(rad2 * cs * cs, 1e-300);                  // N^2
-    const double h = y / (2.0 * e);
-    const double x1 = e / (z + h + sqrt(h * (2.0 * z + h)));        // smaller root; = e^2/y at z = 0
+    const double y = fmax(rad2 * cs * cs, 1e-280);                  // N^2
+    const double h = y * augf::rcp(2.0 * e);
+    const double x1 = e * augf::rcp(z + h + sqrt_pos(h * (2.0 * z + h)));   // smaller root; = e^2/y at z = 0
     // P(x1) = mu/(mu + x1) = e/(e + z x1); other root mu^2/x1 = e^2/(z^2 x1)
     if (augr::u32_mid(w[3]) * (e + z * x1) <= e) return x1;
     return (e / z) * (e / z) / x1;
@@ -158,24 +189,31 @@ __device__ __forceinline__ double frac_propose(const uint32_t (&w)[4], double e,
 __device__ __forceinline__ bool frac_accept(double x, double e, double u) {
     if (!(x <= 48.0)) return false;                                  // R < 2^-63 (also catches inf / nan)
     const double ix = 1.0 / x;
-    const double q = exp(-2.0 * ix);
-    double step = q * exp(-2.0 * e * ix);                            // q^{(2n+1+e)} for n = 0
+    const double q = augf::exp_(fmax(-2.0 * ix, -700.0));
+    double step = q * augf::exp_(fmax(-2.0 * e * ix, -700.0));       // q^{2n+1+e} for n = 0
     const double q2 = q * q;
-    double S = 1.0, tprev = 1.0, cn = 1.0, P = 1.0;
-    for (int n = 0; n < 400; ++n) {
+    // n = 1: t_1 = (2 + e) q^{1+e}; R >= 1 - t_1 whenever t_1 <= 1 (then all terms decrease)
+    double cn = 2.0 + e, P = step;
+    double t = cn * P;
+    double S = 1.0 - t;
+    if (t <= 1.0 && u <= S) return true;
+    double tprev = t;
+    step *= q2;
+#pragma unroll 1
+    for (int n = 1; n < 400; ++n) {
         const double dn = (double)n;
-        cn *= ((dn + e) * (2.0 * dn + 2.0 + e)) / ((dn + 1.0) * (2.0 * dn + e));
+        cn *= ((dn + e) * (2.0 * dn + 2.0 + e)) * augf::rcp((dn + 1.0) * (2.0 * dn + e));
         P *= step;
         step *= q2;
-        const double t = cn * P;
+        t = cn * P;
         const bool dec = t <= tprev;
         tprev = t;
-        if (!(n & 1)) {          // term n + 1 odd: subtract -> S is a lower bound once the terms decrease
-            S -= t;
-            if (dec && u <= S) return true;
-        } else {
+        if (n & 1) {             // term n + 1 even: add -> S is an upper bound once the terms decrease
             S += t;
             if (dec && u > S) return false;
+        } else {
+            S -= t;
+            if (dec && u <= S) return true;
         }
         if (dec && t < 1e-18) break;
     }

@@ -118,6 +118,15 @@ __device__ __forceinline__ double gamma_rand(Philox& g, double shape) {
     }
 }
 
+// 1/k, k = 0..63 (entry 0 unused): the chop-down search below multiplies instead of dividing
+static __constant__ double INV_K[64] = {
+    0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13,
+    1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
+    1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37,
+    1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41, 1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49,
+    1.0 / 50, 1.0 / 51, 1.0 / 52, 1.0 / 53, 1.0 / 54, 1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61,
+    1.0 / 62, 1.0 / 63};
+
 // rand(Poisson(lambda)): sequential inversion for small rates, PTRS (Hörmann 1993) otherwise
 __device__ __forceinline__ int64_t poisson_rand(Philox& g, double lam) {
     if (!(lam > 0.0)) return 0;
@@ -125,14 +134,14 @@ __device__ __forceinline__ int64_t poisson_rand(Philox& g, double lam) {
         // inversion by chop-down search from 0 (exact in law; restart guards the 1e-16 round-off tail)
         for (;;) {
             double u = g.u01();
-            double p = exp(-lam);
-            int64_t k = 0;
+            double p = augf::exp_(-lam);
+            int k = 0;
             while (u > p && k < 200) {
                 u -= p;
                 ++k;
-                p *= lam / (double)k;
+                p *= k < 64 ? lam * INV_K[k] : lam / (double)k;
             }
-            if (k < 200) return k;
+            if (k < 200) return (int64_t)k;
         }
     }
     const double slam = sqrt(lam), loglam = log(lam);

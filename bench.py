@@ -182,12 +182,13 @@ def fp64_peak():
     exe = os.path.join(ROOT, "tools", "fp64_peak")
     if os.path.exists(exe):
         try:
+            os.chmod(exe, 0o755)                 # a snapshot copy may drop the executable bit
             out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
             best = max(json.loads(l)["tflops"] for l in out.splitlines() if '"dmma' in l)
             return best, "measured live (tools/fp64_peak: mma.sync.m8n8k4.f64, all SMs)"
-        except Exception:
-            pass
-    return 37.1, "recorded (profiles/fp64_peak_r1f.jsonl)"
+        except Exception as e:
+            return 37.1, f"recorded (profiles/fp64_peak_r1l.jsonl); the live run of tools/fp64_peak failed: {type(e).__name__}: {e}"
+    return 37.1, "recorded (profiles/fp64_peak_r1l.jsonl); tools/fp64_peak is not built on this box (build() makes it)"
 
 
 def sparse_traffic(m, n):
@@ -251,11 +252,29 @@ def sparse_leg(A, ctx, torch, dist, world, dev, args, rank):
     ms_l, _ = timed(library, max(2, k // 4))
     Pf, rf, sf = res["f"][0], res["f"][1], res["f"][2]
     Pl, rl, sl = res["l"]
-    agree = {"P": float(((Pf - Pl).abs().max() / Pl.abs().max()).item()),
+    Pl, rl = Pl.clone(), rl.clone()
+    if world > 1:
+        # the fused sweep returns the sums over ALL ranks (exchanged inside its finalise launch, or by the library's
+        # ncclAllReduce): the composition must be summed over ranks too before the two can be compared.  In fused
+        # mode cavi_step_ already returned the global ELBO sums; in nccl mode they are rank-local.
+        dist.all_reduce(Pl)
+        dist.all_reduce(rl)
+        if not ctx.fused:
+            sl = sl.clone()
+            dist.all_reduce(sl)
+    scaleP = (torch.sqrt(torch.diag(Pl))[:, None] * torch.sqrt(torch.diag(Pl))[None, :])
+    agree = {"P": float(((Pf - Pl).abs() / scaleP).max().item()),
              "rhs": float(((rf - rl).abs().max() / rl.abs().max()).item()),
              "elbo": float(((sf[2] - sl[2]).abs() / sl[2].abs()).item())}
+    # cuBLAS sums in another order: agreement to rounding of an n-term fp64 sum, far below the 1e-12 parity bar
+    assert agree["P"] <= 1e-11 and agree["rhs"] <= 1e-11 and agree["elbo"] <= 1e-12, agree
+    agree["ok"] = True
     flops = 2.0 * m * m + 6.0 * m            # symmetric quadratic form + symmetric rank-1 update + mu + rhs, per obs
     peak, src = fp64_peak() if rank == 0 else (37.1, "")
+    if world > 1:
+        pk = torch.tensor([peak], dtype=torch.float64, device=dev)
+        dist.broadcast(pk, 0)
+        peak = pk.item()
     ach = flops * n / (ms_f * 1e-3) / 1e12
     return {"workload": f"sparse-GP CAVI iteration (Bernoulli), m={m} inducing points, {n} observations per GPU: "
                         "aug_sparse_cavi_sweep = SVGP marginals + aux_posterior! + E[beta],E[gamma] + ELBO sums + "
@@ -316,6 +335,223 @@ def sparse_cpu(m, n=20000):
                                    "sample": f"{n} observations, the parity oracle itself (long double loops, OpenMP {threads})"}}
 
 
+# ---------------------------------------------------------------------------------------------- workloads
+# (name, BASELINE config, likelihood factory, CAVI bytes / unit with the reference's y copy materialised, Gibbs bytes / unit)
+#   bytes per SURVEY §8(d): CAVI = R y, mu, var + W state, beta, gamma;  Gibbs = R y, f (+g) + W omega (+n)
+WORKLOADS = {
+    "bernoulli": dict(cfg="configs[0]+[1]", bytes_cavi=41, bytes_gibbs=16, n=100_000_000),
+    "negbin": dict(cfg="configs[2]", bytes_cavi=56, bytes_gibbs=24, n=100_000_000),
+    "poisson": dict(cfg="configs[2]", bytes_cavi=64, bytes_gibbs=32, n=100_000_000),
+    "studentt": dict(cfg="configs[3]", bytes_cavi=48, bytes_gibbs=24, n=100_000_000),
+    "laplace": dict(cfg="configs[3]", bytes_cavi=48, bytes_gibbs=24, n=100_000_000),
+    "hetero": dict(cfg="configs[3]", bytes_cavi=96, bytes_gibbs=40, n=100_000_000),
+    "categorical": dict(cfg="configs[4]", bytes_cavi=50, bytes_gibbs=25, n=10_000_000),   # per (obs, class) element, K = 100
+}
+CAVI_KERNEL = {"bernoulli": "cavi_tma_kernel<BERNOULLI, ELBO>", "negbin": "cavi_tma_kernel<NEGBIN, ELBO>",
+               "poisson": "cavi_tma_kernel<POISSON, ELBO>", "studentt": "cavi_tma_kernel<STUDENTT, ELBO>",
+               "laplace": "cavi_tma_kernel<LAPLACE, ELBO>", "hetero": "cavi_tma_kernel<HETERO, ELBO>",
+               "categorical": "cat_row_kernel<ELBO> (row-aligned two-warp tiles, bulk-async ring)"}
+GIBBS_KERNEL = {"bernoulli": "pg1_compact_kernel (warp-compacted Devroye PG(1,c))",
+                "negbin": "pgb_kernel<NEGBIN> (warp-compacted PG(y+r,c): certified Gamma convolution / exact pieces)",
+                "poisson": "pgb_kernel<POISSON> (Poisson draw + warp-compacted PG(y+n,c))",
+                "studentt": "aux_sample_kernel<STUDENTT> (Marsaglia-Tsang Gamma)",
+                "laplace": "aux_sample_kernel<LAPLACE> (inverse Gaussian)",
+                "hetero": "pgb_kernel<HETERO> (Poisson draw + exact PG(n+1/2,c))",
+                "categorical": "cat_gibbs_kernel (row scale + Poisson + per-warp PG queues)"}
+
+
+def make_lik(A, name):
+    return {"bernoulli": lambda: A.BernoulliLikelihood(), "negbin": lambda: A.NegativeBinomialLikelihood(10),
+            "poisson": lambda: A.PoissonLikelihood(10.0), "studentt": lambda: A.StudentTLikelihood(3.0, 1.5),
+            "laplace": lambda: A.LaplaceLikelihood(1.0), "hetero": lambda: A.HeteroscedasticGaussianLikelihood(5.0),
+            "categorical": lambda: A.CategoricalLikelihood(100)}[name]()
+
+
+def make_orc_lik(orc, name):
+    return {"bernoulli": lambda: orc.make_lik(orc.BERNOULLI), "negbin": lambda: orc.make_lik(orc.NEGBIN, 10, r_is_int=True),
+            "poisson": lambda: orc.make_lik(orc.POISSON, 10.0), "studentt": lambda: orc.make_lik(orc.STUDENTT, 3.0, 1.5),
+            "laplace": lambda: orc.make_lik(orc.LAPLACE, 1.0), "hetero": lambda: orc.make_lik(orc.HETERO, 5.0),
+            "categorical": lambda: orc.make_lik(orc.CAT_BIJ, nlatent=99)}[name]()
+
+
+def make_inputs(torch, name, lik, n, dev, seed):
+    """synthetic inputs of SURVEY §8(d), generated on the device: mu ~ N(0,1), var = (0.5+U)^2, f ~ N(0,1), y from the likelihood"""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    rnd = lambda *sh: torch.randn(*sh, dtype=torch.float64, device=dev, generator=g)
+    uni = lambda *sh: torch.rand(*sh, dtype=torch.float64, device=dev, generator=g)
+    nl = lik.nlatent
+    if name == "categorical":
+        mu, var, f = rnd(n, nl), (0.5 + uni(n, nl)) ** 2, rnd(n, nl)
+        cls = torch.randint(0, nl + 1, (n,), device=dev, generator=g)
+        y = torch.zeros(n, nl, dtype=torch.uint8, device=dev)
+        ok = (cls < nl).nonzero().squeeze(1)
+        y[ok, cls[ok]] = 1
+    elif name == "hetero":
+        mu, var, f = rnd(2, n), (0.5 + uni(2, n)) ** 2, rnd(2, n)
+        y = f[0] + rnd(n) / torch.sqrt(5.0 * torch.sigmoid(f[1]))
+    else:
+        mu, var, f = rnd(n), (0.5 + uni(n)) ** 2, rnd(n)
+        sig = torch.sigmoid(f)
+        if name == "bernoulli":
+            y = (uni(n) < sig).to(torch.uint8)
+        elif name == "negbin":      # y ~ NB(r = 10, p = 1 - sigma(f)) as a Gamma-Poisson mixture
+            lam = torch.distributions.Gamma(torch.full((1,), 10.0, dtype=torch.float64, device=dev),
+                                            torch.ones(1, dtype=torch.float64, device=dev)).sample((n,)).view(n)
+            y = torch.poisson(lam * sig / (1 - sig).clamp_min(1e-3)).clamp_max(400).to(torch.int64)
+        elif name == "poisson":
+            y = torch.poisson(10.0 * sig).to(torch.int64)
+        elif name == "laplace":
+            u = uni(n) - 0.5
+            y = f - torch.sign(u) * torch.log1p(-2 * u.abs())
+        else:
+            y = f + 1.5 * rnd(n) / torch.sqrt(torch.distributions.Chi2(torch.tensor([3.0], dtype=torch.float64, device=dev)).sample((n,)).view(n) / 3.0)
+    return y, mu, var, f
+
+
+class Leg:
+    """one likelihood at n observations on this rank: device-resident state, a step = fused CAVI update (+ELBO) + aux_sample!"""
+
+    def __init__(self, A, ctx, torch, name, n, dev, rank, i0, want_elbo=True):
+        self.A, self.ctx, self.torch, self.name, self.n, self.i0 = A, ctx, torch, name, n, i0
+        self.lik = make_lik(A, name)
+        nl = self.lik.nlatent
+        self.y, self.mu, self.var, self.f = make_inputs(torch, name, self.lik, n, dev, 1000 + 17 * rank + sum(map(ord, name)))
+        self.qf = A.Normals(self.mu, self.var)
+        self.q = A.init_aux_posterior(self.lik, n)
+        self.beta = torch.empty((nl, n), dtype=torch.float64, device=dev)
+        self.gamma = torch.empty((nl, n), dtype=torch.float64, device=dev)
+        self.scal = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.Ω = A.init_aux_variables(A.AugPhilox(7, 0), self.lik, n, i0=i0)
+        self.units = n * nl if name == "categorical" else n
+
+    def cavi(self):
+        self.A.cavi_step_(self.q, self.lik, self.y, self.qf, want_elbo=True, out=(self.beta, self.gamma, self.scal))
+
+    def gibbs(self):
+        self.A.aux_sample_(self.Ω, self.lik, self.y, self.f, i0=self.i0)
+
+    def free(self):
+        for k in ("y", "mu", "var", "f", "qf", "q", "beta", "gamma", "Ω"):
+            setattr(self, k, None)
+        self.torch.cuda.empty_cache()
+
+
+def time_leg(leg, torch, dist, world, steps, warmup, collective=None):
+    """W warm-up steps, then EXACTLY `steps` timed steps between barriers; CUDA events on the ctx stream around each half;
+    max over ranks.  Returns ms_total / ms_cavi / ms_gibbs / ms_coll per step and the launch count."""
+    ctx, st = leg.ctx, leg.ctx.stream
+
+    def step(ev=None):
+        if ev:
+            ev[0].record(st)
+        leg.cavi()
+        if ev:
+            ev[1].record(st)
+        leg.gibbs()
+        if ev:
+            ev[2].record(st)
+        if collective is not None:
+            collective(leg.scal)
+        if ev:
+            ev[3].record(st)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    l0 = ctx.launches()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(st)
+    for k in range(steps):
+        step(evs[k])
+    t1.record(st)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = ctx.launches() - l0
+    vals = [t0.elapsed_time(t1) / steps, sum(e[0].elapsed_time(e[1]) for e in evs) / steps,
+            sum(e[1].elapsed_time(e[2]) for e in evs) / steps, sum(e[2].elapsed_time(e[3]) for e in evs) / steps]
+    t = torch.tensor(vals, dtype=torch.float64, device=leg.mu.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_cavi, ms_gibbs, ms_coll = t.tolist()
+    return dict(ms_per_step=ms_total, ms_cavi=ms_cavi, ms_gibbs=ms_gibbs, ms_allreduce=ms_coll, launches=int(launches))
+
+
+def leg_report(leg, tm, world, peak, peak_src, steps, traffic=None):
+    w = WORKLOADS[leg.name]
+    units = leg.units
+    ach = w["bytes_cavi"] * units / (tm["ms_cavi"] * 1e-3) / 1e9
+    gach = w["bytes_gibbs"] * units / (tm["ms_gibbs"] * 1e-3) / 1e9
+    unit = "(obs, class) elements" if leg.name == "categorical" else "obs"
+    return {
+        "baseline_config": w["cfg"], "likelihood": type(leg.lik).__name__, "obs_per_gpu": leg.n, "units_per_gpu": units,
+        "unit_of_rates": unit, "ms_per_step": tm["ms_per_step"], "obs_per_s": leg.n * world / (tm["ms_per_step"] * 1e-3),
+        "cavi": {"ms": tm["ms_cavi"], "units_per_s": units * world / (tm["ms_cavi"] * 1e-3),
+                 "roofline": {"kernel": CAVI_KERNEL[leg.name], "bound": "hbm", "achieved": ach, "peak": peak,
+                              "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
+                              "bytes_per_unit": w["bytes_cavi"], "traffic": traffic}},
+        "gibbs": {"ms": tm["ms_gibbs"], "draws_per_s": units * world / (tm["ms_gibbs"] * 1e-3),
+                  "kernel": GIBBS_KERNEL[leg.name], "bound": "fp64 pipe / issue (not HBM)",
+                  "hbm_GBs": gach, "frac_hbm": gach / peak, "bytes_per_unit": w["bytes_gibbs"]},
+        "gpu_launches_per_step": tm["launches"] // steps,
+    }
+
+
+def oracle_check_and_cpu(leg, torch, m, threads, seed=5):
+    """(1) parity at bench scale: the first m observations of the DEVICE inputs are copied to the host and the CPU oracle is
+    run on exactly those bits; state / beta / gamma of the timed run and the scalars of a GPU call on the same slice must
+    agree to 1e-12.  (2) the same oracle calls, timed, are the cpu_baseline of this workload (`kind: port`)."""
+    import numpy as np
+    from oracle import orc
+    A, name = leg.A, leg.name
+    cat, het = name == "categorical", name == "hetero"
+    m = min(m, leg.n)
+    sl = (slice(None), slice(0, m)) if het else slice(0, m)
+    y_d = leg.y[:m].contiguous()
+    mu_d, var_d, f_d = leg.mu[sl].contiguous(), leg.var[sl].contiguous(), leg.f[sl].contiguous()
+    y, mu, var, f = (t.cpu().numpy() for t in (y_d, mu_d, var_d, f_d))
+    olik = make_orc_lik(orc, name)
+    orc.set_threads(threads)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        rc, st, ob, og, seq, comp = orc.cavi_step(olik, y, mu, var)
+        t1 = time.perf_counter()
+        assert rc == 0
+        best = (t1 - t0) if best is None else min(best, t1 - t0)
+    t_cavi = best
+    mg = m if name in ("bernoulli", "laplace", "studentt") else max(1, m // 8)      # the reference sums b Devroye draws: slower
+    fg = f[:, :mg] if het else f[:mg]
+    t0 = time.perf_counter()
+    orc.aux_sample(olik, seed, np.ascontiguousarray(y[:mg]), np.ascontiguousarray(fg))
+    t_gibbs = (time.perf_counter() - t0) * (m / mg)
+    # --- parity of the timed run's outputs on the slice
+    rel = lambda a, b, floor=1e-300: float(np.max(np.where(a == b, 0.0, np.abs(a - b) / np.maximum(np.abs(b), floor))))
+    state0 = leg.q._s(0)[:m].cpu().numpy()
+    errs = {"state": rel(state0, st[0]),
+            "beta": rel(leg.beta[:, :m].cpu().numpy(), ob, 1.0), "gamma": rel(leg.gamma[:, :m].cpu().numpy(), og)}
+    qs = A.init_aux_posterior(leg.lik, m)
+    _, _, _, sc = A.cavi_step_(qs, leg.lik, y_d, A.Normals(mu_d, var_d), want_elbo=True)
+    sc = sc.cpu().numpy()
+    fused = leg.ctx.fused
+    errs["scalars"] = None if fused else max(abs(sc[k] - comp[k]) / abs(comp[k]) for k in range(3))
+    ok = all(v is None or v <= 1e-12 for v in errs.values())
+    assert ok, (name, errs)
+    units = m * leg.lik.nlatent if cat else m
+    return {"value": m / (t_cavi + t_gibbs), "unit": "obs/s", "cores": threads, "kind": "port",
+            "sample": f"first {m} observations of the GPU leg's own inputs (copied D2H): separate-pass CAVI + ELBO sums on all of "
+                      f"them, aux_sample! on {mg} (extrapolated x{m // mg}); OpenMP {threads} threads; C++ restatement of the Julia "
+                      "reference",
+            "cavi_units_per_s": units / t_cavi, "draws_per_s": units / t_gibbs,
+            "parity_on_this_sample": {"max_rel_err": errs, "tolerance": 1e-12, "ok": ok}}
+
+
 def main():
     # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner under
     # NCCL_DEBUG, torchrun notices) is sent to stderr; the result line is written to the saved descriptor.
@@ -325,8 +561,8 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--n", type=int, default=100_000_000, help="observations per GPU (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-n", type=int, default=20_000_000, help="CPU sample size per step of the reference arm")
@@ -339,6 +575,9 @@ def main():
     ap.add_argument("--sparse-m", type=int, default=128)
     ap.add_argument("--sparse-n", type=int, default=2_000_000, help="observations per GPU of the sparse sweep leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--configs", default="negbin,poisson,studentt,laplace,hetero,categorical",
+                    help="BASELINE configs[2]-[4] legs to run besides the headline (comma-separated, or 'none')")
+    ap.add_argument("--config-steps", type=int, default=10, help="timed steps of each configs[2]-[4] leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -361,127 +600,180 @@ def main():
     ctx = A.Context(local_rank)
     A.set_default_context(ctx)
     if world > 1:
-        if args.collective == "nccl":
-            A.dist.init_comm(ctx)
-        else:
+        A.dist.init_comm(ctx)                                    # NCCL communicator: the `nccl` collective and the cross-check
+        if args.collective == "p2p":
             A.dist.init_p2p(ctx, fused=True)
-    n = args.n
-    i0 = rank * n                                    # global index of this rank's first observation
-    lik = A.BernoulliLikelihood()
     dev = torch.device("cuda", local_rank)
+    peak, peak_src = load_peaks()
+    nccl_coll = (lambda scal: A.dist.allreduce_scalars_(ctx, scal)) if (world > 1 and args.collective == "nccl") else None
+    checks = {}
 
-    # synthetic inputs of SURVEY §8(d), generated on the device
-    g = torch.Generator(device=dev)
-    g.manual_seed(1 + rank)
-    mu = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
-    var = (0.5 + torch.rand(n, dtype=torch.float64, device=dev, generator=g)) ** 2
-    f = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
-    y = (torch.rand(n, dtype=torch.float64, device=dev, generator=g) < torch.sigmoid(f)).to(torch.uint8)
-    qf = A.Normals(mu, var)
-    q = A.init_aux_posterior(lik, n)
-    beta = torch.empty((1, n), dtype=torch.float64, device=dev)
-    gamma = torch.empty((1, n), dtype=torch.float64, device=dev)
-    scal = torch.zeros(8, dtype=torch.float64, device=dev)
-    Ω = A.AuxSamples(torch.empty(n, dtype=torch.float64, device=dev), None)
+    def fused_vs_nccl(leg):
+        """N > 1: the scalars the fused mailbox exchange returned == the NCCL sum of the ranks' local scalars"""
+        if world == 1 or args.collective != "p2p":
+            return None
+        leg.cavi()
+        got = leg.scal.clone()
+        A.dist.set_fused(ctx, False)
+        leg.cavi()
+        loc = leg.scal.clone()
+        A.dist.allreduce_scalars_(ctx, loc)
+        A.dist.set_fused(ctx, True)
+        torch.cuda.synchronize()
+        err = float(((got[:3] - loc[:3]).abs() / loc[:3].abs()).max().item())
+        assert err <= 1e-13, (leg.name, got.tolist(), loc.tolist())
+        return err
+
+    # ------------------------------------------------------------------ headline: Bernoulli, weak scaling (n per GPU)
+    n = args.n
+    head = Leg(A, ctx, torch, "bernoulli", n, dev, rank, rank * n)
     ctx.seed(2026, 0)
-    torch.cuda.synchronize()
-
-    st = ctx.stream                                  # every kernel of the step is launched on this stream
-
-    def step(ev=None):
-        if ev:
-            ev[0].record(st)
-        A.cavi_step_(q, lik, y, qf, want_elbo=True, out=(beta, gamma, scal))
-        if ev:
-            ev[1].record(st)
-        A.aux_sample_(Ω, lik, y, f, i0=i0)
-        if ev:
-            ev[2].record(st)
-        if world > 1 and args.collective == "nccl":
-            A.dist.allreduce_scalars_(ctx, scal)          # p2p: already summed over ranks inside the CAVI kernel
-        if ev:
-            ev[3].record(st)
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    time.sleep(0.25)                                 # every rank waits for the sampler's first rows ...
-    if world > 1:
-        dist.barrier()                               # ... and all ranks enter the timed region together
-    torch.cuda.synchronize()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    l0 = ctx.launches()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record(st)
-    for k in range(args.steps):
-        step(evs[k])
-    t_end.record(st)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches = ctx.launches() - l0
+    time.sleep(0.25)
+    tm = time_leg(head, torch, dist, world, args.steps, args.warmup, nccl_coll)
     clocks = sampler.finish() if rank == 0 else None
-    ms_total = t_start.elapsed_time(t_end)
-    ms_cavi = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    ms_gibbs = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
-    ms_coll = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
-    t = torch.tensor([ms_total, ms_cavi, ms_gibbs, ms_coll], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max over ranks, device-timed
-    ms_total, ms_cavi, ms_gibbs, ms_coll = t.tolist()
-    elbo = float(scal[2].item())
+    elbo = float(head.scal[2].item())
+    checks["fused_mailbox_equals_nccl_sum_of_locals"] = {"bernoulli": fused_vs_nccl(head)}
 
     # ---------------- e2e: host buffers through the plugin calls, copies inside the timed region
-    e2e = None
+    e2e = e2e_full = None
     if not args.no_e2e:
-        import ctypes as C
-        hy = torch.empty(n, dtype=torch.uint8).pin_memory()
-        hmu = torch.empty(n, dtype=torch.float64).pin_memory()
-        hvar = torch.empty(n, dtype=torch.float64).pin_memory()
-        hf = torch.empty(n, dtype=torch.float64).pin_memory()
-        hy.copy_(y); hmu.copy_(mu); hvar.copy_(var); hf.copy_(f)
-        hc = torch.empty(n, dtype=torch.float64).pin_memory()
-        hb = torch.empty(n, dtype=torch.float64).pin_memory()
-        hg = torch.empty(n, dtype=torch.float64).pin_memory()
-        hw = torch.empty(n, dtype=torch.float64).pin_memory()
-        hs = (C.c_double * 8)()
-        d = lik._desc()
-        P = lambda tt: C.c_void_p(tt.data_ptr())
+        lik = head.lik
+        pin = lambda t: t.to("cpu").pin_memory()
+        hy, hmu, hvar, hf = pin(head.y), pin(head.mu), pin(head.var), pin(head.f)
+        hq = A.init_aux_posterior(lik, n, host=True)
+        hb = torch.empty((1, n), dtype=torch.float64).pin_memory()
+        hg = torch.empty((1, n), dtype=torch.float64).pin_memory()
+        hΩ = A.AuxSamples(torch.empty(n, dtype=torch.float64).pin_memory(), None)
+        res = {}
 
-        def e2e_step():
-            A.check(ctx.lib.aug_cavi_step_host(ctx.h, C.byref(d), n, P(hy), P(hmu), P(hvar), 0, P(hc), None, None,
-                                               P(hb), P(hg), n, hs))
-            A.check(ctx.lib.aug_aux_sample_host(ctx.h, C.byref(d), n, i0, P(hy), P(hf), 0, P(hw), None))
+        def e2e_step(full):
+            # the public API with HOST arrays: api.cavi_step_ / api.aux_sample_ -> aug_cavi_step_host / aug_aux_sample_host
+            if full:
+                res["c"] = A.cavi_step_(hq, lik, hy, A.Normals(hmu, hvar), want_elbo=True, out=(hb, hg))
+            else:   # optional outputs: beta = sign(y - 1/2)/2 is a function of y the caller holds, c only feeds the ELBO
+                res["c"] = A.cavi_step_(None, lik, hy, A.Normals(hmu, hvar), want_elbo=True, out=(None, hg), want_beta=False)
+            ctx.seed(2026, 99)
+            A.aux_sample_(hΩ, lik, hy, hf, i0=rank * n)
 
+        def run_e2e(full):
+            torch.cuda.synchronize()
+            e2e_step(full)                                 # warm-up (allocates the staging slots)
+            if world > 1:
+                dist.barrier()
+            ksteps = max(1, min(args.steps, 5))
+            w0 = time.perf_counter()
+            for _ in range(ksteps):
+                e2e_step(full)                             # returns after results are on the host
+            w1 = time.perf_counter()
+            te = torch.tensor([w1 - w0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return te.item() / ksteps, ksteps
+
+        s_full, k_full = run_e2e(True)
+        # parity of the e2e path at bench scale: every array it returned == the device-resident run on the same inputs
+        ctx.seed(2026, 99)
+        head.gibbs()
         torch.cuda.synchronize()
-        e2e_step()                                     # warm-up (allocates the staging slots)
+        eq = {"c": bool(torch.equal(hq.c, head.q.c.cpu())), "beta": bool(torch.equal(hb, head.beta.cpu())),
+              "gamma": bool(torch.equal(hg, head.gamma.cpu())), "omega": bool(torch.equal(hΩ.omega, head.Ω.omega.cpu()))}
+        hs = res["c"][3]
+        head.cavi()
+        loc_elbo = head.scal.clone()
+        if world > 1 and ctx.fused:                        # host verbs are rank-local: compare with this rank's local sums
+            A.dist.set_fused(ctx, False)
+            head.cavi()
+            loc_elbo = head.scal.clone()
+            A.dist.set_fused(ctx, True)
+        torch.cuda.synchronize()
+        eq["scalars_rel_err"] = float(((hs[:3] - loc_elbo[:3].cpu()).abs() / loc_elbo[:3].cpu().abs()).max().item())
+        assert all(eq[k] for k in ("c", "beta", "gamma", "omega")) and eq["scalars_rel_err"] <= 1e-12, eq
+        checks["e2e_outputs_equal_device_run"] = eq
+        s_min, k_min = run_e2e(False)
+        assert bool(torch.equal(hg, head.gamma.cpu()))
+        h2d = n * (1 + 8 + 8) + n * 8                       # y, mu, var | f  (the Bernoulli aux_sample! reads no y)
+        d2h_full, d2h_min = n * (24 + 8) + 64, n * (8 + 8) + 64
+        pcie = ("measured on this pool (tools/pcie_probe.py, profiles/e2e_pcie_probe_r1k.txt): 55.5 GB/s H2D, 57.0 D2H, "
+                "49.8 each way when both run")
+        e2e = {"value": n * world / s_min, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_min,
+               "ms_per_step": 1e3 * s_min, "steps": k_min,
+               "path": "api.cavi_step_ + api.aux_sample_ on pinned HOST arrays -> aug_cavi_step_host + aug_aux_sample_host "
+                       "(3-slot H2D / kernel / D2H pipeline inside the library)",
+               "outputs": "gamma, omega, ELBO scalars (optional outputs skipped: beta = sign(y-1/2)/2 is a function of y the "
+                          "caller holds — bernoulli.jl:28 — and the state c only feeds the ELBO terms the call already returns)",
+               "pcie_GBs": (h2d + d2h_min) / s_min * 1e-9, "pcie_bound": pcie}
+        e2e_full = {"value": n * world / s_full, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
+                    "ms_per_step": 1e3 * s_full, "steps": k_full, "outputs": "c, beta, gamma, omega, ELBO scalars (everything)",
+                    "pcie_GBs": (h2d + d2h_full) / s_full * 1e-9}
+        del hy, hmu, hvar, hf, hq, hb, hg, hΩ
+
+    # ---------------- cpu_baseline + parity on a slice of the device inputs (rank 0)
+    cpu = None
+    threads = 1
+    if rank == 0 and not args.no_cpu:
+        from oracle import orc
+        orc.lib()
+        threads = host_threads(orc)
+        cpu = oracle_check_and_cpu(head, torch, args.cpu_n, threads)
+        n1 = min(args.cpu_n // 10, 2_000_000)
+        t1, c1, g1 = cpu_reference(n1, 1)
+        cpu["single_thread"] = {"value": n1 / t1, "cavi_obs_per_s": n1 / c1, "pg_draws_per_s": n1 / g1,
+                                "sample": f"{n1} obs, 1 thread (the reference is single-threaded)"}
+    if world > 1:
+        dist.barrier()
+    head_report = leg_report(head, tm, world, peak, peak_src, args.steps)
+    head.free()
+
+    # ---------------- strong scaling: the SAME global problem (N = 1e8 in total) sharded over the ranks
+    strong = None
+    if world > 1:
+        lo, hi = A.dist.shard_bounds(args.n, world, rank)
+        sleg = Leg(A, ctx, torch, "bernoulli", hi - lo, dev, rank, lo)
+        stm = time_leg(sleg, torch, dist, world, args.steps, args.warmup, nccl_coll)
+        strong = {"global_obs": args.n, "obs_per_gpu": hi - lo, "ms_per_step": stm["ms_per_step"],
+                  "value": args.n / (stm["ms_per_step"] * 1e-3), "unit": UNIT, "ms_cavi": stm["ms_cavi"],
+                  "ms_gibbs": stm["ms_gibbs"], "ms_allreduce": stm["ms_allreduce"],
+                  "speedup_vs_1gpu_weak_step": tm["ms_per_step"] / stm["ms_per_step"],
+                  "efficiency_vs_ideal": tm["ms_per_step"] / stm["ms_per_step"] / world,
+                  "note": "ideal = this run's per-GPU step on 1e8 observations divided by the number of ranks; SURVEY §8(e) "
+                          "expects ~85-90% at 8 GPUs for the scalar-returning variant (launch + exchange latency against a "
+                          "~0.35 ms step)"}
+        sleg.free()
+
+    # ---------------- BASELINE configs[2]-[4]
+    cfgs = {}
+    names = [] if args.configs in ("", "none") else [c for c in args.configs.split(",") if c]
+    for name in names:
+        w = WORKLOADS[name]
+        nn = w["n"] if args.n >= 100_000_000 else max(1, int(w["n"] * args.n / 100_000_000))
+        leg = Leg(A, ctx, torch, name, nn, dev, rank, rank * nn)
+        ltm = time_leg(leg, torch, dist, world, args.config_steps, 3, nccl_coll)
+        rep = leg_report(leg, ltm, world, peak, peak_src, args.config_steps)
+        rep["scaling"] = "weak"
+        fv = fused_vs_nccl(leg)
+        if fv is not None:
+            rep["fused_mailbox_vs_nccl_sum_rel_err"] = fv
+        if rank == 0 and not args.no_cpu:
+            m = {"categorical": 20_000, "hetero": 4_000_000}.get(name, 8_000_000)
+            rep["cpu_baseline"] = oracle_check_and_cpu(leg, torch, m, threads)
+            rep["speedup_vs_cpu"] = {"cavi": rep["cavi"]["units_per_s"] / rep["cpu_baseline"]["cavi_units_per_s"],
+                                     "gibbs": rep["gibbs"]["draws_per_s"] / rep["cpu_baseline"]["draws_per_s"]}
         if world > 1:
             dist.barrier()
-        ksteps = max(1, min(args.steps, 5))
-        w0 = time.perf_counter()
-        for _ in range(ksteps):
-            e2e_step()                                 # returns after results are on the host
-        w1 = time.perf_counter()
-        te = torch.tensor([w1 - w0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = te.item() / ksteps
-        assert abs(hs[2] - elbo) <= 1e-9 * abs(elbo) or world > 1, (hs[2], elbo)
-        e2e = {"value": n * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * (1 + 8 + 8 + 1 + 8),
-               "d2h_bytes_per_step": n * (24 + 8) + 64, "ms_per_step": 1e3 * e2e_s, "steps": ksteps,
-               "path": "aug_cavi_step_host + aug_aux_sample_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)",
-               "pcie_GBs": (n * (1 + 8 + 8 + 1 + 8) + n * (24 + 8) + 64) / e2e_s * 1e-9,
-               "pcie_bound": "measured on this pool (tools/pcie_probe.py, profiles/e2e_pcie_probe_r1k.txt): 55.5 GB/s H2D, "
-                             "57.0 D2H, 49.8 each way when both run: the D2H side (32 B/obs) bounds the step at ~64 ms"}
-        del hy, hmu, hvar, hf, hc, hb, hg, hw
+        leg.free()
+        if world > 1:                                      # strong: the config's global size sharded over the ranks
+            lo, hi = A.dist.shard_bounds(w["n"], world, rank)
+            sl = Leg(A, ctx, torch, name, hi - lo, dev, rank, lo)
+            stm = time_leg(sl, torch, dist, world, args.config_steps, 3, nccl_coll)
+            rep["strong"] = {"global_obs": w["n"], "obs_per_gpu": hi - lo, "ms_per_step": stm["ms_per_step"],
+                             "ms_cavi": stm["ms_cavi"], "ms_gibbs": stm["ms_gibbs"],
+                             "obs_per_s": w["n"] / (stm["ms_per_step"] * 1e-3),
+                             "efficiency_vs_ideal": ltm["ms_per_step"] / stm["ms_per_step"] / world}
+            sl.free()
+        cfgs[name] = rep
 
     # ---------------- secondary leg (SURVEY §8(f) rows 1-2): one sparse-GP CAVI iteration as one pass over κ
     sparse = None
@@ -494,24 +786,6 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---------------- cpu_baseline: the oracle, timed on this box's host cores (bounded sample)
-    cpu = None
-    if not args.no_cpu:
-        from oracle import orc
-        orc.lib()
-        threads = host_threads(orc)
-        t1, c1, g1 = cpu_reference(min(args.cpu_n // 10, 2_000_000), 1)
-        n1 = min(args.cpu_n // 10, 2_000_000)
-        tt, tc, tg = cpu_reference(args.cpu_n, threads, repeats=2)
-        cpu = {"value": args.cpu_n / tt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_n} Bernoulli obs, same step (separate-pass CAVI + Devroye PG(1) draws), OpenMP "
-                         f"{threads} threads, best of 2; C++ restatement of the Julia reference",
-               "cavi_obs_per_s": args.cpu_n / tc, "pg_draws_per_s": args.cpu_n / tg,
-               "single_thread": {"value": n1 / t1, "cavi_obs_per_s": n1 / c1, "pg_draws_per_s": n1 / g1,
-                                 "sample": f"{n1} obs, 1 thread (the reference is single-threaded)"}}
-
-    peak, peak_src = load_peaks()
-    ach = BYTES_CAVI * n / (ms_cavi * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -521,13 +795,14 @@ def main():
                 traffic = traffic * n / 100_000_000
         except Exception:
             traffic = None
-    ms_step = ms_total / args.steps
+    ms_step, ms_cavi, ms_gibbs = tm["ms_per_step"], tm["ms_cavi"], tm["ms_gibbs"]
+    ach = BYTES_CAVI * n / (ms_cavi * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": n * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1] (Bernoulli-logistic Gibbs aux_sample! PG draws, N=1e8 fp64) + "
-                               "configs[0]'s fused CAVI update at the same N",
+                               "configs[0]'s fused CAVI update at the same N; configs[2]-[4] in `configs`",
                    "obs_per_gpu": n, "global_obs": n * world, "likelihood": "BernoulliLikelihood(LogisticLink)",
                    "l2": "inputs+outputs 5.7 GB per step >> 126 MB L2 (no flush needed)",
                    "sharding": f"contiguous observation blocks, {world} rank(s); only the 8-double scalar block "
@@ -536,16 +811,20 @@ def main():
                                   "fused into cavi_tma_kernel's finaliser over the peer-memory mailbox (NVLink)"
                                   if args.collective == "p2p" else "ncclAllReduce(sum, double, 8) after the step")},
         "parts": {"cavi_obs_per_s": n * world / (ms_cavi * 1e-3), "pg_draws_per_s": n * world / (ms_gibbs * 1e-3),
-                  "ms_cavi": ms_cavi, "ms_gibbs": ms_gibbs, "ms_allreduce": ms_coll},
-        "roofline": {"kernel": "cavi_tma_kernel<BERNOULLI, ELBO> (aux_posterior! + expected potential/precision + ELBO sums)", "bound": "hbm", "achieved": ach,
+                  "ms_cavi": ms_cavi, "ms_gibbs": ms_gibbs, "ms_allreduce": tm["ms_allreduce"]},
+        "roofline": {"kernel": "cavi_tma_kernel<BERNOULLI, ELBO> (aux_posterior! + expected potential/precision + ELBO sums): "
+                               "the HBM-bound kernel of the step; the time-dominant one is the issue-bound sampler in roofline_gibbs",
+                     "bound": "hbm", "achieved": ach,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
-                     "frac_of_8TBs_nominal": ach / 8000.0, "bytes_per_obs": BYTES_CAVI, "traffic": traffic},
-        "roofline_gibbs": {"kernel": "pg1_compact_kernel (warp-compacted Devroye PG(1,c))", "bound": "fp64 pipe / issue (not HBM)",
+                     "frac_of_8TBs_nominal": ach / 8000.0, "bytes_per_obs": BYTES_CAVI, "traffic": traffic,
+                     "share_of_step": ms_cavi / ms_step},
+        "roofline_gibbs": {"kernel": GIBBS_KERNEL["bernoulli"], "bound": "fp64 pipe / issue (not HBM)",
                            "achieved": BYTES_GIBBS * n / (ms_gibbs * 1e-3) / 1e9, "unit": "GB/s",
                            "frac_hbm": BYTES_GIBBS * n / (ms_gibbs * 1e-3) / 1e9 / peak,
-                           "pg_draws_per_s_per_gpu": n / (ms_gibbs * 1e-3)},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "elbo_check": elbo,
+                           "pg_draws_per_s_per_gpu": n / (ms_gibbs * 1e-3), "share_of_step": ms_gibbs / ms_step,
+                           "ncu": "profiles/ (issue-slot utilisation, active lanes, pipe shares of this kernel)"},
+        "cpu_baseline": cpu, "e2e": e2e, "e2e_all_outputs": e2e_full, "gpu_launches": int(tm["launches"]), "clocks": clocks,
+        "elbo_check": elbo, "checks": checks, "strong_scaling": strong, "configs": cfgs,
     }
     if sparse:
         if not args.no_cpu:
