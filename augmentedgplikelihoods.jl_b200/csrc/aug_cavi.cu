@@ -149,7 +149,10 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_MIN_BLOCKS) cavi_kernel(const 
             if (HET) o.s2 = reinterpret_cast<const double*>(a.rs2)[i];
             if (YSTATE && a.rs2 != nullptr) o.ys = (double)reinterpret_cast<const int64_t*>(a.rs2)[i];
         }
-        eval<KIND, FROM_STATE, ELBO, true>(a.L, o);
+        // the result is a function of the observation alone: straight-line math when it is in range, IEEE / libdevice
+        // otherwise — the same choice every kernel makes, so an observation gets the same bits on every route
+        if (fast_ok<KIND, FROM_STATE, ELBO>(o)) eval<KIND, FROM_STATE, ELBO, false>(a.L, o);
+        else eval<KIND, FROM_STATE, ELBO, true>(a.L, o);
         if (!FROM_STATE) {
             if (a.s0) a.s0[i] = o.s0;
             if (HAS_S1 && a.s1) a.s1[i] = o.s1;
@@ -442,7 +445,8 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(co
                     o.mg = o.vg = 0.0;
                     o.s0 = o.s1 = o.s2 = 0.0;
                     if (HET) { o.mg = a.mu_g[i]; o.vg = a.var_g[i]; }
-                    eval<KIND, false, ELBO, true>(a.L, o);
+                    if (fast_ok<KIND, false, ELBO>(o)) eval<KIND, false, ELBO, false>(a.L, o);
+                    else eval<KIND, false, ELBO, true>(a.L, o);
                     if (a.s0) a.s0[i] = o.s0;
                     if (HAS_S1 && a.s1) a.s1[i] = o.s1;
                     if (HET && a.s2) reinterpret_cast<double*>(a.s2)[i] = o.s2;

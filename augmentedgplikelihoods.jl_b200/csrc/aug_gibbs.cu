@@ -251,7 +251,10 @@ struct PgbArgs {
 #define PGB_T_GAM 1u
 #define PGB_T_FRAC 2u
 #define PGB_QCAP 64
-#define PGB_WARPS (AUG_BLOCK / 32)
+#ifndef PGB_BLOCK
+#define PGB_BLOCK 256
+#endif
+#define PGB_WARPS (PGB_BLOCK / 32)
 // dynamic shared memory: r(z) table | per warp 3 queues (Devroye, Gamma, fractional) x { lo[QCAP], hi[QCAP] } double2
 #define PGB_SMEM_BYTES (AUG_PGTAB_N * AUG_PGTAB_DEG * 8 + PGB_WARPS * 3 * 2 * PGB_QCAP * 16)
 
@@ -259,10 +262,10 @@ struct PgbArgs {
 #define PGB_MIN_BLOCKS 2
 #endif
 template <int KIND>
-__global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const PgbArgs a) {
+__global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const PgbArgs a) {
     extern __shared__ __align__(16) unsigned char pgb_smem[];
     double* tab_s = reinterpret_cast<double*>(pgb_smem);
-    augp::pg1_load_table_cm(tab_s, a.tab, AUG_BLOCK);
+    augp::pg1_load_table_cm(tab_s, a.tab, PGB_BLOCK);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double2* qbase = reinterpret_cast<double2*>(pgb_smem + AUG_PGTAB_N * AUG_PGTAB_DEG * 8) + (size_t)warp * 3 * 2 * PGB_QCAP;
@@ -277,6 +280,11 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
     key.k1 = (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32);
     key.c3 = (uint32_t)a.offset;
     constexpr double SCALE = 0.5 / (augp::PI * augp::PI);
+    // b <= BX: exact pieces.  HETERO (b = n + 1/2, n mostly 0..3) keeps ALL its common cases on the exact pieces and
+    // starts no convolution in the fresh step: its hot code (fresh + fractional + Devroye steps) then fits the 32 KB
+    // instruction cache — with the convolution in line ncu showed 44% of the stall samples on instruction fetch.
+    constexpr double BX = KIND == AUG_HETERO ? 12.75 : PGB_BX;
+    constexpr bool INLINE_CONV = KIND != AUG_HETERO;
     int nd = 0, ng = 0, nf = 0;
 
     auto push = [&](double2* lo, double2* hi, int& qn, bool want, uint32_t el, uint32_t st, double acc, double b, double c) {
@@ -308,8 +316,9 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
     uint32_t ch = blockIdx.x * PGB_WARPS + warp;
     for (;;) {
         int mode;                                   // 0 fresh, 1 Devroye queue, 2 gamma queue, 3 fractional queue
-        if (nf >= 32) mode = 3;
-        else if (nd >= 32) mode = 1;
+        // a fractional step feeds the Devroye queue: it may only run while that queue has room for 32 more items
+        if (nd >= 32) mode = 1;
+        else if (nf >= 32) mode = 3;
         else if (ng >= 32) mode = 2;
         else if (ch < nchunks) mode = 0;
         else if (nf > 0) mode = 3;
@@ -334,18 +343,14 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                 } else if (KIND == AUG_POISSON) {                       // poisson.jl:26-28, polyagammapoisson.jl:23-27
                     c = ld_stream1(a.f + el);
                     const int64_t y = __ldg(reinterpret_cast<const int64_t*>(a.y) + el);
-                    augr::Philox g;
-                    g.init(a.seed, a.offset, gi, 192u);                 // tag 6
-                    const int64_t nn = augr::poisson_rand(g, a.p0 * augm::logistic(-c));
+                    const int64_t nn = augb::poisson_draw(key, e_lo, e_hi, a.seed, a.offset, gi, a.p0 * augb::logistic_fast(-c));
                     a.nvar[el] = nn;
                     b = (double)(nn + y);
                 } else if (KIND == AUG_HETERO) {                        // heteroscedasticgaussian.jl:28-32
                     const double f = ld_stream1(a.f + el);
                     c = ld_stream1(a.g + el);
                     const double d = f - ld_stream1(reinterpret_cast<const double*>(a.y) + el);
-                    augr::Philox g;
-                    g.init(a.seed, a.offset, gi, 192u);
-                    const int64_t nn = augr::poisson_rand(g, a.p0 * augm::logistic(-c) * d * d * 0.5);
+                    const int64_t nn = augb::poisson_draw(key, e_lo, e_hi, a.seed, a.offset, gi, a.p0 * augb::logistic_fast(-c) * d * d * 0.5);
                     a.nvar[el] = nn;
                     b = (double)nn + 0.5;
                     isint = false;
@@ -361,34 +366,40 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                 finish(el, 0.0);
                 live = false;
             }
-            const bool conv = live && b > PGB_BX;
+            const bool conv = live && b > BX;
             uint32_t gst = 0;
             double gacc = 0.0;
             bool gpush = false;
-            if (__any_sync(0xffffffffu, conv)) {
-                if (conv) {
-                    // first attempt of the two leading terms and of the tail in line (3 independent Philox blocks)
-                    const augb::Conv s = augb::conv_setup(b, c);
-                    uint32_t w1[4], w2[4], w0[4];
-                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 1u, 0u, 0u), key.c3, w1);
-                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 2u, 0u, 0u), key.c3, w2);
-                    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 0u, 0u, 0u), key.c3, w0);
-                    const double v1 = augb::gamma_attempt(w1, b);
-                    const double v2 = augb::gamma_attempt(w2, b);
-                    const double v0 = augb::gamma_attempt(w0, s.shape);
-                    uint32_t mask = 0;
-                    gacc = s.loc;
-                    if (v1 >= 0.0) gacc = fma(v1, augf::rcp(0.25 + s.w), gacc); else mask |= 1u;
-                    if (v2 >= 0.0) gacc = fma(v2, augf::rcp(2.25 + s.w), gacc); else mask |= 2u;
-                    if (v0 >= 0.0) gacc = fma(v0, s.theta, gacc); else mask |= 4u;
-                    const uint32_t extra = s.kt > 2 ? 3u : 0u;
-                    if (mask == 0u && extra == 0u) {
-                        finish(el, gacc * SCALE);
-                    } else {
-                        gpush = true;
-                        gst = PGB_T_GAM | (mask << 2) | (extra << 5) | ((uint32_t)s.kt << 11) | ((mask ? 1u : 0u) << 17);
+            if (INLINE_CONV) {
+                if (__any_sync(0xffffffffu, conv)) {
+                    if (conv) {
+                        // first attempt of the two leading terms (one Box-Muller pair) and of the tail in line
+                        const augb::Conv s = augb::conv_setup(b, c);
+                        uint32_t w1[4], w0[4];
+                        augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 1u, 0u, 0u), key.c3, w1);
+                        augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 0u, 0u, 0u), key.c3, w0);
+                        double v1, v2;
+                        augb::gamma_pair_attempt(w1, b, v1, v2);
+                        const double v0 = augb::gamma_attempt(w0, s.shape);
+                        uint32_t mask = 0;
+                        gacc = s.loc;
+                        if (v1 >= 0.0) gacc = fma(v1, augf::rcp(0.25 + s.w), gacc); else mask |= 1u;
+                        if (v2 >= 0.0) gacc = fma(v2, augf::rcp(2.25 + s.w), gacc); else mask |= 2u;
+                        if (v0 >= 0.0) gacc = fma(v0, s.theta, gacc); else mask |= 4u;
+                        const uint32_t extra = s.kt > 2 ? 3u : 0u;
+                        if (mask == 0u && extra == 0u) {
+                            finish(el, gacc * SCALE);
+                        } else {
+                            gpush = true;
+                            gst = PGB_T_GAM | (mask << 2) | (extra << 5) | ((uint32_t)s.kt << 11) | ((mask ? 1u : 0u) << 17);
+                        }
                     }
                 }
+            } else if (conv) {
+                // every term is drawn by the gamma steps, one attempt per visit; the tail visit adds loc (bit 31)
+                const uint32_t kt = (uint32_t)augb::conv_kt(fabs(c));
+                gpush = true;
+                gst = PGB_T_GAM | (7u << 2) | ((kt > 2u ? 3u : 0u) << 5) | (kt << 11) | 0x80000000u;
             }
             push(qg_lo, qg_hi, ng, gpush, el, gst, gacc, b, c);
             // exact pieces: fractional part first (if any), then floor(b) Devroye draws
@@ -397,7 +408,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
             double e = b - fl;
             if (e < 1e-250) e = 0.0;
             const uint32_t rem = (uint32_t)fl;
-            push(qf_lo, qf_hi, nf, exact && e > 0.0, el, PGB_T_FRAC | (rem << 2), 0.0, e, c);
+            push(qf_lo, qf_hi, nf, exact && e > 0.0, el, PGB_T_FRAC | (rem << 2), 0.0, e, c);   // rem <= 12: 4 bits
             push(qd_lo, qd_hi, nd, exact && e == 0.0, el, PGB_T_DEV | (rem << 2), 0.0, 0.0, c);
             continue;
         }
@@ -411,15 +422,17 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
             bool again = false;
             if (active) {
                 uint32_t mask = (st >> 2) & 7u, extra = (st >> 5) & 63u, att = (st >> 17) & 0x3fffu;
-                const uint32_t kt = (st >> 11) & 63u;
+                const uint32_t kt = (st >> 11) & 63u, locflag = st & 0x80000000u;
                 const uint32_t k = mask ? ((mask & 1u) ? 1u : ((mask & 2u) ? 2u : 0u)) : extra;
                 const uint64_t gi = (uint64_t)a.i0 + el;
                 const double xp = 0.5 * fabs(c) * (1.0 / augp::PI);
                 double shape = b, wt;
+                double loc = 0.0;
                 if (k == 0u) {
                     const augb::Conv s = augb::conv_setup(b, c);
                     shape = s.shape;
                     wt = s.theta;
+                    if (locflag) loc = s.loc;
                 } else {
                     const double km = (double)k - 0.5;
                     wt = augf::rcp(fma(km, km, xp * xp));
@@ -429,7 +442,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                 const double v = augb::gamma_attempt(w, shape);
                 again = true;
                 if (v >= 0.0) {
-                    acc = fma(v, wt, acc);
+                    acc = fma(v, wt, acc) + loc;
                     if (mask) {
                         mask &= mask - 1u;                         // clear the lowest pending bit (k = 1, then 2, then tail)
                         att = mask ? 1u : 0u;
@@ -445,7 +458,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                     finish(el, augb::pgb_sequential(a.seed, a.offset, gi, b, false, c, a.tab));
                     again = false;
                 }
-                st = PGB_T_GAM | (mask << 2) | (extra << 5) | (kt << 11) | (att << 17);
+                st = PGB_T_GAM | (mask << 2) | (extra << 5) | (kt << 11) | (att << 17) | locflag;
             }
             push(qg_lo, qg_hi, ng, again, el, st, acc, b, c);
             continue;
@@ -458,11 +471,11 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
             double acc = 0.0, e = 0.5, c = 0.0;
             pop(qf_lo, qf_hi, nf, active, el, st, acc, e, c);
             bool again = false, to_dev = false;
-            const uint32_t rem = (st >> 2) & 7u;
+            const uint32_t rem = (st >> 2) & 15u;
             if (active) {
                 const uint64_t gi = (uint64_t)a.i0 + el;
                 const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
-                uint32_t att = (st >> 16) & 0x3fffu;
+                uint32_t att = (st >> 18) & 0x3fffu;
                 uint32_t w1[4], w2[4];
                 augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(4u, 0u, 0u, att), key.c3, w1);
                 augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(5u, 0u, 0u, att), key.c3, w2);
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                     finish(el, augb::pgb_sequential(a.seed, a.offset, gi, e + (double)rem, false, c, a.tab));
                 } else {
                     again = true;
-                    st = PGB_T_FRAC | (rem << 2) | (att << 16);
+                    st = PGB_T_FRAC | (rem << 2) | (att << 18);
                 }
             }
             push(qf_lo, qf_hi, nf, again, el, st, acc, e, c);
@@ -493,7 +506,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
             const uint64_t gi = (uint64_t)a.i0 + el;
             const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
             const double z = 0.5 * fabs(c);
-            uint32_t rem = (st >> 2) & 7u, sub = (st >> 5) & 7u, round = (st >> 8) & 0xffu, att = (st >> 16) & 0x3fffu;
+            uint32_t rem = (st >> 2) & 15u, sub = (st >> 6) & 15u, round = (st >> 10) & 0xffu, att = (st >> 18) & 0x3fffu;
             uint32_t uacc = (uint32_t)__double2loint(bb);
             double x = -1.0;
             bool exhausted = false;
@@ -531,7 +544,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                 finish(el, acc + augb::pgb_sequential(a.seed, a.offset ^ 0x5bd1e995u, gi, (double)rem, true, c, a.tab));
                 again = false;
             }
-            st = PGB_T_DEV | (rem << 2) | (sub << 5) | (round << 8) | (att << 16);
+            st = PGB_T_DEV | (rem << 2) | (sub << 6) | (round << 10) | (att << 18);
             bb = __hiloint2double(0, (int)uacc);
         }
         push(qd_lo, qd_hi, nd, again, el, st, acc, bb, c);
@@ -660,15 +673,15 @@ int32_t launch_pgb(aug_ctx* ctx, const PgbArgs& a) {
     if (occ == 0) {
         if (cudaFuncSetAttribute(pgb_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGB_SMEM_BYTES) != cudaSuccess)
             return (int32_t)cudaGetLastError();
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgb_kernel<KIND>, AUG_BLOCK, PGB_SMEM_BYTES) != cudaSuccess || occ < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgb_kernel<KIND>, PGB_BLOCK, PGB_SMEM_BYTES) != cudaSuccess || occ < 1)
             occ = 1;
     }
     int64_t grid = (int64_t)ctx->sms * occ;
     const int64_t nchunks = (a.n + 31) / 32;
-    const int64_t need = (nchunks + (AUG_BLOCK / 32) - 1) / (AUG_BLOCK / 32);
+    const int64_t need = (nchunks + (PGB_BLOCK / 32) - 1) / (PGB_BLOCK / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    pgb_kernel<KIND><<<(unsigned)grid, AUG_BLOCK, PGB_SMEM_BYTES, ctx->stream>>>(a);
+    pgb_kernel<KIND><<<(unsigned)grid, PGB_BLOCK, PGB_SMEM_BYTES, ctx->stream>>>(a);
     ctx->launches++;
     return (int32_t)cudaGetLastError();
 }

@@ -27,6 +27,7 @@
 //      inversion in tests/test_pg_laws_cpu.py, not estimated from samples.  Cost is independent of b, where the
 //      reference's exact summation costs b Devroye draws (b ~ 20 for the NegBin / Poisson workloads).
 #pragma once
+#include "aug_math.cuh"
 #include "aug_pg.cuh"
 
 namespace augb {
@@ -93,24 +94,13 @@ __device__ __forceinline__ int conv_kt(double absc) {
     return k > PGB_KT_MAX ? PGB_KT_MAX : k;
 }
 
-// tail parameters for b, c  (b > 0)
-__device__ __forceinline__ Conv conv_setup(double b, double c) {
+// tail parameters for |c| > 3 (KT > 2 explicit terms): out of line — it is rare and heavy (exp, divisions)
+__device__ __noinline__ Conv conv_setup_general(double b, double c) {
     Conv s;
     const double x = 0.5 * fabs(c);
     const double xp = x * (1.0 / PI);
     s.w = xp * xp;
     s.kt = conv_kt(fabs(c));
-    if (s.kt == 2) {                                           // |c| <= 3: straight-line, no division
-        double p = TAIL1[0], th = THETA2[0], ka = KAPPA2[0];
-#pragma unroll
-        for (int m = 1; m < 14; ++m) p = fma(p, s.w, TAIL1[m]);
-#pragma unroll
-        for (int m = 1; m < 9; ++m) { th = fma(th, s.w, THETA2[m]); ka = fma(ka, s.w, KAPPA2[m]); }
-        s.theta = th;
-        s.shape = b * ka;
-        s.loc = b * fma(-th, ka, p);
-        return s;
-    }
     double t1, t2, t3;
     if (x <= 2.0) {
         double p = TAIL1[0], q = TAIL2[0], r = TAIL3[0];
@@ -150,10 +140,84 @@ __device__ __forceinline__ Conv conv_setup(double b, double c) {
     return s;
 }
 
+// tail parameters for b, c  (b > 0)
+__device__ __forceinline__ Conv conv_setup(double b, double c) {
+    Conv s;
+    const double x = 0.5 * fabs(c);
+    const double xp = x * (1.0 / PI);
+    s.w = xp * xp;
+    s.kt = conv_kt(fabs(c));
+    if (s.kt != 2) return conv_setup_general(b, c);            // |c| > 3: rare, out of line
+    {                                                          // |c| <= 3: straight-line, no division
+        double p = TAIL1[0], th = THETA2[0], ka = KAPPA2[0];
+#pragma unroll
+        for (int m = 1; m < 14; ++m) p = fma(p, s.w, TAIL1[m]);
+#pragma unroll
+        for (int m = 1; m < 9; ++m) { th = fma(th, s.w, THETA2[m]); ka = fma(ka, s.w, KAPPA2[m]); }
+        s.theta = th;
+        s.shape = b * ka;
+        s.loc = b * fma(-th, ka, p);
+        return s;
+    }
+}
+
 // sqrt of a non-negative normal-range number without the IEEE slow path
 __device__ __forceinline__ double sqrt_pos(double v) {
     v = fmax(v, 1e-290);
     return v * augf::rsqrt_(v);
+}
+
+// (cos, sin) of a UNIFORMLY RANDOM angle out of 32 random bits: 29 bits pick a in (0, pi/4), Taylor polynomials give
+// (cos a, sin a) to 1e-16, and the top 3 bits apply a random symmetry of the octagon (swap, two sign flips) — the point
+// is uniform on the circle, which is all Box-Muller needs (no argument reduction: ~25 instructions against ~40 for cospi)
+__device__ __forceinline__ void rand_unit_vector(uint32_t w, double& cs, double& sn) {
+    const double a = fma((double)(w & 0x1fffffffu), 0x1.0p-29 * (PI / 4.0), 0x1.0p-30 * (PI / 4.0));
+    const double a2 = a * a;
+    double ps = -1.0 / 1307674368000.0;                       // sin a = a (1 - a^2/3! + ... - a^14/15!)
+    ps = fma(ps, a2, 1.0 / 6227020800.0);
+    ps = fma(ps, a2, -1.0 / 39916800.0);
+    ps = fma(ps, a2, 1.0 / 362880.0);
+    ps = fma(ps, a2, -1.0 / 5040.0);
+    ps = fma(ps, a2, 1.0 / 120.0);
+    ps = fma(ps, a2, -1.0 / 6.0);
+    const double sa = fma(a * a2, ps, a);
+    double pc = 1.0 / 20922789888000.0;                       // cos a = 1 - a^2/2! + ... + a^16/16!
+    pc = fma(pc, a2, -1.0 / 87178291200.0);
+    pc = fma(pc, a2, 1.0 / 479001600.0);
+    pc = fma(pc, a2, -1.0 / 3628800.0);
+    pc = fma(pc, a2, 1.0 / 40320.0);
+    pc = fma(pc, a2, -1.0 / 720.0);
+    pc = fma(pc, a2, 1.0 / 24.0);
+    pc = fma(pc, a2, -0.5);
+    const double ca = fma(pc, a2, 1.0);
+    const bool sw = (w >> 29) & 1u;
+    double x = sw ? sa : ca, y = sw ? ca : sa;
+    cs = (w >> 30) & 1u ? -x : x;
+    sn = (w >> 31) ? -y : y;
+}
+
+// Marsaglia-Tsang accept test for a N(0,1) variate x and a uniform u; returns Gamma(shape) or < 0
+__device__ __forceinline__ double mt_test(double x, double u, double d, double ci) {
+    double v = fma(ci, x, 1.0);
+    if (v <= 1e-90) return -1.0;
+    v = v * v * v;
+    const double x2 = x * x;
+    if (u < fma(-0.0331 * x2, x2, 1.0)) return d * v;
+    if (augf::log_(u) < fma(0.5, x2, d * (1.0 - v + augf::log_(v)))) return d * v;
+    return -1.0;
+}
+// TWO independent attempts for Gamma(shape >= 1, 1) out of ONE Philox block: both normals of a Box-Muller pair
+// (w0 radius, w1 angle — 32 bits each: the pair lives on a 2^64-point lattice and is cut at 6.6 sigma, a 3e-11
+// perturbation used only inside the convolution, whose certified distance to the exact law is 3e-6) and w2, w3 as
+// the two accept uniforms.
+__device__ __forceinline__ void gamma_pair_attempt(const uint32_t (&w)[4], double shape, double& v1, double& v2) {
+    const double d = shape - (1.0 / 3.0);
+    const double ci = augf::rsqrt_(9.0 * d);
+    const double r = sqrt_pos(-2.0 * augf::log_(augr::u32_mid(w[0])));
+    double cs, sn;
+    rand_unit_vector(w[1], cs, sn);
+    v1 = mt_test(r * cs, augr::u32_mid(w[2]), d, ci);
+    v2 = mt_test(r * sn, augr::u32_mid(w[3]), d, ci);
 }
 
 // one Marsaglia-Tsang attempt for Gamma(shape >= 1, 1) out of one Philox block; < 0: rejected
@@ -162,28 +226,24 @@ __device__ __forceinline__ double gamma_attempt(const uint32_t (&w)[4], double s
     const double d = shape - (1.0 / 3.0);
     const double ci = augf::rsqrt_(9.0 * d);
     const double rad2 = -2.0 * augf::log_(augr::u53_open0(w[0], w[1]));
-    const double x = sqrt_pos(rad2) * cospi(2.0 * augr::u32_mid(w[2]));
-    double v = fma(ci, x, 1.0);
-    if (v <= 1e-90) return -1.0;
-    v = v * v * v;
-    const double u = augr::u32_mid(w[3]);
-    const double x2 = x * x;
-    if (u < fma(-0.0331 * x2, x2, 1.0)) return d * v;
-    if (augf::log_(u) < fma(0.5, x2, d * (1.0 - v + augf::log_(v)))) return d * v;
-    return -1.0;
+    double cs, sn;
+    rand_unit_vector(w[2], cs, sn);
+    return mt_test(sqrt_pos(rad2) * cs, augr::u32_mid(w[3]), d, ci);
 }
 
 // ---- (2) fractional part: one proposal X ~ IG(mean e/z, shape e^2) (J* scale) out of one Philox block
 // (w0, w1) radius, w2 angle of a normal N; w3 picks the root (Michael-Schucany-Haas).  Stable for z -> 0 (Levy).
 __device__ __forceinline__ double frac_propose(const uint32_t (&w)[4], double e, double z) {
     const double rad2 = -2.0 * augf::log_(augr::u53_open0(w[0], w[1]));
-    const double cs = cospi(2.0 * augr::u32_mid(w[2]));
+    double cs, sn;
+    rand_unit_vector(w[2], cs, sn);
     const double y = fmax(rad2 * cs * cs, 1e-280);                  // N^2
     const double h = y * augf::rcp(2.0 * e);
     const double x1 = e * augf::rcp(z + h + sqrt_pos(h * (2.0 * z + h)));   // smaller root; = e^2/y at z = 0
     // P(x1) = mu/(mu + x1) = e/(e + z x1); other root mu^2/x1 = e^2/(z^2 x1)
     if (augr::u32_mid(w[3]) * (e + z * x1) <= e) return x1;
-    return (e / z) * (e / z) / x1;
+    const double ez = e / z;
+    return ez * ez * augf::rcp(fmax(x1, 1e-280));
 }
 // accept X with probability R(x) = sum_n (-1)^n c_n q^{n(n+e)}; u in (0, 1]
 __device__ __forceinline__ bool frac_accept(double x, double e, double u) {
@@ -221,17 +281,12 @@ __device__ __forceinline__ bool frac_accept(double x, double e, double u) {
 }
 
 // ---- (1) Devroye pieces with this file's counter layout (same arithmetic as aug_pg.cuh: pg1_accept)
-__device__ __forceinline__ bool dev_accept(double x, uint32_t uacc, const Key& k, uint32_t e_lo, uint32_t e_hi,
-                                           uint32_t sub, uint32_t round) {
-    const int xh = __double2hiint(x);
-    const bool mid = xh >= 0x3fe00000 && xh < 0x3fe99999;      // [0.5, 0.8)
-    const bool wide = xh >= 0x3fd99999 && xh < 0x3ff00000;     // [0.39999, 1.0)
-    const uint32_t thr = mid ? 4269197491u : (wide ? 4289813334u : 4294108302u);
-    if (uacc <= thr) return true;
+__device__ __noinline__ bool dev_accept_series(double x, uint32_t uacc, uint32_t k0, uint32_t k1, uint32_t c3, uint32_t e_lo,
+                                               uint32_t e_hi, uint32_t sub, uint32_t round) {
     double u = augr::u32_mid(uacc);
     const double q = x > T ? -0.5 * PI * PI * x : -2.0 / x;
     uint32_t w[4];
-    augr::philox4x32_10(k.k0, k.k1, e_lo, e_hi, ctr(2u, sub, round, 0u), k.c3, w);
+    augr::philox4x32_10(k0, k1, e_lo, e_hi, ctr(2u, sub, round, 0u), c3, w);
     u += ((double)w[0] - 2147483648.0) * 0x1.0p-64;
     double sum = 1.0;
     for (int n = 1;; ++n) {
@@ -244,6 +299,52 @@ __device__ __forceinline__ bool dev_accept(double x, uint32_t uacc, const Key& k
             if (u > sum) return false;
         }
     }
+}
+__device__ __forceinline__ bool dev_accept(double x, uint32_t uacc, const Key& k, uint32_t e_lo, uint32_t e_hi,
+                                           uint32_t sub, uint32_t round) {
+    const int xh = __double2hiint(x);
+    const bool mid = xh >= 0x3fe00000 && xh < 0x3fe99999;      // [0.5, 0.8)
+    const bool wide = xh >= 0x3fd99999 && xh < 0x3ff00000;     // [0.39999, 1.0)
+    const uint32_t thr = mid ? 4269197491u : (wide ? 4289813334u : 4294108302u);
+    if (uacc <= thr) return true;                              // squeeze: >= 99.4% of the proposals
+    return dev_accept_series(x, uacc, k.k0, k.k1, k.c3, e_lo, e_hi, sub, round);
+}
+
+// rand(Poisson(lam)) on the element's own stream (tag 6): chop-down inversion in line for lam < 12, PTRS (Hörmann 1993)
+// out of line above (rare for the rates of poisson.jl:26-28 / heteroscedasticgaussian.jl:28-32 and heavy: lgamma, logs)
+__device__ __noinline__ int64_t poisson_ptrs(uint64_t seed, uint64_t offset, uint64_t gi, double lam) {
+    augr::Philox g;
+    g.init(seed, offset, gi, 193u);
+    return augr::poisson_rand(g, lam);
+}
+__device__ __forceinline__ int64_t poisson_draw(const Key& key, uint32_t e_lo, uint32_t e_hi, uint64_t seed, uint64_t offset,
+                                                uint64_t gi, double lam) {
+    if (!(lam > 0.0)) return 0;
+    if (lam >= 12.0) return poisson_ptrs(seed, offset, gi, lam);
+    // chop-down inversion from 0 with ONE 53-bit uniform (block tag 6); the search multiplies by a table of 1/k.
+    // k reaches 200 only through the 1e-16 round-off tail of the cumulative sum: restart with the block's other half.
+    uint32_t w[4];
+    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, ctr(6u, 0u, 0u, 0u), key.c3, w);
+    const double p0 = augf::exp_(-lam);
+    for (int half = 0;; ++half) {
+        double u = half == 0 ? augr::u53_open0(w[0], w[1]) : augr::u53_open0(w[2], w[3]);
+        double p = p0;
+        int k = 0;
+        while (u > p && k < 200) {
+            u -= p;
+            ++k;
+            p *= k < 64 ? lam * augr::INV_K[k] : lam / (double)k;
+        }
+        if (k < 200 || half == 1) return (int64_t)(k < 200 ? k : 0);
+    }
+}
+// logistic(x) with the LogExpFunctions saturation (augm::logistic) on the straight-line exp / reciprocal
+__device__ __forceinline__ double logistic_fast(double x) {
+    if (x < augm::LOGISTIC_LO) return 0.0;
+    if (x > augm::LOGISTIC_HI) return 1.0;
+    const double e = augf::exp_(-fmin(fabs(x), 700.0));
+    const double r = augf::rcp(1.0 + e);
+    return x >= 0.0 ? r : e * r;
 }
 
 // ---- sequential fall-back (counters exhausted, probability < 1e-70 per draw; also the reference implementation of
