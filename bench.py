@@ -184,7 +184,7 @@ def fp64_peak():
         try:
             os.chmod(exe, 0o755)                 # a snapshot copy may drop the executable bit
             out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
-            best = max(json.loads(l)["tflops"] for l in out.splitlines() if '"dmma' in l)
+            best = max(json.loads(l)["tflops"] for l in out.splitlines() if '"kernel": "dmma' in l)
             return best, "measured live (tools/fp64_peak: mma.sync.m8n8k4.f64, all SMs)"
         except Exception as e:
             return 37.1, f"recorded (profiles/fp64_peak_r1l.jsonl); the live run of tools/fp64_peak failed: {type(e).__name__}: {e}"
