@@ -20,7 +20,7 @@ ERR_PRECONDITION = -3
 
 class AugLik(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nlatent", C.c_int32), ("r_is_int", C.c_int32),
-                ("reserved", C.c_int32), ("p", C.c_double * 4), ("logtheta", C.c_void_p)]
+                ("flags", C.c_int32), ("p", C.c_double * 4), ("logtheta", C.c_void_p)]
 
 
 class AugError(RuntimeError):

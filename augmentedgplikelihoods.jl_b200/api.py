@@ -41,6 +41,7 @@ class Likelihood:
         d.kind = self.kind
         d.nlatent = self.nlatent
         d.r_is_int = int(r_is_int)
+        d.flags = 1 if getattr(self, "faithful_quirks", False) else 0   # AUG_LIK_FAITHFUL_QUIRKS
         for i, v in enumerate(params):
             d.p[i] = float(v)
         if logtheta is not None:
@@ -119,7 +120,10 @@ class CategoricalLikelihood(Likelihood):
     CategoricalLikelihood(LogisticSoftMaxLink(logθ)) — likelihoods/categorical.jl:6-47.
     `logtheta` may be an int (number of classes -> zeros, categorical.jl:10)."""
 
-    def __init__(self, logtheta, bijective=True):
+    def __init__(self, logtheta, bijective=True, faithful_quirks=False):
+        # faithful_quirks: return what the reference's CODE returns where it departs from the intended formulas
+        # (2-class PG log-density sum, NaN for p log p at p = 0) — include/augcuda.h: AUG_LIK_FAITHFUL_QUIRKS
+        self.faithful_quirks = bool(faithful_quirks)
         if isinstance(logtheta, int):
             logtheta = [0.0] * logtheta
         self.logtheta = [float(t) for t in logtheta]

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_cavi_kernel(const CatArgs a) {
                     sx1 += X1[i * nlp + j];
                     sx2 += X2[i * nlp + j];
                     if (p > 0.0) sx3 += p * ((p >= 1e-290 ? augf::log_(p) : log(p)) - a.L.c2);       // negativemultinomial.jl:79-81
+                    else if (a.L.quirks) sx3 += __longlong_as_double(0x7ff8000000000000ll);          // 0 * -Inf as the reference writes it
                 }
             }
             sp = warp_sum(sp);
@@ -212,7 +213,8 @@ struct CatTmaArgs {
 template <bool ELBO, bool SAFE>
 __device__ __forceinline__ void cat_elem(const double m, const double v, const bool yb, const double inv_denom,
                                          const double log_inv_denom, const double c2, double& c, double& p,
-                                         double& h, double& x1, double& x23, double& a0, double& a1) {
+                                         double& h, double& x1, double& x23, double& a0, double& a1,
+                                         const bool quirks = false) {
     using namespace augm;
     const double s2m = fma(m, m, v);
     PGTerms t;
@@ -222,7 +224,8 @@ __device__ __forceinline__ void cat_elem(const double m, const double v, const b
         t = pg_terms_ic<ELBO, true>(c, 0.0);
         sig = approx_expected_logistic<true>(-m, c, t);                   // :90-92, :107
         p = sig * inv_denom;
-        logp = p > 0.0 ? log(p) : 0.0;
+        // p == 0 (σ̃ saturated): the limit p log p = 0, or the reference's 0 * -Inf = NaN (negativemultinomial.jl:80)
+        logp = p > 0.0 ? log(p) : (quirks ? __longlong_as_double(0x7ff8000000000000ll) : 0.0);
     } else {
         double ic;
         augf::sqrt_inv(s2m, c, ic);
@@ -353,8 +356,8 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_tma_kernel(const CatTmaArgs 
                     const double2 m = smu[q], v = svar[q];
                     const bool y0 = yy.x != 0, y1 = yy.y != 0;
                     double c0, p0, h0, c1, p1, h1, xa0 = 0.0, xb0 = 0.0, xa1 = 0.0, xb1 = 0.0;
-                    cat_elem<ELBO, true>(m.x, v.x, y0, inv_denom, ta.log_inv_denom, a.L.c2, c0, p0, h0, xa0, xb0, acc[0], acc[1]);
-                    cat_elem<ELBO, true>(m.y, v.y, y1, inv_denom, ta.log_inv_denom, a.L.c2, c1, p1, h1, xa1, xb1, acc[0], acc[1]);
+                    cat_elem<ELBO, true>(m.x, v.x, y0, inv_denom, ta.log_inv_denom, a.L.c2, c0, p0, h0, xa0, xb0, acc[0], acc[1], a.L.quirks != 0);
+                    cat_elem<ELBO, true>(m.y, v.y, y1, inv_denom, ta.log_inv_denom, a.L.c2, c1, p1, h1, xa1, xb1, acc[0], acc[1], a.L.quirks != 0);
                     const int64_t o = tile * E + 2 * q;
                     if (a.s0) st_stream2(a.s0 + o, c0, c1);
                     if (a.s1) st_stream2(a.s1 + o, p0, p1);
@@ -624,7 +627,7 @@ __global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowA
                         const int64_t o = gro + 2 * q + u;
                         const bool yb = a.y[o] != 0;
                         double c, pp, h, xa = 0.0, xb = 0.0;
-                        cat_elem<ELBO, true>(a.mu[o], a.var[o], yb, inv_denom, ta.log_inv_denom, a.L.c2, c, pp, h, xa, xb, t0, t1);
+                        cat_elem<ELBO, true>(a.mu[o], a.var[o], yb, inv_denom, ta.log_inv_denom, a.L.c2, c, pp, h, xa, xb, t0, t1, a.L.quirks != 0);
                         if (a.s0) a.s0[o] = c;
                         if (a.s1) a.s1[o] = pp;
                         Pr[2 * q + u] = pp;

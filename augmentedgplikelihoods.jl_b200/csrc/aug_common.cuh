@@ -85,6 +85,7 @@ struct aug_ctx {
 // Likelihood constants precomputed on the host once per call (never per observation)
 struct LikConst {
     int kind, nl, r_is_int, bij;
+    int quirks;             // AUG_LIK_FAITHFUL_QUIRKS
     double p0, p1;          // raw parameters (r | λ | β | ν, σ)
     double c0, c1, c2, c3, c4, c5;  // derived constants, meaning per kind (see lik_const())
     const double* table;    // device table or nullptr

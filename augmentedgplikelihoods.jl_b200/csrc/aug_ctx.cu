@@ -132,6 +132,7 @@ int32_t aug_lik_const(aug_ctx* ctx, const aug_lik* lik, LikConst* L, bool need_t
     L->kind = lik->kind;
     L->nl = lik->nlatent;
     L->r_is_int = lik->r_is_int;
+    L->quirks = (lik->flags & AUG_LIK_FAITHFUL_QUIRKS) ? 1 : 0;
     L->p0 = lik->p[0];
     L->p1 = lik->p[1];
     L->pgtab = ctx->pgtab;

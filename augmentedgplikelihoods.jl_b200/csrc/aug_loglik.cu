@@ -140,6 +140,7 @@ struct CatLLArgs {
     const double* omega;
     const int64_t* nvar;
     int with_prior;
+    int quirks;              // AUG_LIK_FAITHFUL_QUIRKS: PG log-densities of classes 1:2 only (pgnm.jl:35)
     double log_prior_p, log_p0;
     double* partials;
     unsigned int* counter;
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_loglik_kernel(const CatLLArgs a
             const double f = a.f[base + j], w = a.omega[base + j];
             lt += -(y + nn) * augm::LN2 + 0.5 * ((y - nn) * f - f * f * w);
             if (a.with_prior) {
-                lp += pg_logpdf_dev(y + nn, 0.0, w) + (nn == 0.0 ? 0.0 : nn * a.log_prior_p) - lgamma(nn + 1.0);
+                if (!a.quirks || j < 2) lp += pg_logpdf_dev(y + nn, 0.0, w);
+                lp += (nn == 0.0 ? 0.0 : nn * a.log_prior_p) - lgamma(nn + 1.0);
                 sn += nn;
             }
         }
@@ -266,6 +268,8 @@ int32_t aug_sampled_loglik_terms(aug_ctx* c, const aug_lik* lik, int64_t n, cons
         a.omega = omega;
         a.nvar = nvar;
         a.with_prior = with_prior;
+        a.quirks = L.quirks;
+        if (with_prior && L.quirks && lik->nlatent < 2) return AUG_ERR_PRECONDITION;   // BoundsError in the reference
         a.log_prior_p = L.c2;
         a.log_p0 = L.c3;
         a.partials = c->partials;

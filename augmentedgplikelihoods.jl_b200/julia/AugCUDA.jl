@@ -31,7 +31,7 @@ struct AugLik               # typedef struct aug_lik
     kind::Int32
     nlatent::Int32
     r_is_int::Int32
-    reserved::Int32
+    flags::Int32            # AUG_LIK_FAITHFUL_QUIRKS = 1 (include/augcuda.h)
     p::NTuple{4,Float64}
     logtheta::Ptr{Float64}  # host pointer
 end

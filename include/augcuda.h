@@ -83,11 +83,21 @@ enum aug_status {
  *            categorical.jl:6-10); NULL means zeros.  K = nlatent (CAT) or
  *            nlatent + 1 (CAT_BIJ).
  */
+/* aug_lik.flags */
+#define AUG_LIK_FAITHFUL_QUIRKS 1 /* reproduce what the reference's CODE returns where it differs from the intended
+                                     mathematics (default 0 = intended):
+                                     - logdensity_def(::PolyaGammaNegativeMultinomial) sums the PG log-densities of
+                                       the first TWO classes only (`sum(1:length(x))` with x a 2-field NamedTuple,
+                                       SpecialDistributions/polyagammanegativemultinomial.jl:33-39; a BoundsError ->
+                                       AUG_ERR_PRECONDITION when nlatent < 2);
+                                     - kldivergence(::NegativeMultinomial, ...) is NaN when a variational p_j is
+                                       exactly 0 (`p * (log(p) - log(q))` = 0 * -Inf,
+                                       SpecialDistributions/negativemultinomial.jl:80) instead of the limit 0. */
 typedef struct aug_lik {
     int32_t kind;
     int32_t nlatent;
     int32_t r_is_int;
-    int32_t reserved;
+    int32_t flags;
     double  p[4];
     const double* logtheta;
 } aug_lik;

@@ -12,7 +12,7 @@
 // (test/SpecialDistributions/polyagamma.jl:27-37, test/utils.jl:1-14,
 // test/likelihoods/laplace.jl:6-9) and the two test_auglik invariants
 // (src/TestUtils.jl:107-148), and (b) an independent 50-digit mpmath
-// re-evaluation of the formulas (oracle/validate_oracle.py); see
+// re-evaluation of the formulas (tests/golden/make_golden.py -> tests/golden/golden_cavi.json); see
 // tests/test_oracle_*.py.  Values that the reference itself never pins
 // (expected_logtilt, aux_kldivergence, all Hetero/Categorical results) are
 // therefore "parity unpinned against Julia output" and pinned only against the
@@ -754,8 +754,10 @@ int orc_expected_elbo_terms(const aug_lik* l, int64_t n, const void* y, const do
                     quad += ((yi - nbar) * mu[e] - (abs2(mu[e]) + var[e]) * tw) / 2;
                     klpg += pg_kl(b, s0[e]);
                     // reference: p.p[i] * (log(p.p[i]) - log(q.p[i])) (negativemultinomial.jl:80) is NaN when
-                    // p.p[i] == 0 (σ̃ saturated, m > 744.44); we take the limit 0
-                    if (s1[e] > 0) klnm += s1[e] * (std::log(s1[e]) - std::log(cc.prior_p));
+                    // p.p[i] == 0 (σ̃ saturated, m > 744.44); the intended value is the limit 0,
+                    // AUG_LIK_FAITHFUL_QUIRKS evaluates the expression exactly as written (0 * -Inf = NaN)
+                    if (s1[e] > 0 || (l->flags & AUG_LIK_FAITHFUL_QUIRKS))
+                        klnm += s1[e] * (std::log(s1[e]) - std::log(cc.prior_p));
                 }
                 elt_l.add(-sum_yn * LOGTWO + quad);
                 kl_l.add(klpg + (1.0 * std::log(p0) - 1.0 * std::log(p0p) + 1.0 / p0 * klnm));
@@ -1052,6 +1054,9 @@ int orc_sampled_loglik_terms(const aug_lik* l, int64_t n, const void* y, const d
             if (with_prior && l->kind == AUG_CAT) return AUG_ERR_PRECONDITION;
             CatConst cc = cat_const(l);
             int nl = cc.nl;
+            const bool quirks = (l->flags & AUG_LIK_FAITHFUL_QUIRKS) != 0;
+            // faithful: `sum(1:length(x))` indexes classes 1 and 2 — a BoundsError for a single latent
+            if (with_prior && quirks && nl < 2) return AUG_ERR_PRECONDITION;
             const uint8_t* yy = (const uint8_t*)y;
             double sp = 0.0;
             for (int j = 0; j < nl; ++j) sp += cc.prior_p;
@@ -1064,9 +1069,9 @@ int orc_sampled_loglik_terms(const aug_lik* l, int64_t n, const void* y, const d
                     syn += yi + ni;
                     quad += (yi - ni) * f[e] - abs2(f[e]) * omega[e];
                     if (with_prior) {
-                        // intended all-class sum (the reference sums 1:length(x)=1:2 only,
-                        // polyagammanegativemultinomial.jl:35 — a bug)
-                        lpw += pg_logpdf(yi + ni, 0.0, omega[e]);
+                        // intended: all classes.  The reference's code sums 1:length(x) = 1:2 only
+                        // (polyagammanegativemultinomial.jl:35, x is the 2-field NamedTuple): AUG_LIK_FAITHFUL_QUIRKS
+                        if (!quirks || j < 2) lpw += pg_logpdf(yi + ni, 0.0, omega[e]);
                         sn += ni;
                         nmterm += (ni == 0.0 ? 0.0 : ni * std::log(cc.prior_p)) - std::lgamma(ni + 1);
                     }

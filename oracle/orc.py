@@ -24,16 +24,17 @@ Y_DTYPE = {
 
 class Lik(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nlatent", C.c_int32), ("r_is_int", C.c_int32),
-                ("reserved", C.c_int32), ("p", C.c_double * 4), ("logtheta", C.c_void_p)]
+                ("flags", C.c_int32), ("p", C.c_double * 4), ("logtheta", C.c_void_p)]
 
 
-def make_lik(kind, *params, nlatent=None, r_is_int=False, logtheta=None):
+def make_lik(kind, *params, nlatent=None, r_is_int=False, logtheta=None, faithful_quirks=False):
     if nlatent is None:
         nlatent = 2 if kind == HETERO else 1
     lik = Lik()
     lik.kind = kind
     lik.nlatent = nlatent
     lik.r_is_int = int(r_is_int)
+    lik.flags = 1 if faithful_quirks else 0
     for i, v in enumerate(params):
         lik.p[i] = float(v)
     if logtheta is not None:

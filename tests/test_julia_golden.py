@@ -1,0 +1,97 @@
+"""Parity against OUTPUT OF THE REFERENCE ITSELF, when it is available.
+
+tests/golden/make_golden_julia.jl runs AugmentedGPLikelihoods.jl on the inputs of golden_cavi.json and writes
+golden_julia.json.  There is no Julia in the build image, so the file is not committed and these tests SKIP; on a machine
+with Julia, run the script once and they hold the CPU oracle and (with -m gpu) libaugcuda to 1e-12 of what the reference
+returned — including the values its own test-suite never checks (expected_logtilt, aux_kldivergence, expected_aug_loglik,
+heteroscedastic and categorical results), which is what "parity unpinned" in DESIGN.md §5 refers to.
+Entries the reference could not compute (it throws: recorded as err_*) are skipped one by one.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import CAT, CAT_BIJ, HETERO, NEGBIN, POISSON, golden_arrays, lik_args, load_golden, relerr
+
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_julia.json")
+pytestmark = pytest.mark.skipif(not os.path.exists(PATH),
+                                reason="golden_julia.json absent: run tests/golden/make_golden_julia.jl where Julia is installed")
+RTOL = 1e-12
+
+
+def _load():
+    with open(PATH) as fh:
+        return json.load(fh)
+
+
+def _arr(x):
+    return np.ascontiguousarray(np.array(x, dtype=np.float64))
+
+
+def _check_vi(ref, kind, state, beta, gamma, scal, tag):
+    for i, key in enumerate(("s0", "s1", "s2")):
+        if key in ref and state[i] is not None:
+            assert relerr(np.asarray(state[i], dtype=np.float64), _arr(ref[key]).reshape(np.shape(state[i]))) < RTOL, tag + (key,)
+    if "beta" in ref:
+        assert relerr(beta, _arr(ref["beta"]), floor=1.0) < RTOL and relerr(gamma, _arr(ref["gamma"])) < RTOL, tag
+    for slot, key in ((0, "elt"), (1, "kl"), (2, "eall")):
+        if ref.get(key) is not None and scal is not None:
+            assert scal[slot] == pytest.approx(ref[key], rel=RTOL, abs=1e-12), tag + (key,)
+
+
+def test_oracle_against_reference_output(orc):
+    J, G = _load(), load_golden()
+    for name, ref in J.items():
+        case = G[name]
+        kind, params, kw = lik_args(case)
+        y, mu, var = golden_arrays(case)
+        olik = orc.make_lik(kind, *params, faithful_quirks=True, **kw)      # the file holds what the CODE returns
+        want = kind != CAT
+        rc, st, b, g, seq, comp = orc.cavi_step(olik, y, mu, var, want_scalars=want)
+        assert rc == 0
+        _check_vi(ref, kind, st, b, g, comp if want else None, (name,))
+        if "omega" in ref:
+            om = _arr(ref["omega"]).reshape(y.shape if kind in (CAT, CAT_BIJ) else (-1,))
+            nv = np.array(ref.get("n", np.zeros(om.shape)), dtype=np.int64).reshape(om.shape)
+            f = mu
+            if "s_beta" in ref:
+                sb, sg = orc.potential_precision(olik, y, f, om, nv)
+                assert relerr(sb, _arr(ref["s_beta"]), floor=1.0) < RTOL and relerr(sg, _arr(ref["s_gamma"])) < RTOL, name
+            if ref.get("logtilt") is not None:
+                seq, comp = orc.sampled_loglik_terms(olik, y, f, om, nv, ref.get("aug_loglik") is not None)
+                assert comp[3] == pytest.approx(ref["logtilt"], rel=RTOL, abs=1e-12), name
+                if ref.get("aug_loglik") is not None:
+                    tol = 1e-7 * y.shape[0] if kind in (NEGBIN, POISSON) else 1e-10     # conditioning of the PG series, DESIGN §3.4
+                    assert comp[5] == pytest.approx(ref["aug_loglik"], rel=1e-11, abs=tol), name
+
+
+@pytest.mark.gpu
+def test_gpu_against_reference_output():
+    import torch
+    from gpu_common import dev, host, make_lik, pkg, stack
+    A = pkg()
+    J, G = _load(), load_golden()
+    for name, ref in J.items():
+        case = G[name]
+        kind, params, kw = lik_args(case)
+        lik = make_lik(kind, params, kw)
+        lik.faithful_quirks = True
+        y, mu, var = golden_arrays(case)
+        want = kind != CAT
+        q = A.init_aux_posterior(lik, y.shape[0])
+        q, b, g, s = A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)), want_elbo=want)
+        st = [host(q._s(i)) if q._s(i) is not None else None for i in range(3)]
+        if kind not in (HETERO,):
+            st[2] = None                                                     # y copies are compared elsewhere
+        _check_vi(ref, kind, st, stack(b), stack(g), host(s) if want else None, (name, "gpu"))
+        if "omega" in ref:
+            om = _arr(ref["omega"]).reshape(y.shape if kind in (CAT, CAT_BIJ) else (-1,))
+            nv = np.array(ref.get("n", np.zeros(om.shape)), dtype=np.int64).reshape(om.shape)
+            Ω = A.AuxSamples(dev(om), dev(nv) if "n" in ref else None)
+            if "s_beta" in ref:
+                sb, sg = A.auglik_potential_and_precision(lik, Ω, dev(y), dev(mu))
+                assert relerr(stack(sb), _arr(ref["s_beta"]), floor=1.0) < RTOL and relerr(stack(sg), _arr(ref["s_gamma"])) < RTOL
+            if ref.get("logtilt") is not None:
+                assert A.logtilt(lik, Ω, dev(y), dev(mu)) == pytest.approx(ref["logtilt"], rel=RTOL, abs=1e-12), name
