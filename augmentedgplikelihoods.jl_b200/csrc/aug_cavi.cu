@@ -430,38 +430,42 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(co
             if (nt < ntiles) issue(nt, s);
         }
     }
+    // one observation straight from global memory (any input): the redo path below and the ragged tail
+    auto scalar_obs = [&](const int64_t i) {
+        Obs o;
+        o.y = load_y1<yt>(a.y, i);
+        o.ys = o.y;
+        o.m = a.mu[i]; o.v = a.var[i];
+        o.mg = o.vg = 0.0;
+        o.s0 = o.s1 = o.s2 = 0.0;
+        if (HET) { o.mg = a.mu_g[i]; o.vg = a.var_g[i]; }
+        if (fast_ok<KIND, false, ELBO>(o)) eval<KIND, false, ELBO, false>(a.L, o);
+        else eval<KIND, false, ELBO, true>(a.L, o);
+        if (a.s0) a.s0[i] = o.s0;
+        if (HAS_S1 && a.s1) a.s1[i] = o.s1;
+        if (HET && a.s2) reinterpret_cast<double*>(a.s2)[i] = o.s2;
+        if (YSTATE && a.s2) store_y1<s2t>(a.s2, i, o.y);
+        if (a.beta) a.beta[i] = o.b0;
+        if (a.gamma) a.gamma[i] = o.g0;
+        if (HET) {
+            if (a.beta_g) a.beta_g[i] = o.b1;
+            if (a.gamma_g) a.gamma_g[i] = o.g1;
+        }
+        if (ELBO) { acc[0] += o.elt; acc[1] += o.kl; }
+    };
     if (bad) {
         // rare: this thread met a value outside the fast-math range -> redo its observations of every tile
         // of this CTA from global memory with the any-input instantiation (outputs are overwritten)
         acc[0] = acc[1] = 0.0;
-        for (int64_t tile = first; tile < ntiles; tile += stride) {
+        for (int64_t tile = first; tile < ntiles; tile += stride)
             for (int q = tid; q < T / 2; q += AUG_BLOCK) {
-                for (int e = 0; e < 2; ++e) {
-                    const int64_t i = tile * T + 2 * q + e;
-                    Obs o;
-                    o.y = load_y1<yt>(a.y, i);
-                    o.ys = o.y;
-                    o.m = a.mu[i]; o.v = a.var[i];
-                    o.mg = o.vg = 0.0;
-                    o.s0 = o.s1 = o.s2 = 0.0;
-                    if (HET) { o.mg = a.mu_g[i]; o.vg = a.var_g[i]; }
-                    if (fast_ok<KIND, false, ELBO>(o)) eval<KIND, false, ELBO, false>(a.L, o);
-                    else eval<KIND, false, ELBO, true>(a.L, o);
-                    if (a.s0) a.s0[i] = o.s0;
-                    if (HAS_S1 && a.s1) a.s1[i] = o.s1;
-                    if (HET && a.s2) reinterpret_cast<double*>(a.s2)[i] = o.s2;
-                    if (YSTATE && a.s2) store_y1<s2t>(a.s2, i, o.y);
-                    if (a.beta) a.beta[i] = o.b0;
-                    if (a.gamma) a.gamma[i] = o.g0;
-                    if (HET) {
-                        if (a.beta_g) a.beta_g[i] = o.b1;
-                        if (a.gamma_g) a.gamma_g[i] = o.g1;
-                    }
-                    if (ELBO) { acc[0] += o.elt; acc[1] += o.kl; }
-                }
+                scalar_obs(tile * T + 2 * q);
+                scalar_obs(tile * T + 2 * q + 1);
             }
-        }
     }
+    // the ragged tail (< one tile) rides in the same launch: the last CTA reads it directly (a.n = all observations)
+    if (blockIdx.x == gridDim.x - 1)
+        for (int64_t i = ntiles * T + tid; i < a.n; i += AUG_BLOCK) scalar_obs(i);
     if (ELBO) {
         double out[2];
         if (block_reduce_and_finalize<2>(acc, a.partials, a.counter, out)) write_scalars(a, out);
@@ -576,45 +580,13 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
                aug_aligned16(a.beta_g) && aug_aligned16(a.gamma_g);
     if (lik->kind == AUG_BERNOULLI) vec = vec && ((((uintptr_t)y) & 1u) == 0);
     else vec = vec && aug_aligned16(y);
-    // Fused calls on 16-byte aligned arrays: the full tiles (cavi_tile(kind) observations) go through the bulk-async
-    // staged kernel, the ragged remainder (< one tile) through the direct-load kernel, whose scalars the
-    // staged kernel then accumulates onto.
+    // Fused calls on 16-byte aligned arrays: ONE launch of the bulk-async staged kernel — the full tiles
+    // (cavi_tile(kind) observations) go through its ring, its last CTA reads the ragged remainder (< one tile) directly.
     const int64_t tile = cavi_tile(lik->kind);
     const bool use_tma = !from_state && vec && !getenv_no_tma() && aug_aligned16(y) && n >= 4 * tile;
     const int64_t ntiles = use_tma ? n / tile : 0;
-    const int64_t n0 = ntiles * tile;   // observations handled by the staged kernel
-    CaviArgs t = a;                          // remainder [n0, n)
-    if (elbo) (ntiles > 0 ? a.xch : t.xch) = aug_xch_for(ctx);   // the verb's last launch carries the exchange
-    if (n0 > 0) {
-        const size_t ysz = lik->kind == AUG_BERNOULLI ? 1 : 8;
-        t.n = n - n0;
-        t.y = (const unsigned char*)y + n0 * ysz;
-        t.mu = mu + n0;
-        t.var = var + n0;
-        if (a.mu_g) t.mu_g = a.mu_g + n0;
-        if (a.var_g) t.var_g = a.var_g + n0;
-        if (a.s0) t.s0 = a.s0 + n0;
-        if (a.s1) t.s1 = a.s1 + n0;
-        if (a.s2) t.s2 = (unsigned char*)a.s2 + n0 * 8;
-        if (a.beta) t.beta = a.beta + n0;
-        if (a.gamma) t.gamma = a.gamma + n0;
-        if (a.beta_g) t.beta_g = a.beta_g + n0;
-        if (a.gamma_g) t.gamma_g = a.gamma_g + n0;
-    }
-    if (t.n > 0) {
-        switch (lik->kind) {
-            case AUG_BERNOULLI: rc = launch1<AUG_BERNOULLI>(ctx, t, from_state, elbo, vec); break;
-            case AUG_NEGBIN: rc = launch1<AUG_NEGBIN>(ctx, t, from_state, elbo, vec); break;
-            case AUG_POISSON: rc = launch1<AUG_POISSON>(ctx, t, from_state, elbo, vec); break;
-            case AUG_LAPLACE: rc = launch1<AUG_LAPLACE>(ctx, t, from_state, elbo, vec); break;
-            case AUG_STUDENTT: rc = launch1<AUG_STUDENTT>(ctx, t, from_state, elbo, vec); break;
-            case AUG_HETERO: rc = launch1<AUG_HETERO>(ctx, t, from_state, elbo, vec); break;
-            default: return AUG_ERR_BAD_KIND;
-        }
-        if (rc) return rc;
-    }
-    if (ntiles > 0) {
-        a.accumulate = (t.n > 0 && elbo) ? 1 : 0;
+    if (elbo) a.xch = aug_xch_for(ctx);      // the verb's (only) launch carries the exchange
+    if (ntiles > 0) {                        // staged kernel: full tiles through the ring, the ragged tail by its last CTA
         switch (lik->kind) {
             case AUG_BERNOULLI: return launch_tma1<AUG_BERNOULLI>(ctx, a, ntiles, elbo);
             case AUG_NEGBIN: return launch_tma1<AUG_NEGBIN>(ctx, a, ntiles, elbo);
@@ -625,5 +597,15 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
             default: return AUG_ERR_BAD_KIND;
         }
     }
+    switch (lik->kind) {
+        case AUG_BERNOULLI: rc = launch1<AUG_BERNOULLI>(ctx, a, from_state, elbo, vec); break;
+        case AUG_NEGBIN: rc = launch1<AUG_NEGBIN>(ctx, a, from_state, elbo, vec); break;
+        case AUG_POISSON: rc = launch1<AUG_POISSON>(ctx, a, from_state, elbo, vec); break;
+        case AUG_LAPLACE: rc = launch1<AUG_LAPLACE>(ctx, a, from_state, elbo, vec); break;
+        case AUG_STUDENTT: rc = launch1<AUG_STUDENTT>(ctx, a, from_state, elbo, vec); break;
+        case AUG_HETERO: rc = launch1<AUG_HETERO>(ctx, a, from_state, elbo, vec); break;
+        default: return AUG_ERR_BAD_KIND;
+    }
+    if (rc) return rc;
     return AUG_OK;
 }
