@@ -87,6 +87,8 @@ SIGNATURES = {
     "aug_comm_p2p_detach": [_vp],
     "aug_comm_set_fused": [_vp, _i32],
     "aug_comm_get_fused": [_vp, C.POINTER(_i32)],
+    "aug_comm_set_deferred": [_vp, _i32],
+    "aug_comm_flush": [_vp],
     "aug_allreduce_scalars_p2p": [_vp, _vp, _i32],
     "aug_cavi_step_host": [_vp, C.POINTER(AugLik), _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "aug_aux_sample_host": [_vp, C.POINTER(AugLik), _i64, _i64, _vp, _vp, _i64, _vp, _vp],

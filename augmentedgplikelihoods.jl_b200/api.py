@@ -226,6 +226,7 @@ class Context:
         self.comm_ready = False     # NCCL communicator attached (dist.init_comm)
         self.p2p_ready = False      # peer-memory mailbox attached (dist.init_p2p)
         self.fused = False          # scalar-producing verbs already return sums over all ranks
+        self.deferred = False       # split-phase exchange: scalars are complete after flush() / sync() / the next aux_sample_
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
@@ -248,6 +249,12 @@ class Context:
 
     def sync(self):
         check(self.lib.aug_ctx_sync(self.h))
+
+    def flush(self):
+        """complete a pending split-phase exchange (dist.set_deferred) on the ctx stream"""
+        self.enter()
+        check(self.lib.aug_comm_flush(self.h))
+        self.leave()
 
     def launches(self):
         n = C.c_uint64()
@@ -531,6 +538,8 @@ def _reduce(ctx, scal):
     if not scal.is_cuda:            # host-buffer verbs are rank-local (include/augcuda.h)
         return scal
     if ctx.fused:                   # exchanged inside the reducing kernel over peer memory
+        if ctx.deferred:            # split-phase: the gather has not run yet
+            ctx.flush()
         return scal
     if ctx.comm_ready:
         ctx.enter()

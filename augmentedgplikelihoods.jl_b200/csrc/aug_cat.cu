@@ -38,6 +38,7 @@ struct CatArgs {
     unsigned int* counter;
     double* scalars;
     AugXchDev* xch;          // final launch of a verb in fused multi-GPU mode (aug_common.cuh)
+    int xch_defer;           // split-phase exchange: publish only (aug_comm_set_deferred)
     unsigned int* dflag;
     LikConst L;
 };
@@ -171,7 +172,8 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_cavi_kernel(const CatArgs a) {
     if (ELBO) {
         double out[3];
         if (block_reduce_and_finalize<3>(acc, a.partials, a.counter, out)) {
-            if (a.xch) xch_allreduce<3>(a.xch, out);
+            if (a.xch && a.xch_defer) xch_publish_deferred(a.xch, a.scalars, AUG_S_EXPECTED_LOGTILT, out, 3);
+            else if (a.xch) xch_allreduce<3>(a.xch, out);
             a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
             a.scalars[AUG_S_KL] = out[1];
             a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
@@ -448,7 +450,8 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_tma_kernel(const CatTmaArgs 
                 out[1] += a.scalars[AUG_S_KL];
                 out[2] += a.scalars[AUG_S_FLAGS];
             }
-            if (a.xch) xch_allreduce<3>(a.xch, out);
+            if (a.xch && a.xch_defer) xch_publish_deferred(a.xch, a.scalars, AUG_S_EXPECTED_LOGTILT, out, 3);
+            else if (a.xch) xch_allreduce<3>(a.xch, out);
             a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
             a.scalars[AUG_S_KL] = out[1];
             a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
@@ -721,7 +724,8 @@ __global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowA
                 out[1] += a.scalars[AUG_S_KL];
                 out[2] += a.scalars[AUG_S_FLAGS];
             }
-            if (a.xch) xch_allreduce<3>(a.xch, out);
+            if (a.xch && a.xch_defer) xch_publish_deferred(a.xch, a.scalars, AUG_S_EXPECTED_LOGTILT, out, 3);
+            else if (a.xch) xch_allreduce<3>(a.xch, out);
             a.scalars[AUG_S_EXPECTED_LOGTILT] = out[0];
             a.scalars[AUG_S_KL] = out[1];
             a.scalars[AUG_S_EXPECTED_AUGLL] = out[0] + out[1];
@@ -1240,6 +1244,10 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
     if (n < 0 || (!y && n > 0)) return AUG_ERR_BAD_ARG;
     const bool elbo = scalars != nullptr;
     if (elbo && lik->kind == AUG_CAT) return AUG_ERR_PRECONDITION;   // categorical.jl:165-170
+    if (elbo && aug_xch_for(ctx)) {          // exchanges happen in call order: complete a pending split-phase one first
+        int32_t rf = aug_xch_flush(ctx);
+        if (rf) return rf;
+    }
     if (n == 0) {
         if (scalars) {
             AUG_CUDA(cudaMemsetAsync(scalars, 0, AUG_NSCALARS * sizeof(double), ctx->stream));
@@ -1271,6 +1279,10 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
     a.scalars = scalars;
     a.dflag = ctx->dflag;
     a.xch = elbo ? aug_xch_for(ctx) : nullptr;
+    if (a.xch && ctx->deferred) {
+        a.xch_defer = 1;
+        ctx->pending = 1;
+    }
     int32_t rc = aug_lik_const(ctx, lik, &a.L, false, false);
     if (rc) return rc;
     // ---- full tiles of a fused call on 16-byte aligned arrays: the bulk-async staged kernel

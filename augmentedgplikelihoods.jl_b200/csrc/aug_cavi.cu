@@ -55,6 +55,7 @@ struct CaviArgs {
     double* scalars;
     int accumulate;       // add to the scalars already in memory (second launch of one verb)
     AugXchDev* xch;       // non-null on the final launch of a verb in fused multi-GPU mode: all-reduce over peer memory
+    int xch_defer;        // split-phase: publish only, a later launch gathers (aug_comm_set_deferred)
     LikConst L;
 };
 
@@ -107,7 +108,10 @@ __device__ __forceinline__ void write_scalars(const CaviArgs& a, const double (&
         e += a.scalars[AUG_S_EXPECTED_LOGTILT];
         k += a.scalars[AUG_S_KL];
     }
-    if (a.xch) {
+    if (a.xch && a.xch_defer) {               // the block holds the local sums until the deferred gather replaces them
+        const double v[3] = {e, k, 0.0};
+        xch_publish_deferred(a.xch, a.scalars, AUG_S_EXPECTED_LOGTILT, v, 2);
+    } else if (a.xch) {
         double v[2] = {e, k};
         xch_allreduce<2>(a.xch, v);
         e = v[0];
@@ -534,6 +538,10 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
                           const void* rs1, const void* rs2, double* beta, double* gamma, int64_t ldo,
                           double* scalars, bool from_state) {
     if (n < 0) return AUG_ERR_BAD_ARG;
+    if (scalars && aug_xch_for(ctx)) {       // exchanges happen in call order: complete a pending split-phase one first
+        int32_t rf = aug_xch_flush(ctx);
+        if (rf) return rf;
+    }
     if (n == 0) {
         if (scalars) {
             AUG_CUDA(cudaMemsetAsync(scalars, 0, AUG_NSCALARS * sizeof(double), ctx->stream));
@@ -586,6 +594,10 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
     const bool use_tma = !from_state && vec && !getenv_no_tma() && aug_aligned16(y) && n >= 4 * tile;
     const int64_t ntiles = use_tma ? n / tile : 0;
     if (elbo) a.xch = aug_xch_for(ctx);      // the verb's (only) launch carries the exchange
+    if (a.xch && ctx->deferred) {
+        a.xch_defer = 1;
+        ctx->pending = 1;
+    }
     if (ntiles > 0) {                        // staged kernel: full tiles through the ring, the ragged tail by its last CTA
         switch (lik->kind) {
             case AUG_BERNOULLI: return launch_tma1<AUG_BERNOULLI>(ctx, a, ntiles, elbo);

@@ -40,6 +40,11 @@ struct AugXchDev {
     unsigned long long epoch;
     unsigned int* err;                 // ctx error flag word: bit 1 = a peer did not arrive within timeout_ns
     unsigned long long timeout_ns;
+    // split-phase exchange (aug_comm_set_deferred): the reducing kernel only PUBLISHES its sums and leaves this note;
+    // a later launch on the same stream (an extra CTA of the next sampling kernel, or a 1-thread flush kernel) gathers
+    // the ranks' sums and completes the scalar block — the wait for the slowest rank is off the reducing kernel
+    double* pend_scalars;              // nullptr: nothing pending
+    int pend_nv, pend_first;           // values published (2 or 3), first slot of the verb's triple
 };
 
 struct aug_ctx {
@@ -75,6 +80,8 @@ struct aug_ctx {
     AugXchDev* xch;                                // device copy of the exchange descriptor (nullptr: not attached)
     int xch_ranks, xch_rank;
     int fused;                                     // reducing verbs return globally reduced scalars
+    int deferred;                                  // fused mode, split-phase: CAVI verbs publish, a later launch gathers
+    int pending;                                   // a published exchange has not been gathered yet (host-side mirror)
     aug_pipe* pipe;
     // sparse-GP sweep (aug_sparse.cu): per-CTA partial P / rhs / ELBO sums, summed in a fixed order by a finalise launch
     double* sparse_scratch;
@@ -97,6 +104,8 @@ int32_t aug_lik_const(aug_ctx* ctx, const aug_lik* lik, LikConst* out, bool need
 int aug_grid_for(aug_ctx* ctx, const void* kernel, int64_t work_items, int items_per_block);
 // exchange descriptor for the FINAL launch of a scalar-producing verb, or nullptr when the ctx is not in fused mode
 static inline AugXchDev* aug_xch_for(aug_ctx* ctx) { return (ctx->fused && ctx->xch) ? ctx->xch : nullptr; }
+// complete a pending split-phase exchange with a 1-thread kernel on the ctx stream (no-op when nothing is pending)
+int32_t aug_xch_flush(aug_ctx* ctx);
 // fused mode with an empty shard: the rank still has to take part in the exchange (aug_ctx.cu)
 int32_t aug_xch_zero_contribution(aug_ctx* ctx, double* scalars, int first_slot, int nslots);
 
@@ -174,9 +183,10 @@ __device__ __forceinline__ unsigned long long xch_globaltimer() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// Called by ONE thread of the grid (the finaliser).  v[0..NV) in: this rank's sums; out: the sums over all ranks.
+// Called by ONE thread of the grid (the finaliser).  Phase 1: push this rank's sums v[0..NV) into every rank's mailbox
+// and publish the new epoch.
 template <int NV>
-__device__ __forceinline__ void xch_allreduce(AugXchDev* __restrict__ x, double (&v)[NV]) {
+__device__ __forceinline__ void xch_publish(AugXchDev* __restrict__ x, const double (&v)[NV]) {
     static_assert(NV < AUG_XCH_SLOT, "slot holds 7 values + flag");
     const int nr = x->nranks, me = x->rank;
     const unsigned long long ep = x->epoch + 1ull;
@@ -192,12 +202,21 @@ __device__ __forceinline__ void xch_allreduce(AugXchDev* __restrict__ x, double 
     __threadfence_system();
     for (int r = 0; r < nr; ++r)                           // publish
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(x->box[r] + mine + (AUG_XCH_SLOT - 1)), "l"(ep) : "memory");
+}
+// Phase 2: wait for the current epoch's slots of all ranks in this rank's own mailbox and add them IN RANK ORDER
+// (bit-identical on every rank, independent of arrival order).  A peer that does not arrive within timeout_ns raises
+// bit 1 of the error flag and yields NaN.
+template <int NV>
+__device__ __forceinline__ void xch_gather(AugXchDev* __restrict__ x, double (&v)[NV]) {
+    const int nr = x->nranks, me = x->rank;
+    const unsigned long long ep = x->epoch;
+    const size_t half = (size_t)(ep & 1ull) * AUG_MAX_RANKS * AUG_XCH_SLOT;
     double tot[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) tot[k] = 0.0;
     const unsigned long long t0 = xch_globaltimer();
     bool ok = true;
-    for (int r = 0; r < nr && ok; ++r) {                   // gather in rank order: identical bits on every rank
+    for (int r = 0; r < nr && ok; ++r) {
         const unsigned long long* p = x->box[me] + half + (size_t)r * AUG_XCH_SLOT;
         for (;;) {
             unsigned long long f;
@@ -221,6 +240,36 @@ __device__ __forceinline__ void xch_allreduce(AugXchDev* __restrict__ x, double 
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k) v[k] = tot[k];
+}
+// v[0..NV) in: this rank's sums; out: the sums over all ranks (both phases back to back: the kernel waits for its peers).
+template <int NV>
+__device__ __forceinline__ void xch_allreduce(AugXchDev* __restrict__ x, double (&v)[NV]) {
+    xch_publish<NV>(x, v);
+    xch_gather<NV>(x, v);
+}
+// Deferred mode, phase 1 from a verb's finaliser: publish, leave the note, and put this rank's LOCAL sums in the block
+// until the gather replaces them.  scalars[first .. first+2] = (a, b, a + b); nv == 3 also carries the flag count.
+__device__ __forceinline__ void xch_publish_deferred(AugXchDev* __restrict__ x, double* __restrict__ scalars, int first,
+                                                     const double (&v)[3], int nv) {
+    xch_publish<3>(x, v);
+    x->pend_scalars = scalars;
+    x->pend_nv = nv;
+    x->pend_first = first;
+    __threadfence();
+}
+// Deferred mode, phase 2 (one thread): complete the scalar block the note points to.
+__device__ __forceinline__ void xch_finish_pending(AugXchDev* __restrict__ x) {
+    double* s = *(double* volatile*)&x->pend_scalars;
+    if (s == nullptr) return;
+    double v[3];
+    xch_gather<3>(x, v);
+    const int first = x->pend_first;
+    s[first] = v[0];
+    s[first + 1] = v[1];
+    s[first + 2] = v[0] + v[1];
+    if (x->pend_nv == 3) s[AUG_S_FLAGS] = v[2];
+    x->pend_scalars = nullptr;
+    __threadfence();
 }
 
 // Every scalar-producing verb owns the WHOLE 8-slot block of its call: the finaliser writes the verb's slots and zeroes

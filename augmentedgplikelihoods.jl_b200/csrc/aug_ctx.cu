@@ -309,7 +309,18 @@ __global__ void xch_only_kernel(AugXchDev* x, double* vals, int count, int first
         if (count == 3) vals[AUG_S_FLAGS] = v[2];
     }
 }
+__global__ void xch_finish_kernel(AugXchDev* x) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) xch_finish_pending(x);
+}
 }  // namespace
+
+int32_t aug_xch_flush(aug_ctx* c) {
+    if (!c->pending || !c->xch) return AUG_OK;
+    c->pending = 0;
+    xch_finish_kernel<<<1, 32, 0, c->stream>>>(c->xch);
+    c->launches++;
+    return (int32_t)cudaGetLastError();
+}
 
 extern "C" {
 static void p2p_close(aug_ctx* c);
@@ -418,6 +429,7 @@ int32_t aug_ctx_get_offset(aug_ctx* c, uint64_t* offset) {
 int32_t aug_ctx_sync(aug_ctx* c) {
     if (!c) return AUG_ERR_NOT_INIT;
     AUG_CUDA(cudaSetDevice(c->device));
+    { int32_t rc = aug_xch_flush(c); if (rc) return rc; }     // a pending split-phase exchange completes here
     AUG_CUDA(cudaStreamSynchronize(c->stream));
     return AUG_OK;
 }
@@ -439,6 +451,7 @@ int32_t aug_ctx_launch_count(aug_ctx* c, uint64_t* n) {
 int32_t aug_ctx_error_flag(aug_ctx* c, uint32_t* flag) {
     if (!c || !flag) return AUG_ERR_NOT_INIT;
     AUG_CUDA(cudaSetDevice(c->device));
+    { int32_t rc = aug_xch_flush(c); if (rc) return rc; }
     AUG_CUDA(cudaMemcpyAsync(flag, c->dflag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     AUG_CUDA(cudaMemsetAsync(c->dflag, 0, sizeof(uint32_t), c->stream));
     AUG_CUDA(cudaStreamSynchronize(c->stream));
@@ -598,6 +611,8 @@ int32_t aug_comm_p2p_export(aug_ctx* c, char handle[64], void** local_ptr) {
 }
 
 static void p2p_close(aug_ctx* c) {
+    aug_xch_flush(c);
+    c->deferred = 0;
     cudaStreamSynchronize(c->stream);   // no exchanging kernel may still be polling / pushing when the maps go away
     for (int r = 0; r < AUG_MAX_RANKS; ++r) {
         if (c->peer_ipc[r] && c->peer_box[r]) cudaIpcCloseMemHandle(c->peer_box[r]);
@@ -626,6 +641,8 @@ static int32_t p2p_finish_attach(aug_ctx* c, int32_t nranks, int32_t rank) {
     if (ce != cudaSuccess) { p2p_close(c); return (int32_t)ce; }
     c->xch_ranks = nranks;
     c->xch_rank = rank;
+    c->pending = 0;
+    c->deferred = 0;
     return AUG_OK;
 }
 
@@ -684,8 +701,33 @@ int32_t aug_comm_p2p_detach(aug_ctx* c) {
 int32_t aug_comm_set_fused(aug_ctx* c, int32_t on) {
     if (!c) return AUG_ERR_NOT_INIT;
     if (on && !c->xch) return AUG_ERR_NOT_INIT;
+    if (!on) {
+        AUG_CUDA(cudaSetDevice(c->device));
+        int32_t rc = aug_xch_flush(c);
+        if (rc) return rc;
+    }
     c->fused = on ? 1 : 0;
     return AUG_OK;
+}
+// Split-phase exchange: with on != 0 (fused mode only) aug_cavi_step / aug_expected_elbo_terms only PUBLISH their sums
+// from the reducing kernel; the gather runs in an extra CTA of the next aug_aux_sample launch on the ctx (scheduled
+// when that kernel drains, by when the peers have long published), or in a 1-thread kernel at the next
+// aug_comm_flush / aug_ctx_sync / other scalar-producing verb.  Until then the block holds this rank's LOCAL sums.
+// The per-step barrier between the ranks disappears from the reducing kernel: a rank may run up to one sampling kernel
+// ahead of its slowest peer (two epochs of mailbox slots are exactly enough for that).
+int32_t aug_comm_set_deferred(aug_ctx* c, int32_t on) {
+    if (!c) return AUG_ERR_NOT_INIT;
+    if (on && !c->xch) return AUG_ERR_NOT_INIT;
+    AUG_CUDA(cudaSetDevice(c->device));
+    int32_t rc = aug_xch_flush(c);
+    if (rc) return rc;
+    c->deferred = on ? 1 : 0;
+    return AUG_OK;
+}
+int32_t aug_comm_flush(aug_ctx* c) {
+    if (!c) return AUG_ERR_NOT_INIT;
+    AUG_CUDA(cudaSetDevice(c->device));
+    return aug_xch_flush(c);
 }
 int32_t aug_comm_get_fused(aug_ctx* c, int32_t* on) {
     if (!c || !on) return AUG_ERR_NOT_INIT;
@@ -699,6 +741,7 @@ int32_t aug_allreduce_scalars_p2p(aug_ctx* c, double* dev, int32_t count) {
     if (!c || !c->xch) return AUG_ERR_NOT_INIT;
     if (!dev || count < 1 || count > AUG_XCH_SLOT - 1) return AUG_ERR_BAD_ARG;
     AUG_CUDA(cudaSetDevice(c->device));
+    { int32_t rc = aug_xch_flush(c); if (rc) return rc; }
     xch_only_kernel<<<1, 32, 0, c->stream>>>(c->xch, dev, count, 0, 0);
     c->launches++;
     return (int32_t)cudaGetLastError();
@@ -716,6 +759,7 @@ int32_t aug_allreduce_scalars(aug_ctx* c, double* dev, int32_t count) {
 }  // extern "C"
 
 int32_t aug_xch_zero_contribution(aug_ctx* c, double* scalars, int first_slot, int nslots) {
+    { int32_t rc = aug_xch_flush(c); if (rc) return rc; }
     xch_only_kernel<<<1, 32, 0, c->stream>>>(c->xch, scalars, nslots, first_slot, 1);
     c->launches++;
     return (int32_t)cudaGetLastError();

@@ -77,6 +77,7 @@ struct Pg1Args {
     double cs;
     double* out;
     const double* tab;
+    AugXchDev* gx;       // non-null: one extra CTA completes a pending split-phase exchange (aug_comm_set_deferred)
 };
 
 // counters exhausted (probability < 1e-14 per draw): finish one draw on a private sequential stream
@@ -99,6 +100,13 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
     __shared__ uint32_t qra_s[AUG_BLOCK / 32][PG1_QCAP];
     __shared__ uint32_t quacc_s[AUG_BLOCK / 32][PG1_QCAP];
     __shared__ double qz_s[AUG_BLOCK / 32][PG1_QCAP];
+    // the extra CTA of a launch that carries a deferred gather: it is scheduled when a working CTA retires, by when the
+    // peers have long published, so the wait for the slowest rank costs this kernel (next to) nothing
+    const unsigned nwork = a.gx ? gridDim.x - 1 : gridDim.x;
+    if (blockIdx.x == nwork) {
+        if (threadIdx.x == 0) xch_finish_pending(a.gx);
+        return;
+    }
     augp::pg1_load_table_cm(tab_s, a.tab, AUG_BLOCK);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
     double* qz = qz_s[warp];
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t nchunks = (uint32_t)((a.n + 31) >> 5);                 // n < 2^32 (host-checked)
-    const uint32_t W = gridDim.x * (AUG_BLOCK / 32);
+    const uint32_t W = nwork * (AUG_BLOCK / 32);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32);
     const uint32_t c3 = (uint32_t)a.offset;
     int qn = 0;
@@ -245,6 +253,7 @@ struct PgbArgs {
     double* omega;
     int64_t* nvar;
     const double* tab;
+    AugXchDev* gx;        // non-null: one extra CTA completes a pending split-phase exchange
 };
 
 #define PGB_T_DEV 0u
@@ -264,6 +273,11 @@ struct PgbArgs {
 template <int KIND>
 __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const PgbArgs a) {
     extern __shared__ __align__(16) unsigned char pgb_smem[];
+    const unsigned nwork = a.gx ? gridDim.x - 1 : gridDim.x;
+    if (blockIdx.x == nwork) {                 // the extra CTA of a launch that carries a deferred gather
+        if (threadIdx.x == 0) xch_finish_pending(a.gx);
+        return;
+    }
     double* tab_s = reinterpret_cast<double*>(pgb_smem);
     augp::pg1_load_table_cm(tab_s, a.tab, PGB_BLOCK);
     __syncthreads();
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
     double2 *qf_lo = qbase + 4 * PGB_QCAP, *qf_hi = qbase + 5 * PGB_QCAP;    // fractional-piece attempts
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t nchunks = (uint32_t)((a.n + 31) >> 5);
-    const uint32_t W = gridDim.x * PGB_WARPS;
+    const uint32_t W = nwork * PGB_WARPS;
     augb::Key key;
     key.k0 = (uint32_t)a.seed;
     key.k1 = (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32);
@@ -637,6 +651,13 @@ int32_t launch_map(aug_ctx* ctx, K kernel, const A& a, int64_t n) {
 }
 
 // PG(1, c) for n elements through the warp-compacted kernel; false if the shape does not fit its item encoding
+// takes over a pending split-phase exchange of the ctx, if any: the launch gets one extra CTA that gathers it
+AugXchDev* take_pending(aug_ctx* ctx) {
+    if (!ctx->pending || !ctx->xch) return nullptr;
+    ctx->pending = 0;
+    return ctx->xch;
+}
+
 bool launch_pg1_compact(aug_ctx* ctx, int64_t n, int64_t i0, uint64_t off, const double* c, double cs, double* out,
                         int32_t* rc) {
     static int occ = 0;
@@ -659,6 +680,8 @@ bool launch_pg1_compact(aug_ctx* ctx, int64_t n, int64_t i0, uint64_t off, const
     a.cs = cs;
     a.out = out;
     a.tab = ctx->pgtab;
+    a.gx = take_pending(ctx);
+    if (a.gx) grid += 1;
     pg1_compact_kernel<<<(unsigned)grid, AUG_BLOCK, 0, ctx->stream>>>(a);
     ctx->launches++;
     *rc = (int32_t)cudaGetLastError();
@@ -668,7 +691,7 @@ bool launch_pg1_compact(aug_ctx* ctx, int64_t n, int64_t i0, uint64_t off, const
 
 // PG(b, c) for n elements through the warp-compacted general-b kernel
 template <int KIND>
-int32_t launch_pgb(aug_ctx* ctx, const PgbArgs& a) {
+int32_t launch_pgb(aug_ctx* ctx, PgbArgs a) {
     static int occ = 0;
     if (occ == 0) {
         if (cudaFuncSetAttribute(pgb_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGB_SMEM_BYTES) != cudaSuccess)
@@ -681,6 +704,8 @@ int32_t launch_pgb(aug_ctx* ctx, const PgbArgs& a) {
     const int64_t need = (nchunks + (PGB_BLOCK / 32) - 1) / (PGB_BLOCK / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    a.gx = take_pending(ctx);
+    if (a.gx) grid += 1;
     pgb_kernel<KIND><<<(unsigned)grid, PGB_BLOCK, PGB_SMEM_BYTES, ctx->stream>>>(a);
     ctx->launches++;
     return (int32_t)cudaGetLastError();
@@ -709,7 +734,11 @@ int32_t aug_cat_potential(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
 int32_t aug_aux_sample_dev(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i0, const void* y, const double* f,
                            int64_t ld, double* omega, int64_t* nvar, uint64_t off) {
     if (n == 0) return AUG_OK;
-    if (is_cat(lik->kind)) return aug_cat_sample(c, lik, n, i0, y, f, omega, nvar, off);
+    if (is_cat(lik->kind)) {
+        int32_t rf = aug_xch_flush(c);
+        if (rf) return rf;
+        return aug_cat_sample(c, lik, n, i0, y, f, omega, nvar, off);
+    }
     GibbsArgs a{};
     a.n = n;
     a.i0 = i0;
@@ -751,6 +780,7 @@ int32_t aug_aux_sample_dev(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i0
         if (lik->kind == AUG_POISSON) return launch_pgb<AUG_POISSON>(c, p);
         return launch_pgb<AUG_HETERO>(c, p);
     }
+    { int32_t rf = aug_xch_flush(c); if (rf) return rf; }     // no gather hook in these kernels: complete a pending exchange first
     switch (lik->kind) {
         case AUG_BERNOULLI: return launch_map(c, aux_sample_kernel<AUG_BERNOULLI>, a, n);
         case AUG_NEGBIN: return launch_map(c, aux_sample_kernel<AUG_NEGBIN>, a, n);

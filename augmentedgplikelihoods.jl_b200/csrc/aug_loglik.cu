@@ -247,6 +247,10 @@ int32_t aug_sampled_loglik_terms(aug_ctx* c, const aug_lik* lik, int64_t n, cons
     if (!c) return AUG_ERR_NOT_INIT;
     if (!lik || n < 0 || !y || !f || !omega || !scalars) return AUG_ERR_BAD_ARG;
     AUG_CUDA(cudaSetDevice(c->device));
+    if (aug_xch_for(c)) {                    // exchanges happen in call order: complete a pending split-phase one first
+        int32_t rf = aug_xch_flush(c);
+        if (rf) return rf;
+    }
     if (n == 0) {
         AUG_CUDA(cudaMemsetAsync(scalars, 0, AUG_NSCALARS * sizeof(double), c->stream));
         if (aug_xch_for(c)) return aug_xch_zero_contribution(c, scalars, AUG_S_LOGTILT, 2);

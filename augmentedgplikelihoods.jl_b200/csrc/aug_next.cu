@@ -192,6 +192,7 @@ int32_t aug_hetero_lambda_stats(aug_ctx* c, int64_t n, const double* y, const do
     a.counter = c->counter;
     a.out = out;
     a.xch = aug_xch_for(c);
+    if (a.xch) { int32_t rf = aug_xch_flush(c); if (rf) return rf; }
     return launch_lambda<false>(c, a);
 }
 
@@ -218,6 +219,7 @@ int32_t aug_hetero_lambda_stats_sampled(aug_ctx* c, int64_t n, const double* y, 
     a.counter = c->counter;
     a.out = out;
     a.xch = aug_xch_for(c);
+    if (a.xch) { int32_t rf = aug_xch_flush(c); if (rf) return rf; }
     return launch_lambda<true>(c, a);
 }
 

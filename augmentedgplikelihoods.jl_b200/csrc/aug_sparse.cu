@@ -794,6 +794,7 @@ int32_t sp_launch(aug_ctx* ctx, SparseArgs& a, const double* P0, const double* r
     const bool want_P = MODE != SP_PRODUCER;
     const bool want_s = MODE == SP_FUSED && scalars != nullptr;
     AugXchDev* xch = want_P ? aug_xch_for(ctx) : nullptr;    // fused multi-GPU mode: the verb is collective
+    if (xch) { int32_t rf = aug_xch_flush(ctx); if (rf) return rf; }
     if (xch) {
         const int nout = a.m * a.m + a.m;
         sparse_finalize_xch_kernel<MT><<<(nout + 7) / 8, 256, 0, ctx->stream>>>(a.scratch, (int)grid, a.m, P0, r0, Pr,

@@ -90,6 +90,17 @@ def init_p2p(ctx, group=None, fused=True):
 def set_fused(ctx, on=True):
     check(ctx.lib.aug_comm_set_fused(ctx.h, 1 if on else 0))
     ctx.fused = bool(on)
+    if not on:
+        ctx.deferred = getattr(ctx, "deferred", False)
+    return ctx
+
+
+def set_deferred(ctx, on=True):
+    """Split-phase exchange (fused mode): cavi_step_ / the expected-ELBO verbs only publish their sums; the gather rides in
+    the next aux_sample_ launch or in ctx.flush() / ctx.sync().  Read device scalars only after one of those
+    (the float-returning verbs flush by themselves).  include/augcuda.h: aug_comm_set_deferred."""
+    check(ctx.lib.aug_comm_set_deferred(ctx.h, 1 if on else 0))
+    ctx.deferred = bool(on)
     return ctx
 
 

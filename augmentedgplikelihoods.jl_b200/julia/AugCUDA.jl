@@ -425,6 +425,9 @@ function init_p2p!(nranks::Integer, rank::Integer, allgather::Function; fused::B
     fused && check(ccall((:aug_comm_set_fused, lib), Int32, (Ptr{Cvoid}, Int32), ctx().h, 1))
     return nothing
 end
+"split-phase exchange: the reducing kernels only publish, the gather rides in the next aux_sample! launch or in `flush!()`"
+set_deferred!(on::Bool=true) = check(ccall((:aug_comm_set_deferred, lib), Int32, (Ptr{Cvoid}, Int32), ctx().h, on))
+flush!() = check(ccall((:aug_comm_flush, lib), Int32, (Ptr{Cvoid},), ctx().h))
 
 # ---- callers on either side of the path (SURVEY §8(f) rows 3-4) --------------------------------------------------
 # opt_lik of examples/heteroscedasticgaussian/script.jl:41-51 for device arguments

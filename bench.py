@@ -577,6 +577,9 @@ def main():
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: all-reduce of the scalar block fused into the CAVI kernel over peer memory (p2p) or "
                          "a separate ncclAllReduce (nccl)")
+    ap.add_argument("--no-defer", action="store_true",
+                    help="p2p: exchange inside the CAVI kernel's finaliser (it then waits for the slowest rank every step) "
+                         "instead of the split-phase publish / deferred gather")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sparse", action="store_true", help="skip the secondary sparse-GP sweep measurement")
     ap.add_argument("--sparse-m", type=int, default=128)
@@ -612,6 +615,8 @@ def main():
         A.dist.init_comm(ctx)                                    # NCCL communicator: the `nccl` collective and the cross-check
         if args.collective == "p2p":
             A.dist.init_p2p(ctx, fused=True)
+            if not args.no_defer:                                # split-phase: publish in the CAVI kernel's finaliser, gather
+                A.dist.set_deferred(ctx, True)                   # in an extra CTA of the next sampling launch
     dev = torch.device("cuda", local_rank)
     peak, peak_src = load_peaks()
     nccl_coll = (lambda scal: A.dist.allreduce_scalars_(ctx, scal)) if (world > 1 and args.collective == "nccl") else None
@@ -622,6 +627,7 @@ def main():
         if world == 1 or args.collective != "p2p":
             return None
         leg.cavi()
+        ctx.flush()
         got = leg.scal.clone()
         A.dist.set_fused(ctx, False)
         leg.cavi()
@@ -643,6 +649,7 @@ def main():
     time.sleep(0.25)
     tm = time_leg(head, torch, dist, world, args.steps, args.warmup, nccl_coll)
     clocks = sampler.finish() if rank == 0 else None
+    ctx.flush()
     elbo = float(head.scal[2].item())
     checks["fused_mailbox_equals_nccl_sum_of_locals"] = {"bernoulli": fused_vs_nccl(head)}
 
@@ -691,6 +698,7 @@ def main():
               "gamma": bool(torch.equal(hg, head.gamma.cpu())), "omega": bool(torch.equal(hΩ.omega, head.Ω.omega.cpu()))}
         hs = res["c"][3]
         head.cavi()
+        ctx.flush()
         loc_elbo = head.scal.clone()
         if world > 1 and ctx.fused:                        # host verbs are rank-local: compare with this rank's local sums
             A.dist.set_fused(ctx, False)
@@ -817,7 +825,9 @@ def main():
                    "sharding": f"contiguous observation blocks, {world} rank(s); only the 8-double scalar block "
                                "is all-reduced",
                    "collective": ("none (1 rank)" if world == 1 else
-                                  "fused into cavi_tma_kernel's finaliser over the peer-memory mailbox (NVLink)"
+                                  ("split-phase over the peer-memory mailbox (NVLink): published by cavi_tma_kernel's finaliser, "
+                                   "gathered by an extra CTA of the sampling kernel" if not args.no_defer else
+                                   "fused into cavi_tma_kernel's finaliser over the peer-memory mailbox (NVLink)")
                                   if args.collective == "p2p" else "ncclAllReduce(sum, double, 8) after the step")},
         "parts": {"cavi_obs_per_s": n * world / (ms_cavi * 1e-3), "pg_draws_per_s": n * world / (ms_gibbs * 1e-3),
                   "ms_cavi": ms_cavi, "ms_gibbs": ms_gibbs, "ms_allreduce": tm["ms_allreduce"]},

@@ -353,6 +353,17 @@ int32_t aug_comm_p2p_attach_ptrs(aug_ctx* ctx, int32_t nranks, int32_t rank, voi
 int32_t aug_comm_p2p_detach(aug_ctx* ctx);
 int32_t aug_comm_set_fused(aug_ctx* ctx, int32_t on);
 int32_t aug_comm_get_fused(aug_ctx* ctx, int32_t* on);
+/* Split-phase exchange (fused mode only).  With on != 0 the finaliser of aug_cavi_step / aug_expected_elbo_terms only
+ * PUBLISHES its sums to the peers' mailboxes and leaves this rank's LOCAL sums in the scalar block; the gather — wait
+ * for every rank's epoch flag, add the sums in rank order, complete the block — runs later on the same stream: in one
+ * extra CTA of the next aug_aux_sample launch (Bernoulli / NegBin / Poisson / heteroscedastic kernels; the CTA is
+ * scheduled as that kernel drains, by when the peers have long published) or in a 1-thread kernel at the next
+ * aug_comm_flush, aug_ctx_sync, aug_ctx_error_flag or scalar-producing verb.  This takes the per-call barrier between
+ * the ranks out of the reducing kernel: a rank may run up to one sampling kernel ahead of its slowest peer (the two
+ * epochs of mailbox slots are exactly enough for that), so rank-to-rank skew is absorbed instead of added to every
+ * step.  Read the scalars only after one of the completing calls. */
+int32_t aug_comm_set_deferred(aug_ctx* ctx, int32_t on);
+int32_t aug_comm_flush(aug_ctx* ctx);
 /* in-place sum over ranks of count <= 7 device doubles through the mailbox (one 32-thread kernel, no NCCL) */
 int32_t aug_allreduce_scalars_p2p(aug_ctx* ctx, double* dev, int32_t count);
 

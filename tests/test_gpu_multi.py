@@ -78,6 +78,8 @@ def _worker(rank, world, port, mode, q):
         A.dist.init_comm(ctx)
     else:
         A.dist.init_p2p(ctx, fused=True)
+        if mode == "p2p_deferred":      # split-phase: publish in the reducing kernel, gather in the next sampling launch
+            A.dist.set_deferred(ctx, True)
     res = _run_rank(A, ctx, rank, world, fused=(mode != "nccl"))
     flag = ctx.error_flag()
     q.put((rank, res, flag))
@@ -120,7 +122,7 @@ def _single_gpu_reference(A, orc):
     return ref
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p_fused"])
+@pytest.mark.parametrize("mode", ["nccl", "p2p_fused", "p2p_deferred"])
 def test_two_rank_scalars_and_draws_match_single_gpu(orc, mode):
     _need2()
     import torch.multiprocessing as mp
