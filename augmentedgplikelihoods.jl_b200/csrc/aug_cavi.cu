@@ -302,21 +302,37 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_MIN_BLOCKS) cavi_kernel(const 
 // tile (observations per stage) and ring depth per likelihood: ~25-35 KB per stage, ~100 KB per CTA
 __host__ __device__ constexpr int cavi_tile(int kind) { return kind == AUG_BERNOULLI ? 2048 : (kind == AUG_HETERO ? 512 : 1024); }
 __host__ __device__ constexpr int cavi_stages(int kind) { return kind == AUG_BERNOULLI ? 3 : (kind == AUG_HETERO ? 5 : 4); }
+__host__ __device__ constexpr int pow2_floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
+__host__ __device__ constexpr int clamp_int(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-template <int KIND>
+// What one ring stage holds.  Fused calls stage y, mu, var (+ the second latent); the FROM_STATE verbs
+// (expected_auglik_potential_and_precision, expected_logtilt / aux_kldivergence from an existing q(Omega)) stage the
+// state arrays next to them and drop mu / var when the verb does not need them.
+template <int KIND, bool FS, bool ELBO>
 struct TileLayout {
     typedef typename YT<KIND>::T yt;
     static constexpr bool HET = KIND == AUG_HETERO;
-    static constexpr int T = cavi_tile(KIND);
-    static constexpr int S = cavi_stages(KIND);
+    static constexpr bool YSTATE = KIND == AUG_NEGBIN || KIND == AUG_POISSON;
+    static constexpr bool HAS_S1 = KIND == AUG_POISSON || KIND == AUG_HETERO;
+    static constexpr bool NEED_MV = !FS || ELBO;
+    static constexpr bool HAS_MUG = HET, HAS_VARG = HET && NEED_MV;
+    static constexpr bool HAS_RS0 = FS, HAS_RS1 = FS && HAS_S1, HAS_RS2 = FS && (HET || YSTATE);
+    static constexpr int N_D = (NEED_MV ? 2 : 0) + (HAS_MUG ? 1 : 0) + (HAS_VARG ? 1 : 0) + (HAS_RS0 ? 1 : 0) +
+                               (HAS_RS1 ? 1 : 0) + (HAS_RS2 ? 1 : 0);
+    static constexpr int OBS_BYTES = (int)sizeof(yt) + 8 * N_D;
+    static constexpr int T = FS ? clamp_int(pow2_floor(36864 / OBS_BYTES), 512, 4096) : cavi_tile(KIND);
     static constexpr int Y_BYTES = T * (int)sizeof(yt);
     static constexpr int D_BYTES = T * 8;
     static constexpr int OFF_MU = (Y_BYTES + 127) / 128 * 128;
-    static constexpr int OFF_VAR = OFF_MU + D_BYTES;
-    static constexpr int OFF_MUG = OFF_VAR + D_BYTES;
-    static constexpr int OFF_VARG = OFF_MUG + D_BYTES;
-    static constexpr int STAGE_BYTES = HET ? OFF_VARG + D_BYTES : OFF_MUG;
-    static constexpr int TX_BYTES = Y_BYTES + D_BYTES * (HET ? 4 : 2);
+    static constexpr int OFF_VAR = OFF_MU + (NEED_MV ? D_BYTES : 0);
+    static constexpr int OFF_MUG = OFF_VAR + (NEED_MV ? D_BYTES : 0);
+    static constexpr int OFF_VARG = OFF_MUG + (HAS_MUG ? D_BYTES : 0);
+    static constexpr int OFF_RS0 = OFF_VARG + (HAS_VARG ? D_BYTES : 0);
+    static constexpr int OFF_RS1 = OFF_RS0 + (HAS_RS0 ? D_BYTES : 0);
+    static constexpr int OFF_RS2 = OFF_RS1 + (HAS_RS1 ? D_BYTES : 0);
+    static constexpr int STAGE_BYTES = OFF_RS2 + (HAS_RS2 ? D_BYTES : 0);
+    static constexpr int S = FS ? clamp_int(110592 / STAGE_BYTES, 2, 6) : cavi_stages(KIND);
+    static constexpr int TX_BYTES = Y_BYTES + D_BYTES * N_D;   // minus D_BYTES when a NegBin / Poisson caller passes no y-state
     static constexpr int SMEM_BYTES = STAGE_BYTES * S + 64;
 };
 
@@ -341,10 +357,11 @@ __device__ __forceinline__ void lds_y2<double>(const unsigned char* ys, int q, d
     b = v.y;
 }
 
-// Fused (not FROM_STATE) CAVI step over the full tiles [0, ntiles * tile) of the shard.
-template <int KIND, bool ELBO>
+// The staged kernel over the full tiles [0, ntiles * tile) of the shard (+ the ragged tail by its last CTA):
+// fused CAVI step (FS = false) or one of the verbs that start from an existing q(Omega) (FS = true).
+template <int KIND, bool FS, bool ELBO>
 __global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(const CaviArgs a, const int64_t ntiles) {
-    typedef TileLayout<KIND> TL;
+    typedef TileLayout<KIND, FS, ELBO> TL;
     typedef typename YT<KIND>::T yt;
     typedef typename S2T<KIND>::T s2t;
     constexpr bool HET = KIND == AUG_HETERO;
@@ -361,18 +378,22 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const bool has_rs2 = TL::HAS_RS2 && a.rs2 != nullptr;   // HETERO: always (host-checked); NegBin / Poisson: optional
 
     auto issue = [&](int64_t tile, int s) {   // one thread: arm the barrier, then the bulk copies of one tile
         unsigned char* st = ring + (size_t)s * TL::STAGE_BYTES;
         const int64_t o = tile * T;
-        mbar_expect_tx(&full[s], TL::TX_BYTES);
+        mbar_expect_tx(&full[s], TL::TX_BYTES - ((TL::HAS_RS2 && !has_rs2) ? TL::D_BYTES : 0));
         bulk_g2s(st, reinterpret_cast<const unsigned char*>(a.y) + o * sizeof(yt), TL::Y_BYTES, &full[s]);
-        bulk_g2s(st + TL::OFF_MU, a.mu + o, TL::D_BYTES, &full[s]);
-        bulk_g2s(st + TL::OFF_VAR, a.var + o, TL::D_BYTES, &full[s]);
-        if (HET) {
-            bulk_g2s(st + TL::OFF_MUG, a.mu_g + o, TL::D_BYTES, &full[s]);
-            bulk_g2s(st + TL::OFF_VARG, a.var_g + o, TL::D_BYTES, &full[s]);
+        if (TL::NEED_MV) {
+            bulk_g2s(st + TL::OFF_MU, a.mu + o, TL::D_BYTES, &full[s]);
+            bulk_g2s(st + TL::OFF_VAR, a.var + o, TL::D_BYTES, &full[s]);
         }
+        if (TL::HAS_MUG) bulk_g2s(st + TL::OFF_MUG, a.mu_g + o, TL::D_BYTES, &full[s]);
+        if (TL::HAS_VARG) bulk_g2s(st + TL::OFF_VARG, a.var_g + o, TL::D_BYTES, &full[s]);
+        if (TL::HAS_RS0) bulk_g2s(st + TL::OFF_RS0, a.rs0 + o, TL::D_BYTES, &full[s]);
+        if (TL::HAS_RS1) bulk_g2s(st + TL::OFF_RS1, a.rs1 + o, TL::D_BYTES, &full[s]);
+        if (has_rs2) bulk_g2s(st + TL::OFF_RS2, reinterpret_cast<const unsigned char*>(a.rs2) + o * 8, TL::D_BYTES, &full[s]);
     };
 
     const int64_t first = blockIdx.x, stride = gridDim.x;
@@ -394,29 +415,53 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(co
         const double2* svar = reinterpret_cast<const double2*>(st + TL::OFF_VAR);
         const double2* smug = reinterpret_cast<const double2*>(st + TL::OFF_MUG);
         const double2* svarg = reinterpret_cast<const double2*>(st + TL::OFF_VARG);
+        const double2* srs0 = reinterpret_cast<const double2*>(st + TL::OFF_RS0);
+        const double2* srs1 = reinterpret_cast<const double2*>(st + TL::OFF_RS1);
         const int64_t base = tile * T;
 #pragma unroll 1
         for (int q = tid; q < T / 2; q += AUG_BLOCK) {
             Obs o0, o1;
             lds_y2<yt>(st, q, o0.y, o1.y);
-            const double2 m = smu[q], v = svar[q];
-            o0.m = m.x; o1.m = m.y;
-            o0.v = v.x; o1.v = v.y;
+            o0.m = o1.m = o0.v = o1.v = 0.0;
+            if (TL::NEED_MV) {
+                const double2 m = smu[q], v = svar[q];
+                o0.m = m.x; o1.m = m.y;
+                o0.v = v.x; o1.v = v.y;
+            }
             o0.mg = o1.mg = o0.vg = o1.vg = 0.0;
-            if (HET) {
-                const double2 mg = smug[q], vg = svarg[q];
+            if (TL::HAS_MUG) {
+                const double2 mg = smug[q];
                 o0.mg = mg.x; o1.mg = mg.y;
+            }
+            if (TL::HAS_VARG) {
+                const double2 vg = svarg[q];
                 o0.vg = vg.x; o1.vg = vg.y;
             }
             o0.ys = o0.y; o1.ys = o1.y;
-            bad = bad || !fast_ok<KIND, false, ELBO>(o0) || !fast_ok<KIND, false, ELBO>(o1);
-            eval<KIND, false, ELBO, false>(a.L, o0);
-            eval<KIND, false, ELBO, false>(a.L, o1);
+            if (FS) {
+                o0.s1 = o1.s1 = o0.s2 = o1.s2 = 0.0;
+                const double2 c = srs0[q];
+                o0.s0 = c.x; o1.s0 = c.y;
+                if (TL::HAS_RS1) {
+                    const double2 l = srs1[q];
+                    o0.s1 = l.x; o1.s1 = l.y;
+                }
+                if (HET) {
+                    const double2 ps = reinterpret_cast<const double2*>(st + TL::OFF_RS2)[q];
+                    o0.s2 = ps.x; o1.s2 = ps.y;
+                }
+                if (YSTATE && has_rs2) lds_y2<int64_t>(st + TL::OFF_RS2, q, o0.ys, o1.ys);
+            }
+            bad = bad || !fast_ok<KIND, FS, ELBO>(o0) || !fast_ok<KIND, FS, ELBO>(o1);
+            eval<KIND, FS, ELBO, false>(a.L, o0);
+            eval<KIND, FS, ELBO, false>(a.L, o1);
             const int64_t i = base + 2 * q;
-            if (a.s0) st_stream2(a.s0 + i, o0.s0, o1.s0);
-            if (HAS_S1 && a.s1) st_stream2(a.s1 + i, o0.s1, o1.s1);
-            if (HET && a.s2) st_stream2(reinterpret_cast<double*>(a.s2) + i, o0.s2, o1.s2);
-            if (YSTATE && a.s2) store_y2<s2t>(a.s2, i >> 1, o0.y, o1.y);
+            if (!FS) {
+                if (a.s0) st_stream2(a.s0 + i, o0.s0, o1.s0);
+                if (HAS_S1 && a.s1) st_stream2(a.s1 + i, o0.s1, o1.s1);
+                if (HET && a.s2) st_stream2(reinterpret_cast<double*>(a.s2) + i, o0.s2, o1.s2);
+                if (YSTATE && a.s2) store_y2<s2t>(a.s2, i >> 1, o0.y, o1.y);
+            }
             if (a.beta) st_stream2(a.beta + i, o0.b0, o1.b0);
             if (a.gamma) st_stream2(a.gamma + i, o0.g0, o1.g0);
             if (HET) {
@@ -439,16 +484,24 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(co
         Obs o;
         o.y = load_y1<yt>(a.y, i);
         o.ys = o.y;
-        o.m = a.mu[i]; o.v = a.var[i];
-        o.mg = o.vg = 0.0;
+        o.m = o.v = o.mg = o.vg = 0.0;
         o.s0 = o.s1 = o.s2 = 0.0;
-        if (HET) { o.mg = a.mu_g[i]; o.vg = a.var_g[i]; }
-        if (fast_ok<KIND, false, ELBO>(o)) eval<KIND, false, ELBO, false>(a.L, o);
-        else eval<KIND, false, ELBO, true>(a.L, o);
-        if (a.s0) a.s0[i] = o.s0;
-        if (HAS_S1 && a.s1) a.s1[i] = o.s1;
-        if (HET && a.s2) reinterpret_cast<double*>(a.s2)[i] = o.s2;
-        if (YSTATE && a.s2) store_y1<s2t>(a.s2, i, o.y);
+        if (TL::NEED_MV) { o.m = a.mu[i]; o.v = a.var[i]; }
+        if (HET) { o.mg = a.mu_g[i]; if (TL::NEED_MV) o.vg = a.var_g[i]; }
+        if (FS) {
+            o.s0 = a.rs0[i];
+            if (HAS_S1) o.s1 = a.rs1[i];
+            if (HET) o.s2 = reinterpret_cast<const double*>(a.rs2)[i];
+            if (YSTATE && has_rs2) o.ys = (double)reinterpret_cast<const int64_t*>(a.rs2)[i];
+        }
+        if (fast_ok<KIND, FS, ELBO>(o)) eval<KIND, FS, ELBO, false>(a.L, o);
+        else eval<KIND, FS, ELBO, true>(a.L, o);
+        if (!FS) {
+            if (a.s0) a.s0[i] = o.s0;
+            if (HAS_S1 && a.s1) a.s1[i] = o.s1;
+            if (HET && a.s2) reinterpret_cast<double*>(a.s2)[i] = o.s2;
+            if (YSTATE && a.s2) store_y1<s2t>(a.s2, i, o.y);
+        }
         if (a.beta) a.beta[i] = o.b0;
         if (a.gamma) a.gamma[i] = o.g0;
         if (HET) {
@@ -476,10 +529,11 @@ __global__ void __launch_bounds__(AUG_BLOCK, CAVI_TMA_BLOCKS) cavi_tma_kernel(co
     }
 }
 
-template <int KIND, bool ELBO>
-int32_t launch_tma(aug_ctx* ctx, const CaviArgs& a, int64_t ntiles) {
-    typedef TileLayout<KIND> TL;
-    const void* k = (const void*)cavi_tma_kernel<KIND, ELBO>;
+template <int KIND, bool FS, bool ELBO>
+int32_t launch_tma(aug_ctx* ctx, const CaviArgs& a) {
+    typedef TileLayout<KIND, FS, ELBO> TL;
+    const int64_t ntiles = a.n / TL::T;
+    const void* k = (const void*)cavi_tma_kernel<KIND, FS, ELBO>;
     static bool configured_dev[64] = {false};   // the attribute is per device: one flag per ordinal
     bool& configured = configured_dev[ctx->device & 63];
     static int occ = 1;
@@ -492,15 +546,19 @@ int32_t launch_tma(aug_ctx* ctx, const CaviArgs& a, int64_t ntiles) {
     int64_t grid = (int64_t)ctx->sms * occ;
     if (grid > AUG_MAX_GRID) grid = AUG_MAX_GRID;
     if (grid > ntiles) grid = ntiles;
-    cavi_tma_kernel<KIND, ELBO><<<(unsigned)grid, AUG_BLOCK, TL::SMEM_BYTES, ctx->stream>>>(a, ntiles);
+    cavi_tma_kernel<KIND, FS, ELBO><<<(unsigned)grid, AUG_BLOCK, TL::SMEM_BYTES, ctx->stream>>>(a, ntiles);
     ctx->launches++;
     return (int32_t)cudaGetLastError();
 }
 
 template <int KIND>
-int32_t launch_tma1(aug_ctx* ctx, const CaviArgs& a, int64_t ntiles, bool elbo) {
-    return elbo ? launch_tma<KIND, true>(ctx, a, ntiles) : launch_tma<KIND, false>(ctx, a, ntiles);
+int32_t launch_tma1(aug_ctx* ctx, const CaviArgs& a, bool from_state, bool elbo) {
+    if (from_state) return elbo ? launch_tma<KIND, true, true>(ctx, a) : launch_tma<KIND, true, false>(ctx, a);
+    return elbo ? launch_tma<KIND, false, true>(ctx, a) : launch_tma<KIND, false, false>(ctx, a);
 }
+
+// the staged kernel wants at least four full tiles (largest tile of the kind's instantiations)
+__host__ constexpr int64_t cavi_tma_min_n(int kind, bool from_state) { return from_state ? 4 * 4096 : 4 * (int64_t)cavi_tile(kind); }
 
 template <int KIND, bool FROM_STATE, bool ELBO>
 int32_t launch2(aug_ctx* ctx, const CaviArgs& a, bool vec) {
@@ -588,24 +646,22 @@ int32_t aug_cavi_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const voi
                aug_aligned16(a.beta_g) && aug_aligned16(a.gamma_g);
     if (lik->kind == AUG_BERNOULLI) vec = vec && ((((uintptr_t)y) & 1u) == 0);
     else vec = vec && aug_aligned16(y);
-    // Fused calls on 16-byte aligned arrays: ONE launch of the bulk-async staged kernel — the full tiles
-    // (cavi_tile(kind) observations) go through its ring, its last CTA reads the ragged remainder (< one tile) directly.
-    const int64_t tile = cavi_tile(lik->kind);
-    const bool use_tma = !from_state && vec && !getenv_no_tma() && aug_aligned16(y) && n >= 4 * tile;
-    const int64_t ntiles = use_tma ? n / tile : 0;
+    // Calls on 16-byte aligned arrays: ONE launch of the bulk-async staged kernel — the full tiles go through its
+    // ring, its last CTA reads the ragged remainder (< one tile) directly.  Fused and from-state verbs alike.
+    const bool use_tma = vec && !getenv_no_tma() && aug_aligned16(y) && n >= cavi_tma_min_n(lik->kind, from_state);
     if (elbo) a.xch = aug_xch_for(ctx);      // the verb's (only) launch carries the exchange
     if (a.xch && ctx->deferred) {
         a.xch_defer = 1;
         ctx->pending = 1;
     }
-    if (ntiles > 0) {                        // staged kernel: full tiles through the ring, the ragged tail by its last CTA
+    if (use_tma) {
         switch (lik->kind) {
-            case AUG_BERNOULLI: return launch_tma1<AUG_BERNOULLI>(ctx, a, ntiles, elbo);
-            case AUG_NEGBIN: return launch_tma1<AUG_NEGBIN>(ctx, a, ntiles, elbo);
-            case AUG_POISSON: return launch_tma1<AUG_POISSON>(ctx, a, ntiles, elbo);
-            case AUG_LAPLACE: return launch_tma1<AUG_LAPLACE>(ctx, a, ntiles, elbo);
-            case AUG_STUDENTT: return launch_tma1<AUG_STUDENTT>(ctx, a, ntiles, elbo);
-            case AUG_HETERO: return launch_tma1<AUG_HETERO>(ctx, a, ntiles, elbo);
+            case AUG_BERNOULLI: return launch_tma1<AUG_BERNOULLI>(ctx, a, from_state, elbo);
+            case AUG_NEGBIN: return launch_tma1<AUG_NEGBIN>(ctx, a, from_state, elbo);
+            case AUG_POISSON: return launch_tma1<AUG_POISSON>(ctx, a, from_state, elbo);
+            case AUG_LAPLACE: return launch_tma1<AUG_LAPLACE>(ctx, a, from_state, elbo);
+            case AUG_STUDENTT: return launch_tma1<AUG_STUDENTT>(ctx, a, from_state, elbo);
+            case AUG_HETERO: return launch_tma1<AUG_HETERO>(ctx, a, from_state, elbo);
             default: return AUG_ERR_BAD_KIND;
         }
     }

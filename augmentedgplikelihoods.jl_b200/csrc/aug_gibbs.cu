@@ -78,6 +78,7 @@ struct Pg1Args {
     double* out;
     const double* tab;
     AugXchDev* gx;       // non-null: one extra CTA completes a pending split-phase exchange (aug_comm_set_deferred)
+    augr::PhiloxKeys keys;   // the ten round keys of (seed, offset): constant-bank operands of the Philox rounds
 };
 
 // counters exhausted (probability < 1e-14 per draw): finish one draw on a private sequential stream
@@ -153,12 +154,21 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
             const uint64_t gi = (uint64_t)a.i0 + el;
             const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
             uint32_t w[4];
-            augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(0u, 0u, 0u), c3, w);
-            const bool exp_branch = augr::u32_mid(w[0]) < s.r;                     // mass_texpon, polyagamma.jl:179-192
-            const double x = fma(-augf::log_(augr::u53_open0(w[1], w[2])), s.invK, augp::T);   // truncated exponential on (t, inf)
-            bool again = valid && !exp_branch;
-            uint32_t ra = 1u << 8;                                                 // round 0, first IG attempt
-            if (valid && exp_branch) {
+            AUG_PHILOX_RK(a.keys, e_lo, e_hi, augp::pg1_ctr(0u, 0u, 0u), c3, w);
+            const double u0 = augr::u32_mid(w[0]);
+            const bool exp_branch = u0 < s.r;                                      // mass_texpon, polyagamma.jl:179-192
+            const double E = -augf::log_(augr::u53_open0(w[1], w[2]));
+            // exponential branch: x = t + E/K.  The other branch (truncated inverse Gaussian on (0, t]) makes its FIRST
+            // attempt right here when mu = 1/z > t: the same E proposes x = t/(1 + tE)^2, and the part of the selector
+            // uniform above r, (u0 - r)/(1 - r) ~ U(0,1) given u0 >= r, decides both of its rejection tests at once
+            // (aug_pg.cuh: trunc_ig_small_z).  72% of those lanes finish here instead of going through the queue.
+            double a_ig;
+            const double x_ig = augp::trunc_ig_small_z(E, s.z, a_ig);
+            const bool ig_ok = s.z < 1.0 / augp::T && u0 <= fma(1.0 - s.r, augf::exp_(-fmin(a_ig, 700.0)), s.r);
+            const double x = exp_branch ? fma(E, s.invK, augp::T) : x_ig;
+            bool again = valid && !exp_branch && !ig_ok;
+            uint32_t ra = 1u << 8;                                                 // round 0, first queued IG attempt
+            if (valid && (exp_branch || ig_ok)) {
                 if (augp::pg1_accept(x, w[3], k0, k1, e_lo, e_hi, c3, 0u)) {
                     st_stream1(a.out + el, 0.25 * x);
                 } else {
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
             double x = -1.0;
             if (attempt != 0 && attempt < PG1_MAXCTR && round < PG1_MAXCTR) {
                 uint32_t w[4];
-                augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(1u, round, attempt), c3, w);
+                AUG_PHILOX_RK(a.keys, e_lo, e_hi, augp::pg1_ctr(1u, round, attempt), c3, w);
                 x = augp::trunc_ig_attempt_w(w, z);
                 if (x < 0.0) {
                     again = true;
@@ -682,6 +692,7 @@ bool launch_pg1_compact(aug_ctx* ctx, int64_t n, int64_t i0, uint64_t off, const
     a.tab = ctx->pgtab;
     a.gx = take_pending(ctx);
     if (a.gx) grid += 1;
+    augr::philox_round_keys((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32), &a.keys);
     pg1_compact_kernel<<<(unsigned)grid, AUG_BLOCK, 0, ctx->stream>>>(a);
     ctx->launches++;
     *rc = (int32_t)cudaGetLastError();
@@ -800,6 +811,10 @@ int32_t aug_init_aux_variables_dev(aug_ctx* c, const aug_lik* lik, int64_t n, in
     if (needs_n && !nvar) return AUG_ERR_BAD_ARG;
     const int64_t per = is_cat(lik->kind) ? lik->nlatent : 1;
     const int64_t m = n * per;
+    if ((lik->kind == AUG_BERNOULLI || lik->kind == AUG_NEGBIN) && !pg1_no_compact()) {   // PG(1, 0) only: the compacted sampler
+        int32_t r2 = 0;
+        if (launch_pg1_compact(c, n, i0, off, nullptr, 0.0, omega, &r2)) return r2;
+    }
     const int grid = aug_grid_for(c, (const void*)init_aux_kernel, m, AUG_BLOCK);
     init_aux_kernel<<<grid, AUG_BLOCK, 0, c->stream>>>(lik->kind, m, i0 * per, c->seed, off, omega,
                                                         needs_n ? nvar : nullptr, c->pgtab);

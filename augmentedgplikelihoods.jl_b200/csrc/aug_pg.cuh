@@ -255,21 +255,21 @@ __device__ __forceinline__ bool pg1_accept(double x, uint32_t uacc, uint32_t k0,
 }
 
 // one proposal attempt from the truncated inverse Gaussian on (0, t] out of one Philox block; < 0: rejected
+// mu = 1/z > t: x = t/(1 + tE)^2 with E ~ Exp(1) kept with probability exp(-t E^2/2), then x kept with probability
+// exp(-z^2 x/2) (polyagamma.jl:195-213).  Both rejections lead to the same retry, so ONE uniform decides both:
+// keep iff U <= exp(-(t E^2/2 + z^2 x/2)) — the same law with one exp and one decision.
+__device__ __forceinline__ double trunc_ig_small_z(double E, double z, double& a) {
+    const double d = fma(T, E, 1.0);
+    const double x = T * augf::rcp(d * d);
+    a = fma(0.5 * T * E, E, 0.5 * z * z * x);
+    return x;
+}
 __device__ __forceinline__ double trunc_ig_attempt_w(const uint32_t (&w)[4], double z) {
     if (z < 1.0 / T) {
         const double E = -augf::log_(augr::u53_open0(w[0], w[1]));
-        const double a1 = 0.5 * T * E * E;
-        // accept E with probability exp(-a1): evaluated without a branch (the squeezes 1-a <= e^-a <= 1-a+a^2/2
-        // leave ~5% of the lanes undecided, i.e. nearly every warp would run the exp anyway, at low occupancy)
-        if (augr::u32_mid(w[2]) > augf::exp_(-fmin(a1, 700.0))) return -1.0;
-        const double d = fma(T, E, 1.0);
-        const double x = T * augf::rcp(d * d);
-        const double a2 = 0.5 * z * z * x;
-        const double u2 = augr::u32_mid(w[3]);
-        if (u2 > 1.0 - a2) {
-            if (u2 > fma(0.5 * a2, a2, 1.0 - a2) || u2 > augf::exp_(-a2)) return -1.0;
-        }
-        return x;
+        double a;
+        const double x = trunc_ig_small_z(E, z, a);
+        return augr::u32_mid(w[2]) > augf::exp_(-fmin(a, 700.0)) ? -1.0 : x;
     }
     const double mu = 1.0 / z;
     const double rad2 = -2.0 * augf::log_(augr::u53_open0(w[0], w[1]));

@@ -28,6 +28,29 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
     w[0] = x0; w[1] = x1; w[2] = x2; w[3] = x3;
 }
 
+// the same block with the ten round keys precomputed by the host (rk[2r] = k0 + r*0x9E3779B9, rk[2r+1] = k1 + r*0xBB67AE85):
+// the key is launch-uniform, so the per-round key additions (20 of ~75 instructions of a block) become constant-bank operands
+struct PhiloxKeys {
+    uint32_t rk[20];
+};
+static inline void philox_round_keys(uint32_t k0, uint32_t k1, PhiloxKeys* out) {
+    for (int r = 0; r < 10; ++r) {
+        out->rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
+        out->rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
+    }
+}
+#define AUG_PHILOX_RK(KEYS, C0, C1, C2, C3, W)                                              \
+    do {                                                                                    \
+        uint32_t x0_ = (C0), x1_ = (C1), x2_ = (C2), x3_ = (C3);                            \
+        _Pragma("unroll") for (int r_ = 0; r_ < 10; ++r_) {                                 \
+            const uint32_t hi0_ = __umulhi(0xD2511F53u, x0_), lo0_ = 0xD2511F53u * x0_;     \
+            const uint32_t hi1_ = __umulhi(0xCD9E8D57u, x2_), lo1_ = 0xCD9E8D57u * x2_;     \
+            const uint32_t y0_ = hi1_ ^ x1_ ^ (KEYS).rk[2 * r_], y2_ = hi0_ ^ x3_ ^ (KEYS).rk[2 * r_ + 1]; \
+            x0_ = y0_; x1_ = lo1_; x2_ = y2_; x3_ = lo0_;                                   \
+        }                                                                                   \
+        (W)[0] = x0_; (W)[1] = x1_; (W)[2] = x2_; (W)[3] = x3_;                             \
+    } while (0)
+
 // uniforms from raw words: 53-bit (0,1] for values that are returned, 32-bit mid-point (0,1) for decisions
 __device__ __forceinline__ double u53_open0(uint32_t lo, uint32_t hi) {
     return (double)(((((uint64_t)hi << 32) | lo) >> 11) + 1ull) * 0x1.0p-53;

@@ -94,7 +94,8 @@ def pg_cdf_table(orc, b, c, npts=400000):
     return xs, cdf / cdf[-1]
 
 
-KS_POINTS = [(2, 0.0), (3, 2.5), (0.5, 0.0), (1.2, 3.2), (25.5, 10.0), (4.5, 2.5), (10, 1.0)]
+# b = 1 goes through pg1_compact_kernel (c = 5: the mu = 1/z <= t branch of the truncated inverse Gaussian)
+KS_POINTS = [(2, 0.0), (3, 2.5), (0.5, 0.0), (1.2, 3.2), (25.5, 10.0), (4.5, 2.5), (10, 1.0), (1, 0.0), (1, 1.5), (1, 5.0)]
 
 
 def test_ks_at_1e8_draws(A, orc):
