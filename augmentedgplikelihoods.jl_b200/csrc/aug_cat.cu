@@ -258,6 +258,40 @@ __device__ __forceinline__ bool cat_slow(double m, double v) {
     return hi - 0x3f700000u >= 0x410d4c00u - 0x3f700000u;
 }
 
+// The element of cat_row_kernel's straight-line pass: cat_slow(m, v) false and the logistic not saturated (-m <= LOGISTIC_HI).
+// c, p, h carry the same operations as cat_elem<., false>; the ELBO terms are regrouped so that no logarithm is left in
+// the per-element work.  With A = -ln2 - s2 h/2 (s2 = m^2 + v = c^2), lid = log(1/denominator):
+//   expected_logtilt:  sum_j nbar_j (A - m/2) + y_j (A + m/2)                                  (nbar_j = p_j / p0)
+//   PG KL:             sum_j (y_j + nbar_j) (logcosh(c/2) - c^2 h/2),  logcosh(c/2) = c/2 + log(1 + e^-c) - ln2
+//   NM KL:             sum_j nbar_j (log p_j - log prior_j),           log p_j = (-m - c)/2 - log(1 + e^-c) + lid
+// the log(1 + e^-c) of the nbar-proportional parts cancel: sum_j nbar_j [KL terms] = sum_j nbar_j (A - m/2) + (lid - log prior) sum_j nbar_j,
+// i.e. the row sum the expected_logtilt needs anyway plus a multiple of sum_j p_j.  What is left of the logarithm is
+// sum_{j: y_j = 1} log(1 + e^-c_j): the factors (1 + e^-c_j) are multiplied up (one per row for one-hot y, at most 25 per lane and
+// tile) and ONE log of the product is taken per lane and tile.
+template <bool ELBO>
+__device__ __forceinline__ void cat_elem_row(const double m, const double v, const bool yb, const double inv_denom, double& c,
+                                             double& p, double& h, double& A1, double& t0, double& t1, double& prod) {
+    const double s2m = fma(m, m, v);
+    double ic;
+    augf::sqrt_inv(s2m, c, ic);                                           // categorical.jl:88,105
+    const double e = augf::exp_(-fmin(c, 708.0));
+    const double inv = augf::rcp(1.0 + e);
+    h = (1.0 - e) * inv * (0.5 * ic);                                     // tanh(c/2)/(2c)
+    const double w = augf::exp_(0.5 * (-m - c)) * inv;                    // :90-92, :107 (utils.jl:11-14, not saturated)
+    p = w * inv_denom;
+    if (ELBO) {
+        const double A = fma(-0.5 * s2m, h, -augm::LN2);
+        const double hm = 0.5 * m;
+        const double yd = yb ? 1.0 : 0.0;
+        A1 = fma(p, A - hm, A1);
+        t0 = fma(yd, A + hm, t0);
+        t1 = fma(yd, fma(0.5, c, A), t1);
+        prod *= fma(yd, e, 1.0);
+    }
+}
+// the saturated logistic (-m > LOGISTIC_HI: sigma~ = 1, utils.jl:12-13) goes with the any-input instantiation in cat_row_kernel
+__device__ __forceinline__ bool cat_row_slow(double m, double v) { return cat_slow(m, v) || -m > augm::LOGISTIC_HI; }
+
 // EVEN: nl is even -> element pairs never straddle rows and the staged rows are padded by two doubles
 // (conflict-free-enough transposed reads); odd nl -> the staged tiles are the plain linear span.
 template <bool ELBO, bool EVEN>
@@ -476,8 +510,9 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_tma_kernel(const CatTmaArgs 
 //   * P and ±h overwrite mu and var IN PLACE in the staged tile (17 B of shared memory per element in flight
 //     instead of 50-66), which is what lets 8 tiles be resident per SM; the stage is refilled (cp.async.bulk on an
 //     mbarrier, one 800-byte row per copy into padded rows when nl is even) as soon as phase 3 has read it.
-#define CAT_ROW_BLOCK 64
-#define CAT_ROW_R 16
+#ifndef CAT_PIPE_DEFAULT
+#define CAT_PIPE_DEFAULT 322     // rows per tile * 10 + stages per CTA
+#endif
 #ifndef CAT_ROW_ILP4
 #define CAT_ROW_ILP4 1
 #endif
@@ -486,33 +521,42 @@ struct CatRowArgs {
     int64_t ntiles;
     int E;                   // elements per tile = 16 * nl
     int rs;                  // row stride of the staged rows in doubles: nl (odd nl) or nl + 2 (even nl)
-    int off_mu, off_var, off_rinv;
+    int off_mu, off_var, off_rinv;   // within a stage; off_rinv = bytes of one stage, rinv[16] and the mbarriers follow the last stage
     int accumulate;
     double log_inv_denom;
 };
 
-template <bool ELBO, bool EVEN>
-__global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowArgs ta) {
+// R / 8 warps per CTA work on one R-row tile at a time (R = 16, 32, 64: the class-major stores of phase 3 are R * 8-byte
+// segments); NS = 1: the tile is refilled in place after its phase 3 (the
+// round-1 kernel: 8 CTAs of two warps per SM hide each other's refill), NS = 2: the CTA owns two stages and the refill of
+// one has the whole processing time of the other to land (ncu, profiles/r2l: 26 % of the stall samples of the NS = 1
+// kernel sit in the mbarrier wait of the refill).
+template <bool ELBO, bool EVEN, int CAT_ROW_R, int NS>
+__global__ void __launch_bounds__(CAT_ROW_R * 4, 128 / (CAT_ROW_R * NS) < 1 ? 1 : 128 / (CAT_ROW_R * NS)) cat_row_kernel(const CatRowArgs ta) {
+    constexpr int NW = CAT_ROW_R / 8;                                      // 4 lanes per row (8 per row pair when nl is odd)
+    constexpr int CAT_ROW_BLOCK = NW * 32;
     const CatArgs& a = ta.a;
-    extern __shared__ __align__(128) unsigned char cat_stage[];
+    extern __shared__ __align__(128) unsigned char cat_stage0[];
     const int nl = a.nl, E = ta.E, rs = ta.rs;
-    const uint8_t* Y = cat_stage;
-    double* P = reinterpret_cast<double*>(cat_stage + ta.off_mu);      // mu, then p
-    double* H = reinterpret_cast<double*>(cat_stage + ta.off_var);     // var, then ±h (sign = y)
-    double* rinv = reinterpret_cast<double*>(cat_stage + ta.off_rinv);
-    uint64_t* full = reinterpret_cast<uint64_t*>(rinv + CAT_ROW_R);
+    double* rinv = reinterpret_cast<double*>(cat_stage0 + (size_t)NS * ta.off_rinv);
+    uint64_t* fulls = reinterpret_cast<uint64_t*>(rinv + CAT_ROW_R);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        mbar_init(full, 1);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&fulls[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const int64_t first = blockIdx.x, stride = gridDim.x;
-    // warp 0 streams a tile into the stage: y as one span; mu/var as one span (odd nl) or one padded row per lane
-    auto issue = [&](int64_t tile) {
+    // warp 0 streams a tile into a stage: y as one span; mu/var as one span (odd nl) or one padded row per lane
+    auto issue = [&](int64_t tile, int s) {
         const int64_t o = tile * E;
+        unsigned char* cat_stage = cat_stage0 + (size_t)s * ta.off_rinv;
+        double* P = reinterpret_cast<double*>(cat_stage + ta.off_mu);
+        double* H = reinterpret_cast<double*>(cat_stage + ta.off_var);
+        uint64_t* full = &fulls[s];
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was written through the generic proxy
             mbar_expect_tx(full, (uint32_t)E * 17u);
@@ -527,31 +571,45 @@ __global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowA
         }
         if (EVEN) {
             __syncwarp();
-            const int r = lane & 15;
-            const double* src = (lane < 16 ? a.mu : a.var) + o + (int64_t)r * nl;
-            double* dst = (lane < 16 ? P : H) + r * rs;
-            bulk_g2s(dst, src, (uint32_t)nl * 8u, full);
+#pragma unroll
+            for (int i = lane; i < 2 * CAT_ROW_R; i += 32) {
+                const int r = i % CAT_ROW_R;
+                const bool is_mu = i < CAT_ROW_R;
+                const double* src = (is_mu ? a.mu : a.var) + o + (int64_t)r * nl;
+                double* dst = (is_mu ? P : H) + r * rs;
+                bulk_g2s(dst, src, (uint32_t)nl * 8u, full);
+            }
         }
     };
-    if (warp == 0 && first < ta.ntiles) issue(first);
+    if (warp == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (first + s * stride < ta.ntiles) issue(first + s * stride, s);
+    }
 
-    const int l8 = lane & 7;
-    const int jj_first = 4 * warp + (lane >> 3);                           // phase 3: class of this thread
+    constexpr int LPC = CAT_ROW_R / 2;                                     // phase 3: lanes per class (two rows each)
+    const int l8 = lane % LPC;
+    const int jj_first = (32 / LPC) * warp + lane / LPC;                   // phase 3: class of this thread
     const double inv_denom = 1.0 / a.L.c0;
     const bool vec_out = ((a.ldo & 1) == 0) && ((((uintptr_t)a.beta) | ((uintptr_t)a.gamma)) & 15u) == 0;
     const bool both_out = a.beta != nullptr && a.gamma != nullptr && vec_out;
     double acc[3] = {0.0, 0.0, 0.0};
-    uint32_t parity = 0;
-    for (int64_t tile = first; tile < ta.ntiles; tile += stride) {
-        mbar_wait(full, parity);
-        parity ^= 1u;
+    uint32_t kt = 0;
+    for (int64_t tile = first; tile < ta.ntiles; tile += stride, ++kt) {
+        const int st = NS == 1 ? 0 : (int)(kt % NS);
+        unsigned char* cat_stage = cat_stage0 + (size_t)st * ta.off_rinv;
+        const uint8_t* Y = cat_stage;
+        double* P = reinterpret_cast<double*>(cat_stage + ta.off_mu);      // mu, then p
+        double* H = reinterpret_cast<double*>(cat_stage + ta.off_var);     // var, then ±h (sign = y)
+        mbar_wait(&fulls[st], (kt / NS) & 1u);
         // ---- phase 1: straight-line element pairs, in place.  Even nl: 4 lanes per row (a row is nl/2 aligned pairs).
         //      Odd nl: 8 lanes per ROW PAIR - rows 2k and 2k+1 are one 16-byte aligned span of nl pairs whose pair
         //      h = (nl-1)/2 straddles the two rows; a lane walks the span upwards, so its row sums switch from the
         //      first to the second row exactly once.
         {
-            const int sub = EVEN ? (tid >> 2) : (tid >> 3);                 // row (even nl) / row pair (odd nl)
-            const int kq = EVEN ? (tid & 3) : (tid & 7), LQ = EVEN ? 4 : 8; // first pair and pair step of this lane
+            constexpr int LQ = EVEN ? 4 : 8;                               // lanes per row (even nl) / row pair (odd nl)
+            const int sub = tid / LQ;                                       // row (even nl) / row pair (odd nl)
+            const int kq = tid % LQ;                                        // first pair of this lane; LQ = its pair step
             const int npairs = EVEN ? (nl >> 1) : nl, hq = nl >> 1;         // odd nl: hq = the straddling pair
             const int so = EVEN ? sub * rs : 2 * sub * nl;
             double* Pr = P + so;
@@ -575,24 +633,21 @@ __global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowA
                 if (ELBO) { A1A = A1; A23A = A23; A1 = 0.0; A23 = 0.0; }
                 sw = true;
             };
+            double prod = 1.0;                                              // ELBO: product of (1 + e^-c) over this lane's y = 1 elements
             auto eval = [&](const int q, const PairIn& in) {
                 PairOut o;
-                bad = bad || cat_slow(in.m.x, in.v.x) || cat_slow(in.m.y, in.v.y);
-                double xa0 = 0.0, xb0 = 0.0, xa1 = 0.0, xb1 = 0.0;
-                cat_elem<ELBO, false>(in.m.x, in.v.x, in.yy.x != 0, inv_denom, ta.log_inv_denom, a.L.c2, o.c0, o.p0, o.h0,
-                                      xa0, xb0, t0, t1);
-                cat_elem<ELBO, false>(in.m.y, in.v.y, in.yy.y != 0, inv_denom, ta.log_inv_denom, a.L.c2, o.c1, o.p1, o.h1,
-                                      xa1, xb1, t0, t1);
+                bad = bad || cat_row_slow(in.m.x, in.v.x) || cat_row_slow(in.m.y, in.v.y);
                 if (EVEN) {
+                    cat_elem_row<ELBO>(in.m.x, in.v.x, in.yy.x != 0, inv_denom, o.c0, o.p0, o.h0, A1, t0, t1, prod);
+                    cat_elem_row<ELBO>(in.m.y, in.v.y, in.yy.y != 0, inv_denom, o.c1, o.p1, o.h1, A1, t0, t1, prod);
                     sp += o.p0 + o.p1;
-                    if (ELBO) { A1 += xa0 + xa1; A23 += xb0 + xb1; }
                 } else {
                     if (q > hq && !sw) next_row();
+                    cat_elem_row<ELBO>(in.m.x, in.v.x, in.yy.x != 0, inv_denom, o.c0, o.p0, o.h0, A1, t0, t1, prod);
                     sp += o.p0;
-                    if (ELBO) { A1 += xa0; A23 += xb0; }
                     if (q == hq) next_row();
+                    cat_elem_row<ELBO>(in.m.y, in.v.y, in.yy.y != 0, inv_denom, o.c1, o.p1, o.h1, A1, t0, t1, prod);
                     sp += o.p1;
-                    if (ELBO) { A1 += xa1; A23 += xb1; }
                 }
                 return o;
             };
@@ -642,6 +697,13 @@ __global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowA
                 }
             }
             if (!EVEN && !sw) next_row();
+            if (ELBO && !bad) {
+                // the straight-line pass left the NM-KL row sums implicit and the log(1 + e^-c) of the y = 1 elements as a product
+                const double K2 = ta.log_inv_denom - a.L.c2;
+                A23 = fma(K2, sp, A1);
+                if (!EVEN) A23A = fma(K2, spA, A1A);
+                t1 += augf::log_(prod);
+            }
             acc[0] += t0;
             acc[1] += t1;
             // row sums over the lanes of the row (pair)
@@ -679,8 +741,8 @@ __global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowA
             }
         }
         __syncthreads();
-        // ---- phase 3: class-major; 8 lanes x 2 rows = the tile's 16 rows = one 128-byte segment per array;
-        //      a warp covers 4 classes, the CTA 8 classes per step
+        // ---- phase 3: class-major; R/2 lanes x 2 rows = the tile's R rows = one R*8-byte segment per array;
+        //      the CTA covers 8 classes per step
         if (a.beta || a.gamma) {
             const int r = 2 * l8;
             const double2 ri = *reinterpret_cast<const double2*>(rinv + r);
@@ -689,9 +751,9 @@ __global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowA
             // (measured: the same stores to contiguous addresses would make the fused call 9 % faster - the class-major
             //  result layout of the reference, one 128-byte segment per class and tile, is what costs the DRAM pages)
             int64_t o = (int64_t)jj_first * a.ldo + (tile * CAT_ROW_R + r);
-            const int64_t ostep = 4 * (CAT_ROW_BLOCK / 32) * a.ldo;
+            const int64_t ostep = 8 * a.ldo;
 #pragma unroll 2
-            for (int jj = jj_first; jj < nl; jj += 4 * (CAT_ROW_BLOCK / 32)) {
+            for (int jj = jj_first; jj < nl; jj += 8) {
                 const double hs0 = Hp[0], hs1 = Hp[rs];
                 const double y0 = __double2hiint(hs0) < 0 ? 1.0 : 0.0, y1 = __double2hiint(hs1) < 0 ? 1.0 : 0.0;
                 const double n0 = Pp[0] * ri.x, n1 = Pp[rs] * ri.y;                  // mean(NM(1,p)) :54
@@ -707,14 +769,14 @@ __global__ void __launch_bounds__(CAT_ROW_BLOCK, 8) cat_row_kernel(const CatRowA
                     if (a.beta) { st_stream1(a.beta + o, b0); st_stream1(a.beta + o + 1, b1); }
                     if (a.gamma) { st_stream1(a.gamma + o, g0); st_stream1(a.gamma + o + 1, g1); }
                 }
-                Pp += 4 * (CAT_ROW_BLOCK / 32);
-                Hp += 4 * (CAT_ROW_BLOCK / 32);
+                Pp += 8;
+                Hp += 8;
                 o += ostep;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of P/H before the async refill
         __syncthreads();   // every thread is done with the stage: refill it
-        if (warp == 0 && tile + stride < ta.ntiles) issue(tile + stride);
+        if (warp == 0 && tile + NS * stride < ta.ntiles) issue(tile + NS * stride, st);
     }
     if (ELBO) {
         double out[3];
@@ -1203,6 +1265,16 @@ bool cat_no_tma() {   // AUGCUDA_NO_TMA=1 keeps every call on the direct-load ke
     return v == 1;
 }
 
+int cat_row_pipe() {   // AUGCUDA_CAT_PIPE = 161 | 321 | 322: rows per tile and stages per CTA of cat_row_kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AUGCUDA_CAT_PIPE");
+        v = e ? atoi(e) : CAT_PIPE_DEFAULT;
+        if (v != 161 && v != 321 && v != 322) v = CAT_PIPE_DEFAULT;
+    }
+    return v;
+}
+
 bool cat_row_enabled() {   // AUGCUDA_CAT_ROW=0 keeps wide rows on the CTA-wide staged kernel (A/B measurements)
     static int v = -1;
     if (v < 0) {
@@ -1288,6 +1360,8 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
     // ---- full tiles of a fused call on 16-byte aligned arrays: the bulk-async staged kernel
     int64_t n0 = 0;   // rows it covers; the ragged tail [n0, n) goes through the direct-load kernel below
     // (a) wide rows (K of the order of 100): the row-aligned two-warp kernel, 7-8 tiles resident per SM
+    const int pipe = cat_row_pipe();                                       // rows per tile * 10 + stages per CTA
+    const int CAT_ROW_R = pipe / 10, NSr = pipe % 10;
     if (!from_state && !cat_no_tma() && cat_row_enabled() && a.nl >= 32 && aug_aligned16(y) && aug_aligned16(mu) &&
         aug_aligned16(var) && aug_aligned16(s0) && aug_aligned16(s1) && aug_aligned16(s2) && n >= CAT_ROW_R) {
         CatRowArgs ta{};
@@ -1299,15 +1373,19 @@ int32_t aug_cat_dispatch(aug_ctx* ctx, const aug_lik* lik, int64_t n, const void
         ta.rs = even ? nl + 2 : nl;
         ta.off_mu = (ta.E + 127) & ~127;
         ta.off_var = (ta.off_mu + CAT_ROW_R * ta.rs * 8 + 127) & ~127;
-        ta.off_rinv = (ta.off_var + CAT_ROW_R * ta.rs * 8 + 15) & ~15;
+        ta.off_rinv = (ta.off_var + CAT_ROW_R * ta.rs * 8 + 127) & ~127;   // = bytes of one stage
         ta.log_inv_denom = -log(a.L.c0);
-        const size_t smem = (size_t)ta.off_rinv + CAT_ROW_R * sizeof(double) + 16;
-        if ((smem + 1024 + 128) * 4 <= (size_t)ctx->smem_per_sm) {       // at least 4 tiles (8 warps) per SM
+        const int CAT_ROW_BLOCK = CAT_ROW_R * 4;
+        const size_t smem = (size_t)NSr * ta.off_rinv + CAT_ROW_R * sizeof(double) + 8 * NSr + 16;
+        if ((smem + 1024 + 128) * (256 / CAT_ROW_BLOCK) <= (size_t)ctx->smem_per_sm) {   // at least 8 warps per SM
             ta.ntiles = n / CAT_ROW_R;
             n0 = ta.ntiles * CAT_ROW_R;
             ta.a.n = n0;
-            const void* k = elbo ? (even ? (const void*)cat_row_kernel<true, true> : (const void*)cat_row_kernel<true, false>)
-                                 : (even ? (const void*)cat_row_kernel<false, true> : (const void*)cat_row_kernel<false, false>);
+#define CAT_ROW_PICK(R_, NS_)                                                                                                \
+    (elbo ? (even ? (const void*)cat_row_kernel<true, true, R_, NS_> : (const void*)cat_row_kernel<true, false, R_, NS_>)      \
+          : (even ? (const void*)cat_row_kernel<false, true, R_, NS_> : (const void*)cat_row_kernel<false, false, R_, NS_>))
+            const void* k = pipe == 321 ? CAT_ROW_PICK(32, 1) : pipe == 322 ? CAT_ROW_PICK(32, 2) : CAT_ROW_PICK(16, 1);
+#undef CAT_ROW_PICK
             AUG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 1;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, CAT_ROW_BLOCK, smem) != cudaSuccess || occ < 1) occ = 1;
