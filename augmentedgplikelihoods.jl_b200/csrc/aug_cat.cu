@@ -1022,8 +1022,13 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
                     uint32_t w[4];
                     augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(0u, round, 0u), c3, w);
                     ua = w[3];
-                    x = fma(-augf::log_(augr::u53_open0(w[1], w[2])), s.invK, augp::T);
-                    have_x = augr::u32_mid(w[0]) < s.r;
+                    // exponential proposal, or the first truncated-IG attempt in line (as in pg1_compact_kernel; aug_pg.cuh)
+                    const double u0 = augr::u32_mid(w[0]);
+                    const double E = -augf::log_(augr::u53_open0(w[1], w[2]));
+                    double a_ig;
+                    const double x_ig = augp::trunc_ig_small_z(E, z, a_ig);
+                    if (u0 < s.r) { x = fma(E, s.invK, augp::T); have_x = true; }
+                    else if (z < 1.0 / augp::T && u0 <= fma(1.0 - s.r, augf::exp_(-fmin(a_ig, 700.0)), s.r)) { x = x_ig; have_x = true; }
                     to_g = !have_x;
                 } else {
                     st_stream1(a.omega + el, pg1_finish_sequential_cat(a.seed, a.offset, gi, z, a.L.pgtab));

@@ -540,7 +540,14 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                 uint32_t w[4];
                 augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(0u, sub, round, 0u), key.c3, w);
                 uacc = w[3];
-                if (augr::u32_mid(w[0]) < s.r) x = fma(-augf::log_(augr::u53_open0(w[1], w[2])), s.invK, augp::T);
+                // as in pg1_compact_kernel: the exponential proposal, or — same E, the selector uniform's part above r as the
+                // decision — the first truncated inverse-Gaussian attempt in line when mu = 1/z > t (aug_pg.cuh: trunc_ig_small_z)
+                const double u0 = augr::u32_mid(w[0]);
+                const double E = -augf::log_(augr::u53_open0(w[1], w[2]));
+                double a_ig;
+                const double x_ig = augp::trunc_ig_small_z(E, z, a_ig);
+                if (u0 < s.r) x = fma(E, s.invK, augp::T);
+                else if (z < 1.0 / augp::T && u0 <= fma(1.0 - s.r, augf::exp_(-fmin(a_ig, 700.0)), s.r)) x = x_ig;
                 else att = 1u;
             } else {
                 uint32_t w[4];
