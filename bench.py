@@ -227,6 +227,7 @@ def sparse_leg(A, ctx, torch, dist, world, dev, args, rank):
         mu = kappa @ mvec
         var = kdiag - ((kappa @ B) * kappa).sum(1)
         _, b, gm, sc = A.cavi_step_(q, lik, y, A.Normals(mu, var))
+        ctx.flush()       # split-phase mode: no sampling launch follows here to gather the published sums
         res["l"] = ((kappa * gm[0][:, None]).T @ kappa, kappa.T @ b[0], sc)
 
     def timed(fn, k):
