@@ -606,6 +606,9 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
+    # before anything is pinned: keep this rank's host buffers and staging copies on the GPU's own NUMA node
+    orig_affinity = os.sched_getaffinity(0)
+    numa = A.dist.bind_host_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
@@ -726,12 +729,46 @@ def main():
         e2e_full = {"value": n * world / s_full, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
                     "ms_per_step": 1e3 * s_full, "steps": k_full, "outputs": "c, beta, gamma, omega, ELBO scalars (everything)",
                     "pcie_GBs": (h2d + d2h_full) / s_full * 1e-9}
+        # the platform's bound for this step: the same bytes as plain concurrent H2D + D2H copies (no kernels), all ranks at once
+        def copy_only():
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            d_y, d_mu, d_var, d_f = (torch.empty_like(t, device=dev) for t in (hy, hmu, hvar, hf))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            reps = 3
+            w0 = time.perf_counter()
+            for _ in range(reps):
+                with torch.cuda.stream(s_in):
+                    for d_, h_ in ((d_y, hy), (d_mu, hmu), (d_var, hvar), (d_f, hf)):
+                        d_.copy_(h_, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    hg.copy_(head.gamma, non_blocking=True)
+                    hΩ.omega.copy_(head.Ω.omega, non_blocking=True)
+                torch.cuda.synchronize()
+            w1 = time.perf_counter()
+            tc = torch.tensor([(w1 - w0) / reps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            return tc.item()
+        s_copy = copy_only()
+        e2e["copy_only"] = {"ms_per_step": 1e3 * s_copy, "GBs_per_gpu": (h2d + d2h_min) / s_copy * 1e-9,
+                            "what": "the step's H2D and D2H bytes as plain concurrent cudaMemcpyAsync on two streams, no kernels, "
+                                    "all ranks at once (max over ranks): the host / PCIe bound of this box for the e2e step",
+                            "e2e_over_copy_only": s_min / s_copy}
+        if world > 1:
+            bound = [None] * world
+            dist.all_gather_object(bound, numa)
+            e2e["numa_binding"] = {"what": "each rank pinned to the CPUs of its GPU's NUMA node before allocating pinned host "
+                                           "buffers (dist.bind_host_to_gpu_numa_node); null = the platform exposes a single NUMA "
+                                           "node (e.g. a one-node VM), nothing to bind", "per_rank": bound}
         del hy, hmu, hvar, hf, hq, hb, hg, hΩ
 
     # ---------------- cpu_baseline + parity on a slice of the device inputs (rank 0)
     cpu = None
     threads = 1
     if rank == 0 and not args.no_cpu:
+        os.sched_setaffinity(0, orig_affinity)     # the CPU arm uses every host core, not just this rank's NUMA node
         from oracle import orc
         orc.lib()
         threads = host_threads(orc)
