@@ -881,6 +881,7 @@ struct CatGibbsArgs {
     unsigned int* dflag;
     int bulk_ok;                 // f and y are 16-byte aligned and R * nl is a multiple of 16
     LikConst L;
+    augr::PhiloxKeys keys;       // round keys of (seed, offset): constant-bank operands of the per-element Philox block
 };
 
 #define CG_STAGES 3
@@ -1160,12 +1161,13 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             }
             const uint64_t gi = e_base + el;
             uint32_t w[4];
-            augr::philox4x32_10(k0, k1, (uint32_t)gi, (uint32_t)(gi >> 32), 5u << 28, c3, w);
-            // inversion by chop-down from 0 on one 53-bit uniform: 4 terms straight-line, the rest in a loop
+            AUG_PHILOX_RK(a.keys, (uint32_t)gi, (uint32_t)(gi >> 32), 5u << 28, c3, w);
+            // inversion by chop-down from 0 on one 53-bit uniform.  exp(-lam) >= 1 - lam: u <= 1 - lam is n = 0 without the
+            // exp (97% of the elements; the warp skips the exp when all its lanes pass)
             int64_t nn = 0;
-            if (valid && lam > 0.0) {
+            double u = (double)(((((uint64_t)w[1] << 32) | w[0]) >> 11)) * 0x1.0p-53;
+            if (valid && lam > 0.0 && u > 1.0 - lam) {
                 if (lam < 12.0) {
-                    double u = (double)(((((uint64_t)w[1] << 32) | w[0]) >> 11)) * 0x1.0p-53;
                     double p = augf::exp_(-lam);
                     int k = 0;
                     if (u > p) {                                                 // P = 1 - exp(-lam): a few percent of the lanes
@@ -1189,8 +1191,8 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             const bool needs = valid && b >= 1;
             const double z = needs ? 0.5 * fabs(Fs[e]) : 0.0;
             push_f(needs && b == 1, el, 0u, z);
-            {
-                const bool wb = needs && b >= 2;
+            const bool wb = needs && b >= 2;
+            if (__any_sync(0xffffffffu, wb)) {                                   // about 1e-3 of the elements
                 const uint32_t m = __ballot_sync(0xffffffffu, wb);
                 if (wb) {
                     const int pos = nb + __popc(m & lt_mask);
@@ -1509,6 +1511,7 @@ int32_t aug_cat_sample(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0, 
         g.dj = AUG_BLOCK % nl;
         g.seed = ctx->seed;
         g.offset = offset;
+        augr::philox_round_keys((uint32_t)g.seed, (uint32_t)(g.seed >> 32) ^ (uint32_t)(g.offset >> 32), &g.keys);
         g.y = (const uint8_t*)y;
         g.f = f;
         g.omega = omega;

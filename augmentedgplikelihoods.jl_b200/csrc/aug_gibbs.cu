@@ -264,6 +264,7 @@ struct PgbArgs {
     int64_t* nvar;
     const double* tab;
     AugXchDev* gx;        // non-null: one extra CTA completes a pending split-phase exchange
+    augr::PhiloxKeys keys;   // round keys of (seed, offset): constant-bank operands of the Philox rounds
 };
 
 #define PGB_T_DEV 0u
@@ -367,14 +368,14 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                 } else if (KIND == AUG_POISSON) {                       // poisson.jl:26-28, polyagammapoisson.jl:23-27
                     c = ld_stream1(a.f + el);
                     const int64_t y = __ldg(reinterpret_cast<const int64_t*>(a.y) + el);
-                    const int64_t nn = augb::poisson_draw(key, e_lo, e_hi, a.seed, a.offset, gi, a.p0 * augb::logistic_fast(-c));
+                    const int64_t nn = augb::poisson_draw(a.keys, key, e_lo, e_hi, a.seed, a.offset, gi, a.p0 * augb::logistic_fast(-c));
                     a.nvar[el] = nn;
                     b = (double)(nn + y);
                 } else if (KIND == AUG_HETERO) {                        // heteroscedasticgaussian.jl:28-32
                     const double f = ld_stream1(a.f + el);
                     c = ld_stream1(a.g + el);
                     const double d = f - ld_stream1(reinterpret_cast<const double*>(a.y) + el);
-                    const int64_t nn = augb::poisson_draw(key, e_lo, e_hi, a.seed, a.offset, gi, a.p0 * augb::logistic_fast(-c) * d * d * 0.5);
+                    const int64_t nn = augb::poisson_draw(a.keys, key, e_lo, e_hi, a.seed, a.offset, gi, a.p0 * augb::logistic_fast(-c) * d * d * 0.5);
                     a.nvar[el] = nn;
                     b = (double)nn + 0.5;
                     isint = false;
@@ -400,8 +401,8 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                         // first attempt of the two leading terms (one Box-Muller pair) and of the tail in line
                         const augb::Conv s = augb::conv_setup(b, c);
                         uint32_t w1[4], w0[4];
-                        augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 1u, 0u, 0u), key.c3, w1);
-                        augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(3u, 0u, 0u, 0u), key.c3, w0);
+                        AUG_PHILOX_RK(a.keys, e_lo, e_hi, augb::ctr(3u, 1u, 0u, 0u), key.c3, w1);
+                        AUG_PHILOX_RK(a.keys, e_lo, e_hi, augb::ctr(3u, 0u, 0u, 0u), key.c3, w0);
                         double v1, v2;
                         augb::gamma_pair_attempt(w1, b, v1, v2);
                         const double v0 = augb::gamma_attempt(w0, s.shape);
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                     wt = augf::rcp(fma(km, km, xp * xp));
                 }
                 uint32_t w[4];
-                augr::philox4x32_10(key.k0, key.k1, (uint32_t)gi, (uint32_t)(gi >> 32), augb::ctr(3u, k, 0u, att), key.c3, w);
+                AUG_PHILOX_RK(a.keys, (uint32_t)gi, (uint32_t)(gi >> 32), augb::ctr(3u, k, 0u, att), key.c3, w);
                 const double v = augb::gamma_attempt(w, shape);
                 again = true;
                 if (v >= 0.0) {
@@ -500,11 +501,11 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                 const uint64_t gi = (uint64_t)a.i0 + el;
                 const uint32_t e_lo = (uint32_t)gi, e_hi = (uint32_t)(gi >> 32);
                 uint32_t att = (st >> 18) & 0x3fffu;
-                uint32_t w1[4], w2[4];
-                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(4u, 0u, 0u, att), key.c3, w1);
-                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(5u, 0u, 0u, att), key.c3, w2);
-                const double x = augb::frac_propose(w1, e, 0.5 * fabs(c));
-                if (augb::frac_accept(x, e, augr::u53_open0(w2[0], w2[1]))) {
+                uint32_t w1[4];
+                AUG_PHILOX_RK(a.keys, e_lo, e_hi, augb::ctr(4u, 0u, 0u, att), key.c3, w1);
+                double uacc;
+                const double x = augb::frac_propose1(w1, e, 0.5 * fabs(c), uacc);
+                if (augb::frac_accept(x, e, uacc)) {
                     acc = 0.25 * x;
                     if (rem == 0u) finish(el, acc);
                     else to_dev = true;
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
             if (att == 0u) {                                       // round start (sample_pg1, polyagamma.jl:225-257)
                 const augp::PG1 s = augp::pg1_setup_cm(c, tab_s);
                 uint32_t w[4];
-                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(0u, sub, round, 0u), key.c3, w);
+                AUG_PHILOX_RK(a.keys, e_lo, e_hi, augb::ctr(0u, sub, round, 0u), key.c3, w);
                 uacc = w[3];
                 // as in pg1_compact_kernel: the exponential proposal, or — same E, the selector uniform's part above r as the
                 // decision — the first truncated inverse-Gaussian attempt in line when mu = 1/z > t (aug_pg.cuh: trunc_ig_small_z)
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
                 else att = 1u;
             } else {
                 uint32_t w[4];
-                augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, augb::ctr(1u, sub, round, att), key.c3, w);
+                AUG_PHILOX_RK(a.keys, e_lo, e_hi, augb::ctr(1u, sub, round, att), key.c3, w);
                 x = augp::trunc_ig_attempt_w(w, z);
                 if (x < 0.0 && ++att > PGB_MAXATT) exhausted = true;
             }
@@ -724,6 +725,7 @@ int32_t launch_pgb(aug_ctx* ctx, PgbArgs a) {
     if (grid < 1) grid = 1;
     a.gx = take_pending(ctx);
     if (a.gx) grid += 1;
+    augr::philox_round_keys((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32), &a.keys);
     pgb_kernel<KIND><<<(unsigned)grid, PGB_BLOCK, PGB_SMEM_BYTES, ctx->stream>>>(a);
     ctx->launches++;
     return (int32_t)cudaGetLastError();

@@ -245,6 +245,29 @@ __device__ __forceinline__ double frac_propose(const uint32_t (&w)[4], double e,
     const double ez = e / z;
     return ez * ez * augf::rcp(fmax(x1, 1e-280));
 }
+// The same proposal AND the uniform of the acceptance test out of ONE block.  N^2 = rad2 cos^2 uses 53 + 30 bits of
+// (w0, w1, w2) — the two sign bits of the random unit vector do not matter for a square — which leaves 11 + 2 spare bits;
+// with w3 they make a 45-bit uniform u.  u picks the root (u <= P(x1)), and GIVEN the root the rescaled u — u / P(x1) or
+// (u - P(x1)) / (1 - P(x1)) — is again uniform and independent of the proposal: it is the acceptance uniform.  The total
+// probability of a decision that differs from infinitely fine uniforms is below 2^-45 per attempt.
+__device__ __forceinline__ double frac_propose1(const uint32_t (&w)[4], double e, double z, double& uacc) {
+    const double rad2 = -2.0 * augf::log_(augr::u53_open0(w[0], w[1]));
+    double cs, sn;
+    rand_unit_vector(w[2], cs, sn);
+    const double y = fmax(rad2 * cs * cs, 1e-280);                  // N^2
+    const double h = y * augf::rcp(2.0 * e);
+    const double x1 = e * augf::rcp(z + h + sqrt_pos(h * (2.0 * z + h)));   // smaller root; = e^2/y at z = 0
+    const uint64_t bits = ((uint64_t)w[3] << 13) | ((uint64_t)(w[0] & 0x7ffu) << 2) | (uint64_t)(w[2] >> 30);
+    const double u = fma((double)bits, 0x1.0p-45, 0x1.0p-46);       // (0, 1) on a 2^-45 grid
+    const double p1 = e * augf::rcp(e + z * x1);                    // P(x1) = mu/(mu + x1) in (0, 1]
+    if (u <= p1) {
+        uacc = u * augf::rcp(p1);
+        return x1;
+    }
+    uacc = (u - p1) * augf::rcp(fmax(1.0 - p1, 1e-300));
+    const double ez = e / z;
+    return ez * ez * augf::rcp(fmax(x1, 1e-280));
+}
 // accept X with probability R(x) = sum_n (-1)^n c_n q^{n(n+e)}; u in (0, 1]
 __device__ __forceinline__ bool frac_accept(double x, double e, double u) {
     if (!(x <= 48.0)) return false;                                  // R < 2^-63 (also catches inf / nan)
@@ -317,14 +340,14 @@ __device__ __noinline__ int64_t poisson_ptrs(uint64_t seed, uint64_t offset, uin
     g.init(seed, offset, gi, 193u);
     return augr::poisson_rand(g, lam);
 }
-__device__ __forceinline__ int64_t poisson_draw(const Key& key, uint32_t e_lo, uint32_t e_hi, uint64_t seed, uint64_t offset,
-                                                uint64_t gi, double lam) {
+__device__ __forceinline__ int64_t poisson_draw(const augr::PhiloxKeys& rk, const Key& key, uint32_t e_lo, uint32_t e_hi,
+                                                uint64_t seed, uint64_t offset, uint64_t gi, double lam) {
     if (!(lam > 0.0)) return 0;
     if (lam >= 12.0) return poisson_ptrs(seed, offset, gi, lam);
     // chop-down inversion from 0 with ONE 53-bit uniform (block tag 6); the search multiplies by a table of 1/k.
     // k reaches 200 only through the 1e-16 round-off tail of the cumulative sum: restart with the block's other half.
     uint32_t w[4];
-    augr::philox4x32_10(key.k0, key.k1, e_lo, e_hi, ctr(6u, 0u, 0u, 0u), key.c3, w);
+    AUG_PHILOX_RK(rk, e_lo, e_hi, ctr(6u, 0u, 0u, 0u), key.c3, w);
     const double p0 = augf::exp_(-lam);
     for (int half = 0;; ++half) {
         double u = half == 0 ? augr::u53_open0(w[0], w[1]) : augr::u53_open0(w[2], w[3]);
