@@ -333,7 +333,7 @@ __device__ __forceinline__ bool dev_accept(double x, uint32_t uacc, const Key& k
     return dev_accept_series(x, uacc, k.k0, k.k1, k.c3, e_lo, e_hi, sub, round);
 }
 
-// rand(Poisson(lam)) on the element's own stream (tag 6): chop-down inversion in line for lam < 12, PTRS (Hörmann 1993)
+// rand(Poisson(lam)) on the element's own stream (tag 6): chop-down inversion in line for lam < 40 (a lone lane's 30 extra search steps cost a quarter of the out-of-line call), PTRS (Hörmann 1993)
 // out of line above (rare for the rates of poisson.jl:26-28 / heteroscedasticgaussian.jl:28-32 and heavy: lgamma, logs)
 __device__ __noinline__ int64_t poisson_ptrs(uint64_t seed, uint64_t offset, uint64_t gi, double lam) {
     augr::Philox g;
@@ -343,7 +343,7 @@ __device__ __noinline__ int64_t poisson_ptrs(uint64_t seed, uint64_t offset, uin
 __device__ __forceinline__ int64_t poisson_draw(const augr::PhiloxKeys& rk, const Key& key, uint32_t e_lo, uint32_t e_hi,
                                                 uint64_t seed, uint64_t offset, uint64_t gi, double lam) {
     if (!(lam > 0.0)) return 0;
-    if (lam >= 12.0) return poisson_ptrs(seed, offset, gi, lam);
+    if (lam >= 40.0) return poisson_ptrs(seed, offset, gi, lam);
     // chop-down inversion from 0 with ONE 53-bit uniform (block tag 6); the search multiplies by a table of 1/k.
     // k reaches 200 only through the 1e-16 round-off tail of the cumulative sum: restart with the block's other half.
     uint32_t w[4];
