@@ -50,7 +50,7 @@ __device__ double pg_logpdf_dev(double b, double c, double x) {
         const double inner = 1.0 - c_nb * exp((Rn + 1.0) * inv2x);
         const double term = prod * Rn * exp(ea) * inner;
         sum += term;
-        if (ea < -48.6 && term < sum * 0x1.0p-70) break;
+        if (ea < -48.6 && fabs(term) < fabs(sum) * 0x1.0p-70) break;   // (inner < 0 for x >> b: compare magnitudes)
         prod *= (1.0 + bm1 / (n + 1.0)) * (1.0 + bm1 / (n + 2.0));
     }
     return ext + log(fmax(sum, 2.2250738585072014e-308));
