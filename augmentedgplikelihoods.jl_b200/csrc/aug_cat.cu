@@ -16,6 +16,7 @@
 #include "aug_common.cuh"
 #include "aug_math.cuh"
 #include "aug_pg.cuh"
+#include "aug_pgb.cuh"
 
 namespace {
 
@@ -853,7 +854,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) cat_sample_kernel(const CatSampleAr
             const int64_t nn = augr::poisson_rand(g, P[e] * rscale[i]);
             const int64_t yv = (int64_t)__ldg(a.y + base + e);
             a.nvar[base + e] = nn;
-            st_stream1(a.omega + base + e, augp::pg_draw(g, (double)(nn + yv), true, a.f[base + e], a.L.pgtab));
+            st_stream1(a.omega + base + e, augb::pg_draw_stream(g, (double)(nn + yv), true, a.f[base + e], a.L.pgtab));
         }
         __syncthreads();
     }
@@ -905,7 +906,7 @@ __device__ __noinline__ int64_t poisson_slow(uint64_t seed, uint64_t offset, uin
 __device__ __noinline__ double pg_slow(uint64_t seed, uint64_t offset, uint64_t gi, double b, double c, const double* tab) {
     augr::Philox g;
     g.init(seed, offset, gi, 6u);
-    return augp::pg_draw(g, b, true, c, tab);
+    return augb::pg_draw_stream(g, b, true, c, tab);
 }
 __device__ __noinline__ double pg1_finish_sequential_cat(uint64_t seed, uint64_t offset, uint64_t gi, double z, const double* tab) {
     augr::Philox g;

@@ -35,15 +35,15 @@ __global__ void __launch_bounds__(AUG_BLOCK) aux_sample_kernel(const GibbsArgs a
         g.init(a.seed, a.offset, (uint64_t)(a.i0 + i));
         const double f = ld_stream1(a.f + i);
         if (KIND == AUG_BERNOULLI) {                              // PG(1, |f|)  bernoulli.jl:13-15
-            st_stream1(a.omega + i, augp::pg_draw(g, 1.0, true, f, a.L.pgtab));
+            st_stream1(a.omega + i, augb::pg_draw_stream(g, 1.0, true, f, a.L.pgtab));
         } else if (KIND == AUG_NEGBIN) {                          // PG(y + r, |f|)  negativebinomial.jl:20-22
             const double y = (double)__ldg(reinterpret_cast<const int64_t*>(a.y) + i);
-            st_stream1(a.omega + i, augp::pg_draw(g, y + a.L.p0, a.L.r_is_int != 0, f, a.L.pgtab));
+            st_stream1(a.omega + i, augb::pg_draw_stream(g, y + a.L.p0, a.L.r_is_int != 0, f, a.L.pgtab));
         } else if (KIND == AUG_POISSON) {                         // poisson.jl:26-28, polyagammapoisson.jl:23-27
             const int64_t y = __ldg(reinterpret_cast<const int64_t*>(a.y) + i);
             const int64_t nn = augr::poisson_rand(g, a.L.p0 * augm::logistic(-f));
             a.nvar[i] = nn;
-            st_stream1(a.omega + i, augp::pg_draw(g, (double)(nn + y), true, f, a.L.pgtab));
+            st_stream1(a.omega + i, augb::pg_draw_stream(g, (double)(nn + y), true, f, a.L.pgtab));
         } else if (KIND == AUG_LAPLACE) {                         // IG(1/(2β|y-f|), 2λ)  laplace.jl:40-42
             const double y = ld_stream1(reinterpret_cast<const double*>(a.y) + i);
             const double mu = a.L.c0 / fabs(y - f);
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) aux_sample_kernel(const GibbsArgs a
             const double rate = a.L.p0 * augm::logistic(-gg) * d * d * 0.5;
             const int64_t nn = augr::poisson_rand(g, rate);
             a.nvar[i] = nn;
-            st_stream1(a.omega + i, augp::pg_draw(g, (double)nn + 0.5, false, gg, a.L.pgtab));
+            st_stream1(a.omega + i, augb::pg_draw_stream(g, (double)nn + 0.5, false, gg, a.L.pgtab));
         }
     }
 }
@@ -536,25 +536,35 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
             double x = -1.0;
             bool exhausted = false;
             again = true;
-            if (att == 0u) {                                       // round start (sample_pg1, polyagamma.jl:225-257)
+            {
+                // ONE code path for a round start (att == 0; sample_pg1, polyagamma.jl:225-257) and for a retry of the truncated
+                // inverse-Gaussian proposal (att >= 1): both draw E ~ Exp(1) and a decision uniform u0 from one Philox block and
+                // evaluate the same straight-line formulas — the exponential proposal t + E/K, the inverse-Gaussian proposal
+                // t/(1 + tE)^2 with its merged acceptance exp(-a) (aug_pg.cuh: trunc_ig_small_z).  A round start picks the
+                // exponential branch when u0 < r and otherwise uses the part of u0 above r as the IG decision; a retry is
+                // already committed to the IG branch and uses u0 itself.  The lanes of a step differ by selects only.
+                const bool retry = att != 0u;
                 const augp::PG1 s = augp::pg1_setup_cm(c, tab_s);
                 uint32_t w[4];
-                AUG_PHILOX_RK(a.keys, e_lo, e_hi, augb::ctr(0u, sub, round, 0u), key.c3, w);
-                uacc = w[3];
-                // as in pg1_compact_kernel: the exponential proposal, or — same E, the selector uniform's part above r as the
-                // decision — the first truncated inverse-Gaussian attempt in line when mu = 1/z > t (aug_pg.cuh: trunc_ig_small_z)
+                AUG_PHILOX_RK(a.keys, e_lo, e_hi, augb::ctr(retry ? 1u : 0u, sub, round, att), key.c3, w);
+                if (!retry) uacc = w[3];
                 const double u0 = augr::u32_mid(w[0]);
                 const double E = -augf::log_(augr::u53_open0(w[1], w[2]));
                 double a_ig;
                 const double x_ig = augp::trunc_ig_small_z(E, z, a_ig);
-                if (u0 < s.r) x = fma(E, s.invK, augp::T);
-                else if (z < 1.0 / augp::T && u0 <= fma(1.0 - s.r, augf::exp_(-fmin(a_ig, 700.0)), s.r)) x = x_ig;
-                else att = 1u;
-            } else {
-                uint32_t w[4];
-                AUG_PHILOX_RK(a.keys, e_lo, e_hi, augb::ctr(1u, sub, round, att), key.c3, w);
-                x = augp::trunc_ig_attempt_w(w, z);
-                if (x < 0.0 && ++att > PGB_MAXATT) exhausted = true;
+                const double p_ig = augf::exp_(-fmin(a_ig, 700.0));
+                const bool small_z = z < 1.0 / augp::T;
+                if (!retry && u0 < s.r) {
+                    x = fma(E, s.invK, augp::T);
+                } else if (small_z) {
+                    if (u0 <= (retry ? p_ig : fma(1.0 - s.r, p_ig, s.r))) x = x_ig;
+                    else if (++att > PGB_MAXATT) exhausted = true;
+                } else if (!retry) {
+                    att = 1u;
+                } else {                                               // mu = 1/z <= t: the other proposal (rare: |c| > 3.1)
+                    x = augp::trunc_ig_attempt_w(w, z);
+                    if (x < 0.0 && ++att > PGB_MAXATT) exhausted = true;
+                }
             }
             if (x > 0.0) {
                 if (augb::dev_accept(x, uacc, key, e_lo, e_hi, sub, round)) {
@@ -597,7 +607,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) init_aux_kernel(int kind, int64_t m
         } else if (kind == AUG_STUDENTT) {
             omega[i] = augr::gamma_rand(g, 1.0);
         } else {
-            omega[i] = augp::pg_draw(g, 1.0, true, 0.0, pgtab);
+            omega[i] = augb::pg_draw_stream(g, 1.0, true, 0.0, pgtab);
             if (nvar) nvar[i] = augr::poisson_rand(g, 1.0);
         }
     }
@@ -612,7 +622,7 @@ __global__ void __launch_bounds__(AUG_BLOCK) pg_rand_kernel(int64_t n, int64_t i
         g.init(seed, offset, (uint64_t)(i0 + i));
         const double bi = b ? b[i] : bs;
         const double ci = c ? c[i] : cs;
-        out[i] = augp::pg_draw(g, bi, b_is_int != 0, ci, pgtab);
+        out[i] = augb::pg_draw_stream(g, bi, b_is_int != 0, ci, pgtab);
     }
 }
 

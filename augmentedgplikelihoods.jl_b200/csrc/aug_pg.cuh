@@ -10,9 +10,7 @@
 //     logcdf + three exp per observation, and is 0 to double precision for z >= 20;
 //   * accept/reject decisions use 32-bit uniforms (refined to 64 bits in the 0.6% of cases that reach the
 //     alternating series) and squeezes 1 - a <= exp(-a) <= 1 - a + a^2/2, values use 53-bit uniforms;
-//   * the non-integer remainder of b, and any b >= PG_GAMMA_THRESH, is drawn as a KT-term Gamma convolution
-//     plus ONE Gamma carrying the exact mean and variance of the infinite tail, instead of the reference's
-//     biased 200-term truncation (polyagamma.jl:157-164) resp. b Devroye draws — see DESIGN.md "PG(b)".
+//   * b != 1 (sums of draws, the fractional remainder, the certified Gamma convolution) lives in aug_pgb.cuh.
 #pragma once
 #include "aug_common.cuh"
 #include "aug_rng.cuh"
@@ -25,7 +23,6 @@ constexpr double PI2_8 = PI * PI / 8.0;              // polyagamma.jl:4
 constexpr double R0 = 0.5776972428360435;            // r(z = 0)  polyagamma.jl:231
 constexpr double INV_SQRT_T = 1.25;                  // 1/sqrt(0.64)
 constexpr double INV_SQRT2 = 0.70710678118654752440;
-constexpr int KT = 4;                                // explicit terms of the Gamma convolution
 
 struct PG1 {
     double z, K, invK, r;
@@ -145,68 +142,6 @@ __device__ __forceinline__ double pg1_draw(augr::Philox& g, const PG1& s) {
             }
         }
     }
-}
-
-// PG(b, c) as the Gamma convolution (1/2pi^2) sum_k G_k / d_k, d_k = (k-1/2)^2 + w, w = (c/2pi)^2,
-// G_k ~ Gamma(b, 1)  (the representation behind rand_gamma_sum, polyagamma.jl:157-164).
-// The reference truncates at 200 terms (biased low by b/(2pi^2 200)).  Here KT terms are explicit and the
-// whole tail sum_{k>KT} is ONE Gamma whose mean b*T1 and variance b*T2 are exact: T1, T2 = closed-form totals
-//   sum_k 1/d_k = pi^2/2 * tanh(x)/x,   sum_k 1/d_k^2 = pi^4/4 * (tanh x - x sech^2 x)/x^3,   x = |c|/2,
-// minus the explicit terms.  The tail holds 2/(pi^4 KT^3) of the variance and the mismatch of its third
-// cumulant shifts the CDF by < 1e-7/sqrt(b): the law is exact for every statistical purpose and, unlike the
-// Devroye summation, the cost does not grow with b.
-__device__ __forceinline__ double pg_gamma_conv(augr::Philox& g, double b, double c) {
-    const double x = 0.5 * fabs(c);
-    const double w = (x * (1.0 / PI)) * (x * (1.0 / PI));
-    double tot1, tot2;
-    const double x2 = x * x;
-    if (x < 0.25) {
-        tot1 = (0.5 * PI * PI) * (1.0 + x2 * (-1.0 / 3.0 + x2 * (2.0 / 15.0 + x2 * (-17.0 / 315.0 + x2 * (62.0 / 2835.0)))));
-        tot2 = (0.25 * PI * PI * PI * PI) *
-               (2.0 / 3.0 + x2 * (-8.0 / 15.0 + x2 * (34.0 / 105.0 + x2 * (-496.0 / 2835.0 + x2 * (2764.0 / 31185.0)))));
-    } else {
-        const double e = exp(-2.0 * x);
-        const double th = (1.0 - e) / (1.0 + e);
-        const double sech2 = 1.0 - th * th;
-        tot1 = (0.5 * PI * PI) * th / x;
-        tot2 = (0.25 * PI * PI * PI * PI) * (th - x * sech2) / (x2 * x);
-    }
-    double acc = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll 1
-    for (int k = 1; k <= KT; ++k) {
-        const double km = (double)k - 0.5;
-        const double id = augf::rcp(fma(km, km, w));
-        s1 += id;
-        s2 = fma(id, id, s2);
-        acc = fma(augr::gamma_rand(g, b), id, acc);
-    }
-    const double T1 = tot1 - s1, T2 = tot2 - s2;
-    const double scale = T2 / T1;
-    acc = fma(scale, augr::gamma_rand(g, b * T1 / scale), acc);
-    return acc * (0.5 / (PI * PI));
-}
-
-#ifndef PG_GAMMA_THRESH
-#define PG_GAMMA_THRESH 2     // b >= 2: the Gamma convolution (KT + 1 Gamma draws) is cheaper than b Devroye draws
-#endif
-
-// rand(PolyaGamma(b, c))  polyagamma.jl:121-154
-//   b == 0            -> 0 (Dirac, :122-124)
-//   b == 1 (integer)  -> Devroye's exact PG(1, c) sampler (:225-257)
-//   everything else   -> Gamma convolution with exact tail moments (replaces the b-fold summation :129-134
-//                        and the truncated rand_gamma_sum :157-164; cost independent of b)
-__device__ __forceinline__ double pg_draw(augr::Philox& g, double b, bool b_is_int, double c,
-                                          const double* __restrict__ tab) {
-    if (!(b > 0.0)) return 0.0;
-    if (b_is_int) b = rint(b);
-    if (b_is_int && b < (double)PG_GAMMA_THRESH) {
-        const PG1 s = pg1_setup(c, tab);
-        double acc = 0.0;
-        const int nb = (int)b;
-        for (int k = 0; k < nb; ++k) acc += pg1_draw(g, s);
-        return acc;
-    }
-    return pg_gamma_conv(g, b, c);
 }
 
 // ------------------------------------------------------------------ PG(1, c), warp-compacted (aug_gibbs.cu: pg1_compact_kernel)

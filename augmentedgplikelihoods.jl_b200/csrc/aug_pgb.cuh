@@ -95,7 +95,7 @@ __device__ __forceinline__ int conv_kt(double absc) {
 }
 
 // tail parameters for |c| > 3 (KT > 2 explicit terms): out of line — it is rare and heavy (exp, divisions)
-__device__ __noinline__ Conv conv_setup_general(double b, double c) {
+static __device__ __noinline__ Conv conv_setup_general(double b, double c) {
     Conv s;
     const double x = 0.5 * fabs(c);
     const double xp = x * (1.0 / PI);
@@ -203,6 +203,7 @@ __device__ __forceinline__ double mt_test(double x, double u, double d, double c
     v = v * v * v;
     const double x2 = x * x;
     if (u < fma(-0.0331 * x2, x2, 1.0)) return d * v;
+    if (augr::mt_squeeze2(x, u, d, ci)) return d * v;               // rigorous second squeeze: no logarithm (aug_rng.cuh)
     if (augf::log_(u) < fma(0.5, x2, d * (1.0 - v + augf::log_(v)))) return d * v;
     return -1.0;
 }
@@ -304,7 +305,7 @@ __device__ __forceinline__ bool frac_accept(double x, double e, double u) {
 }
 
 // ---- (1) Devroye pieces with this file's counter layout (same arithmetic as aug_pg.cuh: pg1_accept)
-__device__ __noinline__ bool dev_accept_series(double x, uint32_t uacc, uint32_t k0, uint32_t k1, uint32_t c3, uint32_t e_lo,
+static __device__ __noinline__ bool dev_accept_series(double x, uint32_t uacc, uint32_t k0, uint32_t k1, uint32_t c3, uint32_t e_lo,
                                                uint32_t e_hi, uint32_t sub, uint32_t round) {
     double u = augr::u32_mid(uacc);
     const double q = x > T ? -0.5 * PI * PI * x : -2.0 / x;
@@ -335,7 +336,7 @@ __device__ __forceinline__ bool dev_accept(double x, uint32_t uacc, const Key& k
 
 // rand(Poisson(lam)) on the element's own stream (tag 6): chop-down inversion in line for lam < 40 (a lone lane's 30 extra search steps cost a quarter of the out-of-line call), PTRS (Hörmann 1993)
 // out of line above (rare for the rates of poisson.jl:26-28 / heteroscedasticgaussian.jl:28-32 and heavy: lgamma, logs)
-__device__ __noinline__ int64_t poisson_ptrs(uint64_t seed, uint64_t offset, uint64_t gi, double lam) {
+static __device__ __noinline__ int64_t poisson_ptrs(uint64_t seed, uint64_t offset, uint64_t gi, double lam) {
     augr::Philox g;
     g.init(seed, offset, gi, 193u);
     return augr::poisson_rand(g, lam);
@@ -370,13 +371,11 @@ __device__ __forceinline__ double logistic_fast(double x) {
     return x >= 0.0 ? r : e * r;
 }
 
-// ---- sequential fall-back (counters exhausted, probability < 1e-70 per draw; also the reference implementation of
-// the three pieces in one place): the whole draw on a private stream
-__device__ __noinline__ double pgb_sequential(uint64_t seed, uint64_t offset, uint64_t gi, double b, bool b_is_int,
-                                              double c, const double* tab) {
-    augr::Philox g;
-    g.init(seed, offset, gi, 224u);                                  // tag 7
-    if (!(b > 0.0)) return 0.0;
+// ---- the whole draw on ONE sequential stream: the three pieces in one place.  Used by the fall-backs (counters exhausted,
+// probability < 1e-70 per draw), by the rare b >= 2 elements of the categorical sampler, and by the one-thread-one-draw
+// kernels (AUGCUDA_NO_COMPACT=1, shards of 2^32 elements and more): every route samples the same exact / certified law.
+static __device__ __noinline__ double pg_draw_stream(augr::Philox& g, double b, bool b_is_int, double c, const double* tab) {
+    if (!(b > 0.0)) return 0.0;                                      // Dirac at 0  polyagamma.jl:122-124
     if (b_is_int) b = rint(b);
     if (b > PGB_BX) {
         const Conv s = conv_setup(b, c);
@@ -395,7 +394,8 @@ __device__ __noinline__ double pgb_sequential(uint64_t seed, uint64_t offset, ui
         return acc * (0.5 / (PI * PI));
     }
     const double fl = floor(b);
-    const double e = b - fl;
+    double e = b - fl;
+    if (e < 1e-250) e = 0.0;
     const double z = 0.5 * fabs(c);
     double acc = 0.0;
     if (e > 0.0) {
@@ -408,6 +408,12 @@ __device__ __noinline__ double pgb_sequential(uint64_t seed, uint64_t offset, ui
     const augp::PG1 s = augp::pg1_setup(c, tab);
     for (int k = 0; k < (int)fl; ++k) acc += augp::pg1_draw(g, s);
     return acc;
+}
+__device__ __forceinline__ double pgb_sequential(uint64_t seed, uint64_t offset, uint64_t gi, double b, bool b_is_int,
+                                                 double c, const double* tab) {
+    augr::Philox g;
+    g.init(seed, offset, gi, 224u);                                  // tag 7
+    return pg_draw_stream(g, b, b_is_int, c, tab);
 }
 
 }  // namespace augb
