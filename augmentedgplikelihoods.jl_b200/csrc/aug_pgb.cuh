@@ -261,18 +261,18 @@ __device__ __forceinline__ double frac_propose1(const uint32_t (&w)[4], double e
     const uint64_t bits = ((uint64_t)w[3] << 13) | ((uint64_t)(w[0] & 0x7ffu) << 2) | (uint64_t)(w[2] >> 30);
     const double u = fma((double)bits, 0x1.0p-45, 0x1.0p-46);       // (0, 1) on a 2^-45 grid
     const double p1 = e * augf::rcp(e + z * x1);                    // P(x1) = mu/(mu + x1) in (0, 1]
-    if (u <= p1) {
-        uacc = u * augf::rcp(p1);
-        return x1;
-    }
-    uacc = (u - p1) * augf::rcp(fmax(1.0 - p1, 1e-300));
-    const double ez = e / z;
-    return ez * ez * augf::rcp(fmax(x1, 1e-280));
+    // both roots and both rescaled uniforms in straight-line code, then selects: the other root is taken by ~20 % of the
+    // lanes, i.e. by some lane of nearly every step (z = 0: p1 = 1, the first root always; the inf below is never selected)
+    const bool first = u <= p1;
+    const double ez = e * augf::rcp(fmax(z, 1e-300));
+    const double x2 = ez * ez * augf::rcp(fmax(x1, 1e-280));        // mu^2 / x1
+    uacc = first ? u * augf::rcp(p1) : (u - p1) * augf::rcp(fmax(1.0 - p1, 1e-300));
+    return first ? x1 : x2;
 }
 // accept X with probability R(x) = sum_n (-1)^n c_n q^{n(n+e)}; u in (0, 1]
 __device__ __forceinline__ bool frac_accept(double x, double e, double u) {
     if (!(x <= 48.0)) return false;                                  // R < 2^-63 (also catches inf / nan)
-    const double ix = 1.0 / x;
+    const double ix = augf::rcp(fmax(x, 1e-290));
     const double q = augf::exp_(fmax(-2.0 * ix, -700.0));
     double step = q * augf::exp_(fmax(-2.0 * e * ix, -700.0));       // q^{2n+1+e} for n = 0
     const double q2 = q * q;
