@@ -13,7 +13,8 @@
 #define AUG_PGTAB_N 160        // intervals: z in [0, 20)
 #define AUG_PGTAB_DEG 8        // coefficients per interval (degree 7)
 #define AUG_MAX_RANKS 8        // GPUs of one NVSwitch box that can share a peer-memory mailbox
-#define AUG_XCH_SLOT 8         // 64-bit words per mailbox slot: 7 values + 1 epoch flag
+#define AUG_XCH_SLOT 16        // 64-bit words per mailbox slot: up to 7 values, two (32 data bits | 32-bit epoch flag) words each
+#define AUG_XCH_NVAL 7         // values every exchange carries (unused ones are zeros)
 #define AUG_XCH_WORDS (2 * AUG_MAX_RANKS * AUG_XCH_SLOT)   // [parity][source rank][slot]
 // bulk area behind the slots: [parity][source rank][AUG_XCH_BULK doubles] — the P / rhs sums of the sparse-GP sweep
 // (m*m + m <= 128*128 + 128 doubles), pushed by the finalise kernel and published with the slot's epoch flag
@@ -183,37 +184,42 @@ __device__ __forceinline__ unsigned long long xch_globaltimer() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// Called by ONE thread of the grid (the finaliser).  Phase 1: push this rank's sums v[0..NV) into every rank's mailbox
-// and publish the new epoch.
+// Slot protocol (the one NCCL's LL protocol uses): every 64-bit word of a slot carries 32 data bits and the low 32 bits of the
+// epoch.  An aligned 8-byte store is single-copy atomic, so a word whose flag matches holds valid data whatever the order the
+// words arrive in: NO fence between data and flag, nothing to wait for on the publishing side — the stores are posted and the
+// kernel moves on (round-2 8-GPU probe: a release store per peer cost +32 us on the CAVI launch, one fence + relaxed flags
+// +13 us, this +a few).  A double takes two words; a slot holds up to 7 values.
+// Called by ONE thread of the grid (the finaliser).  Phase 1: push this rank's sums v[0..NV) into every rank's mailbox.
 template <int NV>
 __device__ __forceinline__ void xch_publish(AugXchDev* __restrict__ x, const double (&v)[NV]) {
-    static_assert(NV < AUG_XCH_SLOT, "slot holds 7 values + flag");
+    static_assert(NV <= AUG_XCH_NVAL && 2 * AUG_XCH_NVAL <= AUG_XCH_SLOT, "slot holds 7 values, two words each");
     const int nr = x->nranks, me = x->rank;
     const unsigned long long ep = x->epoch + 1ull;
     x->epoch = ep;
+    const unsigned long long flag = (ep & 0xffffffffull) << 32;
     const size_t half = (size_t)(ep & 1ull) * AUG_MAX_RANKS * AUG_XCH_SLOT;
     const size_t mine = half + (size_t)me * AUG_XCH_SLOT;
-    for (int r = 0; r < nr; ++r) {                         // push (posted stores over NVLink; local for r == me)
+    for (int r = 0; r < nr; ++r) {                         // posted stores over NVLink; local for r == me
         unsigned long long* p = x->box[r] + mine;
+        // ALL seven value positions are written (zeros beyond NV) and a gather waits for all of them: ranks may enter one
+        // exchange through different code paths with different NV (an empty shard's zero contribution, a deferred verb's
+        // triple against a pair) and must still complete each other's slots
 #pragma unroll
-        for (int k = 0; k < NV; ++k)
-            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p + k), "l"(__double_as_longlong(v[k])) : "memory");
+        for (int k = 0; k < AUG_XCH_NVAL; ++k) {
+            const unsigned long long bits = k < NV ? (unsigned long long)__double_as_longlong(v[k < NV ? k : 0]) : 0ull;
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p + 2 * k), "l"((bits & 0xffffffffull) | flag) : "memory");
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p + 2 * k + 1), "l"((bits >> 32) | flag) : "memory");
+        }
     }
-    // ONE system-scope fence orders every posted value store before every flag store below (fence cumulativity: an
-    // observer that acquires a flag sees the values).  The flags themselves are relaxed stores: a st.release.sys per
-    // peer carries its own fence and waits for the previous peer's store to be acknowledged — seven NVLink round trips
-    // in a row on 8 GPUs (+32 us on the 8-GPU CAVI launch, round-2 SCALE probe) against one here.
-    __threadfence_system();
-    for (int r = 0; r < nr; ++r)                           // publish
-        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(x->box[r] + mine + (AUG_XCH_SLOT - 1)), "l"(ep) : "memory");
 }
-// Phase 2: wait for the current epoch's slots of all ranks in this rank's own mailbox and add them IN RANK ORDER
+// Phase 2: wait for the current epoch's words of all ranks in this rank's own mailbox and add the values IN RANK ORDER
 // (bit-identical on every rank, independent of arrival order).  A peer that does not arrive within timeout_ns raises
 // bit 1 of the error flag and yields NaN.
 template <int NV>
 __device__ __forceinline__ void xch_gather(AugXchDev* __restrict__ x, double (&v)[NV]) {
     const int nr = x->nranks, me = x->rank;
     const unsigned long long ep = x->epoch;
+    const unsigned long long flag = ep & 0xffffffffull;
     const size_t half = (size_t)(ep & 1ull) * AUG_MAX_RANKS * AUG_XCH_SLOT;
     double tot[NV];
 #pragma unroll
@@ -222,20 +228,23 @@ __device__ __forceinline__ void xch_gather(AugXchDev* __restrict__ x, double (&v
     bool ok = true;
     for (int r = 0; r < nr && ok; ++r) {
         const unsigned long long* p = x->box[me] + half + (size_t)r * AUG_XCH_SLOT;
+        unsigned long long w[2 * AUG_XCH_NVAL];
         for (;;) {
-            unsigned long long f;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(p + (AUG_XCH_SLOT - 1)) : "memory");
-            if (f == ep) break;
+            bool all = true;
+#pragma unroll
+            for (int k = 0; k < 2 * AUG_XCH_NVAL; ++k) {   // all loads in flight together
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w[k]) : "l"(p + k) : "memory");
+            }
+#pragma unroll
+            for (int k = 0; k < 2 * AUG_XCH_NVAL; ++k) all = all && (w[k] >> 32) == flag;
+            if (all) break;
             if (xch_globaltimer() - t0 > x->timeout_ns) { ok = false; break; }
             __nanosleep(64);
         }
         if (!ok) break;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            unsigned long long w;
-            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p + k) : "memory");
-            tot[k] += __longlong_as_double((long long)w);
-        }
+        for (int k = 0; k < NV; ++k)
+            tot[k] += __longlong_as_double((long long)((w[2 * k] & 0xffffffffull) | (w[2 * k + 1] << 32)));
     }
     if (!ok) {
         atomicOr(x->err, 2u);

@@ -296,10 +296,10 @@ void aug_pipe_destroy(aug_ctx* ctx);  // aug_host.cu
 namespace {
 __global__ void xch_only_kernel(AugXchDev* x, double* vals, int count, int first, int mode) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double v[AUG_XCH_SLOT - 1];
+    double v[7];
 #pragma unroll
-    for (int k = 0; k < AUG_XCH_SLOT - 1; ++k) v[k] = (mode == 0 && k < count) ? vals[k] : 0.0;
-    xch_allreduce<AUG_XCH_SLOT - 1>(x, v);
+    for (int k = 0; k < 7; ++k) v[k] = (mode == 0 && k < count) ? vals[k] : 0.0;
+    xch_allreduce<7>(x, v);
     if (mode == 0) {                       // plain all-reduce of vals[0..count)
         for (int k = 0; k < count; ++k) vals[k] = v[k];
     } else {                               // zero contribution of an empty shard to a verb's slots
@@ -739,7 +739,7 @@ int32_t aug_comm_get_fused(aug_ctx* c, int32_t* on) {
 // in-place sum over ranks of count <= 7 device doubles through the mailbox, on the ctx stream (no NCCL involved)
 int32_t aug_allreduce_scalars_p2p(aug_ctx* c, double* dev, int32_t count) {
     if (!c || !c->xch) return AUG_ERR_NOT_INIT;
-    if (!dev || count < 1 || count > AUG_XCH_SLOT - 1) return AUG_ERR_BAD_ARG;
+    if (!dev || count < 1 || count > 7) return AUG_ERR_BAD_ARG;
     AUG_CUDA(cudaSetDevice(c->device));
     { int32_t rc = aug_xch_flush(c); if (rc) return rc; }
     xch_only_kernel<<<1, 32, 0, c->stream>>>(c->xch, dev, count, 0, 0);

@@ -702,7 +702,12 @@ __global__ void __launch_bounds__(256) sparse_finalize_xch_kernel(const double* 
         double v[2] = {0.0, 0.0};
         const int nb = grid < 256 ? grid : 256;
         for (int b = 0; b < nb; ++b) { v[0] += se[0][b]; v[1] += se[1][b]; }
-        xch_allreduce<2>(x, v);                               // publishes epoch ep, waits for every rank's flag
+        // every block fenced its bulk stores at system scope before taking its ticket; this fence orders all of them (seen
+        // through the ticket) before the slot words published next, and the one after the gather orders the peers' bulk
+        // stores before the loads below (the slot protocol itself carries no fence)
+        __threadfence_system();
+        xch_allreduce<2>(x, v);                               // publishes epoch ep, waits for every rank's words
+        __threadfence_system();
         s_ok = !(v[0] != v[0]);                               // NaN = a peer did not arrive (error flag bit 1 is set)
         if (scalars != nullptr) {
             scalars[AUG_S_EXPECTED_LOGTILT] = v[0];
