@@ -478,10 +478,18 @@ def time_leg(leg, torch, dist, world, steps, warmup, collective=None):
     vals = [t0.elapsed_time(t1) / steps, sum(e[0].elapsed_time(e[1]) for e in evs) / steps,
             sum(e[1].elapsed_time(e[2]) for e in evs) / steps, sum(e[2].elapsed_time(e[3]) for e in evs) / steps]
     t = torch.tensor(vals, dtype=torch.float64, device=leg.mu.device)
+    per_rank = None
     if world > 1:
+        # every rank's own times next to the max: the spread between the GPUs of the box (HBM-bound kernels differ by a
+        # percent or two from GPU to GPU) is what the max-over-ranks weak-scaling efficiency mostly measures
+        allr = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = {"ms_per_step": [round(float(a[0]), 5) for a in allr], "ms_cavi": [round(float(a[1]), 5) for a in allr],
+                    "ms_gibbs": [round(float(a[2]), 5) for a in allr]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_cavi, ms_gibbs, ms_coll = t.tolist()
-    return dict(ms_per_step=ms_total, ms_cavi=ms_cavi, ms_gibbs=ms_gibbs, ms_allreduce=ms_coll, launches=int(launches))
+    return dict(ms_per_step=ms_total, ms_cavi=ms_cavi, ms_gibbs=ms_gibbs, ms_allreduce=ms_coll, launches=int(launches),
+                per_rank=per_rank)
 
 
 def leg_report(leg, tm, world, peak, peak_src, steps, traffic=None):
@@ -868,7 +876,8 @@ def main():
                                    "fused into cavi_tma_kernel's finaliser over the peer-memory mailbox (NVLink)")
                                   if args.collective == "p2p" else "ncclAllReduce(sum, double, 8) after the step")},
         "parts": {"cavi_obs_per_s": n * world / (ms_cavi * 1e-3), "pg_draws_per_s": n * world / (ms_gibbs * 1e-3),
-                  "ms_cavi": ms_cavi, "ms_gibbs": ms_gibbs, "ms_allreduce": tm["ms_allreduce"]},
+                  "ms_cavi": ms_cavi, "ms_gibbs": ms_gibbs, "ms_allreduce": tm["ms_allreduce"],
+                  "per_rank": tm.get("per_rank")},
         "roofline": {"kernel": "cavi_tma_kernel<BERNOULLI, ELBO> (aux_posterior! + expected potential/precision + ELBO sums): "
                                "the HBM-bound kernel of the step; the time-dominant one is the issue-bound sampler in roofline_gibbs",
                      "bound": "hbm", "achieved": ach,
