@@ -593,6 +593,102 @@ __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const Pg
     }
 }
 
+// ------------------------------------------------------------------ Laplace / StudentT: one Philox block per draw, compacted retries
+// laplace.jl:40-42   omega ~ InverseGaussian(mu = 1/(2 beta |y - f|), 2 lambda): Michael-Schucany-Haas out of ONE block, straight-line
+//                    (stable form x1 = 4 mu lam w / (w + sqrt(w (4 lam + w)))^2, w = mu N^2; other root mu^2 / x1);
+// studentt.jl:46-48  omega ~ Gamma(alpha, 2/(nu/sigma^2 + (y - f)^2)): one Marsaglia-Tsang attempt per block (alpha >= 1); the 4 % of
+//                    rejected attempts wait in a per-warp queue and are retried 32 at a time (the per-thread loop of
+//                    aux_sample_kernel made 3 of 4 warps run a second attempt for one or two lanes).
+// Draws depend on (seed, offset, global index) only: block counter = attempt number.
+struct MapSampleArgs {
+    int64_t n, i0;
+    uint64_t offset;
+    const double* y;
+    const double* f;
+    double* omega;
+    double c0, c1;
+    augr::PhiloxKeys keys;
+};
+#define MS_QCAP 64
+template <int KIND>
+__global__ void __launch_bounds__(AUG_BLOCK, 4) map_sample_kernel(const MapSampleArgs a) {
+    __shared__ uint32_t qel_s[AUG_BLOCK / 32][MS_QCAP];
+    __shared__ uint32_t qat_s[AUG_BLOCK / 32][MS_QCAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* qel = qel_s[warp];
+    uint32_t* qat = qat_s[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t nchunks = (uint32_t)((a.n + 31) >> 5);                 // n < 2^32 (host-checked)
+    const uint32_t W = gridDim.x * (AUG_BLOCK / 32);
+    const uint32_t c3 = (uint32_t)a.offset;
+    int qn = 0;
+    // one attempt for element el (attempt number att): true = omega[el] written
+    auto attempt = [&](uint32_t el, uint32_t att, bool valid) {
+        const uint64_t gi = (uint64_t)a.i0 + el;
+        uint32_t w[4];
+        AUG_PHILOX_RK(a.keys, (uint32_t)gi, (uint32_t)(gi >> 32), att, c3, w);
+        const double y = valid ? ld_stream1(a.y + el) : 1.0, f = valid ? ld_stream1(a.f + el) : 0.0;
+        const double d = y - f;
+        if (KIND == AUG_LAPLACE) {
+            const double lam = 2.0 * a.c1;
+            const double ad = fabs(d);
+            const double mu = ad >= 1e-290 ? a.c0 * augf::rcp(fmin(ad, 1e290)) : a.c0 / ad;
+            const double rad2 = -2.0 * augf::log_(augr::u53_open0(w[0], w[1]));
+            double cs, sn;
+            augb::rand_unit_vector(w[2], cs, sn);
+            const double wv = fmax(mu * rad2 * cs * cs, 1e-290);          // mu N^2
+            const double s = augb::sqrt_pos(wv * fma(4.0, lam, wv));
+            const double den = wv + s;
+            const double x1 = 4.0 * mu * lam * wv * augf::rcp(den * den);
+            const bool first = augr::u32_mid(w[3]) * (mu + x1) <= mu;      // P(x1) = mu / (mu + x1)
+            const double x = first ? x1 : mu * mu * augf::rcp(fmax(x1, 1e-290));
+            if (valid) st_stream1(a.omega + el, x);
+            return true;
+        } else {
+            const double v = augb::gamma_attempt(w, a.c1);
+            const bool ok = v >= 0.0;
+            if (valid && ok) st_stream1(a.omega + el, v * 2.0 * augf::rcp(fma(d, d, a.c0)));
+            return ok || !valid;
+        }
+    };
+    uint32_t ch = blockIdx.x * (AUG_BLOCK / 32) + warp;
+    for (;;) {
+        if (qn < 32 && ch < nchunks) {
+            const uint32_t el = (ch << 5) + lane;
+            const bool valid = el < a.n;
+            const bool done = attempt(el, 0u, valid);
+            ch += W;
+            if (KIND != AUG_LAPLACE) {
+                const uint32_t m = __ballot_sync(0xffffffffu, !done);
+                if (!done) {
+                    const int pos = qn + __popc(m & lt_mask);
+                    qel[pos] = el;
+                    qat[pos] = 1u;
+                }
+                qn += __popc(m);
+                __syncwarp();
+            }
+            continue;
+        }
+        if (qn == 0) break;
+        const int cnt = qn < 32 ? qn : 32;
+        const bool active = lane < cnt;
+        uint32_t el = 0, att = 0;
+        if (active) { el = qel[qn - cnt + lane]; att = qat[qn - cnt + lane]; }
+        __syncwarp();
+        qn -= cnt;
+        const bool done = attempt(el, att, active);
+        const uint32_t m = __ballot_sync(0xffffffffu, active && !done);
+        if (active && !done) {
+            const int pos = qn + __popc(m & lt_mask);
+            qel[pos] = el;
+            qat[pos] = att + 1u;
+        }
+        qn += __popc(m);
+        __syncwarp();
+    }
+}
+
 // init_aux_variables: PG(1,0) [+ Poisson(1)] / InverseGamma(1,1) / Gamma(1,1)
 // bernoulli.jl:3-5, negativebinomial.jl:10-12, poisson.jl:14-18, laplace.jl:29-31, studentt.jl:35-37,
 // heteroscedasticgaussian.jl:16-20, categorical.jl:52-57 (m = nl * n elements)
@@ -811,6 +907,30 @@ int32_t aug_aux_sample_dev(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i0
         return launch_pgb<AUG_HETERO>(c, p);
     }
     { int32_t rf = aug_xch_flush(c); if (rf) return rf; }     // no gather hook in these kernels: complete a pending exchange first
+    if (!pg1_no_compact() && n < ((int64_t)1 << 32) - 64 &&
+        (lik->kind == AUG_LAPLACE || (lik->kind == AUG_STUDENTT && a.L.c1 >= 1.0))) {
+        MapSampleArgs m{};
+        m.n = n;
+        m.i0 = i0;
+        m.offset = off;
+        m.y = reinterpret_cast<const double*>(y);
+        m.f = f;
+        m.omega = omega;
+        m.c0 = a.L.c0;
+        m.c1 = a.L.c1;
+        augr::philox_round_keys((uint32_t)c->seed, (uint32_t)(c->seed >> 32) ^ (uint32_t)(off >> 32), &m.keys);
+        const void* k = lik->kind == AUG_LAPLACE ? (const void*)map_sample_kernel<AUG_LAPLACE> : (const void*)map_sample_kernel<AUG_STUDENTT>;
+        int occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, AUG_BLOCK, 0) != cudaSuccess || occ < 1) occ = 1;
+        int64_t grid = (int64_t)c->sms * occ;
+        const int64_t need = ((n + 31) / 32 + (AUG_BLOCK / 32) - 1) / (AUG_BLOCK / 32);
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        if (lik->kind == AUG_LAPLACE) map_sample_kernel<AUG_LAPLACE><<<(unsigned)grid, AUG_BLOCK, 0, c->stream>>>(m);
+        else map_sample_kernel<AUG_STUDENTT><<<(unsigned)grid, AUG_BLOCK, 0, c->stream>>>(m);
+        c->launches++;
+        return (int32_t)cudaGetLastError();
+    }
     switch (lik->kind) {
         case AUG_BERNOULLI: return launch_map(c, aux_sample_kernel<AUG_BERNOULLI>, a, n);
         case AUG_NEGBIN: return launch_map(c, aux_sample_kernel<AUG_NEGBIN>, a, n);
