@@ -336,7 +336,8 @@ int32_t aug_allreduce_scalars(aug_ctx* ctx, double* dev, int32_t count);
 /* Peer-memory mailbox over NVLink / NVSwitch: the all-reduce of the scalar block FUSED into the reducing kernel.
  * The block is 64 bytes, so an NCCL call is pure launch + protocol latency; with the mailbox attached the
  * finalising thread of aug_cavi_step / aug_expected_elbo_terms / aug_sampled_loglik_terms pushes its sums into
- * every rank's mailbox with peer stores, publishes an epoch flag, gathers the other ranks' sums from its own
+ * every rank's mailbox with peer stores (each aligned 8-byte word carries 32 data bits and a 32-bit epoch flag, so there is
+ * no fence on the publishing side and no ordering between words to rely on), gathers the other ranks' sums from its own
  * mailbox and adds them in rank order (bit-identical on all ranks) before it writes `scalars` — kernel and
  * collective are ONE launch.  Set-up: every rank calls aug_comm_p2p_export, the caller all-gathers the 64-byte
  * cudaIpc handles (torch.distributed / MPI / Julia Distributed), every rank calls aug_comm_p2p_attach, and after a

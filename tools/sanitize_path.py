@@ -29,6 +29,8 @@ for kind, params, kw in [(BERNOULLI, (), {}), (NEGBIN, (10,), dict(r_is_int=True
     q, beta, gamma, scal = A.cavi_step_(q, lik, dev(y), A.Normals(dev(mu), dev(var)), want_elbo=(kind != CAT))
     if kind != CAT:
         A.expected_logtilt(lik, q, dev(y), A.Normals(dev(mu), dev(var)))
+    A.expected_auglik_potential_and_precision(lik, q, dev(y), A.Normals(dev(mu), dev(var)))   # from-state verb (staged kernel)
+    A.init_aux_variables(A.AugPhilox(4, 0), lik, nn)
     Om = A.aux_sample(A.AugPhilox(3, 0), lik, dev(y), dev(f))
     A.auglik_potential_and_precision(lik, Om, dev(y), dev(f))
     if kind != CAT:
