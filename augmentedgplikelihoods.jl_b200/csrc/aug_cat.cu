@@ -888,6 +888,17 @@ struct CatGibbsArgs {
 #define CG_STAGES 3
 #define CG_QCAP 96
 #define CG_BCAP 64
+// Round 2: the counts of a ROW are drawn from the NegativeMultinomial law directly instead of one Poisson draw per element.
+// The reference samples NM(x0 = 1, p) as a Gamma-Poisson mixture (negativemultinomial.jl:35-45: tau ~ Exp(1)/p0, n_ij ~
+// Poisson(p_ij tau) independent).  The same law in two steps (superposition / splitting of Poisson counts, then the mixture
+// over tau in closed form): the row total N_i = sum_j n_ij is GEOMETRIC, P(N_i = k) = p0 (1 - p0)^k, and given N_i the counts are
+// Multinomial(N_i; p_ij / (1 - p0)).  E[N_i] = (1 - p0)/p0 is of order one, so a row needs ONE Philox block — a geometric
+// draw by chop-down (no exp, no log) and the first class pick — and N_i picks by inversion over the row's cumulative p (16 lanes
+// cooperating) instead of K = 100 Philox blocks, exps and searches; the element pass only reads its count from a byte array.
+// Rows with p0 < CG_DENSE_P0 (long geometric tails) keep the per-element mixture draws: exact for any input, the choice depends
+// on p0 only.  Streams: the row block (tag 7, counter 0) gives the geometric uniform and the first pick (dense rows: Exp(1));
+// blocks 1, 2, ... two further picks each.
+#define CG_DENSE_P0 0.2
 
 // logistic(x) with the LogExpFunctions saturation (categorical.jl:23), straight-line
 __device__ __forceinline__ double logistic_fast(double x) {
@@ -921,12 +932,15 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
     // ring of CG_STAGES input tiles (f: E doubles, y: E bytes), filled by cp.async.bulk two tiles ahead
     unsigned char* ring = cg_smem;
     const int off_y = E * 8, stage_bytes = (E * 9 + 127) & ~127;
-    double* tab_s = reinterpret_cast<double*>(ring + CG_STAGES * stage_bytes);   // r(z) table
-    double* Pb = tab_s + AUG_PGTAB_N * AUG_PGTAB_DEG;                        // [2][E]   p_ij of two tiles in flight
-    double* rsc = Pb + 2 * E;                                                // [2][R]   Exp(1)/p0 per row
-    double* qz_all = rsc + 2 * R;                                            // per warp: F and G items
+    // (the r(z) table stays in global memory: only the ~3 % of the elements that need a PG draw read it, through L1)
+    double* Pb = reinterpret_cast<double*>(ring + CG_STAGES * stage_bytes);     // [E]   p_ij of the tile
+    double* rsc = Pb + E;                                                    // [R]   Exp(1)/p0 per row (dense rows)
+    double* qz_all = rsc + R;                                            // per warp: F and G items
     uint32_t* qw_all = reinterpret_cast<uint32_t*>(qz_all + (AUG_BLOCK / 32) * 2 * CG_QCAP);
     uint64_t* full = reinterpret_cast<uint64_t*>(qw_all + (AUG_BLOCK / 32) * (5 * CG_QCAP + 2 * CG_BCAP));
+    uint64_t* empty = full + CG_STAGES;                                           // a stage is free again: one arrival per thread
+    unsigned char* Ncb = reinterpret_cast<unsigned char*>(empty + CG_STAGES);     // [E]  n_ij of the tile
+    unsigned char* Rdb = Ncb + E;                                                 // [R]  1 = dense row (per-element draws)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* fz = qz_all + warp * 2 * CG_QCAP;
     double* gz = fz + CG_QCAP;
@@ -938,7 +952,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
     uint32_t* bel = gua + CG_QCAP;
     uint32_t* bbv = bel + CG_BCAP;
     if (tid == 0) {
-        for (int s = 0; s < CG_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < CG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], AUG_BLOCK); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // a tile is bulk-copied when it is a full one (its y span is then a multiple of 16 bytes at a 16-byte aligned
@@ -951,7 +965,6 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
         bulk_g2s(st, a.f + o, (uint32_t)E * 8u, &full[s]);
         bulk_g2s(st + off_y, a.y + o, (uint32_t)E, &full[s]);
     };
-    for (int t = tid; t < AUG_PGTAB_N * AUG_PGTAB_DEG; t += AUG_BLOCK) tab_s[t] = __ldg(a.L.pgtab + t);
     __syncthreads();
     if (tid == 0) {
         issue((int64_t)blockIdx.x, 0);
@@ -990,16 +1003,24 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
         push_f(newround, el, round + 1u, z);
     };
 
-    const int i_first = tid / nl, j_first = tid - i_first * nl;
     const int l16 = lane & 15;
-    // state of the element pass (phase C) of the current tile; e0 >= Et: the next tile has to be set up first
+    // Every warp owns R / 8 rows of each tile END TO END (p_ij, the row draws, the element pass): no CTA-wide barrier inside a
+    // tile — ncu on the barrier version (profiles/r2y): 27 % of the stall samples at the two __syncthreads per tile, issue slots
+    // 45 % busy.  The warps only meet at the mbarriers of the input ring: full[s] (the bulk copy landed) and empty[s] (all 8
+    // warps are done with the stage; thread 0 waits for it before it refills the stage, two tiles ahead).
+    const int rows_w = R / (AUG_BLOCK / 32);                                  // host: R is a multiple of 8
+    const int di32 = 32 / nl, dj32 = 32 % nl;
+    // state of the element pass (phase C) of the current tile; e0 >= ew1: the next tile has to be set up first
     int64_t tile = (int64_t)blockIdx.x - gridDim.x;
-    int buf = 1, Et = 0, e0 = 0, ci = 0, cj = 0;
+    int e0 = 0, ew1 = 0, ci = 0, cj = 0;
     int stg = CG_STAGES - 1;          // stage of the current tile
     uint32_t par = 1;                 // its mbarrier phase parity (flips when stg wraps to 0)
     uint32_t base = 0;
-    const double* P = Pb;
-    const double* rs = rsc;
+    uint32_t kt = 0;                  // tiles this warp has started (parity of the empty barriers)
+    double* const P = Pb;
+    double* const rs = rsc;
+    unsigned char* const Nc = Ncb;    // counts / dense-row flags of the current tile
+    unsigned char* const Rd = Rdb;
     const double* Fs = nullptr;       // staged f and y of the current tile
     const unsigned char* Ys = nullptr;
     bool drain = false;
@@ -1020,7 +1041,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             uint32_t ua = 0;
             if (active) {
                 if (round < 255u) {
-                    const augp::PG1 s = augp::pg1_setup<true>(2.0 * z, tab_s);
+                    const augp::PG1 s = augp::pg1_setup<false>(2.0 * z, a.L.pgtab);
                     uint32_t w[4];
                     augr::philox4x32_10(k0, k1, e_lo, e_hi, augp::pg1_ctr(0u, round, 0u), c3, w);
                     ua = w[3];
@@ -1084,104 +1105,175 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             continue;
         }
         if (drain) break;
-        if (e0 >= Et) {
-            // ---- next tile of this CTA (every warp takes this branch once per tile, in the same order)
+        if (e0 >= ew1) {
+            // ---- next tile: this warp's rows of it
+            if (tile >= 0) mbar_arrive(&empty[stg]);                             // done with the stage of the tile just finished (every thread
+                                                                                 // arrives for its own reads: one instruction per tile)
             tile += gridDim.x;
-            if (tile >= a.ntiles) { drain = true; continue; }
-            buf ^= 1;
+            if (tile >= a.ntiles) { drain = true; e0 = 0; ew1 = 0; continue; }
             if (++stg == CG_STAGES) { stg = 0; par ^= 1u; }
             const int64_t row0 = tile * R;
             const int rows = (int)min((int64_t)R, a.n - row0);
-            Et = rows * nl;
             base = (uint32_t)(row0 * nl);                                        // n * nl < 2^32 (host-checked)
-            double* Pw = Pb + buf * E;
-            double* rw = rsc + buf * R;
             double* Fw = reinterpret_cast<double*>(ring + (size_t)stg * stage_bytes);
             unsigned char* Yw = ring + (size_t)stg * stage_bytes + off_y;
             const bool bulk = rows == R && a.bulk_ok;
+            // thread 0 keeps the ring two tiles ahead: the stage of the PREVIOUS tile takes tile + 2 grids once all warps left it
+            // (the first tile finds that stage unused; later ones wait for the previous tile's AUG_BLOCK arrivals)
+            if (tid == 0) {
+                const int sp_ = stg == 0 ? CG_STAGES - 1 : stg - 1;
+                if (kt >= 1) mbar_wait(&empty[sp_], ((kt - 1) / CG_STAGES) & 1u);
+                issue(tile + 2 * (int64_t)gridDim.x, sp_);
+            }
+            ++kt;                                                                // (every thread counts its warp's tiles)
+            const int rbeg = warp * rows_w, rend = min(rows, rbeg + rows_w);
+            const int ew0 = rbeg * nl;
+            ew1 = rend > rbeg ? rend * nl : ew0;
             if (bulk) {
                 mbar_wait(&full[stg], par);
             } else {
-                for (int e = tid; e < Et; e += AUG_BLOCK) {
+                // the ragged last tile is written by the warps themselves: not before every warp has left the tile that used
+                // this stage three tiles ago (bulk tiles get that guarantee through full[], which thread 0 only arms then)
+                if (kt > CG_STAGES) mbar_wait(&empty[stg], ((kt - 1) / CG_STAGES - 1) & 1u);
+                for (int e = ew0 + lane; e < ew1; e += 32) {
                     Fw[e] = ld_stream1(a.f + base + e);
                     Yw[e] = __ldg(a.y + base + e);
                 }
+                __syncwarp();
             }
+            double* Pw = P;
+            double* rw = rs;
             // phase A: p_ij = theta_j logistic(f_ij) / sum(theta)   categorical.jl:72-78
             {
-                int j = j_first;
-                for (int e = tid; e < Et; e += AUG_BLOCK) {
+                int j = lane % nl;
+                for (int e = ew0 + lane; e < ew1; e += 32) {
                     Pw[e] = __ldg(a.L.theta + j) * logistic_fast(Fw[e]);
-                    j += a.dj;
+                    j += dj32;
                     if (j >= nl) j -= nl;
                 }
             }
-            __syncthreads();
-            // every warp is past the element pass of the previous tile: its stage can take the tile after next
-            if (tid == 0) issue(tile + 2 * (int64_t)gridDim.x, stg == 0 ? CG_STAGES - 1 : stg - 1);
-            // phase B: 16 lanes per row: p0 = 1 - sum_j p_ij, tau/(1-p0) = Exp(1)/p0   negativemultinomial.jl:35-45
-            for (int r0 = 2 * warp; r0 < rows; r0 += 2 * (AUG_BLOCK / 32)) {       // warp-uniform bound (shuffles)
+            __syncwarp();
+            // phase B: 16 lanes per row: p0 = 1 - sum_j p_ij, then the row's counts (see CG_DENSE_P0 above)
+            unsigned char* Ncw = Nc;
+            unsigned char* Rdw = Rd;
+            const int CH = (nl + 15) >> 4;                                         // classes per lane chunk
+            for (int r0 = rbeg; r0 < rend; r0 += 2) {                              // warp-uniform bound (shuffles)
                 const int r = r0 + (lane >> 4);
-                const bool rv = r < rows;
-                const double* Pr = Pw + r * nl;
-                double sp = 0.0;
-                if (rv) for (int jj = l16; jj < nl; jj += 16) sp += Pr[jj];
+                const bool rv = r < rend;
+                const double* Pr = Pw + (rv ? r : rbeg) * nl;
+                unsigned char* Nr = Ncw + (rv ? r : rbeg) * nl;
+                // chunked sums: lane l16 owns classes [l16*CH, (l16+1)*CH); the inclusive scan over the 16 lanes is the
+                // cumulative p the class picks invert, and its total is the row sum (one association for both)
+                const int j0 = l16 * CH, j1 = min(nl, j0 + CH);
+                double cs = 0.0;
+                if (rv) for (int jj = j0; jj < j1; ++jj) { cs += Pr[jj]; Nr[jj] = 0; }
+                double inc = cs;
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+                for (int o = 1; o < 16; o <<= 1) {
+                    const double up = __shfl_up_sync(0xffffffffu, inc, o, 16);
+                    if (l16 >= o) inc += up;
+                }
+                const double sp = __shfl_sync(0xffffffffu, inc, 15, 16);           // row sum
+                double exc = __shfl_up_sync(0xffffffffu, inc, 1, 16);                // the previous lane's inclusive sum: the chunks'
+                if (l16 == 0) exc = 0.0;                                             // intervals (exc, inc] tile (0, sp] exactly
+                int nrow = 0;
+                double t_first = 2.0;                                            // target of the first pick (> any cumulative sum)
+                const uint64_t gr = (uint64_t)(a.i0 + row0 + (rv ? r : 0));
                 if (rv && l16 == 0) {
                     const double p0 = 1.0 - sp;
                     if (!(sp < 1.0)) atomicOr(a.dflag, 1u);                      // ctor precondition :17-22
-                    const uint64_t gr = (uint64_t)(a.i0 + row0 + r);
                     uint32_t w[4];
                     augr::philox4x32_10(k0, k1, (uint32_t)gr, (uint32_t)(gr >> 32), 7u << 28, c3, w);
-                    rw[r] = -augf::log_(augr::u53_open0(w[0], w[1])) / p0;
+                    const bool dense = !(p0 >= CG_DENSE_P0);                     // also NaN
+                    Rdw[r] = dense ? 1 : 0;
+                    if (dense) {
+                        rw[r] = -augf::log_(augr::u53_open0(w[0], w[1])) / p0;   // tau / (1 - p0) for the per-element draws
+                    } else {
+                        double pk = p0, u = augr::u53_open0(w[0], w[1]);         // geometric by chop-down: P(N = k) = p0 sp^k
+                        while (u > pk && nrow < 250) {
+                            u -= pk;
+                            ++nrow;
+                            pk *= sp;
+                        }
+                        t_first = augr::u53_open0(w[2], w[3]) * sp;              // in (0, sp]
+                    }
+                }
+                nrow = __shfl_sync(0xffffffffu, nrow, 0, 16);
+                __syncwarp();                                                    // the zeroed counts before the increments
+                int maxn = nrow;
+                maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, 16));
+                for (int ev = 0; ev < maxn; ++ev) {                              // warp-uniform trip count (the two rows differ)
+                    double t = 2.0;                                              // > any cumulative sum: no lane matches
+                    if (rv && l16 == 0 && ev < nrow) {
+                        if (ev == 0) {
+                            t = t_first;
+                        } else {                                                 // picks 1, 2 from block 1; 3, 4 from block 2; ...
+                            uint32_t w[4];
+                            augr::philox4x32_10(k0, k1, (uint32_t)gr, (uint32_t)(gr >> 32), (7u << 28) | (uint32_t)((ev + 1) >> 1), c3, w);
+                            const double u = (ev & 1) ? augr::u53_open0(w[0], w[1]) : augr::u53_open0(w[2], w[3]);
+                            t = u * sp;                                          // in (0, sp]
+                        }
+                    }
+                    t = __shfl_sync(0xffffffffu, t, 0, 16);
+                    // the lane whose chunk holds the target scans it; rounding can only push t above the last partial sum of
+                    // a chunk by an ulp, in which case the pick is the chunk's last class
+                    if (rv && t > exc && (t <= inc || (l16 == 15 && t <= 1.5))) {
+                        double acc = exc;
+                        int jp = j1 - 1;
+                        for (int jj = j0; jj < j1; ++jj) {
+                            acc += Pr[jj];
+                            if (t <= acc) { jp = jj; break; }
+                        }
+                        Nr[jp] = (unsigned char)min(255, (int)Nr[jp] + 1);
+                    }
+                    __syncwarp();
                 }
             }
-            __syncthreads();
-            // (no third barrier: the tile after this one writes the OTHER buffer, and nobody reaches it before
-            //  every warp has passed the barrier after its phase A, i.e. has finished the element pass of this one)
-            P = Pw;
-            rs = rw;
+            __syncwarp();
             Fs = Fw;
             Ys = Yw;
-            e0 = 0;
-            ci = i_first;
-            cj = j_first;
+            e0 = ew0;
+            ci = rbeg + lane / nl;
+            cj = lane % nl;
             continue;
         }
-        // ---- element pass step (phase C): n_ij ~ Poisson(p_ij tau/(1-p0)), b = y + n; queue what needs a PG draw
+        // ---- element pass step (phase C): n_ij from the row's split counts (dense rows: n_ij ~ Poisson(p_ij tau/(1-p0)) per
+        //      element), b = y + n; queue what needs a PG draw
         {
-            const int e = e0 + tid;
-            const bool valid = e < Et;
+            const int e = e0 + lane;
+            const bool valid = e < ew1;
             const uint32_t el = base + (uint32_t)e;
-            double lam = 0.0;
             int yv = 0;
+            int64_t nn = 0;
+            bool dense = false;
             if (valid) {
-                lam = P[e] * rs[ci];
                 yv = (int)Ys[e];
+                nn = (int64_t)Nc[e];
+                dense = Rd[ci] != 0;
             }
             const uint64_t gi = e_base + el;
-            uint32_t w[4];
-            AUG_PHILOX_RK(a.keys, (uint32_t)gi, (uint32_t)(gi >> 32), 5u << 28, c3, w);
-            // inversion by chop-down from 0 on one 53-bit uniform.  exp(-lam) >= 1 - lam: u <= 1 - lam is n = 0 without the
-            // exp (97% of the elements; the warp skips the exp when all its lanes pass)
-            int64_t nn = 0;
-            double u = (double)(((((uint64_t)w[1] << 32) | w[0]) >> 11)) * 0x1.0p-53;
-            if (valid && lam > 0.0 && u > 1.0 - lam) {
-                if (lam < 12.0) {
-                    double p = augf::exp_(-lam);
-                    int k = 0;
-                    if (u > p) {                                                 // P = 1 - exp(-lam): a few percent of the lanes
-                        while (u > p && k < 200) {
-                            u -= p;
-                            ++k;
-                            p *= lam / (double)k;
+            if (__any_sync(0xffffffffu, dense)) {                                // rare: rows with Lam >= CG_DENSE_LAM
+                if (dense) {
+                    const double lam = P[e] * rs[ci];
+                    uint32_t w[4];
+                    AUG_PHILOX_RK(a.keys, (uint32_t)gi, (uint32_t)(gi >> 32), 5u << 28, c3, w);
+                    nn = 0;
+                    if (lam > 0.0) {
+                        if (lam < 12.0) {
+                            double u = (double)(((((uint64_t)w[1] << 32) | w[0]) >> 11)) * 0x1.0p-53;
+                            double p = augf::exp_(-lam);
+                            int k = 0;
+                            while (u > p && k < 200) {
+                                u -= p;
+                                ++k;
+                                p *= lam / (double)k;
+                            }
+                            if (k >= 200) k = (int)poisson_slow(a.seed, a.offset, gi, lam);   // round-off tail
+                            nn = k;
+                        } else {
+                            nn = poisson_slow(a.seed, a.offset, gi, lam);
                         }
-                        if (k >= 200) k = (int)poisson_slow(a.seed, a.offset, gi, lam);   // round-off tail
                     }
-                    nn = k;
-                } else {
-                    nn = poisson_slow(a.seed, a.offset, gi, lam);
                 }
             }
             const int b = yv + (int)min(nn, (int64_t)1 << 30);
@@ -1203,9 +1295,9 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
                 nb += __popc(m);
             }
             __syncwarp();
-            e0 += AUG_BLOCK;
-            ci += a.di;
-            cj += a.dj;
+            e0 += 32;
+            ci += di32;
+            cj += dj32;
             if (cj >= nl) { cj -= nl; ++ci; }
         }
     }
@@ -1503,6 +1595,7 @@ int32_t aug_cat_sample(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0, 
         int R = 1792 / nl;
         if (R < 1) R = 1;
         if (R >= 16) R &= ~15;
+        else R = 8;                                  // every warp owns R / 8 rows of a tile
         if (R > 1024) R = 1024;
         g.R = R;
         g.bulk_ok = (((int64_t)R * nl) % 16 == 0) && aug_aligned16(y) && aug_aligned16(f);
@@ -1521,9 +1614,9 @@ int32_t aug_cat_sample(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0, 
         int32_t rc = aug_lik_const(ctx, lik, &g.L, false, true);
         if (rc) return rc;
         const size_t smem = (size_t)CG_STAGES * (((size_t)g.E * 9 + 127) & ~(size_t)127) +
-                            sizeof(double) * (AUG_PGTAB_N * AUG_PGTAB_DEG + 2 * (size_t)g.E + 2 * (size_t)R) +
+                            sizeof(double) * ((size_t)g.E + (size_t)R) +
                             (AUG_BLOCK / 32) * (2 * CG_QCAP * sizeof(double) + (5 * CG_QCAP + 2 * CG_BCAP) * sizeof(uint32_t)) +
-                            CG_STAGES * sizeof(uint64_t) + 128;
+                            2 * CG_STAGES * sizeof(uint64_t) + (size_t)g.E + (size_t)R + 128;
         if (smem <= (size_t)ctx->smem_optin) {
             AUG_CUDA(cudaFuncSetAttribute(cat_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 1;

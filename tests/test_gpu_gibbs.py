@@ -216,6 +216,42 @@ def test_categorical_aux_sample_law(A, orc):
     assert np.all(w[:, 0][nn[:, 0] == 0] == 0.0)             # b = y + n = 0 -> ω = 0
 
 
+@pytest.mark.timeout(300)
+def test_categorical_gibbs_many_tiles_sparse_and_dense_rows(A, orc):
+    """K = 100 (nl = 99), 25 tiles per CTA through the input ring of cat_gibbs_kernel; odd rows have p0 ~ 0.005 (per-element
+    mixture draws), even rows p0 ~ 0.5 (geometric row total + class picks): row totals have the geometric mean (1 - p0)/p0 in
+    both regimes, omega == 0 exactly where y + n == 0, and the draws do not depend on how the rows are sharded."""
+    from gpu_common import dev, host, make_lik
+    n, nl = 120_000, 99
+    lik = make_lik(CAT_BIJ, (), dict(nlatent=nl))
+    rng = np.random.default_rng(12)
+    f = rng.standard_normal((n, nl))
+    f[1::2] = 5.0 + 0.1 * rng.standard_normal((n // 2, nl))
+    y = np.zeros((n, nl), np.uint8)
+    cls = rng.integers(0, nl + 1, n)
+    rows = np.nonzero(cls < nl)[0]
+    y[rows, cls[rows]] = 1
+    Ω = A.aux_sample(A.AugPhilox(31, 2), lik, dev(y), dev(f))
+    w, nn = host(Ω.omega), host(Ω.n)
+    p = (1.0 / (1.0 + np.exp(-f))) / (nl + 0.5)                # theta = 1: sum(theta) = nl + 1/2 for the bijective link
+    p0 = 1.0 - p.sum(1)
+    assert p0[0::2].min() > 0.3 and p0[1::2].max() < 0.05      # both regimes present
+    tot = nn.sum(1).astype(np.float64)
+    for sl in (slice(0, None, 2), slice(1, None, 2)):
+        m = (1 - p0[sl]) / p0[sl]                              # E[N_i], Var[N_i] = m (1 + m) of the geometric row total
+        z = (tot[sl] - m).sum() / np.sqrt((m * (1 + m)).sum())
+        assert abs(z) < 5, z
+    j = 7                                                      # one class across the sparse rows: E[n_ij] = p_ij / p0_i
+    mj = p[0::2, j] / p0[0::2]
+    z = (nn[0::2, j] - mj).sum() / np.sqrt((mj * (1 + mj)).sum())
+    assert abs(z) < 5, z
+    b = nn + y
+    assert np.all(w[b == 0] == 0.0) and np.all(w[b > 0] > 0.0) and np.all(np.isfinite(w))
+    lo = 50_003                                                # not a multiple of the tile height
+    part = A.aux_sample(A.AugPhilox(31, 2), lik, dev(y[lo:]), dev(f[lo:]), i0=lo)
+    assert np.array_equal(host(part.n), nn[lo:]) and np.array_equal(host(part.omega), w[lo:])
+
+
 def test_init_aux_variables(A, orc):
     from gpu_common import host, make_lik
     n = 300_000

@@ -18,6 +18,21 @@ ctx = A.Context(0)
 A.set_default_context(ctx)
 dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 n = int(os.environ.get("SAN_N", "20000"))
+if os.environ.get("SAN_CATGIBBS"):
+    # the input ring of cat_gibbs_kernel (full / empty mbarriers) only wraps when a CTA gets more than three tiles:
+    # SAN_CATGIBBS rows (e.g. 60000 -> ~10 tiles per CTA), odd rows dense (p0 small), even rows sparse
+    nn = int(os.environ["SAN_CATGIBBS"])
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal((nn, 99))
+    f[1::2] += 5.0
+    y = np.zeros((nn, 99), np.uint8)
+    y[np.arange(nn), rng.integers(0, 99, nn)] = 1
+    Om = A.aux_sample(A.AugPhilox(3, 0), make_lik(CAT_BIJ, (), dict(nlatent=99)), dev(y), dev(f))
+    torch.cuda.synchronize()
+    assert ctx.error_flag() == 0
+    print("ok catgibbs", nn, float(Om.omega.sum()), int(Om.n.sum()), flush=True)
+    ctx.close()
+    sys.exit(0)
 for kind, params, kw in [(BERNOULLI, (), {}), (NEGBIN, (10,), dict(r_is_int=True)), (NEGBIN, (5.5,), {}), (POISSON, (10.0,), {}),
                          (LAPLACE, (1.0,), {}), (STUDENTT, (3.0, 1.5), {}), (HETERO, (5.0,), dict(nlatent=2)),
                          (CAT_BIJ, (), dict(nlatent=99)), (CAT, (), dict(nlatent=10))]:
