@@ -364,3 +364,59 @@ def test_extreme_inputs_take_the_any_input_instantiation(A, orc, name, kind, par
                         assert s[k] == pytest.approx(ocomp[k], rel=1e-11), (name, k)
                     else:       # e.g. Laplace/StudentT with a zero residual and zero variance: 1/0 in the reference too
                         assert not np.isfinite(s[k]), (name, k)
+
+
+# ---- first principles (tests/test_first_principles_cpu.py has the derivation and the reference lines of the constants):
+# with q(f) = δ_f the augmented bound is tight, expected_logtilt − aux_kldivergence == Σ log p(y_i | f_i), the TRUE
+# likelihood evaluated with scipy — a pin of the ELBO verbs that does not go through any restatement of their closed forms.
+def _fp():
+    import test_first_principles_cpu as fp
+    return fp
+
+
+@pytest.mark.parametrize("name,kind,params,kw", _fp().SCALAR_LIKS)
+def test_device_bound_is_tight_at_zero_variance(A, name, kind, params, kw):
+    from gpu_common import dev, host, make_lik
+    fp = _fp()
+    n = 100_003
+    y, f = fp.inputs(kind, params, n, 21)
+    lik = make_lik(kind, params, kw)
+    q = A.init_aux_posterior(lik, n)
+    q, beta, gamma, scal = A.cavi_step_(q, lik, dev(y), A.Normals(dev(f), dev(np.zeros(n))))
+    s = host(scal)
+    want = fp.true_loglik(kind, params, y.astype(np.float64), f)
+    total = float(np.sum(want.astype(np.longdouble))) + n * fp.tight_constant(kind, params)
+    assert abs(s[0] - s[1] - total) <= 1e-12 * (abs(s[0]) + abs(s[1])), (s[:3], total)
+    assert s[2] == pytest.approx(s[0] + s[1], rel=1e-15)
+
+
+def test_device_categorical_and_hetero_bounds_at_zero_variance(A):
+    from scipy import special, stats
+    from gpu_common import dev, host, make_lik
+    rng = np.random.default_rng(22)
+    n, nl = 20_011, 7
+    f = 1.5 * rng.standard_normal((n, nl))
+    cls = rng.integers(0, nl + 1, n)
+    y = np.zeros((n, nl), np.uint8)
+    rows = np.nonzero(cls < nl)[0]
+    y[rows, cls[rows]] = 1
+    lik = make_lik(CAT_BIJ, (), dict(nlatent=nl))
+    q = A.init_aux_posterior(lik, n)
+    q, beta, gamma, scal = A.cavi_step_(q, lik, dev(y), A.Normals(dev(f), dev(np.zeros((n, nl)))))
+    s = host(scal)
+    sg = special.expit(f)
+    num = np.where(cls < nl, sg[np.arange(n), np.minimum(cls, nl - 1)], 0.5)
+    logp = np.log(num / (sg.sum(1) + 0.5))
+    total = float(logp.sum()) - np.log(2.0) * len(rows)          # categorical.jl:153-157: the factor θ_K σ(0) per observed class < K
+    assert abs(s[0] - s[1] - total) <= 1e-12 * (abs(s[0]) + abs(s[1])), (s[:3], total)
+    # heteroscedastic: the reference's own formula (heteroscedasticgaussian.jl:129-145), + log 2 per observation
+    lam = 2.5
+    fg = 1.3 * rng.standard_normal((2, n))
+    yr = 1.5 * rng.standard_normal(n)
+    lik = make_lik(HETERO, (lam,), dict(nlatent=2))
+    q = A.init_aux_posterior(lik, n)
+    q, beta, gamma, scal = A.cavi_step_(q, lik, dev(yr), A.Normals(dev(fg), dev(np.zeros((2, n)))))
+    s = host(scal)
+    logp = stats.norm.logpdf(yr, fg[0], 1.0 / np.sqrt(lam * special.expit(fg[1])))
+    total = float(logp.sum()) + n * np.log(2.0)
+    assert abs(s[0] - s[1] - total) <= 1e-12 * (abs(s[0]) + abs(s[1])), (s[:3], total)
