@@ -172,14 +172,13 @@ __device__ __forceinline__ bool pg1_accept(double x, uint32_t uacc, uint32_t k0,
     const uint32_t thr = mid ? 4269197491u : (wide ? 4289813334u : 4294108302u);
     if (uacc <= thr) return true;
     double u = augr::u32_mid(uacc);
-    const double q = x > T ? -0.5 * PI * PI * x : -2.0 * augf::rcp(x);
+    const double q = x > T ? -0.5 * PI * PI * x : -2.0 / x;
     uint32_t w[4];
     augr::philox4x32_10(k0, k1, e_lo, e_hi, pg1_ctr(2u, round, 0u), c3, w);
     u += ((double)w[0] - 2147483648.0) * 0x1.0p-64;   // refine the uniform to 64 bits
     double sum = 1.0;
     for (int n = 1;; ++n) {
-        // straight-line exp (terms below e^-700 ~ 1e-304 are noise against sum ~ 1; the loop ends long before)
-        const double rho = (double)(2 * n + 1) * augf::exp_(fmax(q * (double)(n * (n + 1)), -700.0));
+        const double rho = (double)(2 * n + 1) * exp(q * (double)(n * (n + 1)));
         if (n & 1) {
             sum -= rho;
             if (u <= sum) return true;
@@ -207,16 +206,12 @@ __device__ __forceinline__ double trunc_ig_attempt_w(const uint32_t (&w)[4], dou
         const double x = trunc_ig_small_z(E, z, a);
         return augr::u32_mid(w[2]) > augf::exp_(-fmin(a, 700.0)) ? -1.0 : x;
     }
-    // mu = 1/z <= t: IG(mu, 1) by Michael-Schucany-Haas, kept when it falls in (0, t] (polyagamma.jl:214-221); straight-line
-    // arithmetic, stable form of the smaller root x1 = 4 mu v / (v + sqrt(v (4 + v)))^2 with v = mu N^2 (lambda = 1)
-    const double mu = augf::rcp(z);
+    const double mu = 1.0 / z;
     const double rad2 = -2.0 * augf::log_(augr::u53_open0(w[0], w[1]));
-    double cs, sn;
-    augr::rand_unit_vector(w[2], cs, sn);
-    const double v = fmax(mu * rad2 * cs * cs, 1e-290);
-    const double den = v + augr::sqrt_pos(v * (4.0 + v));
-    const double x1 = 4.0 * mu * v * augf::rcp(den * den);
-    const double x = augr::u32_mid(w[3]) * (mu + x1) > mu ? mu * mu * augf::rcp(x1) : x1;
+    const double cs = cospi(2.0 * augr::u32_mid(w[2]));
+    const double muy = mu * rad2 * cs * cs;                      // mu * N(0,1)^2
+    double x = mu + 0.5 * mu * muy - 0.5 * mu * sqrt(fma(muy, muy, 4.0 * muy));
+    if (augr::u32_mid(w[3]) * (mu + x) > mu) x = mu * mu / x;
     return x > T ? -1.0 : x;
 }
 
