@@ -881,13 +881,15 @@ struct CatGibbsArgs {
     int64_t* nvar;
     unsigned int* dflag;
     int bulk_ok;                 // f and y are 16-byte aligned and R * nl is a multiple of 16
+    int vec_ok;                  // omega and nvar are 16-byte aligned: the element pass stores two elements per lane
     LikConst L;
     augr::PhiloxKeys keys;       // round keys of (seed, offset): constant-bank operands of the per-element Philox block
 };
 
 #define CG_STAGES 3
 #define CG_QCAP 96
-#define CG_BCAP 64
+#define CG_BCAP 96           // a two-element step starts with < 32 items and appends up to 64
+#define CG_DENSE_MARK 255    // count byte of every element of a dense row (sparse rows hold at most 250 picks)
 // Round 2: the counts of a ROW are drawn from the NegativeMultinomial law directly instead of one Poisson draw per element.
 // The reference samples NM(x0 = 1, p) as a Gamma-Poisson mixture (negativemultinomial.jl:35-45: tau ~ Exp(1)/p0, n_ij ~
 // Poisson(p_ij tau) independent).  The same law in two steps (superposition / splitting of Poisson counts, then the mixture
@@ -939,8 +941,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
     uint32_t* qw_all = reinterpret_cast<uint32_t*>(qz_all + (AUG_BLOCK / 32) * 2 * CG_QCAP);
     uint64_t* full = reinterpret_cast<uint64_t*>(qw_all + (AUG_BLOCK / 32) * (5 * CG_QCAP + 2 * CG_BCAP));
     uint64_t* empty = full + CG_STAGES;                                           // a stage is free again: one arrival per thread
-    unsigned char* Ncb = reinterpret_cast<unsigned char*>(empty + CG_STAGES);     // [E]  n_ij of the tile
-    unsigned char* Rdb = Ncb + E;                                                 // [R]  1 = dense row (per-element draws)
+    unsigned char* Ncb = reinterpret_cast<unsigned char*>(empty + CG_STAGES);     // [E]  n_ij of the tile (CG_DENSE_MARK: dense row)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* fz = qz_all + warp * 2 * CG_QCAP;
     double* gz = fz + CG_QCAP;
@@ -1009,18 +1010,17 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
     // 45 % busy.  The warps only meet at the mbarriers of the input ring: full[s] (the bulk copy landed) and empty[s] (all 8
     // warps are done with the stage; thread 0 waits for it before it refills the stage, two tiles ahead).
     const int rows_w = R / (AUG_BLOCK / 32);                                  // host: R is a multiple of 8
-    const int di32 = 32 / nl, dj32 = 32 % nl;
+    const int dj32 = 32 % nl;
     // state of the element pass (phase C) of the current tile; e0 >= ew1: the next tile has to be set up first
     int64_t tile = (int64_t)blockIdx.x - gridDim.x;
-    int e0 = 0, ew1 = 0, ci = 0, cj = 0;
+    int e0 = 0, ew0 = 0, ew1 = 0;     // this warp's element range [ew0, ew1) of the tile and its position e0 in it
     int stg = CG_STAGES - 1;          // stage of the current tile
     uint32_t par = 1;                 // its mbarrier phase parity (flips when stg wraps to 0)
     uint32_t base = 0;
     uint32_t kt = 0;                  // tiles this warp has started (parity of the empty barriers)
     double* const P = Pb;
     double* const rs = rsc;
-    unsigned char* const Nc = Ncb;    // counts / dense-row flags of the current tile
-    unsigned char* const Rd = Rdb;
+    unsigned char* const Nc = Ncb;    // counts of the current tile
     const double* Fs = nullptr;       // staged f and y of the current tile
     const unsigned char* Ys = nullptr;
     bool drain = false;
@@ -1127,7 +1127,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             }
             ++kt;                                                                // (every thread counts its warp's tiles)
             const int rbeg = warp * rows_w, rend = min(rows, rbeg + rows_w);
-            const int ew0 = rbeg * nl;
+            ew0 = rbeg * nl;
             ew1 = rend > rbeg ? rend * nl : ew0;
             if (bulk) {
                 mbar_wait(&full[stg], par);
@@ -1155,7 +1155,6 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             __syncwarp();
             // phase B: 16 lanes per row: p0 = 1 - sum_j p_ij, then the row's counts (see CG_DENSE_P0 above)
             unsigned char* Ncw = Nc;
-            unsigned char* Rdw = Rd;
             const int CH = (nl + 15) >> 4;                                         // classes per lane chunk
             for (int r0 = rbeg; r0 < rend; r0 += 2) {                              // warp-uniform bound (shuffles)
                 const int r = r0 + (lane >> 4);
@@ -1185,7 +1184,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
                     uint32_t w[4];
                     augr::philox4x32_10(k0, k1, (uint32_t)gr, (uint32_t)(gr >> 32), 7u << 28, c3, w);
                     const bool dense = !(p0 >= CG_DENSE_P0);                     // also NaN
-                    Rdw[r] = dense ? 1 : 0;
+                    nrow = dense ? -1 : 0;
                     if (dense) {
                         rw[r] = -augf::log_(augr::u53_open0(w[0], w[1])) / p0;   // tau / (1 - p0) for the per-element draws
                     } else {
@@ -1199,6 +1198,10 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
                     }
                 }
                 nrow = __shfl_sync(0xffffffffu, nrow, 0, 16);
+                if (nrow < 0) {                                                  // dense row: every count byte holds CG_DENSE_MARK
+                    if (rv) for (int jj = j0; jj < j1; ++jj) Nr[jj] = CG_DENSE_MARK;
+                    nrow = 0;
+                }
                 __syncwarp();                                                    // the zeroed counts before the increments
                 int maxn = nrow;
                 maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, 16));
@@ -1224,7 +1227,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
                             acc += Pr[jj];
                             if (t <= acc) { jp = jj; break; }
                         }
-                        Nr[jp] = (unsigned char)min(255, (int)Nr[jp] + 1);
+                        Nr[jp] = (unsigned char)((int)Nr[jp] + 1);              // <= 250 picks per row: never CG_DENSE_MARK
                     }
                     __syncwarp();
                 }
@@ -1233,15 +1236,15 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             Fs = Fw;
             Ys = Yw;
             e0 = ew0;
-            ci = rbeg + lane / nl;
-            cj = lane % nl;
             continue;
         }
-        // ---- element pass step (phase C): n_ij from the row's split counts (dense rows: n_ij ~ Poisson(p_ij tau/(1-p0)) per
-        //      element), b = y + n; queue what needs a PG draw
-        {
-            const int e = e0 + lane;
-            const bool valid = e < ew1;
+        // ---- element pass (phase C): n_ij from the row's split counts (dense rows: n_ij ~ Poisson(p_ij tau/(1-p0)) per element),
+        //      b = y + n; queue what needs a PG draw.  98 % of the elements have b = 0 (omega = 0, n = 0, nothing to draw), so the
+        //      common step takes TWO adjacent elements per lane: 16-byte stores of (0.0, 0.0) and (n, n') and no queue work unless
+        //      some lane of the warp has b > 0.  ncu on the one-element step (profiles/r2z): 74 warp-instructions per 32 elements,
+        //      26 % of the kernel.
+        // one element per lane (any input: dense rows, unaligned outputs, the odd element in front of the pairs)
+        auto elem_step = [&](int e, bool valid) {
             const uint32_t el = base + (uint32_t)e;
             int yv = 0;
             int64_t nn = 0;
@@ -1249,12 +1252,12 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             if (valid) {
                 yv = (int)Ys[e];
                 nn = (int64_t)Nc[e];
-                dense = Rd[ci] != 0;
+                dense = nn == CG_DENSE_MARK;
             }
             const uint64_t gi = e_base + el;
-            if (__any_sync(0xffffffffu, dense)) {                                // rare: rows with Lam >= CG_DENSE_LAM
+            if (__any_sync(0xffffffffu, dense)) {                                // rare: rows with p0 < CG_DENSE_P0
                 if (dense) {
-                    const double lam = P[e] * rs[ci];
+                    const double lam = P[e] * rs[e / nl];
                     uint32_t w[4];
                     AUG_PHILOX_RK(a.keys, (uint32_t)gi, (uint32_t)(gi >> 32), 5u << 28, c3, w);
                     nn = 0;
@@ -1295,10 +1298,60 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
                 nb += __popc(m);
             }
             __syncwarp();
+        };
+        if (!a.vec_ok) {
+            elem_step(e0 + lane, e0 + lane < ew1);
             e0 += 32;
-            ci += di32;
-            cj += dj32;
-            if (cj >= nl) { cj -= nl; ++ci; }
+        } else if (e0 == ew0 && ((base + (uint32_t)e0) & 1u)) {
+            elem_step(e0, lane == 0);                                            // pairs start at even element indices
+            e0 += 1;
+        } else {
+            const int ea = e0 + 2 * lane;
+            const bool va = ea < ew1, vb = ea + 1 < ew1;
+            int na = 0, nbb = 0, ya = 0, yb = 0;
+            if (va) { na = (int)Nc[ea]; ya = (int)Ys[ea]; }
+            if (vb) { nbb = (int)Nc[ea + 1]; yb = (int)Ys[ea + 1]; }
+            if (__any_sync(0xffffffffu, na == CG_DENSE_MARK || nbb == CG_DENSE_MARK)) {
+                elem_step(e0 + lane, e0 + lane < ew1);
+                elem_step(e0 + 32 + lane, e0 + 32 + lane < ew1);
+            } else {
+                const uint32_t el = base + (uint32_t)ea;
+                const int ba = ya + na, bb = yb + nbb;
+                if (vb) {
+                    st_stream2_i64(a.nvar + el, (int64_t)na, (int64_t)nbb);
+                    if ((ba | bb) == 0) st_stream2(a.omega + el, 0.0, 0.0);
+                } else if (va) {
+                    a.nvar[el] = (int64_t)na;
+                }
+                if (__any_sync(0xffffffffu, (ba | bb) != 0)) {                   // (also false for the invalid lanes: all zero)
+                    if (vb && (ba | bb) != 0) {
+                        if (ba == 0) st_stream1(a.omega + el, 0.0);
+                        if (bb == 0) st_stream1(a.omega + el + 1, 0.0);
+                    }
+                    push_f(ba == 1, el, 0u, ba == 1 ? 0.5 * fabs(Fs[ea]) : 0.0);
+                    push_f(bb == 1, el + 1u, 0u, bb == 1 ? 0.5 * fabs(Fs[ea + 1]) : 0.0);
+                    const bool wa = ba >= 2, wbb = bb >= 2;
+                    if (__any_sync(0xffffffffu, wa || wbb)) {                    // about 1e-3 of the elements
+                        const uint32_t m1 = __ballot_sync(0xffffffffu, wa);
+                        if (wa) {
+                            const int pos = nb + __popc(m1 & lt_mask);
+                            bel[pos] = el;
+                            bbv[pos] = (uint32_t)ba;
+                        }
+                        nb += __popc(m1);
+                        const uint32_t m2 = __ballot_sync(0xffffffffu, wbb);
+                        if (wbb) {
+                            const int pos = nb + __popc(m2 & lt_mask);
+                            bel[pos] = el + 1u;
+                            bbv[pos] = (uint32_t)bb;
+                        }
+                        nb += __popc(m2);
+                    }
+                }
+                if (va && !vb && ba == 0) st_stream1(a.omega + el, 0.0);         // the odd last element of the warp's rows
+                __syncwarp();
+            }
+            e0 += 64;
         }
     }
 }
@@ -1599,6 +1652,7 @@ int32_t aug_cat_sample(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0, 
         if (R > 1024) R = 1024;
         g.R = R;
         g.bulk_ok = (((int64_t)R * nl) % 16 == 0) && aug_aligned16(y) && aug_aligned16(f);
+        g.vec_ok = aug_aligned16(omega) && aug_aligned16(nvar);
         g.E = R * nl;
         g.ntiles = (n + R - 1) / R;
         g.di = AUG_BLOCK / nl;

@@ -310,6 +310,9 @@ __device__ __forceinline__ void st_stream2(double* p, double a, double b) {
 __device__ __forceinline__ void st_stream1(double* p, double a) {
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(a) : "memory");
 }
+__device__ __forceinline__ void st_stream2_i64(int64_t* p, int64_t a, int64_t b) {
+    asm volatile("st.global.cs.v2.s64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
 // ---------------------------------------------------------------- bulk-async (TMA 1-D) + mbarrier helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -250,6 +250,13 @@ def test_categorical_gibbs_many_tiles_sparse_and_dense_rows(A, orc):
     lo = 50_003                                                # not a multiple of the tile height
     part = A.aux_sample(A.AugPhilox(31, 2), lik, dev(y[lo:]), dev(f[lo:]), i0=lo)
     assert np.array_equal(host(part.n), nn[lo:]) and np.array_equal(host(part.omega), w[lo:])
+    # outputs that are only 8-byte aligned take the one-element-per-lane element pass: same draws
+    import torch
+    bw = torch.empty(n * nl + 1, dtype=torch.float64, device="cuda")
+    bn = torch.empty(n * nl + 1, dtype=torch.int64, device="cuda")
+    Ωu = A.aux_sample_(A.AugPhilox(31, 2), A.AuxSamples(bw[1:].view(n, nl), bn[1:].view(n, nl)), lik, dev(y), dev(f))
+    assert Ωu.omega.data_ptr() % 16 == 8
+    assert np.array_equal(host(Ωu.n), nn) and np.array_equal(host(Ωu.omega), w)
 
 
 def test_init_aux_variables(A, orc):
