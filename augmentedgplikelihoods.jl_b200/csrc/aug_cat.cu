@@ -886,6 +886,12 @@ struct CatGibbsArgs {
     augr::PhiloxKeys keys;       // round keys of (seed, offset): constant-bank operands of the per-element Philox block
 };
 
+#ifndef CG_BLOCK
+#define CG_BLOCK 256
+#endif
+#ifndef CG_MIN_BLOCKS
+#define CG_MIN_BLOCKS 2
+#endif
 #define CG_STAGES 3
 #define CG_QCAP 96
 #define CG_BCAP 96           // a two-element step starts with < 32 items and appends up to 64
@@ -928,7 +934,7 @@ __device__ __noinline__ double pg1_finish_sequential_cat(uint64_t seed, uint64_t
     return augp::pg1_draw(g, s);
 }
 
-__global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsArgs a) {
+__global__ void __launch_bounds__(CG_BLOCK, CG_MIN_BLOCKS) cat_gibbs_kernel(const CatGibbsArgs a) {
     extern __shared__ __align__(128) unsigned char cg_smem[];
     const int nl = a.nl, R = a.R, E = a.E;
     // ring of CG_STAGES input tiles (f: E doubles, y: E bytes), filled by cp.async.bulk two tiles ahead
@@ -938,8 +944,8 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
     double* Pb = reinterpret_cast<double*>(ring + CG_STAGES * stage_bytes);     // [E]   p_ij of the tile
     double* rsc = Pb + E;                                                    // [R]   Exp(1)/p0 per row (dense rows)
     double* qz_all = rsc + R;                                            // per warp: F and G items
-    uint32_t* qw_all = reinterpret_cast<uint32_t*>(qz_all + (AUG_BLOCK / 32) * 2 * CG_QCAP);
-    uint64_t* full = reinterpret_cast<uint64_t*>(qw_all + (AUG_BLOCK / 32) * (5 * CG_QCAP + 2 * CG_BCAP));
+    uint32_t* qw_all = reinterpret_cast<uint32_t*>(qz_all + (CG_BLOCK / 32) * 2 * CG_QCAP);
+    uint64_t* full = reinterpret_cast<uint64_t*>(qw_all + (CG_BLOCK / 32) * (5 * CG_QCAP + 2 * CG_BCAP));
     uint64_t* empty = full + CG_STAGES;                                           // a stage is free again: one arrival per thread
     unsigned char* Ncb = reinterpret_cast<unsigned char*>(empty + CG_STAGES);     // [E]  n_ij of the tile (CG_DENSE_MARK: dense row)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -953,7 +959,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
     uint32_t* bel = gua + CG_QCAP;
     uint32_t* bbv = bel + CG_BCAP;
     if (tid == 0) {
-        for (int s = 0; s < CG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], AUG_BLOCK); }
+        for (int s = 0; s < CG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CG_BLOCK); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // a tile is bulk-copied when it is a full one (its y span is then a multiple of 16 bytes at a 16-byte aligned
@@ -1009,8 +1015,8 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
     // tile — ncu on the barrier version (profiles/r2y): 27 % of the stall samples at the two __syncthreads per tile, issue slots
     // 45 % busy.  The warps only meet at the mbarriers of the input ring: full[s] (the bulk copy landed) and empty[s] (all 8
     // warps are done with the stage; thread 0 waits for it before it refills the stage, two tiles ahead).
-    const int rows_w = R / (AUG_BLOCK / 32);                                  // host: R is a multiple of 8
-    const int dj32 = 32 % nl;
+    const int rows_w = R / (CG_BLOCK / 32);                                  // host: R is a multiple of the warp count
+    const int dj64 = 64 % nl;
     // state of the element pass (phase C) of the current tile; e0 >= ew1: the next tile has to be set up first
     int64_t tile = (int64_t)blockIdx.x - gridDim.x;
     int e0 = 0, ew0 = 0, ew1 = 0;     // this warp's element range [ew0, ew1) of the tile and its position e0 in it
@@ -1119,7 +1125,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             unsigned char* Yw = ring + (size_t)stg * stage_bytes + off_y;
             const bool bulk = rows == R && a.bulk_ok;
             // thread 0 keeps the ring two tiles ahead: the stage of the PREVIOUS tile takes tile + 2 grids once all warps left it
-            // (the first tile finds that stage unused; later ones wait for the previous tile's AUG_BLOCK arrivals)
+            // (the first tile finds that stage unused; later ones wait for the previous tile's CG_BLOCK arrivals)
             if (tid == 0) {
                 const int sp_ = stg == 0 ? CG_STAGES - 1 : stg - 1;
                 if (kt >= 1) mbar_wait(&empty[sp_], ((kt - 1) / CG_STAGES) & 1u);
@@ -1144,13 +1150,21 @@ __global__ void __launch_bounds__(AUG_BLOCK, 2) cat_gibbs_kernel(const CatGibbsA
             double* Pw = P;
             double* rw = rs;
             // phase A: p_ij = theta_j logistic(f_ij) / sum(theta)   categorical.jl:72-78
+            // (two independent elements per lane and iteration: the exp / reciprocal chains are latency-bound at 4 warps per
+            //  scheduler)
             {
-                int j = lane % nl;
-                for (int e = ew0 + lane; e < ew1; e += 32) {
-                    Pw[e] = __ldg(a.L.theta + j) * logistic_fast(Fw[e]);
-                    j += dj32;
+                int j = lane % nl, j2 = (lane + 32) % nl;
+                int e = ew0 + lane;
+                for (; e + 32 < ew1; e += 64) {
+                    const double la = logistic_fast(Fw[e]), lb = logistic_fast(Fw[e + 32]);
+                    Pw[e] = __ldg(a.L.theta + j) * la;
+                    Pw[e + 32] = __ldg(a.L.theta + j2) * lb;
+                    j += dj64;
                     if (j >= nl) j -= nl;
+                    j2 += dj64;
+                    if (j2 >= nl) j2 -= nl;
                 }
+                if (e < ew1) Pw[e] = __ldg(a.L.theta + j) * logistic_fast(Fw[e]);
             }
             __syncwarp();
             // phase B: 16 lanes per row: p0 = 1 - sum_j p_ij, then the row's counts (see CG_DENSE_P0 above)
@@ -1645,11 +1659,11 @@ int32_t aug_cat_sample(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0, 
         g.n = n;
         g.i0 = i0;
         g.nl = nl;
-        int R = 1792 / nl;
-        if (R < 1) R = 1;
-        if (R >= 16) R &= ~15;
-        else R = 8;                                  // every warp owns R / 8 rows of a tile
+        const int W = CG_BLOCK / 32;                 // every warp owns R / W rows of a tile, two at a time when it can
+        int R = (7 * CG_BLOCK) / nl;
         if (R > 1024) R = 1024;
+        if (R >= 2 * W) R -= R % (2 * W);
+        else R = W;
         g.R = R;
         g.bulk_ok = (((int64_t)R * nl) % 16 == 0) && aug_aligned16(y) && aug_aligned16(f);
         g.vec_ok = aug_aligned16(omega) && aug_aligned16(nvar);
@@ -1669,16 +1683,16 @@ int32_t aug_cat_sample(aug_ctx* ctx, const aug_lik* lik, int64_t n, int64_t i0, 
         if (rc) return rc;
         const size_t smem = (size_t)CG_STAGES * (((size_t)g.E * 9 + 127) & ~(size_t)127) +
                             sizeof(double) * ((size_t)g.E + (size_t)R) +
-                            (AUG_BLOCK / 32) * (2 * CG_QCAP * sizeof(double) + (5 * CG_QCAP + 2 * CG_BCAP) * sizeof(uint32_t)) +
+                            (CG_BLOCK / 32) * (2 * CG_QCAP * sizeof(double) + (5 * CG_QCAP + 2 * CG_BCAP) * sizeof(uint32_t)) +
                             2 * CG_STAGES * sizeof(uint64_t) + (size_t)g.E + (size_t)R + 128;
         if (smem <= (size_t)ctx->smem_optin) {
             AUG_CUDA(cudaFuncSetAttribute(cat_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cat_gibbs_kernel, AUG_BLOCK, smem) != cudaSuccess || occ < 1)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cat_gibbs_kernel, CG_BLOCK, smem) != cudaSuccess || occ < 1)
                 occ = 1;
             int64_t grid = (int64_t)ctx->sms * occ;
             if (grid > g.ntiles) grid = g.ntiles;
-            cat_gibbs_kernel<<<(unsigned)grid, AUG_BLOCK, smem, ctx->stream>>>(g);
+            cat_gibbs_kernel<<<(unsigned)grid, CG_BLOCK, smem, ctx->stream>>>(g);
             ctx->launches++;
             return (int32_t)cudaGetLastError();
         }

@@ -92,15 +92,22 @@ __device__ __noinline__ double pg1_finish_sequential(uint64_t seed, uint64_t off
 #define PG1_QCAP 64
 #define PG1_MAXCTR 255u
 
-#ifndef PG1_MIN_BLOCKS
-#define PG1_MIN_BLOCKS 3
+// CTA shape (A/B on B200, gpurun_out/ab_pg1.txt, ms per 1e8 draws): 256 x 3 CTAs/SM at 80 registers (24-byte spill) 1.57;
+// 256 x 2 (106 registers) 1.54; 320 x 2 (96 registers, no spill) 1.48; 128 x 5 1.52; 608 x 1 1.46; ONE CTA of 640 threads per SM
+// (20 warps, 96 registers, no spill) 1.40.  The alternating-series tail of pg1_accept is out of line (aug_pg.cuh): in line it
+// costs the fresh step 10 registers (1.54 -> 1.48 at 320 x 2).
+#ifndef PG1_BLOCK
+#define PG1_BLOCK 640
 #endif
-__global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(const Pg1Args a) {
+#ifndef PG1_MIN_BLOCKS
+#define PG1_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(PG1_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(const Pg1Args a) {
     __shared__ __align__(16) double tab_s[AUG_PGTAB_N * AUG_PGTAB_DEG];   // r(z) table, coefficient-major: 10 KB, read by every fresh step
-    __shared__ uint32_t qel_s[AUG_BLOCK / 32][PG1_QCAP];
-    __shared__ uint32_t qra_s[AUG_BLOCK / 32][PG1_QCAP];
-    __shared__ uint32_t quacc_s[AUG_BLOCK / 32][PG1_QCAP];
-    __shared__ double qz_s[AUG_BLOCK / 32][PG1_QCAP];
+    __shared__ uint32_t qel_s[PG1_BLOCK / 32][PG1_QCAP];
+    __shared__ uint32_t qra_s[PG1_BLOCK / 32][PG1_QCAP];
+    __shared__ uint32_t quacc_s[PG1_BLOCK / 32][PG1_QCAP];
+    __shared__ double qz_s[PG1_BLOCK / 32][PG1_QCAP];
     // the extra CTA of a launch that carries a deferred gather: it is scheduled when a working CTA retires, by when the
     // peers have long published, so the wait for the slowest rank costs this kernel (next to) nothing
     const unsigned nwork = a.gx ? gridDim.x - 1 : gridDim.x;
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
         if (threadIdx.x == 0) xch_finish_pending(a.gx);
         return;
     }
-    augp::pg1_load_table_cm(tab_s, a.tab, AUG_BLOCK);
+    augp::pg1_load_table_cm(tab_s, a.tab, PG1_BLOCK);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* qel = qel_s[warp];
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
     double* qz = qz_s[warp];
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t nchunks = (uint32_t)((a.n + 31) >> 5);                 // n < 2^32 (host-checked)
-    const uint32_t W = nwork * (AUG_BLOCK / 32);
+    const uint32_t W = nwork * (PG1_BLOCK / 32);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32);
     const uint32_t c3 = (uint32_t)a.offset;
     int qn = 0;
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, PG1_MIN_BLOCKS) pg1_compact_kernel(
         __syncwarp();
     };
 
-    uint32_t ch = blockIdx.x * (AUG_BLOCK / 32) + warp;
+    uint32_t ch = blockIdx.x * (PG1_BLOCK / 32) + warp;
     // the tilt of the NEXT fresh chunk is loaded one step ahead (its latency hides behind the work steps)
     auto load_c = [&](uint32_t chunk) {
         const uint32_t e = (chunk << 5) + lane;
@@ -271,15 +278,19 @@ struct PgbArgs {
 #define PGB_T_GAM 1u
 #define PGB_T_FRAC 2u
 #define PGB_QCAP 64
+// CTA shape (A/B on B200, gpurun_out/ab_pgb.txt, ab_pgb2.txt; NegBin / Poisson / Hetero ms per 1e8): 256 x 2 CTAs/SM at 128
+// registers 3.35 / 5.44 / 7.6; 512 x 1 3.27 / 5.33 / 7.4; 320 x 2 (96 registers) 3.28 / 5.13 / 7.1; 640 x 1 (96) 3.10 / 4.87 / 6.8;
+// ONE CTA of 768 threads per SM (24 warps, 80 registers) 2.95 / 4.71 / 6.6: the kernels wait on fixed-latency dependencies, more
+// warps hide them better than more registers, and one large CTA beats two of half the size at equal warps and registers.
 #ifndef PGB_BLOCK
-#define PGB_BLOCK 256
+#define PGB_BLOCK 768
 #endif
 #define PGB_WARPS (PGB_BLOCK / 32)
 // dynamic shared memory: r(z) table | per warp 3 queues (Devroye, Gamma, fractional) x { lo[QCAP], hi[QCAP] } double2
 #define PGB_SMEM_BYTES (AUG_PGTAB_N * AUG_PGTAB_DEG * 8 + PGB_WARPS * 3 * 2 * PGB_QCAP * 16)
 
 #ifndef PGB_MIN_BLOCKS
-#define PGB_MIN_BLOCKS 2
+#define PGB_MIN_BLOCKS 1
 #endif
 template <int KIND>
 __global__ void __launch_bounds__(PGB_BLOCK, PGB_MIN_BLOCKS) pgb_kernel(const PgbArgs a) {
@@ -610,16 +621,24 @@ struct MapSampleArgs {
     augr::PhiloxKeys keys;
 };
 #define MS_QCAP 64
+// CTA shape (A/B on B200, gpurun_out/ab_ms.txt; Laplace / StudentT ms per 1e8 draws): 256 x 4 CTAs/SM 1.15 / 1.59; 512 x 2
+// 1.10 / 1.50; 1024 x 1 1.07 / 1.39; ONE CTA of 768 threads per SM (71 registers for StudentT) 1.06 / 1.38
+#ifndef MS_BLOCK
+#define MS_BLOCK 768
+#endif
+#ifndef MS_MIN_BLOCKS
+#define MS_MIN_BLOCKS 1
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(AUG_BLOCK, 4) map_sample_kernel(const MapSampleArgs a) {
-    __shared__ uint32_t qel_s[AUG_BLOCK / 32][MS_QCAP];
-    __shared__ uint32_t qat_s[AUG_BLOCK / 32][MS_QCAP];
+__global__ void __launch_bounds__(MS_BLOCK, MS_MIN_BLOCKS) map_sample_kernel(const MapSampleArgs a) {
+    __shared__ uint32_t qel_s[MS_BLOCK / 32][MS_QCAP];
+    __shared__ uint32_t qat_s[MS_BLOCK / 32][MS_QCAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* qel = qel_s[warp];
     uint32_t* qat = qat_s[warp];
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t nchunks = (uint32_t)((a.n + 31) >> 5);                 // n < 2^32 (host-checked)
-    const uint32_t W = gridDim.x * (AUG_BLOCK / 32);
+    const uint32_t W = gridDim.x * (MS_BLOCK / 32);
     const uint32_t c3 = (uint32_t)a.offset;
     int qn = 0;
     // one attempt for element el (attempt number att): true = omega[el] written
@@ -651,7 +670,7 @@ __global__ void __launch_bounds__(AUG_BLOCK, 4) map_sample_kernel(const MapSampl
             return ok || !valid;
         }
     };
-    uint32_t ch = blockIdx.x * (AUG_BLOCK / 32) + warp;
+    uint32_t ch = blockIdx.x * (MS_BLOCK / 32) + warp;
     for (;;) {
         if (qn < 32 && ch < nchunks) {
             const uint32_t el = (ch << 5) + lane;
@@ -786,12 +805,12 @@ bool launch_pg1_compact(aug_ctx* ctx, int64_t n, int64_t i0, uint64_t off, const
                         int32_t* rc) {
     static int occ = 0;
     if (occ == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pg1_compact_kernel, AUG_BLOCK, 0) != cudaSuccess || occ < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pg1_compact_kernel, PG1_BLOCK, 0) != cudaSuccess || occ < 1)
             occ = 1;
     }
     int64_t grid = (int64_t)ctx->sms * occ;
     const int64_t nchunks = (n + 31) / 32;
-    const int64_t need = (nchunks + (AUG_BLOCK / 32) - 1) / (AUG_BLOCK / 32);
+    const int64_t need = (nchunks + (PG1_BLOCK / 32) - 1) / (PG1_BLOCK / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (n >= ((int64_t)1 << 32) - 64) return false;   // element offsets are queued as 32-bit words
@@ -807,7 +826,7 @@ bool launch_pg1_compact(aug_ctx* ctx, int64_t n, int64_t i0, uint64_t off, const
     a.gx = take_pending(ctx);
     if (a.gx) grid += 1;
     augr::philox_round_keys((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)(a.offset >> 32), &a.keys);
-    pg1_compact_kernel<<<(unsigned)grid, AUG_BLOCK, 0, ctx->stream>>>(a);
+    pg1_compact_kernel<<<(unsigned)grid, PG1_BLOCK, 0, ctx->stream>>>(a);
     ctx->launches++;
     *rc = (int32_t)cudaGetLastError();
     return true;
@@ -921,13 +940,13 @@ int32_t aug_aux_sample_dev(aug_ctx* c, const aug_lik* lik, int64_t n, int64_t i0
         augr::philox_round_keys((uint32_t)c->seed, (uint32_t)(c->seed >> 32) ^ (uint32_t)(off >> 32), &m.keys);
         const void* k = lik->kind == AUG_LAPLACE ? (const void*)map_sample_kernel<AUG_LAPLACE> : (const void*)map_sample_kernel<AUG_STUDENTT>;
         int occ = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, AUG_BLOCK, 0) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, MS_BLOCK, 0) != cudaSuccess || occ < 1) occ = 1;
         int64_t grid = (int64_t)c->sms * occ;
-        const int64_t need = ((n + 31) / 32 + (AUG_BLOCK / 32) - 1) / (AUG_BLOCK / 32);
+        const int64_t need = ((n + 31) / 32 + (MS_BLOCK / 32) - 1) / (MS_BLOCK / 32);
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
-        if (lik->kind == AUG_LAPLACE) map_sample_kernel<AUG_LAPLACE><<<(unsigned)grid, AUG_BLOCK, 0, c->stream>>>(m);
-        else map_sample_kernel<AUG_STUDENTT><<<(unsigned)grid, AUG_BLOCK, 0, c->stream>>>(m);
+        if (lik->kind == AUG_LAPLACE) map_sample_kernel<AUG_LAPLACE><<<(unsigned)grid, MS_BLOCK, 0, c->stream>>>(m);
+        else map_sample_kernel<AUG_STUDENTT><<<(unsigned)grid, MS_BLOCK, 0, c->stream>>>(m);
         c->launches++;
         return (int32_t)cudaGetLastError();
     }

@@ -159,18 +159,9 @@ __device__ __forceinline__ uint32_t pg1_ctr(uint32_t tag, uint32_t round, uint32
     return (tag << 28) | (round << 14) | attempt;
 }
 
-// final accept/reject of a proposal x: alternating series of rho_n = a_n/a_0 = (2n+1) exp(q n(n+1)) with
-// q = -pi^2 x/2 for x > t, -2/x for x <= t   (polyagamma.jl:243-255, 167-177)
-__device__ __forceinline__ bool pg1_accept(double x, uint32_t uacc, uint32_t k0, uint32_t k1, uint32_t e_lo,
-                                           uint32_t e_hi, uint32_t c3, uint32_t round) {
-    // squeeze on rho_1(x) = 3 exp(-pi^2 x) (x > t) resp. 3 exp(-4/x) (x <= t), which peaks at x = t (0.0058):
-    //   x in [0.5, 0.8]: rho_1 <= 0.0058 -> accept if u <= 0.994;   x in [0.4, 1.0]: rho_1 <= 0.00111 -> u <= 0.9988;
-    //   elsewhere: rho_1 <= 1.6e-4 -> u <= 0.9998.   (u = (uacc + 0.5) 2^-32; compares are on the high word of x > 0)
-    const int xh = __double2hiint(x);
-    const bool mid = xh >= 0x3fe00000 && xh < 0x3fe99999;      // [0.5, 0.8)
-    const bool wide = xh >= 0x3fd99999 && xh < 0x3ff00000;     // [0.39999, 1.0)
-    const uint32_t thr = mid ? 4269197491u : (wide ? 4289813334u : 4294108302u);
-    if (uacc <= thr) return true;
+// the alternating series itself (0.6 % of the proposals), out of line: in line it costs its callers ~10 registers
+static __device__ __noinline__ bool pg1_accept_series(double x, uint32_t uacc, uint32_t k0, uint32_t k1, uint32_t e_lo, uint32_t e_hi, uint32_t c3,
+                       uint32_t round) {
     double u = augr::u32_mid(uacc);
     const double q = x > T ? -0.5 * PI * PI * x : -2.0 / x;
     uint32_t w[4];
@@ -187,6 +178,21 @@ __device__ __forceinline__ bool pg1_accept(double x, uint32_t uacc, uint32_t k0,
             if (u > sum) return false;
         }
     }
+}
+
+// final accept/reject of a proposal x: alternating series of rho_n = a_n/a_0 = (2n+1) exp(q n(n+1)) with
+// q = -pi^2 x/2 for x > t, -2/x for x <= t   (polyagamma.jl:243-255, 167-177)
+__device__ __forceinline__ bool pg1_accept(double x, uint32_t uacc, uint32_t k0, uint32_t k1, uint32_t e_lo,
+                                           uint32_t e_hi, uint32_t c3, uint32_t round) {
+    // squeeze on rho_1(x) = 3 exp(-pi^2 x) (x > t) resp. 3 exp(-4/x) (x <= t), which peaks at x = t (0.0058):
+    //   x in [0.5, 0.8]: rho_1 <= 0.0058 -> accept if u <= 0.994;   x in [0.4, 1.0]: rho_1 <= 0.00111 -> u <= 0.9988;
+    //   elsewhere: rho_1 <= 1.6e-4 -> u <= 0.9998.   (u = (uacc + 0.5) 2^-32; compares are on the high word of x > 0)
+    const int xh = __double2hiint(x);
+    const bool mid = xh >= 0x3fe00000 && xh < 0x3fe99999;      // [0.5, 0.8)
+    const bool wide = xh >= 0x3fd99999 && xh < 0x3ff00000;     // [0.39999, 1.0)
+    const uint32_t thr = mid ? 4269197491u : (wide ? 4289813334u : 4294108302u);
+    if (uacc <= thr) return true;
+    return pg1_accept_series(x, uacc, k0, k1, e_lo, e_hi, c3, round);
 }
 
 // one proposal attempt from the truncated inverse Gaussian on (0, t] out of one Philox block; < 0: rejected
