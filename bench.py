@@ -358,7 +358,7 @@ GIBBS_KERNEL = {"bernoulli": "pg1_compact_kernel (warp-compacted Devroye PG(1,c)
                 "studentt": "aux_sample_kernel<STUDENTT> (Marsaglia-Tsang Gamma)",
                 "laplace": "aux_sample_kernel<LAPLACE> (inverse Gaussian)",
                 "hetero": "pgb_kernel<HETERO> (Poisson draw + exact PG(n+1/2,c))",
-                "categorical": "cat_gibbs_kernel (row scale + Poisson + per-warp PG queues)"}
+                "categorical": "cat_gibbs_kernel (geometric row total + class picks of the NegativeMultinomial, per-warp PG queues)"}
 
 
 def make_lik(A, name):
