@@ -1,5 +1,3 @@
-set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_gibbs.py tests/test_gpu_host.py -m gpu -x -q -k "categorical or cat" 2>&1 | tail -3
-python tools/roofline_all.py --only cat_bij_K100 2>&1 | tail -1
-python tools/roofline_all.py --only cat_bij_K100 2>&1 | tail -1
+bash tools/ab.sh bernoulli 20 variants/libaugcuda_sup4.so variants/libaugcuda_sup16.so > gpurun_out/ab_super.txt 2>&1
+AUGCUDA_LIB=variants/libaugcuda_sup4.so timeout 300 python -m pytest tests/test_gpu_gibbs.py -m gpu -x -q -k "not categorical" 2>&1 | tail -2 >> gpurun_out/ab_super.txt
