@@ -70,6 +70,8 @@ struct aug_ctx {
     // categorical logθ-derived constants
     double* dtheta;        // exp(logθ_j)/Σθ  (device, capacity dtheta_cap)
     int dtheta_cap;
+    double* htheta;        // host copy of what dtheta holds (htheta_n values; 0: nothing cached): a verb whose logθ
+    int htheta_n;          // matches skips the upload and its stream synchronisation
     // NCCL (resolved with dlopen at aug_comm_init)
     void* nccl_lib;
     void* nccl_comm;

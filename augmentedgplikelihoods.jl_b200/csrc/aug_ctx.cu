@@ -209,19 +209,32 @@ int32_t aug_lik_const(aug_ctx* ctx, const aug_lik* lik, LikConst* L, bool need_t
             L->c3 = log(1.0 - spp);                                          // log p0 of the prior NM
             L->c4 = sum_theta;
             if (need_theta) {
-                if (ctx->dtheta_cap < nl) {
-                    if (ctx->dtheta) cudaFree(ctx->dtheta);
-                    ctx->dtheta = nullptr;
-                    AUG_CUDA(cudaMalloc(&ctx->dtheta, sizeof(double) * nl));
-                    ctx->dtheta_cap = nl;
-                }
                 double* h = (double*)malloc(sizeof(double) * nl);
+                if (!h) return (int32_t)cudaErrorMemoryAllocation;
                 for (int j = 0; j < nl; ++j) h[j] = exp(lt(j)) / sum_theta;  // _scale_σf / _sum_θ :72-78
-                cudaError_t e = cudaMemcpyAsync(ctx->dtheta, h, sizeof(double) * nl, cudaMemcpyHostToDevice,
-                                                ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-                free(h);
-                if (e != cudaSuccess) return (int32_t)e;
+                // cached by value, like the integer-y table below: the chunks of a host-buffer call and the iterations of
+                // a Gibbs loop pass the same logθ, and only a change of it costs an upload + stream synchronisation
+                if (ctx->htheta && ctx->htheta_n == nl && memcmp(ctx->htheta, h, sizeof(double) * nl) == 0) {
+                    free(h);
+                } else {
+                    ctx->htheta_n = 0;
+                    free(ctx->htheta);
+                    ctx->htheta = nullptr;
+                    if (ctx->dtheta_cap < nl) {
+                        if (ctx->dtheta) cudaFree(ctx->dtheta);
+                        ctx->dtheta = nullptr;
+                        ctx->dtheta_cap = 0;
+                        cudaError_t em = cudaMalloc(&ctx->dtheta, sizeof(double) * nl);
+                        if (em != cudaSuccess) { free(h); return (int32_t)em; }
+                        ctx->dtheta_cap = nl;
+                    }
+                    cudaError_t e = cudaMemcpyAsync(ctx->dtheta, h, sizeof(double) * nl, cudaMemcpyHostToDevice,
+                                                    ctx->stream);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                    if (e != cudaSuccess) { free(h); return (int32_t)e; }
+                    ctx->htheta = h;
+                    ctx->htheta_n = nl;
+                }
                 L->theta = ctx->dtheta;
             }
             break;
@@ -408,6 +421,7 @@ int32_t aug_ctx_destroy(aug_ctx* c) {
     if (c->table) cudaFree(c->table);
     if (c->pgtab) cudaFree(c->pgtab);
     if (c->dtheta) cudaFree(c->dtheta);
+    free(c->htheta);
     if (c->sparse_scratch) cudaFree(c->sparse_scratch);
     aug_cublas_destroy(c);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);

@@ -216,6 +216,34 @@ def test_categorical_aux_sample_law(A, orc):
     assert np.all(w[:, 0][nn[:, 0] == 0] == 0.0)             # b = y + n = 0 -> ω = 0
 
 
+def test_categorical_theta_upload_is_cached_by_value(A, orc):
+    """exp(logθ)/Σθ of the sampling verb lives in a per-context device vector that is re-uploaded only when logθ changes
+    (aug_lik_const): same logθ -> same draws (hit), another logθ of the same length -> the other law (miss), back again ->
+    the first draws bit for bit."""
+    from gpu_common import dev, host, make_lik
+    n, nl = 50_000, 4
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal((n, nl))
+    y = np.zeros((n, nl), np.uint8)
+    y[np.arange(n), rng.integers(0, nl, n)] = 1
+    lt_a, lt_b = [0.2, -0.1, 0.4, 0.0, 0.3], [-1.5, 0.7, 0.0, 1.1, -0.4]
+    draw = lambda lt: A.aux_sample(A.AugPhilox(9, 4), make_lik(CAT_BIJ, (), dict(nlatent=nl, logtheta=lt)), dev(y), dev(f))
+    a1 = draw(lt_a)
+    a2 = draw(lt_a)
+    b1 = draw(lt_b)
+    a3 = draw(lt_a)
+    na, nb = host(a1.n), host(b1.n)
+    for o in (a2, a3):
+        assert np.array_equal(host(o.n), na) and np.array_equal(host(o.omega), host(a1.omega))
+    assert not np.array_equal(nb, na)
+    for lt, nn in ((lt_a, na), (lt_b, nb)):                   # each law has its own NegativeMultinomial means
+        p = np.exp(lt[:4]) / (1 + np.exp(-f)) / (np.exp(lt[4]) / 2 + np.sum(np.exp(lt[:4])))
+        p0 = 1 - p.sum(1)
+        m = p[:, 1] / p0
+        z = (nn[:, 1] - m).sum() / np.sqrt((m * (1 + m)).sum())
+        assert abs(z) < 5, (lt, z)
+
+
 @pytest.mark.timeout(300)
 def test_categorical_gibbs_many_tiles_sparse_and_dense_rows(A, orc):
     """K = 100 (nl = 99), 25 tiles per CTA through the input ring of cat_gibbs_kernel; odd rows have p0 ~ 0.005 (per-element
