@@ -11,6 +11,15 @@
 # so the "plugin" is a set of METHODS of the reference's generic functions, specialised on a device array
 # type.  qΩ stays a MeasureTheory.For over a TupleVector and Ω stays a TupleVector — only their field
 # arrays are device vectors — so `only(qΩ.inds).c`, `Ω.ω`, `length(Ω)` keep working.
+#
+# Dispatch: the reference specialises most verbs on the LIKELIHOOD type with loosely typed arrays, e.g.
+# `aux_posterior!(qΩ, ::BernoulliLikelihood{<:LogisticLink}, ::AbstractVector, qf::AbstractVector{<:Normal})`
+# (src/likelihoods/bernoulli.jl:17-22).  A method `(qΩ::For, lik::AbstractLikelihood, y::AugDeviceVector, …)` would be
+# AMBIGUOUS with it (each is more specific in one argument) and Julia would throw at the call.  So the file has two
+# layers: implementations `dev_*` / `host_*` (one ccall each, any likelihood `withdesc` knows), and a generated dispatch
+# layer at the end that adds, for every likelihood type the reference dispatches on (REFERENCE_LIKELIHOODS, same aliases
+# as the reference), methods whose likelihood argument is EXACTLY the reference's and whose other arguments are
+# subtypes of the reference's — strictly more specific, never ambiguous.
 module AugCUDA
 
 using AugmentedGPLikelihoods
@@ -146,29 +155,50 @@ withdesc(f, l::AbstractLikelihood) = f(Ref(desc(l)))
 
 const DV = AugDeviceVector
 state(qΩ::For) = only(qΩ.inds)                                   # the SoA of variational parameters
-s0(φ) = haskey(φ, :c) ? φ.c : haskey(φ, :μ) ? φ.μ : φ.β          # bernoulli.jl:7-11 ... studentt.jl:39-44
-s1(φ) = haskey(φ, :λ) ? φ.λ : haskey(φ, :p) ? φ.p : nothing
-s2(φ) = haskey(φ, :ψ) ? φ.ψ : haskey(φ, :y) ? φ.y : nothing
+s0(φ) = hasproperty(φ, :c) ? φ.c : hasproperty(φ, :μ) ? φ.μ : φ.β          # bernoulli.jl:7-11 ... studentt.jl:39-44
+s1(φ) = hasproperty(φ, :λ) ? φ.λ : hasproperty(φ, :p) ? φ.p : nothing
+s2(φ) = hasproperty(φ, :ψ) ? φ.ψ : hasproperty(φ, :y) ? φ.y : nothing
+iscat(lik) = lik isa CategoricalLikelihood
+"number of observations behind a field array: the Categorical fields are flat [n][nl] device vectors (class fastest)"
+nobs(lik, v::AbstractVector) = iscat(lik) ? length(v) ÷ AGPL.nlatent(lik) : length(v)
+nobs(lik, qΩ::For) = nobs(lik, s0(state(qΩ)))
 ptr(::Nothing) = C_NULL
 ptr(v::DV) = Ptr{Cvoid}(v.ptr)
 
-# ---------------------------------------------------------------- variational verbs
+# ---------------------------------------------------------------- variational verbs (implementations)
+# init_aux_posterior(T, lik, n)                        -> aug_init_aux_posterior      (a3)
+# The For closure (row of the SoA -> the law of that observation's auxiliary variables) is the reference's own
+# (bernoulli.jl:7-11 ... categorical.jl:59-70), taken from a zero-length CPU instance; only the field arrays differ.
+function dev_init_aux_posterior(lik::AbstractLikelihood, n::Integer)
+    q0 = AGPL.init_aux_posterior(Float64, lik, 0)
+    names = propertynames(only(q0.inds))                        # (:c,), (:y, :c, :λ), (:c, :λ, :ψ), (:y, :c, :p), ...
+    m = iscat(lik) ? n * AGPL.nlatent(lik) : n
+    arrays = map(names) do k
+        k === :y ? (iscat(lik) ? DV{Bool}(undef, m) : DV{Int64}(undef, m)) : DV{Float64}(undef, m)
+    end
+    φ = TupleVector(NamedTuple{names}(arrays))
+    withdesc(lik) do d
+        check(ccall((:aug_init_aux_posterior, lib), Int32, (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    ctx().h, d, n, ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ))))
+    end
+    return For(q0.f, φ)
+end
+
 # aux_posterior!(qΩ, lik, y, qf)                       -> aug_aux_posterior           (a5)
-function AGPL.aux_posterior!(qΩ::For, lik::AbstractLikelihood, y::DV, qf::DeviceNormals)
+function dev_aux_posterior!(qΩ::For, lik::AbstractLikelihood, y::DV, qf::DeviceNormals)
     φ = state(qΩ)
     withdesc(lik) do d
         check(ccall((:aug_aux_posterior, lib), Int32,
                     (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64,
                      Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
-                    ctx().h, d, length(qΩ), y.ptr, qf.μ.ptr, qf.σ².ptr, qf.ld, ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ))))
+                    ctx().h, d, nobs(lik, qΩ), y.ptr, qf.μ.ptr, qf.σ².ptr, qf.ld, ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ))))
     end
     return qΩ                                                    # bernoulli.jl:24
 end
 
 # expected_auglik_potential_and_precision(lik, qΩ, y[, qf]) -> aug_expected_potential_precision   (a7)
-function AGPL.expected_auglik_potential_and_precision(lik::AbstractLikelihood, qΩ::For, y::DV,
-                                                      qf::Union{Nothing,DeviceNormals}=nothing)
-    n, nl = length(qΩ), AGPL.nlatent(lik)
+function dev_expected_potential_precision(lik::AbstractLikelihood, qΩ::For, y::DV, qf::Union{Nothing,DeviceNormals})
+    n, nl = nobs(lik, qΩ), AGPL.nlatent(lik)
     β, γ = DV{Float64}(undef, n * nl), DV{Float64}(undef, n * nl)
     φ = state(qΩ)
     withdesc(lik) do d
@@ -180,32 +210,32 @@ function AGPL.expected_auglik_potential_and_precision(lik::AbstractLikelihood, q
     end
     return split_latents(β, n, nl), split_latents(γ, n, nl)
 end
-AGPL.expected_auglik_potential(lik::AbstractLikelihood, qΩ::For, y::DV, qf=nothing) =
-    first(AGPL.expected_auglik_potential_and_precision(lik, qΩ, y, qf))
-AGPL.expected_auglik_precision(lik::AbstractLikelihood, qΩ::For, y::DV, qf=nothing) =
-    last(AGPL.expected_auglik_potential_and_precision(lik, qΩ, y, qf))
 
 # expected_logtilt / aux_kldivergence / expected_aug_loglik -> aug_expected_elbo_terms (a9, a11, a13)
-function elbo_terms(lik, qΩ::For, y::DV, qf::DeviceNormals)
+function dev_elbo_terms(lik::AbstractLikelihood, qΩ::For, y::DV, qf::DeviceNormals)
     sc = DV{Float64}(undef, 8)
     φ = state(qΩ)
     withdesc(lik) do d
         check(ccall((:aug_expected_elbo_terms, lib), Int32,
                     (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Cvoid},
                      Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
-                    ctx().h, d, length(qΩ), y.ptr, qf.μ.ptr, qf.σ².ptr, qf.ld, ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ)), sc.ptr))
+                    ctx().h, d, nobs(lik, qΩ), y.ptr, qf.μ.ptr, qf.σ².ptr, qf.ld, ptr(s0(φ)), ptr(s1(φ)), ptr(s2(φ)), sc.ptr))
     end
     return Array(sc)          # multi-GPU callers run aug_allreduce_scalars on `sc` first (INTEGRATION.md)
 end
-AGPL.expected_logtilt(lik::AbstractLikelihood, qΩ::For, y::DV, qf::DeviceNormals) = elbo_terms(lik, qΩ, y, qf)[S_ELT]
-AGPL.expected_aug_loglik(lik::AbstractLikelihood, qΩ::For, y::DV, qf::DeviceNormals) = elbo_terms(lik, qΩ, y, qf)[S_EAUGLL]
-# aux_kldivergence(lik, qΩ, y) has no qf in the reference; the KL kernels only read the state and y, so a
-# zero qf of the right length is passed (the heteroscedastic prior needs the real qf: use elbo_terms).
+# aux_kldivergence(lik, qΩ, y) has no qf in the reference (generic.jl:56-58); the KL kernels only read the state and
+# y, so a zero qf of the right length is passed.  (The heteroscedastic likelihood has no prior / tilt split: its KL is
+# part of expected_aug_loglik, heteroscedasticgaussian.jl:129-143, and needs the real qf.)
+function dev_kldivergence(lik::AbstractLikelihood, qΩ::For, y::DV)
+    z = AugDeviceVector(zeros(Float64, length(s0(state(qΩ)))))
+    return dev_elbo_terms(lik, qΩ, y, DeviceNormals(z, z))[S_KL]
+end
 
 # The fused call of a CAVI iteration (examples/bernoulli/script.jl:29-39): aux_posterior!(qΩ, lik, y, qf) +
 # expected_auglik_potential_and_precision + the expected_logtilt / aux_kldivergence sums in ONE pass -> aug_cavi_step
+# (AugCUDA's own function: the reference has no fused verb, so there is nothing to be ambiguous with)
 function cavi_step!(qΩ::For, lik::AbstractLikelihood, y::DV, qf::DeviceNormals)
-    n, nl = length(qΩ), AGPL.nlatent(lik)
+    n, nl = nobs(lik, qΩ), AGPL.nlatent(lik)
     β, γ = DV{Float64}(undef, n * nl), DV{Float64}(undef, n * nl)
     sc = DV{Float64}(undef, 8)
     φ = state(qΩ)
@@ -219,84 +249,91 @@ function cavi_step!(qΩ::For, lik::AbstractLikelihood, y::DV, qf::DeviceNormals)
     return qΩ, split_latents(β, n, nl), split_latents(γ, n, nl), Array(sc)      # sc[S_ELT], sc[S_KL], sc[S_EAUGLL]
 end
 
-# ---------------------------------------------------------------- sampling verbs
+# ---------------------------------------------------------------- sampling verbs (implementations)
+needs_n(lik) = lik isa Union{PoissonLikelihood,HeteroscedasticGaussianLikelihood,CategoricalLikelihood}
+"uninitialised device Ω with the reference's field names (ω, and n where the law has an integer part)"
+function dev_alloc_aux_variables(lik::AbstractLikelihood, n::Integer)
+    m = iscat(lik) ? n * AGPL.nlatent(lik) : n
+    ω = DV{Float64}(undef, m)
+    return needs_n(lik) ? TupleVector((; ω, n=DV{Int64}(undef, m))) : TupleVector((; ω))
+end
+
 # aux_sample!(rng, Ω, lik, y, f)                      -> aug_aux_sample                 (a14-a19)
-function AGPL.aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::AbstractLikelihood, y::DV, f::DV; i0::Integer=0)
+function dev_aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::AbstractLikelihood, y::DV, f::DV; i0::Integer=0)
     seed!(rng)
     nv = hasproperty(Ω, :n) ? Ω.n : nothing
+    n = nobs(lik, Ω.ω)
     withdesc(lik) do d
         check(ccall((:aug_aux_sample, lib), Int32,
                     (Ptr{Cvoid}, Ref{AugLik}, Int64, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}),
-                    ctx().h, d, length(y) ÷ max(1, AGPL.nlatent(lik) * (lik isa CategoricalLikelihood)), i0,
-                    y.ptr, f.ptr, lik isa HeteroscedasticGaussianLikelihood ? length(f) ÷ 2 : 0, Ω.ω.ptr, ptr(nv)))
+                    ctx().h, d, n, i0, y.ptr, f.ptr, ldof(lik, n), Ω.ω.ptr, ptr(nv)))
     end
     sync_offset!(rng)
     return Ω                                                     # generic.jl:11
 end
-AGPL.aux_sample!(Ω::TupleVector, lik::AbstractLikelihood, y::DV, f::DV) = AGPL.aux_sample!(GLOBAL_PHILOX, Ω, lik, y, f)
 
 # init_aux_variables(rng, lik, n)                     -> aug_init_aux_variables          (a4)
-function AGPL.init_aux_variables(rng::AugPhilox, lik::AbstractLikelihood, n::Int; i0::Integer=0)
+function dev_init_aux_variables(rng::AugPhilox, lik::AbstractLikelihood, n::Integer; i0::Integer=0)
     seed!(rng)
-    m = lik isa CategoricalLikelihood ? n * AGPL.nlatent(lik) : n
-    ω = DV{Float64}(undef, m)
-    needs_n = lik isa Union{PoissonLikelihood,HeteroscedasticGaussianLikelihood,CategoricalLikelihood}
-    nv = needs_n ? DV{Int64}(undef, m) : nothing
+    Ω = dev_alloc_aux_variables(lik, n)
+    nv = hasproperty(Ω, :n) ? Ω.n : nothing
     withdesc(lik) do d
         check(ccall((:aug_init_aux_variables, lib), Int32,
-                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Int64, Ptr{Float64}, Ptr{Int64}), ctx().h, d, n, i0, ω.ptr, ptr(nv)))
+                    (Ptr{Cvoid}, Ref{AugLik}, Int64, Int64, Ptr{Float64}, Ptr{Int64}), ctx().h, d, n, i0, Ω.ω.ptr, ptr(nv)))
     end
     sync_offset!(rng)
-    return needs_n ? TupleVector((; ω, n=nv)) : TupleVector((; ω))
+    return Ω
 end
 
 # auglik_potential_and_precision(lik, Ω, y[, f])      -> aug_potential_precision         (a20)
-function AGPL.auglik_potential_and_precision(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::Union{Nothing,DV}=nothing)
+function dev_potential_precision(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::Union{Nothing,DV})
     nl = AGPL.nlatent(lik)
-    n = length(Ω.ω) ÷ (lik isa CategoricalLikelihood ? nl : 1)
+    n = nobs(lik, Ω.ω)
     β, γ = DV{Float64}(undef, n * nl), DV{Float64}(undef, n * nl)
     nv = hasproperty(Ω, :n) ? Ω.n : nothing
     withdesc(lik) do d
         check(ccall((:aug_potential_precision, lib), Int32,
                     (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64},
                      Ptr{Float64}, Ptr{Float64}, Int64),
-                    ctx().h, d, n, y.ptr, f === nothing ? C_NULL : f.ptr, f === nothing ? 0 : length(f) ÷ 2,
+                    ctx().h, d, n, y.ptr, f === nothing ? C_NULL : f.ptr, f === nothing ? 0 : ldof(lik, n),
                     Ω.ω.ptr, ptr(nv), β.ptr, γ.ptr, n))
     end
     return split_latents(β, n, nl), split_latents(γ, n, nl)
 end
 
 # logtilt / aug_loglik                                -> aug_sampled_loglik_terms         (a21-a24)
-function sampled_terms(lik, Ω::TupleVector, y::DV, f::DV, with_prior::Bool)
+function dev_sampled_terms(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::DV, with_prior::Bool)
     sc = DV{Float64}(undef, 8)
     nv = hasproperty(Ω, :n) ? Ω.n : nothing
-    n = lik isa CategoricalLikelihood ? length(Ω.ω) ÷ AGPL.nlatent(lik) : length(Ω.ω)
+    n = nobs(lik, Ω.ω)
     withdesc(lik) do d
         check(ccall((:aug_sampled_loglik_terms, lib), Int32,
                     (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}, Int32,
                      Ptr{Float64}),
-                    ctx().h, d, n, y.ptr, f.ptr, lik isa HeteroscedasticGaussianLikelihood ? n : 0, Ω.ω.ptr, ptr(nv),
-                    with_prior, sc.ptr))
+                    ctx().h, d, n, y.ptr, f.ptr, ldof(lik, n), Ω.ω.ptr, ptr(nv), with_prior, sc.ptr))
     end
     return Array(sc)
 end
-AGPL.logtilt(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::DV) = sampled_terms(lik, Ω, y, f, false)[S_LOGTILT]
-AGPL.aug_loglik(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::DV) = sampled_terms(lik, Ω, y, f, true)[S_AUGLL]
 
-# ---------------------------------------------------------------- host `Vector` methods (the reference's own argument types)
-# src/generic.jl:1-88 dispatches every verb on plain host vectors.  These methods keep those signatures — y::Vector,
-# qf::AbstractVector{<:Normal}, f::Vector, Ω / qΩ with Vector fields — and bind to the *_host entry points: the
-# library stages chunks through the GPU (H2D, kernel, D2H overlapped) and the results come back in host vectors.
-# The only host-side work is the AoS → SoA split of qf (mean.(qf), var.(qf)): the ABI takes struct-of-arrays.
-const HV = Vector
+# ---------------------------------------------------------------- host `Vector` implementations (the reference's own argument types)
+# src/generic.jl:1-88 dispatches every verb on plain host vectors.  These bind to the *_host entry points: the library
+# stages chunks through the GPU (H2D, kernel, D2H overlapped) and the results come back in host vectors.  The only
+# host-side work is the AoS → SoA split of qf (mean.(qf), var.(qf)): the ABI takes struct-of-arrays.  Covered: the six
+# likelihoods whose reference containers are plain `Vector`s.  The Categorical containers of the reference are
+# ArraysOfArrays nested views (over a BitMatrix for y, categorical.jl:59-70): bind those through the device methods.
 hptr(::Nothing) = C_NULL
 hptr(v::Vector) = Ptr{Cvoid}(pointer(v))
 moments(qf::AbstractVector{<:Normal}) = (convert(Vector{Float64}, mean.(qf)), convert(Vector{Float64}, var.(qf)))
-# two-latent heteroscedastic qfg = (qf, qg) (heteroscedasticgaussian.jl:38): latent-major [2][n]
-moments(qfg::Tuple) = (vcat((mean.(q) for q in qfg)...), vcat((var.(q) for q in qfg)...))
+# two-latent heteroscedastic qfg[i] = (qf_i, qg_i) (heteroscedasticgaussian.jl:34-46) -> latent-major [2][n]
+moments(qfg::AbstractVector{<:AbstractVector{<:Normal}}) =
+    (convert(Vector{Float64}, vcat(mean.(first.(qfg)), mean.(last.(qfg)))),
+     convert(Vector{Float64}, vcat(var.(first.(qfg)), var.(last.(qfg)))))
+# f for the sampling side: a plain vector, or fg[i] = (f_i, g_i) (heteroscedasticgaussian.jl:28-32) -> latent-major
+latents(f::Vector{Float64}) = f
+latents(fg::AbstractVector) = convert(Vector{Float64}, vcat(first.(fg), last.(fg)))
 ldof(lik, n) = lik isa HeteroscedasticGaussianLikelihood ? n : 0
 
-function AGPL.aux_posterior!(qΩ::For, lik::AbstractLikelihood, y::HV, qf)
+function host_aux_posterior!(qΩ::For, lik::AbstractLikelihood, y::Vector, qf)
     φ = state(qΩ); μ, σ² = moments(qf); n = length(qΩ)
     withdesc(lik) do d
         GC.@preserve y μ σ² φ check(ccall((:aug_aux_posterior_host, lib), Int32,
@@ -307,7 +344,7 @@ function AGPL.aux_posterior!(qΩ::For, lik::AbstractLikelihood, y::HV, qf)
     return qΩ
 end
 
-function AGPL.expected_auglik_potential_and_precision(lik::AbstractLikelihood, qΩ::For, y::HV, qf=nothing)
+function host_expected_potential_precision(lik::AbstractLikelihood, qΩ::For, y::Vector, qf)
     n, nl = length(qΩ), AGPL.nlatent(lik)
     β, γ = Vector{Float64}(undef, n * nl), Vector{Float64}(undef, n * nl)
     φ = state(qΩ)
@@ -322,7 +359,7 @@ function AGPL.expected_auglik_potential_and_precision(lik::AbstractLikelihood, q
     return split_latents(β, n, nl), split_latents(γ, n, nl)
 end
 
-function elbo_terms(lik, qΩ::For, y::HV, qf)
+function host_elbo_terms(lik::AbstractLikelihood, qΩ::For, y::Vector, qf)
     sc = zeros(Float64, 8); φ = state(qΩ); μ, σ² = moments(qf); n = length(qΩ)
     withdesc(lik) do d
         GC.@preserve y μ σ² φ check(ccall((:aug_expected_elbo_terms_host, lib), Int32,
@@ -332,11 +369,11 @@ function elbo_terms(lik, qΩ::For, y::HV, qf)
     end
     return sc
 end
-AGPL.expected_logtilt(lik::AbstractLikelihood, qΩ::For, y::HV, qf) = elbo_terms(lik, qΩ, y, qf)[S_ELT]
-AGPL.expected_aug_loglik(lik::AbstractLikelihood, qΩ::For, y::HV, qf) = elbo_terms(lik, qΩ, y, qf)[S_EAUGLL]
+host_kldivergence(lik::AbstractLikelihood, qΩ::For, y::Vector) =
+    host_elbo_terms(lik, qΩ, y, fill(Normal(0.0, 0.0), length(qΩ)))[S_KL]
 
 "fused CAVI iteration on host vectors; `want_state = false` / `want_β = false` skip those outputs (and their D2H bytes)"
-function cavi_step!(qΩ::For, lik::AbstractLikelihood, y::HV, qf; want_state::Bool=true, want_β::Bool=true)
+function cavi_step!(qΩ::For, lik::AbstractLikelihood, y::Vector, qf; want_state::Bool=true, want_β::Bool=true)
     n, nl = length(qΩ), AGPL.nlatent(lik)
     β = want_β ? Vector{Float64}(undef, n * nl) : nothing
     γ = Vector{Float64}(undef, n * nl)
@@ -352,10 +389,11 @@ function cavi_step!(qΩ::For, lik::AbstractLikelihood, y::HV, qf; want_state::Bo
     return qΩ, (β === nothing ? nothing : split_latents(β, n, nl)), split_latents(γ, n, nl), sc
 end
 
-function AGPL.aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::AbstractLikelihood, y::HV, f::HV; i0::Integer=0)
+function host_aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::AbstractLikelihood, y::Vector, fs::AbstractVector; i0::Integer=0)
     seed!(rng)
+    f = latents(fs)
     nv = hasproperty(Ω, :n) ? Ω.n : nothing
-    n = lik isa CategoricalLikelihood ? length(Ω.ω) ÷ AGPL.nlatent(lik) : length(Ω.ω)
+    n = length(Ω.ω)
     withdesc(lik) do d
         GC.@preserve y f Ω check(ccall((:aug_aux_sample_host, lib), Int32,
                     (Ptr{Cvoid}, Ref{AugLik}, Int64, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}),
@@ -365,26 +403,27 @@ function AGPL.aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::AbstractLikeliho
     return Ω
 end
 
+"init_aux_variables on the device into HOST vectors (the counter-based stream instead of the reference's CPU rng)"
 function init_aux_variables_host(rng::AugPhilox, lik::AbstractLikelihood, n::Int; i0::Integer=0)
     seed!(rng)
-    m = lik isa CategoricalLikelihood ? n * AGPL.nlatent(lik) : n
+    m = iscat(lik) ? n * AGPL.nlatent(lik) : n
     ω = Vector{Float64}(undef, m)
-    needs_n = lik isa Union{PoissonLikelihood,HeteroscedasticGaussianLikelihood,CategoricalLikelihood}
-    nv = needs_n ? Vector{Int64}(undef, m) : nothing
+    nv = needs_n(lik) ? Vector{Int64}(undef, m) : nothing
     withdesc(lik) do d
         GC.@preserve ω nv check(ccall((:aug_init_aux_variables_host, lib), Int32,
                     (Ptr{Cvoid}, Ref{AugLik}, Int64, Int64, Ptr{Float64}, Ptr{Int64}),
                     ctx().h, d, n, i0, ω, nv === nothing ? C_NULL : pointer(nv)))
     end
     sync_offset!(rng)
-    return needs_n ? TupleVector((; ω, n=nv)) : TupleVector((; ω))
+    return nv === nothing ? TupleVector((; ω)) : TupleVector((; ω, n=nv))
 end
 
-function AGPL.auglik_potential_and_precision(lik::AbstractLikelihood, Ω::TupleVector, y::HV, f::Union{Nothing,HV}=nothing)
+function host_potential_precision(lik::AbstractLikelihood, Ω::TupleVector, y::Vector, fs)
     nl = AGPL.nlatent(lik)
-    n = length(Ω.ω) ÷ (lik isa CategoricalLikelihood ? nl : 1)
+    n = length(Ω.ω)
     β, γ = Vector{Float64}(undef, n * nl), Vector{Float64}(undef, n * nl)
     nv = hasproperty(Ω, :n) ? Ω.n : nothing
+    f = fs === nothing ? nothing : latents(fs)
     withdesc(lik) do d
         GC.@preserve y f Ω β γ check(ccall((:aug_potential_precision_host, lib), Int32,
                     (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64},
@@ -395,10 +434,11 @@ function AGPL.auglik_potential_and_precision(lik::AbstractLikelihood, Ω::TupleV
     return split_latents(β, n, nl), split_latents(γ, n, nl)
 end
 
-function sampled_terms(lik, Ω::TupleVector, y::HV, f::HV, with_prior::Bool)
+function host_sampled_terms(lik::AbstractLikelihood, Ω::TupleVector, y::Vector, fs::AbstractVector, with_prior::Bool)
     sc = zeros(Float64, 8)
+    f = latents(fs)
     nv = hasproperty(Ω, :n) ? Ω.n : nothing
-    n = lik isa CategoricalLikelihood ? length(Ω.ω) ÷ AGPL.nlatent(lik) : length(Ω.ω)
+    n = length(Ω.ω)
     withdesc(lik) do d
         GC.@preserve y f Ω check(ccall((:aug_sampled_loglik_terms_host, lib), Int32,
                     (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}, Int32,
@@ -408,8 +448,106 @@ function sampled_terms(lik, Ω::TupleVector, y::HV, f::HV, with_prior::Bool)
     end
     return sc
 end
-AGPL.logtilt(lik::AbstractLikelihood, Ω::TupleVector, y::HV, f::HV) = sampled_terms(lik, Ω, y, f, false)[S_LOGTILT]
-AGPL.aug_loglik(lik::AbstractLikelihood, Ω::TupleVector, y::HV, f::HV) = sampled_terms(lik, Ω, y, f, true)[S_AUGLL]
+
+# ---------------------------------------------------------------- the dispatch layer: methods of the reference's verbs
+# (likelihood type as the reference dispatches on it, element type of y as the C ABI takes it, container of qf / f as
+#  the reference's own methods take it)
+const NormalVec = AbstractVector{<:Normal}
+const NormalVecVec = AbstractVector{<:AbstractVector{<:Normal}}
+const REFERENCE_LIKELIHOODS = (
+    (BernoulliLikelihood{<:LogisticLink}, Bool, NormalVec),               # bernoulli.jl:3-70    (Julia Bool = 1 byte)
+    (AGPL.NegBinomialLikelihood, Int64, NormalVec),                       # negativebinomial.jl:1
+    (AGPL.AugPoisson, Int64, NormalVec),                                  # poisson.jl:7
+    (LaplaceLikelihood, Float64, NormalVec),                              # laplace.jl:13-17
+    (StudentTLikelihood, Float64, NormalVec),                             # studentt.jl:14-21
+    (AGPL.AugHeteroGaussian, Float64, NormalVecVec),                      # heteroscedasticgaussian.jl:7, :34-39
+    (AGPL.BijectiveLogisticSoftMaxLikelihood, Bool, nothing),             # categorical.jl:38-41 (device containers only)
+    (AGPL.LogisticSoftMaxLikelihood, Bool, nothing),
+)
+
+for (L, Y, QF) in REFERENCE_LIKELIHOODS
+    # ---- device containers: every argument is a subtype of the reference's, the likelihood type is the reference's
+    @eval begin
+        AGPL.init_aux_posterior(::Type{AugDeviceVector}, lik::$L, n::Int) = dev_init_aux_posterior(lik, n)
+        AGPL.aux_posterior!(qΩ::For, lik::$L, y::DV{$Y}, qf::DeviceNormals) = dev_aux_posterior!(qΩ, lik, y, qf)
+        AGPL.aux_posterior(lik::$L, y::DV{$Y}, qf::DeviceNormals) =
+            dev_aux_posterior!(dev_init_aux_posterior(lik, nobs(lik, y)), lik, y, qf)          # generic.jl:22-24
+        AGPL.expected_auglik_potential_and_precision(lik::$L, qΩ::For, y::DV{$Y}) =
+            dev_expected_potential_precision(lik, qΩ, y, nothing)
+        AGPL.expected_auglik_potential_and_precision(lik::$L, qΩ::For, y::DV{$Y}, qf::Union{Nothing,DeviceNormals}) =
+            dev_expected_potential_precision(lik, qΩ, y, qf)
+        AGPL.expected_auglik_potential(lik::$L, qΩ::For, y::DV{$Y}) = first(dev_expected_potential_precision(lik, qΩ, y, nothing))
+        AGPL.expected_auglik_potential(lik::$L, qΩ::For, y::DV{$Y}, qf::Union{Nothing,DeviceNormals}) =
+            first(dev_expected_potential_precision(lik, qΩ, y, qf))
+        AGPL.expected_auglik_precision(lik::$L, qΩ::For, y::DV{$Y}) = last(dev_expected_potential_precision(lik, qΩ, y, nothing))
+        AGPL.expected_auglik_precision(lik::$L, qΩ::For, y::DV{$Y}, qf::Union{Nothing,DeviceNormals}) =
+            last(dev_expected_potential_precision(lik, qΩ, y, qf))
+        AGPL.expected_logtilt(lik::$L, qΩ::For, y::DV{$Y}, qf::DeviceNormals) = dev_elbo_terms(lik, qΩ, y, qf)[S_ELT]
+        AGPL.expected_aug_loglik(lik::$L, qΩ::For, y::DV{$Y}, qf::DeviceNormals) = dev_elbo_terms(lik, qΩ, y, qf)[S_EAUGLL]
+        AGPL.init_aux_variables(rng::AugPhilox, lik::$L, n::Int; i0::Integer=0) = dev_init_aux_variables(rng, lik, n; i0=i0)
+        AGPL.aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::$L, y::DV{$Y}, f::DV{Float64}; i0::Integer=0) =
+            dev_aux_sample!(rng, Ω, lik, y, f; i0=i0)
+        AGPL.aux_sample!(Ω::TupleVector, lik::$L, y::DV{$Y}, f::DV{Float64}) = dev_aux_sample!(GLOBAL_PHILOX, Ω, lik, y, f)
+        AGPL.aux_sample(rng::AugPhilox, lik::$L, y::DV{$Y}, f::DV{Float64}; i0::Integer=0) =
+            dev_aux_sample!(rng, dev_alloc_aux_variables(lik, nobs(lik, y)), lik, y, f; i0=i0)   # generic.jl:18-20
+        AGPL.aux_sample(lik::$L, y::DV{$Y}, f::DV{Float64}) = AGPL.aux_sample(GLOBAL_PHILOX, lik, y, f)
+        AGPL.auglik_potential_and_precision(lik::$L, Ω::TupleVector, y::DV{$Y}) = dev_potential_precision(lik, Ω, y, nothing)
+        AGPL.auglik_potential_and_precision(lik::$L, Ω::TupleVector, y::DV{$Y}, f::Union{Nothing,DV{Float64}}) =
+            dev_potential_precision(lik, Ω, y, f)
+        AGPL.auglik_potential(lik::$L, Ω::TupleVector, y::DV{$Y}) = first(dev_potential_precision(lik, Ω, y, nothing))
+        AGPL.auglik_potential(lik::$L, Ω::TupleVector, y::DV{$Y}, f::Union{Nothing,DV{Float64}}) =
+            first(dev_potential_precision(lik, Ω, y, f))
+        AGPL.auglik_precision(lik::$L, Ω::TupleVector, y::DV{$Y}) = last(dev_potential_precision(lik, Ω, y, nothing))
+        AGPL.auglik_precision(lik::$L, Ω::TupleVector, y::DV{$Y}, f::Union{Nothing,DV{Float64}}) =
+            last(dev_potential_precision(lik, Ω, y, f))
+        AGPL.logtilt(lik::$L, Ω::TupleVector, y::DV{$Y}, f::DV{Float64}) = dev_sampled_terms(lik, Ω, y, f, false)[S_LOGTILT]
+        AGPL.aug_loglik(lik::$L, Ω::TupleVector, y::DV{$Y}, f::DV{Float64}) = dev_sampled_terms(lik, Ω, y, f, true)[S_AUGLL]
+    end
+    if L !== AGPL.AugHeteroGaussian        # no prior / tilt split (see dev_kldivergence)
+        @eval AGPL.aux_kldivergence(lik::$L, qΩ::For, y::DV{$Y}) = dev_kldivergence(lik, qΩ, y)
+    end
+    QF === nothing && continue
+    # ---- host Vectors.  y::Vector{Y} and qf::QF are subtypes of (or equal to) what the reference's methods take, qΩ::For /
+    # Ω::TupleVector are narrower than its untyped arguments: with AugCUDA loaded these calls run on the GPU.  The
+    # sampling verbs go to the GPU when the rng is an AugPhilox (the reference's CPU rngs keep the CPU path).
+    @eval begin
+        AGPL.aux_posterior!(qΩ::For, lik::$L, y::Vector{$Y}, qf::$QF) = host_aux_posterior!(qΩ, lik, y, qf)
+        AGPL.expected_auglik_potential_and_precision(lik::$L, qΩ::For, y::Vector{$Y}) =
+            host_expected_potential_precision(lik, qΩ, y, nothing)
+        AGPL.expected_auglik_potential_and_precision(lik::$L, qΩ::For, y::Vector{$Y}, ::Nothing) =
+            host_expected_potential_precision(lik, qΩ, y, nothing)
+        AGPL.expected_auglik_potential_and_precision(lik::$L, qΩ::For, y::Vector{$Y}, qf::$QF) =
+            host_expected_potential_precision(lik, qΩ, y, qf)
+        AGPL.expected_auglik_potential(lik::$L, qΩ::For, y::Vector{$Y}) = first(host_expected_potential_precision(lik, qΩ, y, nothing))
+        AGPL.expected_auglik_potential(lik::$L, qΩ::For, y::Vector{$Y}, qf::$QF) =
+            first(host_expected_potential_precision(lik, qΩ, y, qf))
+        AGPL.expected_auglik_precision(lik::$L, qΩ::For, y::Vector{$Y}) = last(host_expected_potential_precision(lik, qΩ, y, nothing))
+        AGPL.expected_auglik_precision(lik::$L, qΩ::For, y::Vector{$Y}, qf::$QF) =
+            last(host_expected_potential_precision(lik, qΩ, y, qf))
+        AGPL.expected_logtilt(lik::$L, qΩ::For, y::Vector{$Y}, qf::$QF) = host_elbo_terms(lik, qΩ, y, qf)[S_ELT]
+        AGPL.expected_aug_loglik(lik::$L, qΩ::For, y::Vector{$Y}, qf::$QF) = host_elbo_terms(lik, qΩ, y, qf)[S_EAUGLL]
+        AGPL.aux_sample!(rng::AugPhilox, Ω::TupleVector, lik::$L, y::Vector{$Y}, f::AbstractVector; i0::Integer=0) =
+            host_aux_sample!(rng, Ω, lik, y, f; i0=i0)
+        AGPL.auglik_potential_and_precision(lik::$L, Ω::TupleVector, y::Vector{$Y}) = host_potential_precision(lik, Ω, y, nothing)
+        AGPL.auglik_potential_and_precision(lik::$L, Ω::TupleVector, y::Vector{$Y}, ::Nothing) =
+            host_potential_precision(lik, Ω, y, nothing)
+        AGPL.logtilt(lik::$L, Ω::TupleVector, y::Vector{$Y}, f::Vector{Float64}) = host_sampled_terms(lik, Ω, y, f, false)[S_LOGTILT]
+        AGPL.aug_loglik(lik::$L, Ω::TupleVector, y::Vector{$Y}, f::Vector{Float64}) = host_sampled_terms(lik, Ω, y, f, true)[S_AUGLL]
+    end
+    if L !== AGPL.AugHeteroGaussian
+        @eval AGPL.aux_kldivergence(lik::$L, qΩ::For, y::Vector{$Y}) = host_kldivergence(lik, qΩ, y)
+    else
+        # the sampled-side containers of the reference for two latents: fg[i] = (f_i, g_i) (heteroscedasticgaussian.jl:48-66)
+        @eval begin
+            AGPL.auglik_potential_and_precision(lik::$L, Ω::TupleVector, y::Vector{$Y}, fg::AbstractVector{<:AbstractVector{<:Real}}) =
+                host_potential_precision(lik, Ω, y, fg)
+            AGPL.auglik_potential(lik::$L, Ω::TupleVector, y::Vector{$Y}, fg::AbstractVector{<:AbstractVector{<:Real}}) =
+                first(host_potential_precision(lik, Ω, y, fg))
+            AGPL.auglik_precision(lik::$L, Ω::TupleVector, y::Vector{$Y}, fg::AbstractVector{<:AbstractVector{<:Real}}) =
+                last(host_potential_precision(lik, Ω, y, fg))
+        end
+    end
+end
 
 # ---- multi-GPU (one Julia process per GPU, e.g. Distributed / MPI.jl) ------------------------------------------
 # Peer-memory mailbox: the all-reduce of the 64-byte scalar block runs INSIDE the reducing kernels (include/augcuda.h).
@@ -443,7 +581,7 @@ end
 
 # (l::LogisticSoftMaxLink)(f) row-wise on a device matrix stored class-fastest (categorical.jl:32-35)
 function logisticsoftmax_rows(lik::CategoricalLikelihood, f::DV, n::Integer)
-    K = lik.invlink isa BijectiveSimplexLink ? nlatent(lik) + 1 : nlatent(lik)
+    K = lik.invlink isa BijectiveSimplexLink ? AGPL.nlatent(lik) + 1 : AGPL.nlatent(lik)
     out = AugDeviceVector{Float64}(undef, n * K)
     withdesc(lik) do d
         check(ccall((:aug_logisticsoftmax, lib), Int32, (Ptr{Cvoid}, Ref{AugLik}, Int64, Ptr{Float64}, Ptr{Float64}),

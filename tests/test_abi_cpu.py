@@ -202,3 +202,37 @@ def test_julia_glue_binds_only_declared_symbols_with_matching_arity():
                  "aug_expected_elbo_terms_host", "aug_aux_sample_host", "aug_init_aux_variables_host",
                  "aug_potential_precision_host", "aug_sampled_loglik_terms_host"):
         assert must in seen, must
+
+
+def test_julia_glue_methods_cannot_be_ambiguous_with_the_reference():
+    """The reference specialises its verbs on the likelihood type with loosely typed arrays (e.g. bernoulli.jl:17-22
+    `aux_posterior!(qΩ, ::BernoulliLikelihood{<:LogisticLink}, ::AbstractVector, qf::AbstractVector{<:Normal})`).  A glue
+    method with `lik::AbstractLikelihood` and a device / Vector array type is more specific in one argument and less in
+    another: Julia raises an ambiguity MethodError at the call.  Static guard (no Julia here): every method AugCUDA.jl adds
+    to a verb of the reference takes the likelihood as `lik::$L` inside the loop over REFERENCE_LIKELIHOODS, whose entries
+    are the aliases the reference itself dispatches on."""
+    src = open(os.path.join(ROOT, "augmentedgplikelihoods.jl_b200", "julia", "AugCUDA.jl")).read()
+    code = "\n".join(l.split("#")[0] for l in src.splitlines())
+    defs = re.findall(r"^\s*(?:@eval\s+)?(?:function\s+)?AGPL\.([a-z_]+!?)\(([^)]*)\)", code, flags=re.M)
+    assert len(defs) >= 40
+    verbs = {v for v, _ in defs}
+    for must in ("init_aux_posterior", "aux_posterior!", "aux_posterior", "expected_auglik_potential_and_precision",
+                 "expected_auglik_potential", "expected_auglik_precision", "expected_logtilt", "aux_kldivergence",
+                 "expected_aug_loglik", "init_aux_variables", "aux_sample!", "aux_sample", "auglik_potential_and_precision",
+                 "auglik_potential", "auglik_precision", "logtilt", "aug_loglik"):
+        assert must in verbs, must
+    for verb, args in defs:
+        assert "lik::$L" in args, (verb, args)
+        assert "AbstractLikelihood" not in args, (verb, args)
+    # the loop's likelihood types are the reference's own dispatch aliases, read from the reference when it is present
+    table = re.search(r"const REFERENCE_LIKELIHOODS = \((.*?)\n\)", src, flags=re.S).group(1)
+    for alias in ("BernoulliLikelihood{<:LogisticLink}", "AGPL.NegBinomialLikelihood", "AGPL.AugPoisson", "LaplaceLikelihood",
+                  "StudentTLikelihood", "AGPL.AugHeteroGaussian", "AGPL.BijectiveLogisticSoftMaxLikelihood",
+                  "AGPL.LogisticSoftMaxLikelihood"):
+        assert alias in table, alias
+    ref = "/root/reference/src/likelihoods"
+    if os.path.isdir(ref):
+        txt = "".join(open(os.path.join(ref, f)).read() for f in os.listdir(ref))
+        for alias in ("NegBinomialLikelihood", "AugPoisson", "AugHeteroGaussian", "BijectiveLogisticSoftMaxLikelihood",
+                      "LogisticSoftMaxLikelihood"):
+            assert re.search(rf"^const {alias} = ", txt, flags=re.M), alias
