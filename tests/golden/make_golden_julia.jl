@@ -41,9 +41,6 @@ catch e
     (nothing, sprint(showerror, e))
 end
 
-# the heteroscedastic full conditional takes per-observation (f, g) pairs (heteroscedasticgaussian.jl:28-32)
-SplitApplyCombine_invert(f) = [[f[1][i], f[2][i]] for i in eachindex(f[1])]
-
 out = Dict{String,Any}()
 for (name, c) in cases
     lik = make_lik(c)
@@ -55,10 +52,11 @@ for (name, c) in cases
         y = nestedview(hcat([Bool.(row .!= 0) for row in c["y"]]...))
         qf = [Normal.(Float64.(c["mu"][i]), sqrt.(Float64.(c["var"][i]))) for i in 1:n]
         f = [Float64.(c["mu"][i]) for i in 1:n]
-    elseif k == 5                                    # (qf, qg): heteroscedasticgaussian.jl:34-39
-        y = Float64.(c["y"])
-        qf = [Normal.(Float64.(c["mu"][j]), sqrt.(Float64.(c["var"][j]))) for j in 1:2]
-        f = [Float64.(c["mu"][j]) for j in 1:2]
+    elseif k == 5                                    # per-observation pairs qfg[i] = [qf_i, qg_i], fg[i] = [f_i, g_i]: the verbs
+        y = Float64.(c["y"])                         # broadcast first / last over them (heteroscedasticgaussian.jl:34-45, 48-66;
+        n = length(y)                                # examples/heteroscedasticgaussian/script.jl:59-60 passes invert(posts_fs))
+        qf = [[Normal(Float64(c["mu"][j][i]), sqrt(Float64(c["var"][j][i]))) for j in 1:2] for i in 1:n]
+        f = [[Float64(c["mu"][j][i]) for j in 1:2] for i in 1:n]
     else
         y = k == 0 ? Bool.(c["y"] .!= 0) : (k in (1, 2) ? Int.(c["y"]) : Float64.(c["y"]))
         qf = Normal.(Float64.(c["mu"]), sqrt.(Float64.(c["var"])))
@@ -86,7 +84,7 @@ for (name, c) in cases
         end
     end
     # ---- sampling side: Ω drawn by the reference, then the deterministic verbs on it
-    Ω, err = attempt(() -> aux_sample(MersenneTwister(1), lik, y, k == 5 ? SplitApplyCombine_invert(f) : f))
+    Ω, err = attempt(() -> aux_sample(MersenneTwister(1), lik, y, f))
     r["err_aux_sample"] = err
     if Ω !== nothing
         r["omega"] = tovec(Ω.ω)
