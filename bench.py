@@ -31,6 +31,27 @@ METRIC = "CAVI obs/sec & Polya-Gamma draws/sec (Bernoulli-logistic; one fused CA
 UNIT = "obs/s"
 BYTES_CAVI = 41   # R y 1 + mu 8 + var 8, W c 8 + beta 8 + gamma 8
 BYTES_GIBBS = 16  # R f 8, W omega 8
+# pg1_compact_kernel: warp-instructions per draw = ncu smsp__inst_executed.sum / draws at the bench's input law (f ~ N(0,1)),
+# profiles/r2zz_ncu_summary.txt (1 126 289 538 for 1e8 draws; 28.4 of 32 lanes active per instruction)
+PG1_WARP_INSTR_PER_DRAW = 11.263
+
+
+def issue_roofline(draws, ms, sms, clocks):
+    """Issue-slot roofline of the sampler, the time-dominant and issue-bound kernel of the step: achieved = executed
+    warp-instructions per second from the LIVE kernel time and the instruction count ncu measured for this kernel; peak = SMs x 4
+    schedulers x SM clock (one warp-instruction per scheduler per cycle, clock = the median sampled under load)."""
+    try:
+        mhz = float((clocks or {}).get("sm_mhz") or 0.0)
+        if mhz <= 0.0 or not sms or ms <= 0.0:
+            return None
+        ach = PG1_WARP_INSTR_PER_DRAW * draws / (ms * 1e-3)
+        peak = float(sms) * 4.0 * mhz * 1e6
+        return {"bound": "issue", "achieved": ach, "peak": peak, "unit": "warp-instructions/s", "frac": ach / peak,
+                "warp_instructions_per_draw": PG1_WARP_INSTR_PER_DRAW,
+                "source": "instruction count: ncu (profiles/r2zz_ncu_summary.txt, issue-active 71.1 % under ncu); "
+                          "time and clock: this run"}
+    except Exception:
+        return None
 
 
 _OUT = None
@@ -859,6 +880,10 @@ def main():
         except Exception:
             traffic = None
     ms_step, ms_cavi, ms_gibbs = tm["ms_per_step"], tm["ms_cavi"], tm["ms_gibbs"]
+    try:
+        sm_count = int(ctx.sm_count())
+    except Exception:
+        sm_count = 0
     ach = BYTES_CAVI * n / (ms_cavi * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": n * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -888,7 +913,8 @@ def main():
                            "achieved": BYTES_GIBBS * n / (ms_gibbs * 1e-3) / 1e9, "unit": "GB/s",
                            "frac_hbm": BYTES_GIBBS * n / (ms_gibbs * 1e-3) / 1e9 / peak,
                            "pg_draws_per_s_per_gpu": n / (ms_gibbs * 1e-3), "share_of_step": ms_gibbs / ms_step,
-                           "ncu": "profiles/ (issue-slot utilisation, active lanes, pipe shares of this kernel)"},
+                           "issue": issue_roofline(n, ms_gibbs, sm_count, clocks),
+                           "ncu": "profiles/r2zz_ncu_summary.txt (issue-slot utilisation, active lanes, pipe shares of this kernel)"},
         "cpu_baseline": cpu, "e2e": e2e, "e2e_all_outputs": e2e_full, "gpu_launches": int(tm["launches"]), "clocks": clocks,
         "elbo_check": elbo, "checks": checks, "strong_scaling": strong, "configs": cfgs,
     }
