@@ -315,6 +315,29 @@ function dev_sampled_terms(lik::AbstractLikelihood, Ω::TupleVector, y::DV, f::D
     return Array(sc)
 end
 
+# ---------------------------------------------------------------- the two auxiliary-variable laws as handles (a10, a14)
+# aux_prior(lik, y) and aux_full_conditional(lik, y, f) build one distribution object per observation in the reference
+# (bernoulli.jl:13-15, 51-53, generic.jl:26-30).  The device side never materialises those: a handle carries the
+# arguments, `logdensity_def(prior, Ω)` (generic.jl:49) and `tvrand(rng, cond)` (TestUtils.jl:108-110) run on the device.
+struct DeviceAuxPrior{L<:AbstractLikelihood,Y}
+    lik::L
+    y::AugDeviceVector{Y}
+end
+struct DeviceAuxFullConditional{L<:AbstractLikelihood,Y}
+    lik::L
+    y::AugDeviceVector{Y}
+    f::AugDeviceVector{Float64}
+end
+Base.length(p::DeviceAuxPrior) = nobs(p.lik, p.y)
+Base.length(p::DeviceAuxFullConditional) = nobs(p.lik, p.y)
+# the prior does not depend on f: slot S_LOGPRIOR of the sampled terms at f = 0
+function AGPL.logdensity_def(p::DeviceAuxPrior, Ω::TupleVector)
+    f0 = AugDeviceVector(zeros(Float64, length(Ω.ω) * (p.lik isa HeteroscedasticGaussianLikelihood ? 2 : 1)))
+    return dev_sampled_terms(p.lik, Ω, p.y, f0, true)[S_LOGPRIOR]
+end
+AGPL.SpecialDistributions.tvrand(rng::AugPhilox, d::DeviceAuxFullConditional; i0::Integer=0) =
+    dev_aux_sample!(rng, dev_alloc_aux_variables(d.lik, length(d)), d.lik, d.y, d.f; i0=i0)
+
 # ---------------------------------------------------------------- host `Vector` implementations (the reference's own argument types)
 # src/generic.jl:1-88 dispatches every verb on plain host vectors.  These bind to the *_host entry points: the library
 # stages chunks through the GPU (H2D, kernel, D2H overlapped) and the results come back in host vectors.  The only
@@ -500,11 +523,13 @@ for (L, Y, QF) in REFERENCE_LIKELIHOODS
         AGPL.auglik_precision(lik::$L, Ω::TupleVector, y::DV{$Y}) = last(dev_potential_precision(lik, Ω, y, nothing))
         AGPL.auglik_precision(lik::$L, Ω::TupleVector, y::DV{$Y}, f::Union{Nothing,DV{Float64}}) =
             last(dev_potential_precision(lik, Ω, y, f))
+        AGPL.aux_full_conditional(lik::$L, y::DV{$Y}, f::DV{Float64}) = DeviceAuxFullConditional(lik, y, f)
         AGPL.logtilt(lik::$L, Ω::TupleVector, y::DV{$Y}, f::DV{Float64}) = dev_sampled_terms(lik, Ω, y, f, false)[S_LOGTILT]
         AGPL.aug_loglik(lik::$L, Ω::TupleVector, y::DV{$Y}, f::DV{Float64}) = dev_sampled_terms(lik, Ω, y, f, true)[S_AUGLL]
     end
     if L !== AGPL.AugHeteroGaussian        # no prior / tilt split (see dev_kldivergence)
         @eval AGPL.aux_kldivergence(lik::$L, qΩ::For, y::DV{$Y}) = dev_kldivergence(lik, qΩ, y)
+        @eval AGPL.aux_prior(lik::$L, y::DV{$Y}) = DeviceAuxPrior(lik, y)
     end
     QF === nothing && continue
     # ---- host Vectors.  y::Vector{Y} and qf::QF are subtypes of (or equal to) what the reference's methods take, qΩ::For /
