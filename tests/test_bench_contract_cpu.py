@@ -60,3 +60,14 @@ def test_committed_gpu_line_has_the_contract_keys():
     # the parts add up to the step
     p = d["parts"]
     assert abs(p["ms_cavi"] + p["ms_gibbs"] + p["ms_allreduce"] - d["ms_per_step"]) < 0.02 * d["ms_per_step"]
+
+
+def test_reference_arm_under_torchrun_prints_from_rank_0_only():
+    """N > 1: the driver launches the reference arm like the GPU arm; rank 0 alone runs and prints, the others exit 0."""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = _json_lines(out.stdout)
+    assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2
